@@ -1,0 +1,99 @@
+"""Oracle (families O and P) against fixtures produced by the reference's own code -- CPU only."""
+import math
+
+import numpy as np
+import torch
+
+from oracle import franka as ofr
+from oracle import pd as opd
+from test_isaacgym_b200 import synthetic as syn
+
+
+def _inputs(g, dt):
+    n = g["mm"].shape[0]
+    t = lambda k: torch.from_numpy(g[k]).to(dt)
+    ds = t("dof_state")
+    return dict(n=n, j=t("j_eef"), mm=t("mm"), pos=ds[:, 0].view(n, 9, 1), vel=ds[:, 1].view(n, 9, 1),
+                hv=t("hand_vel"), dpose=t("dpose"), qdef=t("default_dof_pos"))
+
+
+def test_franka_oracle_matches_reference_fp64(franka_golden):
+    g = franka_golden
+    kp, kd, kpn, kdn, damping = g["gains"]
+    a = _inputs(g, torch.float64)
+    ik = ofr.control_ik(a["dpose"], a["j"], damping)
+    assert np.abs(ik.numpy() - g["ik_f64"]).max() < 1e-12
+    osc = ofr.control_osc(a["dpose"], a["j"], a["mm"], a["pos"], a["vel"], a["hv"], a["qdef"], kp, kd, kpn, kdn)
+    scale = np.abs(g["osc_f64"]).max()
+    assert np.abs(osc.numpy() - g["osc_f64"]).max() < 1e-10 * scale
+    oe = ofr.orientation_error(torch.from_numpy(g["goal_rot"]).double(), torch.from_numpy(g["hand_rot"]).double())
+    assert np.abs(oe.numpy() - g["orn_err_f64"]).max() < 1e-15
+
+
+def test_franka_oracle_matches_reference_fp32(franka_golden):
+    g = franka_golden
+    kp, kd, kpn, kdn, damping = g["gains"]
+    a = _inputs(g, torch.float32)
+    ik = ofr.control_ik(a["dpose"], a["j"], float(damping))
+    assert np.array_equal(ik.numpy(), g["ik_f32"])      # same torch ops, same order
+    osc = ofr.control_osc(a["dpose"], a["j"], a["mm"], a["pos"], a["vel"], a["hv"], a["qdef"],
+                          float(kp), float(kd), float(kpn), float(kdn))
+    assert np.allclose(osc.numpy(), g["osc_f32"], rtol=1e-5, atol=1e-5 * np.abs(g["osc_f32"]).max())
+
+
+def test_franka_views_regenerate_from_seed(franka_golden):
+    fi = syn.franka_inputs(256, seed=int(franka_golden["seed"]))
+    assert fi.j_eef.stride() == (540, 9, 1) and fi.mm.stride() == (81, 9, 1)
+    assert np.array_equal(fi.j_eef.numpy(), franka_golden["j_eef"])
+    assert np.array_equal(fi.mm.numpy(), franka_golden["mm"])
+    assert np.array_equal(fi.hand_vel.numpy(), franka_golden["hand_vel"])
+
+
+def test_quat_helpers_against_scipy():
+    from scipy.spatial.transform import Rotation as R
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(128, 4, generator=g, dtype=torch.float64)
+    b = torch.randn(128, 4, generator=g, dtype=torch.float64)
+    a, b = a / a.norm(dim=1, keepdim=True), b / b.norm(dim=1, keepdim=True)
+    prod = ofr.quat_mul(a, ofr.quat_conjugate(b)).numpy()
+    ref = (R.from_quat(a.numpy()) * R.from_quat(b.numpy()).inv()).as_quat()
+    d = np.minimum(np.abs(prod - ref).max(1), np.abs(prod + ref).max(1))
+    assert d.max() < 1e-14
+
+
+# ------------------------------------------------------------------ family P: the three reductions
+def test_pd_reduces_to_u_null_fragment(pd_fragments):
+    """kp=kp_null, kd=kd_null, WRAP, no saturation, q_target=q_default == franka_cube_ik_osc.py:74-75."""
+    g = pd_fragments
+    ds = torch.from_numpy(g["franka_dof_state"])
+    n = ds.shape[0] // 9
+    qdef = torch.from_numpy(g["default_dof_pos"])
+    tau = opd.pd_torque(ds, qdef.view(1, 9).expand(n, 9), torch.full((9,), float(g["kp_null"])),
+                        torch.full((9,), float(g["kd_null"])), flags=opd.WRAP_ANGLE)
+    assert np.array_equal(tau.numpy(), g["u_null"].reshape(n, 9))
+
+
+def test_pd_reduces_to_dof_controls_effort(pd_fragments):
+    """kp=50, kd=0, q_target=0 == dof_controls.py:181 (effort = -pos*50)."""
+    g = pd_fragments
+    ds = torch.from_numpy(g["anymal_dof_state"])
+    n = ds.shape[0] // 12
+    tau = opd.pd_torque(ds, torch.zeros(n, 12), torch.full((12,), 50.0), torch.zeros(12))
+    assert np.array_equal(tau.numpy(), g["effort_p50"])
+
+
+def test_pd_reduces_to_damping_factor():
+    """kp=0, kd=kv == the joint-space factor -kv*qd of franka_osc.py:241."""
+    pi_ = syn.pd_inputs(64, 9, seed=8)
+    kv = 2.0 * math.sqrt(150.0)
+    tau = opd.pd_torque(pi_.dof_state, pi_.q_target, torch.zeros(9), torch.full((9,), kv))
+    assert torch.equal(tau, kv * -pi_.dof_state[:, 1].view(64, 9) + 0.0 * (pi_.q_target - pi_.dof_state[:, 0].view(64, 9)))
+
+
+def test_pd_saturation_and_clamp():
+    pi_ = syn.pd_inputs(256, 12, seed=2)
+    tau = opd.pd_torque(pi_.dof_state, pi_.q_target, pi_.kp, pi_.kd, tau_max=pi_.tau_max,
+                        q_lo=pi_.q_lo, q_hi=pi_.q_hi, flags=opd.CLAMP_TARGET)
+    assert (tau.abs() <= pi_.tau_max.view(1, -1)).all()
+    st = opd.pd_stats(tau, pi_.tau_max)
+    assert st[0] == 256 and st[3] > 0 and st[4] == 0
