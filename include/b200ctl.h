@@ -1,0 +1,219 @@
+/*
+ * b200ctl.h -- C ABI of libb200ctl.so: the per-environment control laws of
+ * wp133716/test_isaacgym as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI layer: its hot path is plain Python functions on
+ * torch / numpy arrays.  Each entry point below replaces the arithmetic of one
+ * of those functions (cited per function as reference file:line); the Python
+ * package test_isaacgym_b200/ keeps the reference's call signatures and binds
+ * these symbols with ctypes (see INTEGRATION.md for the stub a maintainer of
+ * the reference would add).
+ *
+ * Conventions
+ *   - Every tensor argument is a DLPack `DLTensor` (data pointer, shape, element
+ *     strides, dtype, device): strided / sliced views of the Isaac Gym tensors are
+ *     consumed in place, never copied.  No torch types cross the boundary.
+ *   - Device entry points are stream-ordered: no host synchronisation, no
+ *     allocation, re-entrant.  `stream` is a `cudaStream_t` passed as void*.
+ *   - Return value: 0 = OK; < 0 = argument error (B200CTL_E_*); > 0 = cudaError_t.
+ *     `b200ctl_last_error()` returns a thread-local message for the last failure.
+ *   - Built for sm_100a only.  There is no CPU implementation behind this ABI.
+ */
+#ifndef B200CTL_H_
+#define B200CTL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CTL_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define B200CTL_API __attribute__((visibility("default")))
+#else
+#define B200CTL_API
+#endif
+
+/* ---- DLPack tensor descriptor (layout-identical to dlpack.h's DLTensor) ---- */
+#ifndef DLPACK_DLPACK_H_
+typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3 } DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef enum { kDLInt = 0, kDLUInt = 1, kDLFloat = 2 } DLDataTypeCode;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
+typedef struct {
+  void* data;
+  DLDevice device;
+  int32_t ndim;
+  DLDataType dtype;
+  int64_t* shape;
+  int64_t* strides; /* in elements; NULL = compact row-major */
+  uint64_t byte_offset;
+} DLTensor;
+#endif
+
+typedef void* b200ctl_stream_t; /* cudaStream_t */
+
+/* ---- status codes (< 0: argument errors) ---- */
+enum {
+  B200CTL_OK = 0,
+  B200CTL_E_NULL = -1,     /* required argument is NULL */
+  B200CTL_E_DEVICE = -2,   /* tensor not on a CUDA device / devices differ */
+  B200CTL_E_DTYPE = -3,    /* unsupported dtype for this argument */
+  B200CTL_E_SHAPE = -4,    /* rank / extent mismatch */
+  B200CTL_E_LAYOUT = -5,   /* layout not supported by this entry point (see its comment) */
+  B200CTL_E_VALUE = -6,    /* scalar argument out of range */
+  B200CTL_E_NCCL = -7,     /* NCCL unavailable or returned an error */
+  B200CTL_E_ALIAS = -8     /* output overlaps an input where that is not allowed */
+};
+
+B200CTL_API int b200ctl_version(void);
+B200CTL_API const char* b200ctl_last_error(void);
+/* Number of kernels this library has launched on behalf of the calling process
+ * (monotonic, all threads); lets a harness report its own launch count. */
+B200CTL_API uint64_t b200ctl_launch_count(void);
+
+/* ---- per-step statistics vector -------------------------------------------
+ * double[B200CTL_STATS_LEN] in device memory, ACCUMULATED (atomicAdd) by the
+ * kernels that take a `stats` argument; the caller zeroes it.  All entries are
+ * sums, so one ncclAllReduce(sum) merges env slices across GPUs.
+ * The reference has no episode statistics: this is new surface. */
+#define B200CTL_STATS_LEN 8
+enum {
+  B200CTL_STAT_N_ENV = 0,     /* environments processed */
+  B200CTL_STAT_SUM_ABS = 1,   /* P,O: sum |tau|        S: sum |pixel error| (L2 norm per env) */
+  B200CTL_STAT_SUM_SQ = 2,    /* P,O: sum tau^2        S: sum |pixel error|^2 */
+  B200CTL_STAT_N_SAT = 3,     /* P: elements at the +-tau_max limit   S: envs with target behind the camera */
+  B200CTL_STAT_N_NONFINITE = 4 /* non-finite outputs */
+};
+
+/* =========================== family P: joint PD torque =====================
+ * tau[n,d] = sat_{+-tau_max[d]}( kp[d]*wrap?(q_target[n,d] - q[n,d]) + kd[d]*(qd_target[n,d] - qd[n,d]) )
+ * Restates the reference's joint-space PD fragments:
+ *   examples/franka_cube_ik_osc.py:74-75 (u_null), examples/franka_osc.py:241 (-kv*qd),
+ *   examples/dof_controls.py:180-181 (-pos*50); layout examples/franka_cube_ik_osc.py:323-326.
+ * dof_state : (N*D, 2) f32, [:,0]=pos [:,1]=vel, any row/col strides
+ * q_target  : (N, D) f32         qd_target : (N, D) f32 or NULL (= 0)
+ * kp, kd    : (D,) f32           tau_max   : (D,) f32 or NULL (= no saturation)
+ * q_lo,q_hi : (D,) f32, required iff B200CTL_PD_CLAMP_TARGET
+ * tau_out   : (N, D) f32         stats     : device double[8] or NULL
+ * fp32 arithmetic in the operand order of franka_cube_ik_osc.py:74-75 without
+ * FMA contraction, so results are bit-identical to the torch-fp32 expression. */
+#define B200CTL_PD_WRAP_ANGLE 1   /* e = ((q* - q + pi) mod 2pi) - pi, floor-mod (franka_cube_ik_osc.py:75) */
+#define B200CTL_PD_CLAMP_TARGET 2 /* q* <- clamp(q*, q_lo, q_hi) first (joint_monkey.py:121-150 limits) */
+B200CTL_API int b200ctl_pd_torque(const DLTensor* dof_state, const DLTensor* q_target, const DLTensor* qd_target,
+                      const DLTensor* kp, const DLTensor* kd, const DLTensor* tau_max,
+                      const DLTensor* q_lo, const DLTensor* q_hi, int flags,
+                      DLTensor* tau_out, double* stats, b200ctl_stream_t stream);
+
+/* Host-buffer variant: same law on HOST arrays (compact row-major), chunked and
+ * pipelined H2D -> kernel -> D2H on `device` with an internal, cached workspace;
+ * returns after the result is in `tau_out`.  Pinned host memory overlaps copies
+ * with compute; pageable memory works but serialises.  stats_out: host double[8] or NULL. */
+B200CTL_API int b200ctl_pd_torque_host(const float* dof_state, const float* q_target, const float* qd_target,
+                           const float* kp, const float* kd, const float* tau_max,
+                           const float* q_lo, const float* q_hi, int flags,
+                           int64_t num_envs, int32_t num_dofs, float* tau_out, double* stats_out,
+                           int32_t device);
+
+/* =========================== family S: gimbal visual-servo chain ===========
+ * dtype: tensors may be f32 or f64 unless stated; arithmetic is fp64 (the
+ * reference's numpy/scipy stages are fp64) except cclvf, which is evaluated in
+ * the dtype of `pos` like the reference's torch expression. */
+
+/* cclvf2, common/controller6.py:92-118.  pos,tgt,vel_out: (N,3), any strides. */
+B200CTL_API int b200ctl_cclvf(const DLTensor* pos, const DLTensor* tgt, double speed, double radius,
+                  DLTensor* vel_out, b200ctl_stream_t stream);
+
+/* CameraController.world2pixel, common/controller6.py:214-253.
+ * uav_pos, car_pos: (N,3); uav_rot: (N,3,3) rotation matrix or (N,4) xyzw quaternion
+ * (normalised like scipy from_quat, test10_servo_vecenv.py:423); pixel_out: (N,3) = [u,v,1]. */
+B200CTL_API int b200ctl_world2pixel(const DLTensor* uav_pos, const DLTensor* car_pos, const DLTensor* uav_rot,
+                        double fx, double fy, double u0, double v0,
+                        DLTensor* pixel_out, b200ctl_stream_t stream);
+
+/* SecondaryControl.servo_ext_pixel, common/secondary_control_vecenv.py:99-200.
+ * K: (3,3) or (N,3,3); cam_rot: (N,3,3); pixel_move: (N,2); angles_out: (N,3[,1]) degrees
+ * [roll,pitch,yaw].  flags select the scalar files' conventions
+ * (common/servo_controller.py:158-159): */
+#define B200CTL_SERVO_SCALAR_ROLL_SIGN 1 /* negate roll iff mv_z < 0 (scalar) instead of !(mv_z > 0) (batched) */
+#define B200CTL_SERVO_NO_CLIP 2          /* no clip before acos (servo_controller.py:158) */
+B200CTL_API int b200ctl_servo_ext_pixel(const DLTensor* K, const DLTensor* cam_rot, const DLTensor* pixel_move,
+                            double width, double height, int flags,
+                            DLTensor* angles_out, b200ctl_stream_t stream);
+
+/* SecondaryControl.pixel2phy, common/secondary_control_vecenv.py:35-51 (scalar: servo_controller.py:49-61):
+ * unit bearing (fwd,right,down) of a pixel.  K: (3,3) or (N,3,3); pixel: (N,2); out: (N,3[,1]). */
+B200CTL_API int b200ctl_pixel2phy(const DLTensor* K, const DLTensor* pixel, DLTensor* out, b200ctl_stream_t stream);
+
+/* euler2quaternion, common/controller6.py:46-51: extrinsic xyz (rad) -> xyzw.  (N,3) -> (N,4). */
+B200CTL_API int b200ctl_euler_xyz_to_quat(const DLTensor* euler, DLTensor* quat_out, b200ctl_stream_t stream);
+
+/* R.from_quat(q).as_matrix(), test10_servo_vecenv.py:423.  (N,4) -> (N,3,3). */
+B200CTL_API int b200ctl_quat_to_matrix(const DLTensor* quat, DLTensor* mat_out, b200ctl_stream_t stream);
+
+/* Fused control step of test10_servo_vecenv.py:403-456 (a1..a7 of SURVEY section 8):
+ * reads uav pos+quat and car pos of each env, writes uav quat+linvel and car
+ * quat+linvel IN PLACE; every other column keeps its bits.
+ * root_state: (N,2,13) or (2N,13) f32, compact (the actor root-state tensor). */
+typedef struct {
+  double width, height; /* camera resolution (cam_props.width/height) */
+  double zoom;          /* per-step zoom, fx = fy = width*zoom/2 (controller6.py:178-186; test11:410) */
+  double car_speed, car_radius;                /* test10:406  (50, 30) */
+  double car_target[3];                        /* test10:406  (1,1,1)  */
+  double uav_speed, uav_radius, uav_height;    /* test10:412-414 (50, 50, 260) */
+  int32_t precision;    /* 0 = fp64 stages like the reference; 1 = all-fp32 fast path (atan2 forms) */
+  int32_t reserved;
+} b200ctl_servo_params;
+/* aux_out: optional (N,5) f64 compact device buffer [u, v, roll_deg, pitch_deg, yaw_deg] or NULL. */
+B200CTL_API int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_params* params,
+                       double* aux_out, double* stats, b200ctl_stream_t stream);
+
+/* =========================== family O: OSC + damped-least-squares IK =======
+ * All tensors f32, any strides (the reference passes views: j_eef strides
+ * (540,9,1), mm (81,9,1), dof_pos stride-2 views, out = effort_action[:, :7]). */
+
+/* control_ik, examples/franka_cube_ik_osc.py:53-59 (explicit-arg twin franka_nut_bolt_ik_osc.py:33-38):
+ * out = [dof_pos +] J^T (J J^T + lambda^2 I)^-1 dpose.
+ * j_eef (N,6,D) D in {7,9}; dpose (N,6[,1]); dof_pos (N,>=D[,1]) or NULL; out (N,D). */
+B200CTL_API int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, double lambda,
+                   const DLTensor* dof_pos, DLTensor* out, b200ctl_stream_t stream);
+
+/* control_osc, examples/franka_cube_ik_osc.py:62-79.
+ * j_eef (N,6,7); mm (N,7,7); dof_pos, dof_vel (N,>=7[,1]); hand_vel (M,6) with
+ * hand_index (N,) int64 row gather or NULL (then M == N); dpose (N,6[,1]);
+ * q_default (>=7,); out (N,7). */
+B200CTL_API int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_pos, const DLTensor* dof_vel,
+                const DLTensor* hand_vel, const DLTensor* hand_index, const DLTensor* dpose,
+                const DLTensor* q_default, double kp, double kd, double kp_null, double kd_null,
+                DLTensor* out, double* stats, b200ctl_stream_t stream);
+
+/* OSC of examples/franka_osc.py:229-241 over all D DOFs: out = J^T (J M^-1 J^T)^-1 (kp dpose) - kv M qd.
+ * j_eef (N,6,D), mm (N,D,D), dof_vel (N,D[,1]), dpose (N,6[,1]), out (N,D[,1]); D in {7,9}. */
+B200CTL_API int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_vel, const DLTensor* dpose,
+                     double kp, double kv, DLTensor* out, b200ctl_stream_t stream);
+
+/* orientation_error, examples/franka_cube_ik_osc.py:34-37.  (N,4) xyzw x2 -> (N,3). */
+B200CTL_API int b200ctl_orientation_error(const DLTensor* q_desired, const DLTensor* q_current,
+                              DLTensor* out, b200ctl_stream_t stream);
+
+/* Row gather / scatter of the index-list views of examples/franka_cube_ik_osc.py:348-353
+ * (rb_states[hand_idxs, 7:]) -- bit-exact copies.  src (M,C) f32, index (N,) int64,
+ * dst (N,ncols): dst[i, j] = src[index[i], col0 + j]. */
+B200CTL_API int b200ctl_gather_rows(const DLTensor* src, const DLTensor* index, int32_t col0, int32_t ncols,
+                        DLTensor* dst, b200ctl_stream_t stream);
+
+/* =========================== multi-GPU: statistics all-reduce ==============
+ * ncclAllReduce(sum, double) of `n` stats entries in place.  `comm` is an
+ * ncclComm_t; NCCL is resolved at run time from the already-loaded libnccl
+ * (no link-time dependency).  The control step itself moves no bytes between GPUs. */
+B200CTL_API int b200ctl_nccl_unique_id(void* id_out_128_bytes);
+B200CTL_API int b200ctl_nccl_comm_init(void** comm_out, int32_t world_size, const void* id_128_bytes, int32_t rank);
+B200CTL_API int b200ctl_nccl_comm_destroy(void* comm);
+B200CTL_API int b200ctl_stats_allreduce(void* comm, double* stats, int32_t n, b200ctl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CTL_H_ */

@@ -1,0 +1,177 @@
+"""ctypes binding of ``libb200ctl.so`` (the C ABI declared in ``include/b200ctl.h``).
+
+This is the only module that touches the shared library.  There is no fallback:
+a missing library, a missing symbol or a non-CUDA tensor raises.  torch is used
+for device memory and streams only; every tensor crosses the boundary as a
+DLPack ``DLTensor`` (pointer, shape, element strides, dtype, device).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_uint16, c_uint64, c_void_p
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200ctl.so")
+
+STATS_LEN = 8
+PD_WRAP_ANGLE = 1
+PD_CLAMP_TARGET = 2
+SERVO_SCALAR_ROLL_SIGN = 1
+SERVO_NO_CLIP = 2
+
+_ERRNAMES = {-1: "E_NULL", -2: "E_DEVICE", -3: "E_DTYPE", -4: "E_SHAPE", -5: "E_LAYOUT", -6: "E_VALUE",
+             -7: "E_NCCL", -8: "E_ALIAS"}
+
+
+class B200CtlError(RuntimeError):
+    """Raised for every non-zero status returned across the C ABI."""
+
+    def __init__(self, code: int, message: str):
+        self.code = code
+        kind = _ERRNAMES.get(code, f"cudaError {code}" if code > 0 else str(code))
+        super().__init__(f"b200ctl [{kind}]: {message}")
+
+
+class DLDevice(ctypes.Structure):
+    _fields_ = [("device_type", c_int32), ("device_id", c_int32)]
+
+
+class DLDataType(ctypes.Structure):
+    _fields_ = [("code", c_uint8), ("bits", c_uint8), ("lanes", c_uint16)]
+
+
+class DLTensor(ctypes.Structure):
+    _fields_ = [("data", c_void_p), ("device", DLDevice), ("ndim", c_int32), ("dtype", DLDataType),
+                ("shape", POINTER(c_int64)), ("strides", POINTER(c_int64)), ("byte_offset", c_uint64)]
+
+
+class ServoParams(ctypes.Structure):
+    """``b200ctl_servo_params``; defaults are the constants of ``test10_servo_vecenv.py:406-414``."""
+    _fields_ = [("width", c_double), ("height", c_double), ("zoom", c_double),
+                ("car_speed", c_double), ("car_radius", c_double), ("car_target", c_double * 3),
+                ("uav_speed", c_double), ("uav_radius", c_double), ("uav_height", c_double),
+                ("precision", c_int32), ("reserved", c_int32)]
+
+
+_DL = POINTER(DLTensor)
+_SIGNATURES = {
+    "b200ctl_version": (c_int, []),
+    "b200ctl_last_error": (c_char_p, []),
+    "b200ctl_launch_count": (c_uint64, []),
+    "b200ctl_pd_torque": (c_int, [_DL, _DL, _DL, _DL, _DL, _DL, _DL, _DL, c_int, _DL, c_void_p, c_void_p]),
+    "b200ctl_pd_torque_host": (c_int, [c_void_p] * 8 + [c_int, c_int64, c_int32, c_void_p, c_void_p, c_int32]),
+    "b200ctl_cclvf": (c_int, [_DL, _DL, c_double, c_double, _DL, c_void_p]),
+    "b200ctl_world2pixel": (c_int, [_DL, _DL, _DL, c_double, c_double, c_double, c_double, _DL, c_void_p]),
+    "b200ctl_servo_ext_pixel": (c_int, [_DL, _DL, _DL, c_double, c_double, c_int, _DL, c_void_p]),
+    "b200ctl_pixel2phy": (c_int, [_DL, _DL, _DL, c_void_p]),
+    "b200ctl_euler_xyz_to_quat": (c_int, [_DL, _DL, c_void_p]),
+    "b200ctl_quat_to_matrix": (c_int, [_DL, _DL, c_void_p]),
+    "b200ctl_servo_step": (c_int, [_DL, POINTER(ServoParams), c_void_p, c_void_p, c_void_p]),
+    "b200ctl_ik_dls": (c_int, [_DL, _DL, c_double, _DL, _DL, c_void_p]),
+    "b200ctl_osc": (c_int, [_DL, _DL, _DL, _DL, _DL, _DL, _DL, _DL, c_double, c_double, c_double, c_double,
+                            _DL, c_void_p, c_void_p]),
+    "b200ctl_osc_full": (c_int, [_DL, _DL, _DL, _DL, c_double, c_double, _DL, c_void_p]),
+    "b200ctl_orientation_error": (c_int, [_DL, _DL, _DL, c_void_p]),
+    "b200ctl_gather_rows": (c_int, [_DL, _DL, c_int32, c_int32, _DL, c_void_p]),
+    "b200ctl_nccl_unique_id": (c_int, [c_void_p]),
+    "b200ctl_nccl_comm_init": (c_int, [POINTER(c_void_p), c_int32, c_void_p, c_int32]),
+    "b200ctl_nccl_comm_destroy": (c_int, [c_void_p]),
+    "b200ctl_stats_allreduce": (c_int, [c_void_p, c_void_p, c_int32, c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library once.  Fails loudly: there is nothing to fall back to."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C test_isaacgym_b200/csrc` or "
+                "`python -c 'import __graft_entry__ as g; g.build()'`. b200ctl has no CPU or eager fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the ABI and the binding disagree
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B200CtlError(rc, lib().b200ctl_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib().b200ctl_launch_count())
+
+
+# --------------------------------------------------------------------------- tensors
+_DTYPES = {torch.float32: (2, 32), torch.float64: (2, 64), torch.int64: (0, 64)}
+
+
+class _Packed:
+    """A DLTensor plus the ctypes arrays it points into (kept alive for the call)."""
+    __slots__ = ("dl", "_shape", "_strides", "_tensor")
+
+    def __init__(self, t: torch.Tensor):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"expected a torch.Tensor, got {type(t).__name__}")
+        if not t.is_cuda:
+            raise B200CtlError(-2, "tensor is not on a CUDA device; b200ctl has no CPU path")
+        if t.dtype not in _DTYPES:
+            raise B200CtlError(-3, f"unsupported dtype {t.dtype}")
+        nd = t.dim()
+        self._shape = (c_int64 * max(nd, 1))(*t.shape)
+        self._strides = (c_int64 * max(nd, 1))(*t.stride())
+        code, bits = _DTYPES[t.dtype]
+        self.dl = DLTensor(c_void_p(t.data_ptr()), DLDevice(2, t.device.index or 0), nd, DLDataType(code, bits, 1),
+                           ctypes.cast(self._shape, POINTER(c_int64)), ctypes.cast(self._strides, POINTER(c_int64)), 0)
+        self._tensor = t
+
+
+def dl(t):
+    """torch CUDA tensor -> (pointer-to-DLTensor, keep-alive); None -> (NULL, None)."""
+    if t is None:
+        return None, None
+    p = _Packed(t)
+    return ctypes.byref(p.dl), p
+
+
+def stream_ptr(device: torch.device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device visible: b200ctl runs its control laws on the GPU only (no CPU path)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def is_host(x) -> bool:
+    """True for numpy arrays / python sequences / CPU torch tensors."""
+    return not (isinstance(x, torch.Tensor) and x.is_cuda)
+
+
+def to_device(x, device: torch.device, dtype: torch.dtype | None = None) -> torch.Tensor:
+    """Stage a host array on the device (async copy on the current stream); CUDA tensors pass through
+    untouched (views stay views -- no ``.contiguous()``)."""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            return x if dtype is None or x.dtype == dtype else x.to(dtype)
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(device, non_blocking=t.is_pinned())
+
+
+def stats_buffer(device: torch.device) -> torch.Tensor:
+    return torch.zeros(STATS_LEN, dtype=torch.float64, device=device)

@@ -1,0 +1,158 @@
+// Shared host/device plumbing for libb200ctl: error reporting, DLTensor
+// validation, strided tensor views, launch helpers.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/b200ctl.h"
+
+namespace b200ctl {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+
+#define B200_FAIL(code, ...)             \
+  do {                                   \
+    ::b200ctl::set_error(__VA_ARGS__);   \
+    return (code);                       \
+  } while (0)
+
+#define B200_CUDA(expr)                                                          \
+  do {                                                                           \
+    cudaError_t e__ = (expr);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      ::b200ctl::set_error("%s failed: %s", #expr, cudaGetErrorString(e__));     \
+      return (int)e__;                                                           \
+    }                                                                            \
+  } while (0)
+
+#define B200_TRY(expr)              \
+  do {                              \
+    int rc__ = (expr);              \
+    if (rc__ != 0) return rc__;     \
+  } while (0)
+
+// ---------------------------------------------------------------- tensor views
+enum DType : int { F32 = 0, F64 = 1, I64 = 2 };
+
+// POD view passed to kernels by value: base pointer + element strides.
+struct TView {
+  const void* p;
+  int64_t n[4];
+  int64_t s[4];
+  int ndim;
+  int dtype;
+};
+
+constexpr unsigned M_F32 = 1u << F32, M_F64 = 1u << F64, M_I64 = 1u << I64;
+
+// Validates a DLTensor and converts it to a TView.  `dev` is in/out: -1 accepts
+// any CUDA device and records it, otherwise the tensor must live on that device.
+int view_of(const DLTensor* t, const char* name, unsigned dtype_mask, int min_ndim, int max_ndim,
+            int* dev, TView* out);
+
+// Drops a trailing extent-1 dimension (the reference passes (N,6,1) / (N,9,1) columns).
+inline void squeeze_last(TView& v) {
+  if (v.ndim >= 2 && v.n[v.ndim - 1] == 1) v.ndim -= 1;
+}
+
+inline bool is_compact(const TView& v) {
+  int64_t expect = 1;
+  for (int i = v.ndim - 1; i >= 0; --i) {
+    if (v.n[i] != 1 && v.s[i] != expect) return false;
+    expect *= v.n[i];
+  }
+  return true;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int sm_count(int dev);
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  int enter(int dev) {
+    B200_CUDA(cudaGetDevice(&prev));
+    if (prev != dev) {
+      B200_CUDA(cudaSetDevice(dev));
+      switched = true;
+    }
+    return 0;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+inline int post_launch(const char* kernel) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("launch of %s failed: %s", kernel, cudaGetErrorString(e));
+    return (int)e;
+  }
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+// dtype-dispatched scalar load / store of a strided element (f32 or f64 storage).
+template <typename T>
+__device__ __forceinline__ T ld_as(const TView& v, int64_t off) {
+  return v.dtype == F32 ? (T) reinterpret_cast<const float*>(v.p)[off]
+                        : (T) reinterpret_cast<const double*>(v.p)[off];
+}
+template <typename T>
+__device__ __forceinline__ void st_as(const TView& v, int64_t off, T x) {
+  if (v.dtype == F32) reinterpret_cast<float*>(const_cast<void*>(v.p))[off] = (float)x;
+  else reinterpret_cast<double*>(const_cast<void*>(v.p))[off] = (double)x;
+}
+
+// Streaming 128-bit global accesses: data is touched exactly once per step.
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Block-level reduction of NS double partial sums into stats[] (one atomicAdd per
+// block per entry).  Every thread of the block must call it.
+template <int NS>
+__device__ __forceinline__ void block_stats_commit(double (&acc)[NS], double* stats, const int* slot) {
+  __shared__ double s_part[NS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[k][warp] = v;
+  }
+  __syncthreads();
+  const int nwarp = (blockDim.x + 31) >> 5;
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      double v = lane < nwarp ? s_part[k][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v != 0.0) atomicAdd(stats + slot[k], v);
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b200ctl

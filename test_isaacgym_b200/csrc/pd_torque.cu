@@ -1,0 +1,425 @@
+// Family P: batched joint PD / servo torque law.
+//
+//   tau[n,d] = sat( kp[d] * wrap?(q*[n,d] - q[n,d]) + kd[d] * (qd*[n,d] - qd[n,d]) )
+//
+// Restates the reference's joint-space PD fragments
+// (examples/franka_cube_ik_osc.py:74-75, examples/franka_osc.py:241,
+// examples/dof_controls.py:180-181) on the Isaac Gym dof_state layout
+// (examples/franka_cube_ik_osc.py:323-326).
+//
+// Roofline: HBM.  Algorithmic traffic per (env, dof): 8 B state + 4 B target
+// + 4 B output (+4 B with a qd target) -> 192 B per env at D = 12.
+//
+// Kernel shape: one thread owns 4 consecutive (env,dof) elements per iteration:
+// two 128-bit streaming loads of interleaved (q, qd) pairs, one 128-bit load of
+// targets, one 128-bit store.  Per-DOF gains / limits sit in shared memory.  The
+// grid is a multiple of the SM count and strides over the element range, so
+// the per-block statistics epilogue costs one atomic per block per entry.
+// Arithmetic is fp32 with explicit round-to-nearest intrinsics (no FMA
+// contraction): bit-identical to the torch expression of the reference.
+#include "common.cuh"
+
+#include <mutex>
+
+namespace b200ctl {
+
+constexpr float kPiF = 3.14159265358979323846f;       // float(math.pi)
+constexpr float kTwoPiF = 6.28318530717958647692f;    // float(2 * math.pi)
+
+struct PdParams {
+  const float* kp;
+  const float* kd;
+  const float* tau_max;  // nullable
+  const float* q_lo;     // nullable
+  const float* q_hi;     // nullable
+  int64_t s_kp, s_kd, s_tmax, s_lo, s_hi;
+};
+
+// One element of the law, operand order of franka_cube_ik_osc.py:74-75:
+//   kd * -vel + kp * ((tgt - pos + pi) % (2 pi) - pi)
+template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX>
+__device__ __forceinline__ float pd_element(float pos, float vel, float tgt, float qd_tgt, float kp, float kd,
+                                            float tmax, float lo, float hi) {
+  if (CLAMP_TGT) {
+    // torch.max(torch.min(tgt, hi), lo): NaN-propagating like torch
+    tgt = (tgt > hi) ? hi : tgt;
+    tgt = (tgt < lo) ? lo : tgt;
+  }
+  float err = __fsub_rn(tgt, pos);
+  if (WRAP) {
+    float m = fmodf(__fadd_rn(err, kPiF), kTwoPiF);      // fmod is exact
+    if (m < 0.0f) m = __fadd_rn(m, kTwoPiF);             // python / torch floor-mod for a positive modulus
+    err = __fsub_rn(m, kPiF);
+  }
+  const float dterm = HAS_QD ? __fmul_rn(kd, __fsub_rn(qd_tgt, vel)) : __fmul_rn(kd, -vel);
+  float tau = __fadd_rn(dterm, __fmul_rn(kp, err));
+  if (HAS_TMAX) {
+    tau = (tau > tmax) ? tmax : tau;
+    tau = (tau < -tmax) ? -tmax : tau;
+  }
+  return tau;
+}
+
+struct PdAcc {
+  float sum_abs = 0.f, sum_sq = 0.f;
+  unsigned n_sat = 0, n_bad = 0;
+  template <bool HAS_TMAX>
+  __device__ __forceinline__ void add(float tau, float tmax) {
+    const bool fin = isfinite(tau);
+    const float t = fin ? tau : 0.f;
+    sum_abs += fabsf(t);
+    sum_sq = fmaf(t, t, sum_sq);
+    n_bad += fin ? 0u : 1u;
+    if (HAS_TMAX) n_sat += (fin && fabsf(tau) >= tmax) ? 1u : 0u;
+  }
+};
+
+__device__ __forceinline__ void pd_commit_stats(const PdAcc& a, double* stats, int64_t n_env_block0) {
+  double acc[5] = {(double)n_env_block0, (double)a.sum_abs, (double)a.sum_sq, (double)a.n_sat, (double)a.n_bad};
+  const int slot[5] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_SAT,
+                       B200CTL_STAT_N_NONFINITE};
+  block_stats_commit<5>(acc, stats, slot);
+}
+
+// ---------------------------------------------------------------- fast path
+// Compact tensors, 16-byte aligned bases, D % 4 == 0.  `nvec` = N*D/4.
+template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS>
+__global__ void __launch_bounds__(256)
+pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict__ q_tgt,
+                      const float4* __restrict__ qd_tgt, PdParams pp, int num_dofs, int64_t nvec, int64_t num_envs,
+                      float4* __restrict__ tau_out, double* __restrict__ stats) {
+  extern __shared__ float s_par[];   // [5][D]: kp, kd, tmax, lo, hi
+  float* s_kp = s_par;
+  float* s_kd = s_par + num_dofs;
+  float* s_tm = s_par + 2 * num_dofs;
+  float* s_lo = s_par + 3 * num_dofs;
+  float* s_hi = s_par + 4 * num_dofs;
+  for (int d = threadIdx.x; d < num_dofs; d += blockDim.x) {
+    s_kp[d] = pp.kp[d * pp.s_kp];
+    s_kd[d] = pp.kd[d * pp.s_kd];
+    s_tm[d] = HAS_TMAX ? pp.tau_max[d * pp.s_tmax] : 0.f;
+    s_lo[d] = CLAMP_TGT ? pp.q_lo[d * pp.s_lo] : 0.f;
+    s_hi[d] = CLAMP_TGT ? pp.q_hi[d * pp.s_hi] : 0.f;
+  }
+  __syncthreads();
+
+  const int vec_per_env = num_dofs >> 2;
+  PdAcc acc;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    // issue every load of the iteration before the first use
+    const float4 s0 = ldg_stream4(state + 2 * v);       // q0 qd0 q1 qd1
+    const float4 s1 = ldg_stream4(state + 2 * v + 1);   // q2 qd2 q3 qd3
+    const float4 tg = ldg_stream4(q_tgt + v);
+    float4 qd = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (HAS_QD) qd = ldg_stream4(qd_tgt + v);
+    const int d0 = (int)(v % vec_per_env) << 2;
+    const float4 kp = *reinterpret_cast<const float4*>(s_kp + d0);
+    const float4 kd = *reinterpret_cast<const float4*>(s_kd + d0);
+    float4 tm = make_float4(0.f, 0.f, 0.f, 0.f), lo = tm, hi = tm;
+    if (HAS_TMAX) tm = *reinterpret_cast<const float4*>(s_tm + d0);
+    if (CLAMP_TGT) {
+      lo = *reinterpret_cast<const float4*>(s_lo + d0);
+      hi = *reinterpret_cast<const float4*>(s_hi + d0);
+    }
+    float4 o;
+    o.x = pd_element<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX>(s0.x, s0.y, tg.x, qd.x, kp.x, kd.x, tm.x, lo.x, hi.x);
+    o.y = pd_element<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX>(s0.z, s0.w, tg.y, qd.y, kp.y, kd.y, tm.y, lo.y, hi.y);
+    o.z = pd_element<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX>(s1.x, s1.y, tg.z, qd.z, kp.z, kd.z, tm.z, lo.z, hi.z);
+    o.w = pd_element<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX>(s1.z, s1.w, tg.w, qd.w, kp.w, kd.w, tm.w, lo.w, hi.w);
+    stg_stream4(tau_out + v, o);
+    if (STATS) {
+      acc.add<HAS_TMAX>(o.x, tm.x);
+      acc.add<HAS_TMAX>(o.y, tm.y);
+      acc.add<HAS_TMAX>(o.z, tm.z);
+      acc.add<HAS_TMAX>(o.w, tm.w);
+    }
+  }
+  if (STATS) pd_commit_stats(acc, stats, (blockIdx.x == 0 && threadIdx.x == 0) ? num_envs : 0);
+}
+
+// ---------------------------------------------------------------- generic path
+// Any strides / alignment / D: one element per thread iteration.
+template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS>
+__global__ void __launch_bounds__(256)
+pd_torque_strided_kernel(TView state, TView q_tgt, TView qd_tgt, PdParams pp, int num_dofs, int64_t num_envs,
+                         TView tau_out, double* __restrict__ stats) {
+  const float* st = reinterpret_cast<const float*>(state.p);
+  const float* tg = reinterpret_cast<const float*>(q_tgt.p);
+  const float* qd = reinterpret_cast<const float*>(qd_tgt.p);
+  float* out = reinterpret_cast<float*>(const_cast<void*>(tau_out.p));
+  const int64_t total = num_envs * num_dofs;
+  PdAcc acc;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = e / num_dofs;
+    const int d = (int)(e - n * num_dofs);
+    const float pos = st[e * state.s[0]];
+    const float vel = st[e * state.s[0] + state.s[1]];
+    const float t = tg[n * q_tgt.s[0] + d * q_tgt.s[1]];
+    const float qdt = HAS_QD ? qd[n * qd_tgt.s[0] + d * qd_tgt.s[1]] : 0.f;
+    const float tm = HAS_TMAX ? pp.tau_max[d * pp.s_tmax] : 0.f;
+    const float lo = CLAMP_TGT ? pp.q_lo[d * pp.s_lo] : 0.f;
+    const float hi = CLAMP_TGT ? pp.q_hi[d * pp.s_hi] : 0.f;
+    const float tau = pd_element<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX>(pos, vel, t, qdt, pp.kp[d * pp.s_kp],
+                                                                     pp.kd[d * pp.s_kd], tm, lo, hi);
+    out[n * tau_out.s[0] + d * tau_out.s[1]] = tau;
+    if (STATS) acc.add<HAS_TMAX>(tau, tm);
+  }
+  if (STATS) pd_commit_stats(acc, stats, (blockIdx.x == 0 && threadIdx.x == 0) ? num_envs : 0);
+}
+
+// ---------------------------------------------------------------- dispatch
+struct PdLaunch {
+  bool vec4;
+  const float4 *state4, *tgt4, *qd4;
+  float4* out4;
+  TView state, tgt, qd, out;
+  PdParams pp;
+  int num_dofs;
+  int64_t num_envs;
+  double* stats;
+  int grid;
+  cudaStream_t stream;
+};
+
+template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS>
+static void pd_launch_one(const PdLaunch& L) {
+  if (L.vec4) {
+    const size_t smem = 5 * (size_t)L.num_dofs * sizeof(float);
+    pd_torque_vec4_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS><<<L.grid, 256, smem, L.stream>>>(
+        L.state4, L.tgt4, L.qd4, L.pp, L.num_dofs, L.num_envs * L.num_dofs / 4, L.num_envs, L.out4, L.stats);
+  } else {
+    pd_torque_strided_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS><<<L.grid, 256, 0, L.stream>>>(
+        L.state, L.tgt, L.qd, L.pp, L.num_dofs, L.num_envs, L.out, L.stats);
+  }
+}
+
+template <bool WRAP, bool CLAMP_TGT, bool HAS_QD>
+static void pd_launch_tm(const PdLaunch& L, bool tmax, bool stats) {
+  if (tmax) { if (stats) pd_launch_one<WRAP, CLAMP_TGT, HAS_QD, true, true>(L); else pd_launch_one<WRAP, CLAMP_TGT, HAS_QD, true, false>(L); }
+  else      { if (stats) pd_launch_one<WRAP, CLAMP_TGT, HAS_QD, false, true>(L); else pd_launch_one<WRAP, CLAMP_TGT, HAS_QD, false, false>(L); }
+}
+
+static void pd_launch(const PdLaunch& L, bool wrap, bool clamp, bool has_qd, bool tmax, bool stats) {
+  if (wrap) {
+    if (clamp) { if (has_qd) pd_launch_tm<true, true, true>(L, tmax, stats); else pd_launch_tm<true, true, false>(L, tmax, stats); }
+    else       { if (has_qd) pd_launch_tm<true, false, true>(L, tmax, stats); else pd_launch_tm<true, false, false>(L, tmax, stats); }
+  } else {
+    if (clamp) { if (has_qd) pd_launch_tm<false, true, true>(L, tmax, stats); else pd_launch_tm<false, true, false>(L, tmax, stats); }
+    else       { if (has_qd) pd_launch_tm<false, false, true>(L, tmax, stats); else pd_launch_tm<false, false, false>(L, tmax, stats); }
+  }
+}
+
+// Grid: resident-CTA multiple of the SM count (8 CTAs of 256 threads per SM), never more than the work.
+static int pd_grid(int dev, int64_t work_items) {
+  const int64_t full = (int64_t)sm_count(dev) * 8;
+  const int64_t need = (work_items + 255) / 256;
+  return (int)(need < full ? (need > 0 ? need : 1) : full);
+}
+
+static int pd_vector_param(const DLTensor* t, const char* name, int num_dofs, int* dev, const float** p, int64_t* stride) {
+  TView v;
+  B200_TRY(view_of(t, name, M_F32, 1, 1, dev, &v));
+  if (v.n[0] != num_dofs) B200_FAIL(B200CTL_E_SHAPE, "%s: expected (%d,), got (%lld,)", name, num_dofs, (long long)v.n[0]);
+  *p = reinterpret_cast<const float*>(v.p);
+  *stride = v.s[0];
+  return 0;
+}
+
+}  // namespace b200ctl
+
+using namespace b200ctl;
+
+extern "C" int b200ctl_pd_torque(const DLTensor* dof_state, const DLTensor* q_target, const DLTensor* qd_target,
+                                 const DLTensor* kp, const DLTensor* kd, const DLTensor* tau_max,
+                                 const DLTensor* q_lo, const DLTensor* q_hi, int flags,
+                                 DLTensor* tau_out, double* stats, b200ctl_stream_t stream) {
+  int dev = -1;
+  PdLaunch L{};
+  B200_TRY(view_of(q_target, "q_target", M_F32, 2, 2, &dev, &L.tgt));
+  const int64_t N = L.tgt.n[0], D = L.tgt.n[1];
+  if (D <= 0 || D > 4096) B200_FAIL(B200CTL_E_SHAPE, "q_target: num_dofs %lld out of range [1,4096]", (long long)D);
+  B200_TRY(view_of(dof_state, "dof_state", M_F32, 2, 2, &dev, &L.state));
+  if (L.state.n[0] != N * D || L.state.n[1] != 2)
+    B200_FAIL(B200CTL_E_SHAPE, "dof_state: expected (%lld,2), got (%lld,%lld)", (long long)(N * D),
+              (long long)L.state.n[0], (long long)L.state.n[1]);
+  B200_TRY(view_of(tau_out, "tau_out", M_F32, 2, 2, &dev, &L.out));
+  if (L.out.n[0] != N || L.out.n[1] != D) B200_FAIL(B200CTL_E_SHAPE, "tau_out: expected (%lld,%lld)", (long long)N, (long long)D);
+  const bool has_qd = qd_target != nullptr;
+  if (has_qd) {
+    B200_TRY(view_of(qd_target, "qd_target", M_F32, 2, 2, &dev, &L.qd));
+    if (L.qd.n[0] != N || L.qd.n[1] != D) B200_FAIL(B200CTL_E_SHAPE, "qd_target: expected (%lld,%lld)", (long long)N, (long long)D);
+  } else {
+    L.qd = L.tgt;
+  }
+  if (flags & ~(B200CTL_PD_WRAP_ANGLE | B200CTL_PD_CLAMP_TARGET)) B200_FAIL(B200CTL_E_VALUE, "unknown flag bits 0x%x", flags);
+  const bool wrap = flags & B200CTL_PD_WRAP_ANGLE, clamp = flags & B200CTL_PD_CLAMP_TARGET;
+  B200_TRY(pd_vector_param(kp, "kp", (int)D, &dev, &L.pp.kp, &L.pp.s_kp));
+  B200_TRY(pd_vector_param(kd, "kd", (int)D, &dev, &L.pp.kd, &L.pp.s_kd));
+  const bool tmax = tau_max != nullptr;
+  if (tmax) B200_TRY(pd_vector_param(tau_max, "tau_max", (int)D, &dev, &L.pp.tau_max, &L.pp.s_tmax));
+  if (clamp) {
+    if (!q_lo || !q_hi) B200_FAIL(B200CTL_E_NULL, "CLAMP_TARGET needs q_lo and q_hi");
+    B200_TRY(pd_vector_param(q_lo, "q_lo", (int)D, &dev, &L.pp.q_lo, &L.pp.s_lo));
+    B200_TRY(pd_vector_param(q_hi, "q_hi", (int)D, &dev, &L.pp.q_hi, &L.pp.s_hi));
+  }
+  if (N == 0) return 0;
+
+  L.num_dofs = (int)D;
+  L.num_envs = N;
+  L.stats = stats;
+  L.stream = (cudaStream_t)stream;
+  L.vec4 = (D % 4 == 0) && is_compact(L.state) && is_compact(L.tgt) && is_compact(L.out) &&
+           (!has_qd || is_compact(L.qd)) && aligned16(L.state.p) && aligned16(L.tgt.p) && aligned16(L.out.p) &&
+           (!has_qd || aligned16(L.qd.p));
+  L.state4 = reinterpret_cast<const float4*>(L.state.p);
+  L.tgt4 = reinterpret_cast<const float4*>(L.tgt.p);
+  L.qd4 = reinterpret_cast<const float4*>(L.qd.p);
+  L.out4 = reinterpret_cast<float4*>(const_cast<void*>(L.out.p));
+  L.grid = pd_grid(dev, L.vec4 ? N * D / 4 : N * D);
+
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  pd_launch(L, wrap, clamp, has_qd, tmax, stats != nullptr);
+  return post_launch(L.vec4 ? "pd_torque_vec4_kernel" : "pd_torque_strided_kernel");
+}
+
+// ---------------------------------------------------------------- host-buffer pipeline
+// Chunked H2D -> kernel -> D2H over a ring of device buffers on dedicated streams,
+// so the upload of chunk i+1, the kernel of chunk i and the download of chunk i-1 overlap
+// (uploads and downloads use different copy engines).
+namespace {
+struct HostPipe {
+  static constexpr int kSlots = 3;
+  int dev = -1;
+  size_t cap_elems = 0;                    // capacity of one slot, in (env,dof) elements
+  float* d_state[kSlots] = {};
+  float* d_tgt[kSlots] = {};
+  float* d_qd[kSlots] = {};
+  float* d_out[kSlots] = {};
+  float* d_par = nullptr;                  // 5 * 4096 floats
+  double* d_stats = nullptr;
+  cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+  cudaEvent_t uploaded[kSlots] = {}, computed[kSlots] = {}, drained[kSlots] = {};
+  std::mutex mu;
+};
+HostPipe g_pipe[16];
+
+int pipe_prepare(HostPipe& P, int dev, size_t chunk_elems) {
+  if (P.dev < 0) {
+    B200_CUDA(cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamCreateWithFlags(&P.run, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+      B200_CUDA(cudaEventCreateWithFlags(&P.uploaded[i], cudaEventDisableTiming));
+      B200_CUDA(cudaEventCreateWithFlags(&P.computed[i], cudaEventDisableTiming));
+      B200_CUDA(cudaEventCreateWithFlags(&P.drained[i], cudaEventDisableTiming));
+    }
+    B200_CUDA(cudaMalloc(&P.d_par, 5 * 4096 * sizeof(float)));
+    B200_CUDA(cudaMalloc(&P.d_stats, B200CTL_STATS_LEN * sizeof(double)));
+    P.dev = dev;
+  }
+  if (chunk_elems > P.cap_elems) {
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+      cudaFree(P.d_state[i]); cudaFree(P.d_tgt[i]); cudaFree(P.d_qd[i]); cudaFree(P.d_out[i]);
+      B200_CUDA(cudaMalloc(&P.d_state[i], chunk_elems * 2 * sizeof(float)));
+      B200_CUDA(cudaMalloc(&P.d_tgt[i], chunk_elems * sizeof(float)));
+      B200_CUDA(cudaMalloc(&P.d_qd[i], chunk_elems * sizeof(float)));
+      B200_CUDA(cudaMalloc(&P.d_out[i], chunk_elems * sizeof(float)));
+    }
+    P.cap_elems = chunk_elems;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" int b200ctl_pd_torque_host(const float* dof_state, const float* q_target, const float* qd_target,
+                                      const float* kp, const float* kd, const float* tau_max,
+                                      const float* q_lo, const float* q_hi, int flags,
+                                      int64_t num_envs, int32_t num_dofs, float* tau_out, double* stats_out,
+                                      int32_t device) {
+  if (!dof_state || !q_target || !kp || !kd || !tau_out) B200_FAIL(B200CTL_E_NULL, "required host pointer is NULL");
+  if (num_dofs <= 0 || num_dofs > 4096 || num_envs < 0) B200_FAIL(B200CTL_E_SHAPE, "bad num_envs / num_dofs");
+  if (device < 0 || device >= 16) B200_FAIL(B200CTL_E_DEVICE, "device %d out of range", device);
+  if (flags & ~(B200CTL_PD_WRAP_ANGLE | B200CTL_PD_CLAMP_TARGET)) B200_FAIL(B200CTL_E_VALUE, "unknown flag bits 0x%x", flags);
+  const bool clamp = flags & B200CTL_PD_CLAMP_TARGET;
+  if (clamp && (!q_lo || !q_hi)) B200_FAIL(B200CTL_E_NULL, "CLAMP_TARGET needs q_lo and q_hi");
+  if (num_envs == 0) return 0;
+
+  DeviceGuard g;
+  B200_TRY(g.enter(device));
+  HostPipe& P = g_pipe[device];
+  std::lock_guard<std::mutex> lock(P.mu);
+
+  const int D = num_dofs;
+  // chunk: ~8 MB of state per slot keeps the copy engines busy while bounding the first-chunk latency
+  int64_t chunk_envs = (int64_t)(1 << 20) / D;
+  if (chunk_envs < 1) chunk_envs = 1;
+  if (D % 4 == 0 && chunk_envs >= 4) chunk_envs &= ~(int64_t)3;
+  if (chunk_envs > num_envs) chunk_envs = num_envs;
+  B200_TRY(pipe_prepare(P, device, (size_t)chunk_envs * D));
+
+  // per-DOF parameters
+  B200_CUDA(cudaMemcpyAsync(P.d_par, kp, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
+  B200_CUDA(cudaMemcpyAsync(P.d_par + 4096, kd, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
+  if (tau_max) B200_CUDA(cudaMemcpyAsync(P.d_par + 2 * 4096, tau_max, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
+  if (clamp) {
+    B200_CUDA(cudaMemcpyAsync(P.d_par + 3 * 4096, q_lo, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
+    B200_CUDA(cudaMemcpyAsync(P.d_par + 4 * 4096, q_hi, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
+  }
+  if (stats_out) B200_CUDA(cudaMemsetAsync(P.d_stats, 0, B200CTL_STATS_LEN * sizeof(double), P.run));
+
+  PdLaunch L{};
+  L.pp.kp = P.d_par; L.pp.kd = P.d_par + 4096;
+  L.pp.tau_max = tau_max ? P.d_par + 2 * 4096 : nullptr;
+  L.pp.q_lo = P.d_par + 3 * 4096; L.pp.q_hi = P.d_par + 4 * 4096;
+  L.pp.s_kp = L.pp.s_kd = L.pp.s_tmax = L.pp.s_lo = L.pp.s_hi = 1;
+  L.num_dofs = D;
+  L.stats = stats_out ? P.d_stats : nullptr;
+  L.stream = P.run;
+
+  int64_t done = 0;
+  for (int64_t c = 0; done < num_envs; ++c) {
+    const int slot = (int)(c % HostPipe::kSlots);
+    const int64_t n = (num_envs - done) < chunk_envs ? (num_envs - done) : chunk_envs;
+    const size_t elems = (size_t)n * D, off = (size_t)done * D;
+    // the slot is free once its previous result has been downloaded
+    if (c >= HostPipe::kSlots) B200_CUDA(cudaStreamWaitEvent(P.up, P.drained[slot], 0));
+    B200_CUDA(cudaMemcpyAsync(P.d_state[slot], dof_state + 2 * off, elems * 2 * sizeof(float), cudaMemcpyHostToDevice, P.up));
+    B200_CUDA(cudaMemcpyAsync(P.d_tgt[slot], q_target + off, elems * sizeof(float), cudaMemcpyHostToDevice, P.up));
+    if (qd_target) B200_CUDA(cudaMemcpyAsync(P.d_qd[slot], qd_target + off, elems * sizeof(float), cudaMemcpyHostToDevice, P.up));
+    B200_CUDA(cudaEventRecord(P.uploaded[slot], P.up));
+
+    B200_CUDA(cudaStreamWaitEvent(P.run, P.uploaded[slot], 0));
+    L.num_envs = n;
+    L.vec4 = (D % 4 == 0);
+    L.state4 = reinterpret_cast<const float4*>(P.d_state[slot]);
+    L.tgt4 = reinterpret_cast<const float4*>(P.d_tgt[slot]);
+    L.qd4 = reinterpret_cast<const float4*>(P.d_qd[slot]);
+    L.out4 = reinterpret_cast<float4*>(P.d_out[slot]);
+    if (!L.vec4) {
+      auto mk = [&](float* p, int64_t rows, int64_t cols, TView& v) {
+        v.p = p; v.ndim = 2; v.dtype = F32; v.n[0] = rows; v.n[1] = cols; v.s[0] = cols; v.s[1] = 1;
+      };
+      mk(P.d_state[slot], n * D, 2, L.state);
+      mk(P.d_tgt[slot], n, D, L.tgt);
+      mk(P.d_qd[slot], n, D, L.qd);
+      mk(P.d_out[slot], n, D, L.out);
+    }
+    L.grid = pd_grid(device, L.vec4 ? (int64_t)elems / 4 : (int64_t)elems);
+    pd_launch(L, flags & B200CTL_PD_WRAP_ANGLE, clamp, qd_target != nullptr, tau_max != nullptr, stats_out != nullptr);
+    B200_TRY(post_launch("pd_torque (host pipeline)"));
+    B200_CUDA(cudaEventRecord(P.computed[slot], P.run));
+
+    B200_CUDA(cudaStreamWaitEvent(P.down, P.computed[slot], 0));
+    B200_CUDA(cudaMemcpyAsync(tau_out + off, P.d_out[slot], elems * sizeof(float), cudaMemcpyDeviceToHost, P.down));
+    B200_CUDA(cudaEventRecord(P.drained[slot], P.down));
+    done += n;
+  }
+  if (stats_out) {
+    B200_CUDA(cudaStreamSynchronize(P.run));
+    B200_CUDA(cudaMemcpy(stats_out, P.d_stats, B200CTL_STATS_LEN * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  B200_CUDA(cudaStreamSynchronize(P.down));
+  return 0;
+}

@@ -1,0 +1,444 @@
+// Family S kernels: the UAV / gimbal visual-servo chain of
+// test10_servo_vecenv.py:403-456 -- cclvf2 (common/controller6.py:92-118),
+// world2pixel (:214-253), servo_ext_pixel (common/secondary_control_vecenv.py:99-200),
+// euler2quaternion (controller6.py:46-51) and the root-state scatter (test10:451-454).
+//
+// servo_step is the fused kernel: one thread per environment, the (uav, car)
+// root-state rows of a 64-env tile staged through shared memory with 128-bit
+// coalesced loads, results written back in place touching only the columns the
+// reference writes.  Roofline: HBM at 96 algorithmic B/env (read 40, write 56);
+// the fp64 "reference precision" mode is FP64-pipe bound instead.
+#include "servo_math.cuh"
+
+namespace b200ctl {
+
+constexpr int kRow = 13;            // floats per actor root-state row
+constexpr int kEnvRow = 2 * kRow;   // [uav, car]
+constexpr int kTile = 64;           // envs per CTA
+
+struct ServoConst {
+  double width, height, fx, fy, u0, v0;
+  float car_speed, car_rd, car_rd2, car_rd4, car_tx, car_ty, car_tz;
+  float uav_speed, uav_rd, uav_rd2, uav_rd4, uav_height;
+};
+
+// PREC 0: fp32 cclvf + fp64 projection / servo stages (dtype-for-dtype the reference).
+// PREC 1: everything fp32, atan2 formulations, bearing taken directly from the body-frame
+//         direction (skips the project -> subtract -> unproject pixel round trip).
+template <int PREC>
+__global__ void __launch_bounds__(kTile)
+servo_step_kernel(float* __restrict__ state, int64_t num_envs, ServoConst k, double* __restrict__ aux,
+                  double* __restrict__ stats, int vec_ok) {
+  __shared__ __align__(16) float tile[kTile * kEnvRow];
+  const int64_t env0 = (int64_t)blockIdx.x * kTile;
+  const int nenv = (int)((num_envs - env0) < kTile ? (num_envs - env0) : kTile);
+  const int nfl = nenv * kEnvRow;
+  float* gbase = state + env0 * kEnvRow;
+
+  // ---- stage the tile: 128-bit coalesced loads (tile base is 16-byte aligned: 64*104 B)
+  const int nv4 = vec_ok ? (nfl >> 2) : 0;
+  for (int i = threadIdx.x; i < nv4; i += kTile)
+    reinterpret_cast<float4*>(tile)[i] = __ldg(reinterpret_cast<const float4*>(gbase) + i);
+  for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += kTile) tile[i] = __ldg(gbase + i);
+  __syncthreads();
+
+  double acc[5] = {0, 0, 0, 0, 0};
+  if (threadIdx.x < nenv) {
+    float* row = tile + threadIdx.x * kEnvRow;
+    const float ux = row[0], uy = row[1], uz = row[2];
+    const float qx = row[3], qy = row[4], qz = row[5], qw = row[6];
+    const float cx = row[13], cy = row[14], cz = row[15];
+
+    // ---- car: velocity command, heading quaternion (test10:406-410), fp32 like the reference's torch ops
+    float cvx, cvy, cvz;
+    cclvf_core<float>(cx, cy, cz, k.car_tx, k.car_ty, k.car_tz, k.car_speed, k.car_rd, k.car_rd2, k.car_rd4, cvx, cvy, cvz);
+    // ---- uav: velocity command toward (car.x, car.y, height) (test10:412-414)
+    float uvx, uvy, uvz;
+    cclvf_core<float>(ux, uy, uz, cx, cy, k.uav_height, k.uav_speed, k.uav_rd, k.uav_rd2, k.uav_rd4, uvx, uvy, uvz);
+
+    float oq[4], cq[4];
+    double pu, pv, rolld, pitchd, yawd;
+    bool behind;
+    if (PREC == 0) {
+      // torch.atan2 on fp32 (:407): correctly rounded fp32 result via fp64
+      const float car_yaw = (float)atan2((double)cvy, (double)cvx);
+      double s, c;
+      sincos((double)car_yaw * 0.5, &s, &c);     // scipy from_euler('xyz', [0,0,yaw]) in fp64 (:410)
+      cq[0] = 0.f; cq[1] = 0.f; cq[2] = (float)s; cq[3] = (float)c;
+
+      double R[9];
+      quat_to_mat<double>(qx, qy, qz, qw, R);    // :423
+      // the difference car - uav is formed in the state dtype (fp32) before promotion (controller6.py:172-173,221)
+      const double dx = (double)__fsub_rn(cx, ux), dy = (double)__fsub_rn(cy, uy), dz = (double)__fsub_rn(cz, uz);
+      const double bx = R[0] * dx + R[3] * dy + R[6] * dz;   // inv(R) = R^T for the normalised quaternion
+      const double by = R[1] * dx + R[4] * dy + R[7] * dz;
+      const double bz = R[2] * dx + R[5] * dy + R[8] * dz;
+      project_body<double>(bx, by, bz, k.fx, k.fy, k.u0, k.v0, pu, pv, behind);   // :226-246
+      const double hw = k.width * 0.5, hh = k.height * 0.5;
+      const double mvx = hw - pu, mvy = hh - pv;             // order_pixel_move, test10:432
+      const double Kinv[9] = {1.0 / k.fx, 0.0, -k.u0 / k.fx, 0.0, 1.0 / k.fy, -k.v0 / k.fy, 0.0, 0.0, 1.0};
+      double mx, my, mz, tx, ty, tz;
+      pixel_bearing<double>(Kinv, mvx + hw, mvy + hh, mx, my, mz);   // secondary_control_vecenv.py:101,107
+      pixel_bearing<double>(Kinv, hw, hh, tx, ty, tz);              // :102-103,108
+      double roll, pitch, yaw;
+      servo_angles<double, false>(mx, my, mz, tx, ty, tz, R, 0, roll, pitch, yaw);
+      constexpr double kRad2Deg = 180.0 / 3.141592653589793238462643383279502884;
+      constexpr double kDeg2Rad = 3.141592653589793238462643383279502884 / 180.0;
+      rolld = roll * 180.0 / 3.141592653589793238462643383279502884;   // :196 (x * 180 / pi)
+      pitchd = pitch * 180.0 / 3.141592653589793238462643383279502884;
+      yawd = yaw * 180.0 / 3.141592653589793238462643383279502884;
+      (void)kRad2Deg;
+      double x, y, z, w;
+      euler_xyz_to_quat<double>(rolld * kDeg2Rad, pitchd * kDeg2Rad, yawd * kDeg2Rad, x, y, z, w);   // test10:444-447
+      oq[0] = (float)x; oq[1] = (float)y; oq[2] = (float)z; oq[3] = (float)w;   // fp64 -> fp32 on assignment (:451)
+      acc[1] = sqrt(mvx * mvx + mvy * mvy);
+    } else {
+      const float car_yaw = atan2f(cvy, cvx);
+      float s, c;
+      sincosf(car_yaw * 0.5f, &s, &c);
+      cq[0] = 0.f; cq[1] = 0.f; cq[2] = s; cq[3] = c;
+
+      float R[9];
+      quat_to_mat<float>(qx, qy, qz, qw, R);
+      const float dx = cx - ux, dy = cy - uy, dz = cz - uz;
+      const float bx = R[0] * dx + R[3] * dy + R[6] * dz;
+      const float by = R[1] * dx + R[4] * dy + R[7] * dz;
+      const float bz = R[2] * dx + R[5] * dy + R[8] * dz;
+      float fu, fv;
+      project_body<float>(bx, by, bz, (float)k.fx, (float)k.fy, (float)k.u0, (float)k.v0, fu, fv, behind);
+      pu = fu; pv = fv;
+      // bearing of the moved pixel == normalised body-frame direction with the clamped depth
+      const float bxc = behind ? 1e-7f : bx;
+      const float inv = rsqrtf(bxc * bxc + by * by + bz * bz);
+      float roll, pitch, yaw;
+      servo_angles<float, true>(bxc * inv, by * inv, bz * inv, 1.f, 0.f, 0.f, R, 0, roll, pitch, yaw);
+      rolld = roll * 57.29577951308232f; pitchd = pitch * 57.29577951308232f; yawd = yaw * 57.29577951308232f;
+      float x, y, z, w;
+      euler_xyz_to_quat<float>(roll, pitch, yaw, x, y, z, w);
+      oq[0] = x; oq[1] = y; oq[2] = z; oq[3] = w;
+      const float ex = (float)(k.width * 0.5) - fu, ey = (float)(k.height * 0.5) - fv;
+      acc[1] = sqrtf(ex * ex + ey * ey);
+    }
+
+    // ---- scatter into the staged rows (test10:451-454)
+    row[3] = oq[0]; row[4] = oq[1]; row[5] = oq[2]; row[6] = oq[3];
+    row[7] = uvx; row[8] = uvy; row[9] = uvz;
+    row[16] = cq[0]; row[17] = cq[1]; row[18] = cq[2]; row[19] = cq[3];
+    row[20] = cvx; row[21] = cvy; row[22] = cvz;
+
+    if (aux) {
+      double* a = aux + (env0 + threadIdx.x) * 5;
+      a[0] = pu; a[1] = pv; a[2] = rolld; a[3] = pitchd; a[4] = yawd;
+    }
+    const bool finite = isfinite(oq[0]) && isfinite(oq[1]) && isfinite(oq[2]) && isfinite(oq[3]);
+    acc[0] = 1.0;
+    if (!isfinite(acc[1])) acc[1] = 0.0;
+    acc[2] = acc[1] * acc[1];
+    acc[3] = behind ? 1.0 : 0.0;
+    acc[4] = finite ? 0.0 : 1.0;
+  }
+  __syncthreads();
+
+  // ---- write back only the columns the reference assigns: 3..9 of each actor row
+  for (int i = threadIdx.x; i < nfl; i += kTile) {
+    const int col = i % kRow;
+    if (col >= 3 && col <= 9) gbase[i] = tile[i];
+  }
+  if (stats) {
+    const int slot[5] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_SAT,
+                         B200CTL_STAT_N_NONFINITE};
+    block_stats_commit<5>(acc, stats, slot);
+  }
+}
+
+// ---------------------------------------------------------------- standalone entry points
+// One thread per env, strided dtype-dispatched loads; these mirror the reference's
+// individual functions and are not the throughput path (servo_step is).
+template <typename T>
+__global__ void cclvf_kernel(TView pos, TView tgt, T speed, T rd, T rd2, T rd4, TView out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T vx, vy, vz;
+  cclvf_core<T>(ld_as<T>(pos, i * pos.s[0]), ld_as<T>(pos, i * pos.s[0] + pos.s[1]), ld_as<T>(pos, i * pos.s[0] + 2 * pos.s[1]),
+                ld_as<T>(tgt, i * tgt.s[0]), ld_as<T>(tgt, i * tgt.s[0] + tgt.s[1]), ld_as<T>(tgt, i * tgt.s[0] + 2 * tgt.s[1]),
+                speed, rd, rd2, rd4, vx, vy, vz);
+  st_as<T>(out, i * out.s[0], vx);
+  st_as<T>(out, i * out.s[0] + out.s[1], vy);
+  st_as<T>(out, i * out.s[0] + 2 * out.s[1], vz);
+}
+
+__device__ __forceinline__ void load_mat3(const TView& m, int64_t i, double (&R)[9]) {
+  // (N,3,3) or broadcast (3,3)
+  const int64_t base = m.ndim == 3 ? i * m.s[0] : 0;
+  const int64_t sr = m.ndim == 3 ? m.s[1] : m.s[0], sc = m.ndim == 3 ? m.s[2] : m.s[1];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[r * 3 + c] = ld_as<double>(m, base + r * sr + c * sc);
+}
+
+__global__ void world2pixel_kernel(TView uav, TView car, TView rot, double fx, double fy, double u0, double v0,
+                                   TView out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d[3];
+  // the difference is formed in the callers' dtype before promotion (controller6.py:172-173,221)
+  const bool f32 = uav.dtype == F32 && car.dtype == F32;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (f32) d[c] = (double)__fsub_rn(ld_as<float>(car, i * car.s[0] + c * car.s[1]), ld_as<float>(uav, i * uav.s[0] + c * uav.s[1]));
+    else d[c] = ld_as<double>(car, i * car.s[0] + c * car.s[1]) - ld_as<double>(uav, i * uav.s[0] + c * uav.s[1]);
+  }
+  double R[9], Ri[9];
+  if (rot.ndim == 2) {   // (N,4) quaternion
+    quat_to_mat<double>(ld_as<double>(rot, i * rot.s[0]), ld_as<double>(rot, i * rot.s[0] + rot.s[1]),
+                        ld_as<double>(rot, i * rot.s[0] + 2 * rot.s[1]), ld_as<double>(rot, i * rot.s[0] + 3 * rot.s[1]), R);
+  } else {
+    load_mat3(rot, i, R);
+  }
+  inv3<double>(R, Ri);   // np.linalg.inv(uav_matrix) :226
+  const double bx = Ri[0] * d[0] + Ri[1] * d[1] + Ri[2] * d[2];
+  const double by = Ri[3] * d[0] + Ri[4] * d[1] + Ri[5] * d[2];
+  const double bz = Ri[6] * d[0] + Ri[7] * d[1] + Ri[8] * d[2];
+  double u, v;
+  bool behind;
+  project_body<double>(bx, by, bz, fx, fy, u0, v0, u, v, behind);
+  st_as<double>(out, i * out.s[0], u);
+  st_as<double>(out, i * out.s[0] + out.s[1], v);
+  st_as<double>(out, i * out.s[0] + 2 * out.s[1], 1.0);
+}
+
+__global__ void servo_ext_pixel_kernel(TView K, TView cam, TView move, double width, double height, int flags,
+                                       TView out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double Km[9], Kinv[9], C[9];
+  load_mat3(K, i, Km);
+  inv3<double>(Km, Kinv);      // np.linalg.inv(camera_matrix) :47
+  load_mat3(cam, i, C);
+  const double hw = width / 2, hh = height / 2;
+  const double px = ld_as<double>(move, i * move.s[0]) + hw, py = ld_as<double>(move, i * move.s[0] + move.s[1]) + hh;
+  double mx, my, mz, tx, ty, tz, roll, pitch, yaw;
+  pixel_bearing<double>(Kinv, px, py, mx, my, mz);
+  pixel_bearing<double>(Kinv, hw, hh, tx, ty, tz);
+  servo_angles<double, false>(mx, my, mz, tx, ty, tz, C, flags, roll, pitch, yaw);
+  constexpr double kPi = 3.141592653589793238462643383279502884;
+  st_as<double>(out, i * out.s[0], roll * 180 / kPi);
+  st_as<double>(out, i * out.s[0] + out.s[1], pitch * 180 / kPi);
+  st_as<double>(out, i * out.s[0] + 2 * out.s[1], yaw * 180 / kPi);
+}
+
+__global__ void pixel2phy_kernel(TView K, TView pixel, TView out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double Km[9], Kinv[9], mx, my, mz;
+  load_mat3(K, i, Km);
+  inv3<double>(Km, Kinv);
+  pixel_bearing<double>(Kinv, ld_as<double>(pixel, i * pixel.s[0]), ld_as<double>(pixel, i * pixel.s[0] + pixel.s[1]), mx, my, mz);
+  st_as<double>(out, i * out.s[0], mx);
+  st_as<double>(out, i * out.s[0] + out.s[1], my);
+  st_as<double>(out, i * out.s[0] + 2 * out.s[1], mz);
+}
+
+__global__ void euler_to_quat_kernel(TView e, TView q, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x, y, z, w;
+  euler_xyz_to_quat<double>(ld_as<double>(e, i * e.s[0]), ld_as<double>(e, i * e.s[0] + e.s[1]),
+                            ld_as<double>(e, i * e.s[0] + 2 * e.s[1]), x, y, z, w);
+  st_as<double>(q, i * q.s[0], x);
+  st_as<double>(q, i * q.s[0] + q.s[1], y);
+  st_as<double>(q, i * q.s[0] + 2 * q.s[1], z);
+  st_as<double>(q, i * q.s[0] + 3 * q.s[1], w);
+}
+
+__global__ void quat_to_matrix_kernel(TView q, TView m, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double R[9];
+  quat_to_mat<double>(ld_as<double>(q, i * q.s[0]), ld_as<double>(q, i * q.s[0] + q.s[1]),
+                      ld_as<double>(q, i * q.s[0] + 2 * q.s[1]), ld_as<double>(q, i * q.s[0] + 3 * q.s[1]), R);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st_as<double>(m, i * m.s[0] + r * m.s[1] + c * m.s[2], R[r * 3 + c]);
+}
+
+static int expect_rows(const TView& v, const char* name, int64_t n, int64_t cols) {
+  if (v.ndim != 2 || v.n[0] != n || v.n[1] != cols)
+    B200_FAIL(B200CTL_E_SHAPE, "%s: expected (%lld,%lld)", name, (long long)n, (long long)cols);
+  return 0;
+}
+
+static inline int grid1d(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+}  // namespace b200ctl
+
+using namespace b200ctl;
+
+extern "C" int b200ctl_cclvf(const DLTensor* pos, const DLTensor* tgt, double speed, double radius,
+                             DLTensor* vel_out, b200ctl_stream_t stream) {
+  int dev = -1;
+  TView p, t, o;
+  B200_TRY(view_of(pos, "pos", M_F32 | M_F64, 2, 2, &dev, &p));
+  const int64_t n = p.n[0];
+  B200_TRY(expect_rows(p, "pos", n, 3));
+  B200_TRY(view_of(tgt, "tgt", M_F32 | M_F64, 2, 2, &dev, &t));
+  B200_TRY(expect_rows(t, "tgt", n, 3));
+  B200_TRY(view_of(vel_out, "vel_out", M_F32 | M_F64, 2, 2, &dev, &o));
+  B200_TRY(expect_rows(o, "vel_out", n, 3));
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  // python-scalar gains: rd*rd and rd**4 are evaluated in double, then take the tensor dtype
+  if (p.dtype == F32 && t.dtype == F32)
+    cclvf_kernel<float><<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        p, t, (float)speed, (float)radius, (float)(radius * radius), (float)(radius * radius * radius * radius), o, n);
+  else
+    cclvf_kernel<double><<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        p, t, speed, radius, radius * radius, radius * radius * radius * radius, o, n);
+  return post_launch("cclvf_kernel");
+}
+
+extern "C" int b200ctl_world2pixel(const DLTensor* uav_pos, const DLTensor* car_pos, const DLTensor* uav_rot,
+                                   double fx, double fy, double u0, double v0,
+                                   DLTensor* pixel_out, b200ctl_stream_t stream) {
+  int dev = -1;
+  TView u, c, r, o;
+  B200_TRY(view_of(uav_pos, "uav_pos", M_F32 | M_F64, 2, 2, &dev, &u));
+  const int64_t n = u.n[0];
+  B200_TRY(expect_rows(u, "uav_pos", n, 3));
+  B200_TRY(view_of(car_pos, "car_pos", M_F32 | M_F64, 2, 2, &dev, &c));
+  B200_TRY(expect_rows(c, "car_pos", n, 3));
+  B200_TRY(view_of(uav_rot, "uav_rot", M_F32 | M_F64, 2, 3, &dev, &r));
+  if (!((r.ndim == 2 && r.n[0] == n && r.n[1] == 4) || (r.ndim == 3 && r.n[0] == n && r.n[1] == 3 && r.n[2] == 3)))
+    B200_FAIL(B200CTL_E_SHAPE, "uav_rot: expected (N,3,3) matrices or (N,4) xyzw quaternions");
+  B200_TRY(view_of(pixel_out, "pixel_out", M_F32 | M_F64, 2, 2, &dev, &o));
+  B200_TRY(expect_rows(o, "pixel_out", n, 3));
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  world2pixel_kernel<<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(u, c, r, fx, fy, u0, v0, o, n);
+  return post_launch("world2pixel_kernel");
+}
+
+extern "C" int b200ctl_servo_ext_pixel(const DLTensor* K, const DLTensor* cam_rot, const DLTensor* pixel_move,
+                                       double width, double height, int flags,
+                                       DLTensor* angles_out, b200ctl_stream_t stream) {
+  int dev = -1;
+  TView k, c, m, o;
+  B200_TRY(view_of(pixel_move, "pixel_move", M_F32 | M_F64, 2, 2, &dev, &m));
+  const int64_t n = m.n[0];
+  B200_TRY(expect_rows(m, "pixel_move", n, 2));
+  B200_TRY(view_of(K, "K", M_F32 | M_F64, 2, 3, &dev, &k));
+  if (!((k.ndim == 2 && k.n[0] == 3 && k.n[1] == 3) || (k.ndim == 3 && k.n[0] == n && k.n[1] == 3 && k.n[2] == 3)))
+    B200_FAIL(B200CTL_E_SHAPE, "K: expected (3,3) or (N,3,3)");
+  B200_TRY(view_of(cam_rot, "cam_rot", M_F32 | M_F64, 3, 3, &dev, &c));
+  if (c.n[0] != n || c.n[1] != 3 || c.n[2] != 3) B200_FAIL(B200CTL_E_SHAPE, "cam_rot: expected (N,3,3)");
+  B200_TRY(view_of(angles_out, "angles_out", M_F32 | M_F64, 2, 3, &dev, &o));
+  squeeze_last(o);
+  B200_TRY(expect_rows(o, "angles_out", n, 3));
+  if (flags & ~(B200CTL_SERVO_SCALAR_ROLL_SIGN | B200CTL_SERVO_NO_CLIP)) B200_FAIL(B200CTL_E_VALUE, "unknown flag bits 0x%x", flags);
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  servo_ext_pixel_kernel<<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(k, c, m, width, height, flags, o, n);
+  return post_launch("servo_ext_pixel_kernel");
+}
+
+extern "C" int b200ctl_pixel2phy(const DLTensor* K, const DLTensor* pixel, DLTensor* out, b200ctl_stream_t stream) {
+  int dev = -1;
+  TView k, p, o;
+  B200_TRY(view_of(pixel, "pixel", M_F32 | M_F64, 2, 2, &dev, &p));
+  const int64_t n = p.n[0];
+  B200_TRY(expect_rows(p, "pixel", n, 2));
+  B200_TRY(view_of(K, "K", M_F32 | M_F64, 2, 3, &dev, &k));
+  if (!((k.ndim == 2 && k.n[0] == 3 && k.n[1] == 3) || (k.ndim == 3 && k.n[0] == n && k.n[1] == 3 && k.n[2] == 3)))
+    B200_FAIL(B200CTL_E_SHAPE, "K: expected (3,3) or (N,3,3)");
+  B200_TRY(view_of(out, "out", M_F32 | M_F64, 2, 3, &dev, &o));
+  squeeze_last(o);
+  B200_TRY(expect_rows(o, "out", n, 3));
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  pixel2phy_kernel<<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(k, p, o, n);
+  return post_launch("pixel2phy_kernel");
+}
+
+extern "C" int b200ctl_euler_xyz_to_quat(const DLTensor* euler, DLTensor* quat_out, b200ctl_stream_t stream) {
+  int dev = -1;
+  TView e, q;
+  B200_TRY(view_of(euler, "euler", M_F32 | M_F64, 2, 2, &dev, &e));
+  const int64_t n = e.n[0];
+  B200_TRY(expect_rows(e, "euler", n, 3));
+  B200_TRY(view_of(quat_out, "quat_out", M_F32 | M_F64, 2, 2, &dev, &q));
+  B200_TRY(expect_rows(q, "quat_out", n, 4));
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  euler_to_quat_kernel<<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(e, q, n);
+  return post_launch("euler_to_quat_kernel");
+}
+
+extern "C" int b200ctl_quat_to_matrix(const DLTensor* quat, DLTensor* mat_out, b200ctl_stream_t stream) {
+  int dev = -1;
+  TView q, m;
+  B200_TRY(view_of(quat, "quat", M_F32 | M_F64, 2, 2, &dev, &q));
+  const int64_t n = q.n[0];
+  B200_TRY(expect_rows(q, "quat", n, 4));
+  B200_TRY(view_of(mat_out, "mat_out", M_F32 | M_F64, 3, 3, &dev, &m));
+  if (m.n[0] != n || m.n[1] != 3 || m.n[2] != 3) B200_FAIL(B200CTL_E_SHAPE, "mat_out: expected (N,3,3)");
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  quat_to_matrix_kernel<<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(q, m, n);
+  return post_launch("quat_to_matrix_kernel");
+}
+
+extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_params* params,
+                                  double* aux_out, double* stats, b200ctl_stream_t stream) {
+  if (!params) B200_FAIL(B200CTL_E_NULL, "params is NULL");
+  int dev = -1;
+  TView s;
+  B200_TRY(view_of(root_state, "root_state", M_F32, 2, 3, &dev, &s));
+  int64_t n;
+  if (s.ndim == 3) {
+    if (s.n[1] != 2 || s.n[2] != kRow) B200_FAIL(B200CTL_E_SHAPE, "root_state: expected (N,2,13) or (2N,13)");
+    n = s.n[0];
+  } else {
+    if (s.n[1] != kRow || (s.n[0] & 1)) B200_FAIL(B200CTL_E_SHAPE, "root_state: expected (N,2,13) or (2N,13)");
+    n = s.n[0] / 2;
+  }
+  if (!is_compact(s)) B200_FAIL(B200CTL_E_LAYOUT, "root_state must be the compact actor root-state tensor");
+  if (params->precision != 0 && params->precision != 1) B200_FAIL(B200CTL_E_VALUE, "precision must be 0 or 1");
+  if (!(params->width > 0) || !(params->height > 0) || !(params->zoom > 0)) B200_FAIL(B200CTL_E_VALUE, "width / height / zoom must be positive");
+  if (n == 0) return 0;
+
+  ServoConst k;
+  k.width = params->width; k.height = params->height;
+  // controller6.py:136-152,178-186: fx = (W / (36 * 0.001)) * (zoom * 18) * 0.001, same operation order
+  const double alpha = params->width / (36 * 0.001);
+  k.fx = alpha * (params->zoom * 18) * 0.001;
+  k.fy = k.fx;
+  k.u0 = params->width / 2; k.v0 = params->height / 2;
+  auto f = [](double x) { return (float)x; };
+  k.car_speed = f(params->car_speed); k.car_rd = f(params->car_radius);
+  k.car_rd2 = f(params->car_radius * params->car_radius);
+  k.car_rd4 = f(params->car_radius * params->car_radius * params->car_radius * params->car_radius);
+  k.car_tx = f(params->car_target[0]); k.car_ty = f(params->car_target[1]); k.car_tz = f(params->car_target[2]);
+  k.uav_speed = f(params->uav_speed); k.uav_rd = f(params->uav_radius);
+  k.uav_rd2 = f(params->uav_radius * params->uav_radius);
+  k.uav_rd4 = f(params->uav_radius * params->uav_radius * params->uav_radius * params->uav_radius);
+  k.uav_height = f(params->uav_height);
+
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  float* st = reinterpret_cast<float*>(const_cast<void*>(s.p));
+  const int grid = grid1d(n, kTile);
+  const int vec_ok = aligned16(st) ? 1 : 0;
+  if (params->precision == 0)
+    servo_step_kernel<0><<<grid, kTile, 0, (cudaStream_t)stream>>>(st, n, k, aux_out, stats, vec_ok);
+  else
+    servo_step_kernel<1><<<grid, kTile, 0, (cudaStream_t)stream>>>(st, n, k, aux_out, stats, vec_ok);
+  return post_launch("servo_step_kernel");
+}

@@ -1,0 +1,184 @@
+// Family S device math: circular-loiter vector field, pin-hole projection,
+// gimbal servo angles, Euler/quaternion conversions.  Templated on the compute
+// type: double reproduces the reference's fp64 numpy/scipy stages operation by
+// operation; float is the all-fp32 fast path (atan2 formulations).
+#pragma once
+#include "common.cuh"
+
+namespace b200ctl {
+
+// Arithmetic without FMA contraction, so fp32 evaluation rounds like the
+// reference's separate torch / numpy ops.
+template <typename T> struct Ar;
+template <> struct Ar<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+  // torch pow(x, 4) is a libm-grade pow: emulate with an fp64 product rounded once
+  static __device__ __forceinline__ float pow4(float a) { const double d = (double)a * a; return (float)(d * d); }
+};
+template <> struct Ar<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+  static __device__ __forceinline__ double pow4(double a) { return ::pow(a, 4.0); }
+};
+
+template <typename T> struct Fn;
+template <> struct Fn<double> {
+  static __device__ __forceinline__ double sqrt(double a) { return ::sqrt(a); }
+  static __device__ __forceinline__ double asin(double a) { return ::asin(a); }
+  static __device__ __forceinline__ double acos(double a) { return ::acos(a); }
+  static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+  static __device__ __forceinline__ void sincos(double a, double* s, double* c) { ::sincos(a, s, c); }
+};
+template <> struct Fn<float> {
+  static __device__ __forceinline__ float sqrt(float a) { return ::sqrtf(a); }
+  static __device__ __forceinline__ float asin(float a) { return ::asinf(a); }
+  static __device__ __forceinline__ float acos(float a) { return ::acosf(a); }
+  static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
+  static __device__ __forceinline__ void sincos(float a, float* s, float* c) { ::sincosf(a, s, c); }
+};
+
+// ------------------------------------------------------------------ a1: cclvf2
+// common/controller6.py:92-118, operand order preserved (see oracle/servo.py).
+template <typename T>
+__device__ __forceinline__ void cclvf_core(T px, T py, T pz, T tx, T ty, T tz, T speed, T rd, T rd2, T rd4,
+                                           T& vx, T& vy, T& vz) {
+  using A = Ar<T>;
+  const T dx = A::sub(px, tx), dy = A::sub(py, ty), dz = A::sub(pz, tz);
+  T r = A::sqrt(A::add(A::mul(dx, dx), A::mul(dy, dy)));      // :98 torch.norm over the planar pair
+  r = (r < (T)0.01) ? (T)0.01 : r;                             // :99 torch.max(r, 0.01), NaN-propagating
+  const T c = (r < rd) ? A::div(r, rd) : A::div(rd, r);       // :105
+  const T rr = A::mul(r, r);
+  const T gap = A::sub(rr, rd2);                               // :108
+  const T quart = A::add(A::add(A::pow4(r), A::mul(A::mul(A::sub(A::mul(c, c), (T)2), rd2), rr)), rd4);
+  const T factor = A::div(speed, A::sqrt(quart));              // :110
+  const T crd = A::mul(c, rd);
+  vx = A::mul(-factor, A::add(A::div(A::mul(dx, gap), r), A::mul(crd, dy)));   // :112
+  vy = A::mul(-factor, A::sub(A::div(A::mul(dy, gap), r), A::mul(crd, dx)));   // :113
+  vz = -dz;                                                    // :114
+}
+
+// ------------------------------------------------------------------ a3: quaternion -> matrix
+// scipy Rotation.from_quat(q).as_matrix(): q is normalised first (test10_servo_vecenv.py:423).
+template <typename T>
+__device__ __forceinline__ void quat_to_mat(T x, T y, T z, T w, T (&R)[9]) {
+  const T n = Fn<T>::sqrt(x * x + y * y + z * z + w * w);
+  x /= n; y /= n; z /= n; w /= n;
+  const T x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w;
+  const T xy = x * y, zw = z * w, xz = x * z, yw = y * w, yz = y * z, xw = x * w;
+  R[0] = x2 - y2 - z2 + w2; R[1] = 2 * (xy - zw);      R[2] = 2 * (xz + yw);
+  R[3] = 2 * (xy + zw);      R[4] = -x2 + y2 - z2 + w2; R[5] = 2 * (yz - xw);
+  R[6] = 2 * (xz - yw);      R[7] = 2 * (yz + xw);      R[8] = -x2 - y2 + z2 + w2;
+}
+
+// General 3x3 inverse (adjugate / determinant): what np.linalg.inv returns up to rounding.
+template <typename T>
+__device__ __forceinline__ void inv3(const T (&m)[9], T (&o)[9]) {
+  const T c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  const T det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  const T id = (T)1 / det;
+  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+
+// ------------------------------------------------------------------ a4: world2pixel
+// common/controller6.py:214-253.  `b` = target in the UAV body frame (inv(uav_matrix) @ (car - uav)).
+// Returns the pin-hole pixel; `depth_clamped` reports the 1e-7 clamp of :241.
+template <typename T>
+__device__ __forceinline__ void project_body(T bx, T by, T bz, T fx, T fy, T u0, T v0, T& u, T& v, bool& depth_clamped) {
+  const T cx = -by, cy = -bz;                 // rot_coord3 :234-240
+  depth_clamped = !(bx > (T)1e-7);
+  const T cz = (bx > (T)1e-7) ? bx : ((bx != bx) ? bx : (T)1e-7);   // np.maximum propagates NaN
+  u = fx * (cx / cz) + u0;                    // K @ (p / p_z) :245-246
+  v = fy * (cy / cz) + v0;
+}
+
+// ------------------------------------------------------------------ a5: pixel2phy
+// common/secondary_control_vecenv.py:35-51: unit bearing, axes (fwd, right, down).
+template <typename T>
+__device__ __forceinline__ void pixel_bearing(const T (&Kinv)[9], T px, T py, T& mx, T& my, T& mz) {
+  const T a0 = Kinv[0] * px + Kinv[1] * py + Kinv[2];
+  const T a1 = Kinv[3] * px + Kinv[4] * py + Kinv[5];
+  const T a2 = Kinv[6] * px + Kinv[7] * py + Kinv[8];
+  const T n = Fn<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+  mx = a2 / n; my = a0 / n; mz = a1 / n;
+}
+
+// where(y > 0, acos(x/|xy|), -acos(x/|xy|))  (:125-135, :143-148); y == 0 takes the negative branch.
+template <typename T, bool ATAN_FORM>
+__device__ __forceinline__ T signed_planar_angle(T x, T y) {
+  if (ATAN_FORM) {
+    return (y > (T)0) ? Fn<T>::atan2(y, x) : -Fn<T>::atan2(-y, x);
+  } else {
+    const T n = Fn<T>::sqrt(x * x + y * y);
+    const T ux = x / n, uy = y / n;
+    const T a = Fn<T>::acos(ux);
+    return (uy > (T)0) ? a : -a;
+  }
+}
+
+// ------------------------------------------------------------------ a6: servo_ext_pixel
+// common/secondary_control_vecenv.py:99-200 given the two bearings m (moved pixel) and
+// t (centre pixel) and the camera rotation matrix C (row-major).  Angles in radians.
+template <typename T, bool ATAN_FORM>
+__device__ __forceinline__ void servo_angles(T mx, T my, T mz, T tx_, T ty_, T tz_, const T (&C)[9], int flags,
+                                             T& roll, T& pitch, T& yaw) {
+  using F = Fn<T>;
+  const T px = C[0] * mx + C[1] * my + C[2] * mz;          // :113
+  const T py = C[3] * mx + C[4] * my + C[5] * mz;
+  const T pz = C[6] * mx + C[7] * my + C[8] * mz;
+  if (ATAN_FORM) pitch = F::atan2(tz_, F::sqrt(tx_ * tx_ + ty_ * ty_)) - F::atan2(pz, F::sqrt(px * px + py * py));
+  else pitch = F::asin(tz_) - F::asin(pz);                  // :120
+  yaw = signed_planar_angle<T, ATAN_FORM>(px, py);          // :125-135
+  const T cyaw = signed_planar_angle<T, ATAN_FORM>(mx, my); // :143-148
+  // mv = Rot(rotvec = cyaw * unit_z) @ unit_y   (:153-163), Rodrigues about the camera z column
+  const T yx = C[1], yy = C[4], yz = C[7];
+  const T zx = C[2], zy = C[5], zz = C[8];
+  const T nz = F::sqrt(zx * zx + zy * zy + zz * zz);
+  T mvx = yx, mvy = yy, mvz = yz;
+  if (nz > (T)0) {
+    const T kx = zx / nz, ky = zy / nz, kz = zz / nz;
+    T s, c;
+    F::sincos(cyaw * nz, &s, &c);
+    const T kd = (kx * yx + ky * yy + kz * yz) * ((T)1 - c);
+    mvx = yx * c + (ky * yz - kz * yy) * s + kx * kd;
+    mvy = yy * c + (kz * yx - kx * yz) * s + ky * kd;
+    mvz = yz * c + (kx * yy - ky * yx) * s + kz * kd;
+  }
+  // rv = R_xyz(0, pitch, yaw) @ e_y = (-sin yaw, cos yaw, 0)   (:168)
+  T sy, cy;
+  F::sincos(yaw, &sy, &cy);
+  T dot = -sy * mvx + cy * mvy;                              // :177
+  if (ATAN_FORM) {
+    const T ex = cy * mvz, ey = sy * mvz, ez = -sy * mvy - cy * mvx;
+    roll = F::atan2(F::sqrt(ex * ex + ey * ey + ez * ez), dot);
+  } else {
+    if (!(flags & B200CTL_SERVO_NO_CLIP)) dot = (dot > (T)1) ? (T)1 : ((dot < (T)-1) ? (T)-1 : dot);   // :179
+    roll = F::acos(dot);
+  }
+  if (flags & B200CTL_SERVO_SCALAR_ROLL_SIGN) roll = (mvz < (T)0) ? -roll : roll;   // servo_controller.py:159
+  else roll = (mvz > (T)0) ? roll : -roll;                                           // :181
+}
+
+// ------------------------------------------------------------------ a2: euler2quaternion
+// scipy from_euler('xyz', e).as_quat(): extrinsic x-y-z = qz(yaw) * qy(pitch) * qx(roll), xyzw.
+template <typename T>
+__device__ __forceinline__ void euler_xyz_to_quat(T roll, T pitch, T yaw, T& x, T& y, T& z, T& w) {
+  T sr, cr, sp, cp, sy, cy;
+  Fn<T>::sincos(roll * (T)0.5, &sr, &cr);
+  Fn<T>::sincos(pitch * (T)0.5, &sp, &cp);
+  Fn<T>::sincos(yaw * (T)0.5, &sy, &cy);
+  x = sr * cp * cy - cr * sp * sy;
+  y = cr * sp * cy + sr * cp * sy;
+  z = cr * cp * sy - sr * sp * cy;
+  w = cr * cp * cy + sr * sp * sy;
+}
+
+}  // namespace b200ctl

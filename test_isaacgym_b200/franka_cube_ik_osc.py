@@ -1,0 +1,122 @@
+"""Drop-in for the control functions of ``examples/franka_cube_ik_osc.py`` (family O).
+
+The reference's ``control_ik(dpose)`` / ``control_osc(dpose)`` read MODULE GLOBALS
+(``global damping, j_eef, num_envs`` :54; ``global kp, kd, kp_null, kd_null,
+default_dof_pos_tensor, mm, j_eef, num_envs, dof_pos, dof_vel, hand_vel`` :63).  This
+module keeps that calling convention: assign the same names on this module (or call
+``bind(**names)``) once the Isaac Gym tensors are wrapped, then call the functions
+exactly as the reference loop does (:395,:397)::
+
+    import test_isaacgym_b200.franka_cube_ik_osc as ctl
+    ctl.bind(j_eef=jacobian[:, hand_index - 1, :, :7], mm=mm[:, :7, :7], dof_pos=dof_pos, dof_vel=dof_vel,
+             default_dof_pos_tensor=default_dof_pos_tensor, num_envs=num_envs)
+    ...
+    ctl.hand_vel = rb_states[hand_idxs, 7:]            # or ctl.bind_hand(rb_states, hand_idxs): in-kernel gather
+    effort_action[:, :7] = ctl.control_osc(dpose)       # or ctl.control_osc(dpose, out=effort_action[:, :7])
+
+The explicit-argument form of ``examples/franka_nut_bolt_ik_osc.py:33-38``,
+``control_ik(dpose, damping, j_eef, num_envs)``, is accepted too.  Views are consumed
+with their strides -- ``j_eef`` (540,9,1), ``mm`` (81,9,1), stride-2 ``dof_pos`` -- no copies.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+# ---- the reference's module globals (examples/franka_cube_ik_osc.py:130-138) ----
+damping = 0.05
+kp = 150.
+kd = 2.0 * math.sqrt(kp)
+kp_null = 10.
+kd_null = 2.0 * math.sqrt(kp_null)
+default_dof_pos_tensor = None
+mm = None
+j_eef = None
+num_envs = None
+dof_pos = None
+dof_vel = None
+hand_vel = None
+_hand_index = None       # optional (N,) int64: hand_vel is then the (M,6) view rb_states[:, 7:]
+
+
+def bind(**names) -> None:
+    """Assign controller globals by name (same names as the reference script)."""
+    g = globals()
+    for k, v in names.items():
+        if k not in g or k.startswith("_"):
+            raise KeyError(f"{k!r} is not a controller global of franka_cube_ik_osc")
+        g[k] = v
+
+
+def bind_hand(rb_states: torch.Tensor, hand_idxs) -> None:
+    """Fuse ``hand_vel = rb_states[hand_idxs, 7:]`` (:353) into the OSC kernel: bind the live
+    rigid-body-state tensor and the index list once instead of gathering every step."""
+    global hand_vel, _hand_index
+    hand_vel = rb_states[:, 7:13]
+    _hand_index = torch.as_tensor(hand_idxs, dtype=torch.int64, device=rb_states.device)
+
+
+def gather_rows(src: torch.Tensor, index, col0: int = 0, ncols: int | None = None) -> torch.Tensor:
+    """``src[index, col0:col0+ncols]`` as one bit-exact kernel (the index-list views of :348-353)."""
+    idx = torch.as_tensor(index, dtype=torch.int64, device=src.device)
+    ncols = src.shape[1] - col0 if ncols is None else ncols
+    out = torch.empty((idx.shape[0], ncols), dtype=src.dtype, device=src.device)
+    a, b, c = _lib.dl(src), _lib.dl(idx), _lib.dl(out)
+    _lib.check(_lib.lib().b200ctl_gather_rows(a[0], b[0], int(col0), int(ncols), c[0], _lib.stream_ptr(src.device)))
+    return out
+
+
+def orientation_error(desired: torch.Tensor, current: torch.Tensor) -> torch.Tensor:
+    """``examples/franka_cube_ik_osc.py:34-37``: (N,4) xyzw x2 -> (N,3)."""
+    out = torch.empty((desired.shape[0], 3), dtype=torch.float32, device=desired.device)
+    a, b, c = _lib.dl(desired), _lib.dl(current), _lib.dl(out)
+    _lib.check(_lib.lib().b200ctl_orientation_error(a[0], b[0], c[0], _lib.stream_ptr(desired.device)))
+    return out
+
+
+def control_ik(dpose: torch.Tensor, damping=None, j_eef=None, num_envs=None, dof_pos=None,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """``u = J^T (J J^T + lambda^2 I)^-1 dpose`` -> (N, 7)  (``examples/franka_cube_ik_osc.py:53-59``).
+
+    ``dof_pos`` (optional, (N,>=7[,1])) fuses the caller's ``dof_pos[:, :7] + control_ik(dpose)`` (:395);
+    ``out`` may be the ``pos_action[:, :7]`` view.
+    """
+    g = globals()
+    lam = g["damping"] if damping is None else damping
+    j = g["j_eef"] if j_eef is None else j_eef
+    n, _, d = j.shape
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=j.device)
+    a, b, c, e = _lib.dl(j), _lib.dl(dpose), _lib.dl(dof_pos), _lib.dl(out)
+    _lib.check(_lib.lib().b200ctl_ik_dls(a[0], b[0], float(lam), c[0], e[0], _lib.stream_ptr(j.device)))
+    return out
+
+
+def control_osc(dpose: torch.Tensor, out: torch.Tensor | None = None, stats: torch.Tensor | None = None) -> torch.Tensor:
+    """Operational-space control torques -> (N, 7)  (``examples/franka_cube_ik_osc.py:62-79``)."""
+    g = globals()
+    j, m = g["j_eef"], g["mm"]
+    n = j.shape[0]
+    if out is None:
+        out = torch.empty((n, 7), dtype=torch.float32, device=j.device)
+    packed = [_lib.dl(t) for t in (j, m, g["dof_pos"], g["dof_vel"], g["hand_vel"], g["_hand_index"], dpose,
+                                   g["default_dof_pos_tensor"], out)]
+    sp = ctypes.c_void_p(stats.data_ptr()) if stats is not None else None
+    _lib.check(_lib.lib().b200ctl_osc(*(p[0] for p in packed[:8]), float(g["kp"]), float(g["kd"]), float(g["kp_null"]),
+                                      float(g["kd_null"]), packed[8][0], sp, _lib.stream_ptr(j.device)))
+    return out
+
+
+def control_osc_full(dpose: torch.Tensor, j_eef: torch.Tensor, mm: torch.Tensor, dof_vel: torch.Tensor,
+                     kp: float, kv: float, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``examples/franka_osc.py:229-241``: ``u = J^T M_eef (kp dpose) - kv M qd`` over all D DOFs -> (N, D, 1)."""
+    n, _, d = j_eef.shape
+    if out is None:
+        out = torch.empty((n, d, 1), dtype=torch.float32, device=j_eef.device)
+    a, b, c, e, f = _lib.dl(j_eef), _lib.dl(mm), _lib.dl(dof_vel), _lib.dl(dpose), _lib.dl(out)
+    _lib.check(_lib.lib().b200ctl_osc_full(a[0], b[0], c[0], e[0], float(kp), float(kv), f[0], _lib.stream_ptr(j_eef.device)))
+    return out

@@ -1,0 +1,66 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol the header
+declares, the ctypes binding covers exactly that set, and the product refuses to run on CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from test_isaacgym_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200ctl.h"), encoding="utf-8").read()
+    return sorted(set(re.findall(r"B200CTL_API\s+[\w\s\*]+?\b(b200ctl_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(handle, s), f"{s} declared in include/b200ctl.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == syms, "ctypes binding and header disagree"
+
+
+def test_version_and_error_channel():
+    L = _lib.lib()
+    assert L.b200ctl_version() == 100
+    # NULL tensor -> E_NULL, with a message, without touching a GPU
+    rc = L.b200ctl_cclvf(None, None, 1.0, 1.0, None, None)
+    assert rc == -1
+    assert b"NULL" in L.b200ctl_last_error()
+
+
+def test_servo_params_layout_matches_header():
+    # 3 + 2 + 3 + 3 doubles + 2 int32 = 96 bytes, no padding
+    assert ctypes.sizeof(_lib.ServoParams) == 11 * 8 + 8
+    assert ctypes.sizeof(_lib.DLTensor) == 48
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from test_isaacgym_b200.pd_control import pd_torque
+    from test_isaacgym_b200.controller6 import cclvf2
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pd_torque(torch.zeros(24, 2), torch.zeros(2, 12), 1.0, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cclvf2(torch.zeros(4, 3), torch.zeros(4, 3), 50, 30)
+
+
+def test_cpu_tensor_rejected_at_the_abi():
+    t = torch.zeros(4, 3)
+    with pytest.raises(_lib.B200CtlError):
+        _lib.dl(t)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "test_isaacgym_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"

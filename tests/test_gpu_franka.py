@@ -1,0 +1,140 @@
+"""GPU parity, family O: IK / OSC kernels (through the C ABI) vs the reference-generated fixtures and the
+fp64 oracle.  Tolerance: ||u - u_ref64|| / ||u_ref64|| <= 1e-4 per env on envs with
+cond(J M^-1 J^T) <= 1e4 (IK: cond(J J^T + lambda^2 I)); the rest is reported, alongside the reference's own
+fp32-vs-fp64 error on the same inputs.  Index gathers / column-slice scatters are bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import franka as ofr
+from test_isaacgym_b200 import synthetic as syn
+from test_isaacgym_b200 import _lib
+import test_isaacgym_b200.franka_cube_ik_osc as ctl
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+KP, KP_NULL, DAMPING = 150.0, 10.0, 0.05
+KD, KD_NULL = 2.0 * np.sqrt(KP), 2.0 * np.sqrt(KP_NULL)
+
+
+def _rel(u, ref):
+    u, ref = np.asarray(u, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return np.linalg.norm(u - ref, axis=1) / np.linalg.norm(ref, axis=1)
+
+
+def _bind(fi: syn.FrankaInputs):
+    d = fi.__class__(**{k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+    # the reference assigns module globals; bind() does the same by name
+    ctl.bind(damping=DAMPING, kp=KP, kd=KD, kp_null=KP_NULL, kd_null=KD_NULL, j_eef=d.j_eef, mm=d.mm,
+             dof_pos=d.dof_pos, dof_vel=d.dof_vel, default_dof_pos_tensor=d.default_dof_pos, num_envs=d.num_envs,
+             hand_vel=d.hand_vel)
+    ctl._hand_index = None
+    return d
+
+
+def test_franka_fixture(franka_golden):
+    g = franka_golden
+    fi = syn.franka_inputs(256, seed=int(g["seed"]))
+    d = _bind(fi)
+    assert d.j_eef.stride() == (540, 9, 1) and d.mm.stride() == (81, 9, 1) and d.dof_pos.stride()[1] == 2
+    ik = ctl.control_ik(d.dpose)
+    osc = ctl.control_osc(d.dpose)
+    cond_ik = ofr.conditioning(fi.j_eef, None, DAMPING).numpy()
+    cond_osc = ofr.conditioning(fi.j_eef, fi.mm).numpy()
+    r_ik, r_osc = _rel(ik.cpu(), g["ik_f64"]), _rel(osc.cpu(), g["osc_f64"])
+    ref_ik, ref_osc = _rel(g["ik_f32"], g["ik_f64"]), _rel(g["osc_f32"], g["osc_f64"])
+    print(f"IK  rel err kernel max {r_ik.max():.2e} | reference fp32 max {ref_ik.max():.2e}")
+    print(f"OSC rel err kernel max {r_osc.max():.2e} (gated {r_osc[cond_osc <= 1e4].max():.2e}) | reference fp32 max {ref_osc.max():.2e}")
+    assert r_ik[cond_ik <= 1e4].max() <= 1e-4
+    assert r_osc[cond_osc <= 1e4].max() <= 1e-4
+    # orientation_error
+    oe = ctl.orientation_error(torch.from_numpy(g["goal_rot"]).to(DEV), torch.from_numpy(g["hand_rot"]).to(DEV))
+    assert np.abs(oe.cpu().numpy() - g["orn_err_f32"]).max() <= 2e-7
+    assert np.abs(oe.cpu().numpy() - g["orn_err_f64"]).max() <= 1e-6
+
+
+def test_franka_c3_size_vs_oracle():
+    """Config C3: 16,384 envs, gated 1e-4 tolerance, error distribution printed next to the reference's own."""
+    n = 16_384
+    fi = syn.franka_inputs(n, seed=0)
+    d = _bind(fi)
+    ctl.bind_hand(d.rb_states, d.hand_idxs)                 # in-kernel gather of rb_states[hand_idxs, 7:]
+    st = _lib.stats_buffer(torch.device(DEV))
+    osc = ctl.control_osc(d.dpose, stats=st).cpu()
+    ik = ctl.control_ik(d.dpose).cpu()
+    f = lambda t: t.double()
+    ref_osc = ofr.control_osc(f(fi.dpose), f(fi.j_eef), f(fi.mm), f(fi.dof_pos), f(fi.dof_vel), f(fi.hand_vel),
+                              f(fi.default_dof_pos), KP, KD, KP_NULL, KD_NULL)
+    ref_ik = ofr.control_ik(f(fi.dpose), f(fi.j_eef), DAMPING)
+    r32_osc = ofr.control_osc(fi.dpose, fi.j_eef, fi.mm, fi.dof_pos, fi.dof_vel, fi.hand_vel, fi.default_dof_pos,
+                              KP, KD, KP_NULL, KD_NULL)
+    cond = ofr.conditioning(fi.j_eef, fi.mm).numpy()
+    r, rr = _rel(osc, ref_osc), _rel(r32_osc, ref_osc)
+    q = lambda x: (np.median(x), np.quantile(x, 0.99), x.max())
+    print("OSC kernel    rel err median/p99/max: %.2e %.2e %.2e" % q(r))
+    print("OSC reference rel err median/p99/max: %.2e %.2e %.2e (its own fp32 vs fp64)" % q(rr))
+    print("envs over the cond gate: %d of %d" % ((cond > 1e4).sum(), n))
+    assert r[cond <= 1e4].max() <= 1e-4
+    assert np.median(r) <= 2 * np.median(rr)
+    ri = _rel(ik, ref_ik)
+    assert ri.max() <= 1e-4
+    assert st.cpu()[0] == n and st.cpu()[4] == 0
+
+
+def test_franka_gather_scatter_bit_exact():
+    n = 1000
+    fi = syn.franka_inputs(n, seed=4)
+    d = _bind(fi)
+    hv = ctl.gather_rows(d.rb_states, d.hand_idxs, 7, 6)
+    assert torch.equal(hv.cpu(), fi.rb_states[fi.hand_idxs, 7:])
+    bp = ctl.gather_rows(d.rb_states, d.box_idxs.tolist(), 0, 3)            # python list like the reference
+    assert torch.equal(bp.cpu(), fi.rb_states[fi.box_idxs, :3])
+    # column-slice scatter: effort_action[:, :7] written in place, columns 7:9 untouched
+    effort = torch.full((n, 9), 5.0, device=DEV)
+    ctl.control_osc(d.dpose, out=effort[:, :7])
+    assert (effort[:, 7:] == 5.0).all()
+    assert torch.equal(effort[:, :7], ctl.control_osc(d.dpose))
+    # fused "dof_pos[:, :7] + control_ik(dpose)" into pos_action[:, :7] (:395)
+    pos_action = torch.zeros(n, 9, device=DEV)
+    ctl.control_ik(d.dpose, dof_pos=d.dof_pos, out=pos_action[:, :7])
+    ref = d.dof_pos.squeeze(-1)[:, :7] + ctl.control_ik(d.dpose)
+    assert torch.equal(pos_action[:, :7], ref) and (pos_action[:, 7:] == 0).all()
+    # in-kernel gather == pre-gathered hand_vel
+    a = ctl.control_osc(d.dpose)
+    ctl.bind_hand(d.rb_states, d.hand_idxs)
+    assert torch.equal(ctl.control_osc(d.dpose), a)
+
+
+def test_franka_explicit_arg_ik_and_full_osc():
+    n = 512
+    fi = syn.franka_inputs(n, seed=6)
+    d = _bind(fi)
+    u = ctl.control_ik(d.dpose, 0.1, d.j_eef, n)                            # franka_nut_bolt_ik_osc.py:33 signature
+    ref = ofr.control_ik(fi.dpose.double(), fi.j_eef.double(), 0.1)
+    assert _rel(u.cpu(), ref).max() <= 1e-4
+    # franka_osc.py:229-241 over all 9 DOFs
+    j9 = d.jacobian[:, syn.FRANKA_JACOBIAN_SLOT]                             # (N,6,9) strided
+    kv = 2 * np.sqrt(KP)
+    dp = d.dpose.squeeze(-1)
+    u9 = ctl.control_osc_full(dp, j9, d.mass_matrix, d.dof_vel, KP, kv)
+    ref9 = ofr.control_osc_full(fi.dpose.squeeze(-1).double(), fi.jacobian[:, syn.FRANKA_JACOBIAN_SLOT].double(),
+                                fi.mass_matrix.double(), fi.dof_vel.double(), KP, kv)
+    cond = ofr.conditioning(fi.jacobian[:, syn.FRANKA_JACOBIAN_SLOT], fi.mass_matrix).numpy()
+    r = _rel(u9.cpu().squeeze(-1), ref9.squeeze(-1))
+    assert r[cond <= 1e4].max() <= 1e-4
+
+
+def test_franka_edges():
+    with pytest.raises(_lib.B200CtlError, match="E_SHAPE"):
+        ctl.control_ik(torch.zeros(4, 6, 1, device=DEV), 0.05, torch.zeros(4, 6, 8, device=DEV), 4)
+    out = ctl.control_ik(torch.zeros(0, 6, 1, device=DEV), 0.05, torch.zeros(0, 6, 7, device=DEV), 0)
+    assert out.shape == (0, 7)
+    # zero pose error and zero joint error -> zero torque
+    n = 8
+    fi = syn.franka_inputs(n, seed=1)
+    d = _bind(fi)
+    ctl.dof_pos = d.default_dof_pos.view(1, 9, 1).expand(n, 9, 1)
+    ctl.dof_vel = torch.zeros(n, 9, 1, device=DEV)
+    ctl.hand_vel = torch.zeros(n, 6, device=DEV)
+    u = ctl.control_osc(torch.zeros(n, 6, 1, device=DEV))
+    assert u.abs().max().item() < 1e-5

@@ -1,0 +1,207 @@
+"""GPU parity, family S: servo chain kernels (through the C ABI) vs the reference fixtures and the oracle.
+
+Tolerances: velocities 1e-5 relative to max(|v|,1); angles compared on the circle,
+|d| <= 1e-5 * max(|ref|, 1 deg); quaternions compared up to sign.  The reference-precision mode is held
+to far tighter bounds (fp64 stages), the fp32 fast mode to the stated ones with an outlier report."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import angle_diff_deg, quat_diff
+from oracle import servo as osv
+from test_isaacgym_b200 import synthetic as syn
+from test_isaacgym_b200 import _lib
+from test_isaacgym_b200.controller6 import cclvf2, euler2quaternion, quat2matrix, CameraController
+from test_isaacgym_b200.secondary_control_vecenv import SecondaryControl
+from test_isaacgym_b200.servo_controller import ServoExtPixelParam, servoExtPixel, servoExtPixelMatrix
+from test_isaacgym_b200.servo_step import ServoStep, PRECISION_FAST
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+W, H = 1600, 900
+
+
+class _Cam:
+    width, height = W, H
+
+
+# ------------------------------------------------------------------ known-answer vectors of the reference
+def test_kat_vecenv(servo_kat):
+    sc = SecondaryControl(W, H, 2)
+    out = sc.servo_ext_pixel(servo_kat["vecenv_K"], servo_kat["vecenv_cam"], servo_kat["vecenv_move"])
+    assert isinstance(out, np.ndarray) and out.shape == (2, 3, 1) and out.dtype == np.float64
+    assert np.abs(out - servo_kat["vecenv_out"]).max() < 1e-9
+
+
+def test_kat_scalar_files(servo_kat):
+    p = ServoExtPixelParam()
+    p.width, p.height = W, H
+    p.camAngle = servo_kat["scalar_cam_deg"]
+    p.cameraMatrix = servo_kat["K"]
+    assert np.abs(servoExtPixel(p, 25, 46) - servo_kat["scalar_out"]).max() < 1e-9
+    assert p.moveRoiCam.x == W / 2 + 25 and p.targetRoiCam.y == H / 2
+    p.camAngle = servo_kat["debug_cam"]
+    mv = servo_kat["debug_move"]
+    assert np.abs(servoExtPixelMatrix(p, mv[0], mv[1]) - servo_kat["debug_out"]).max() < 1e-9
+
+
+def test_edges(servo_edges):
+    """y == 0 sign branches, identity camera, straight-down camera: same values, same NaNs."""
+    sc = SecondaryControl(W, H, len(servo_edges["move"]))
+    out = sc.servo_ext_pixel(servo_edges["K"], servo_edges["cam"], servo_edges["move"])
+    ref = servo_edges["out"]
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    assert np.nanmax(angle_diff_deg(out, ref)) < 1e-9
+    assert out[1, 2, 0] == -180.0           # quirk A.5(1): negative branch at p_y == 0
+    # looking exactly along +-z divides by zero in the reference -> NaN there and here
+    cam = np.array([[[0.0, 0, 1], [0, 1, 0], [-1, 0, 0]]])
+    with np.errstate(all="ignore"):
+        ref = osv.servo_ext_pixel(servo_edges["K"], cam, np.zeros((1, 2)), W, H)
+    got = SecondaryControl(W, H, 1).servo_ext_pixel(servo_edges["K"], cam, np.zeros((1, 2)))
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+
+
+# ------------------------------------------------------------------ the individual reference functions
+@pytest.mark.parametrize("tag", ["ref_z1", "uni_z1", "ref_z11"])
+def test_functions_match_reference_fixture(servo_chain, tag):
+    g = lambda k: servo_chain[f"{tag}_{k}"]
+    state = torch.from_numpy(g("state_in"))
+    n = state.shape[0]
+    dstate = state.to(DEV)
+    uav, car = dstate[:, 0], dstate[:, 1]                       # strided views (row stride 26)
+    car_vel = cclvf2(car[:, :3], torch.ones(n, 3, device=DEV), 50, 30)
+    uav_tgt = car[:, :3].clone()
+    uav_tgt[:, 2] = 260
+    uav_vel = cclvf2(uav[:, :3], uav_tgt, 50, 50)
+    for got, key in ((car_vel, "car_vel"), (uav_vel, "uav_vel")):
+        ref = g(key)
+        err = np.abs(got.cpu().numpy() - ref).max(axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1.0)
+        assert err.max() <= 1e-5
+        assert (got.cpu().numpy() == ref).mean() > 0.9        # nearly always bit-exact
+
+    m = quat2matrix(uav[:, 3:7])
+    assert np.abs(m.cpu().numpy() - g("uav_matrix")).max() < 1e-14
+    cam = CameraController(_Cam, n)
+    cam.set_params(None, None, uav[:, :3], car[:, :3], m, None, None, float(g("zoom")))
+    assert np.allclose(cam.camera_matrix, g("K"), rtol=0, atol=1e-12)
+    pix = cam.world2pixel()
+    scale = np.maximum(np.abs(g("pixel")), 1.0)
+    assert (np.abs(pix[:, :2].cpu().numpy() - g("pixel")) / scale).max() < 1e-10
+    # quaternion input instead of the matrix: same projection
+    cam.set_params(None, None, uav[:, :3], car[:, :3], uav[:, 3:7], None, None, float(g("zoom")))
+    assert (np.abs(cam.world2pixel()[:, :2].cpu().numpy() - g("pixel")) / scale).max() < 1e-10
+
+    move = torch.from_numpy(g("move")).to(DEV)
+    ang = SecondaryControl(W, H, n).servo_ext_pixel(g("K"), m, move)
+    assert ang.shape == (n, 3, 1) and ang.is_cuda
+    assert angle_diff_deg(ang.cpu().numpy().reshape(n, 3), g("angles")).max() < 1e-8
+    q = euler2quaternion(torch.deg2rad(ang.reshape(n, 3)))
+    assert quat_diff(q.cpu().numpy(), g("uav_quat")).max() < 1e-12
+    assert np.abs(q.cpu().numpy() - g("uav_quat")).max() < 1e-12, "sign convention differs from scipy"
+
+
+def test_host_inputs_return_reference_types(servo_chain):
+    """numpy / CPU-torch in -> the reference's host types out (drop-in for the CPU-pipeline scripts)."""
+    g = lambda k: servo_chain[f"ref_z1_{k}"]
+    state = torch.from_numpy(g("state_in"))
+    car = state[:, 1]
+    v = cclvf2(car[:, :3], torch.ones_like(car[:, :3]), speed=50, radius=30)
+    assert isinstance(v, torch.Tensor) and not v.is_cuda and v.dtype == torch.float32
+    q = euler2quaternion(np.zeros((4, 3)))
+    assert isinstance(q, np.ndarray) and q.dtype == np.float64 and np.array_equal(q, np.tile([0, 0, 0, 1.0], (4, 1)))
+    b = SecondaryControl(W, H, 2).pixel2phy(np.array([[800.0, 450.0], [825.0, 496.0]]), g("K"))
+    ref = osv.pixel2phy(np.array([[800.0, 450.0], [825.0, 496.0]]), g("K"))
+    assert b.shape == (2, 3, 1) and np.abs(b - ref).max() < 1e-15
+
+
+# ------------------------------------------------------------------ fused step
+@pytest.mark.parametrize("tag", ["ref_z1", "uni_z1", "ref_z11"])
+def test_fused_step_reference_precision(servo_chain, tag):
+    g = lambda k: servo_chain[f"{tag}_{k}"]
+    state = torch.from_numpy(g("state_in")).to(DEV)
+    n = state.shape[0]
+    before = state.clone()
+    aux = torch.zeros(n, 5, dtype=torch.float64, device=DEV)
+    st = _lib.stats_buffer(torch.device(DEV))
+    ServoStep(W, H, zoom=float(g("zoom")))(state, aux=aux, stats=st)
+    out, ref = state.cpu().numpy(), g("state_out")
+    # untouched columns keep their bits (a7: bit-exact scatter)
+    for rows in (slice(0, 3), slice(10, 13)):
+        assert np.array_equal(out[:, :, rows], before.cpu().numpy()[:, :, rows])
+    assert np.array_equal(out[:, :, 0:3], ref[:, :, 0:3]) and np.array_equal(out[:, :, 10:13], ref[:, :, 10:13])
+    # velocities
+    for a in (0, 1):
+        err = np.abs(out[:, a, 7:10] - ref[:, a, 7:10]).max(axis=1) / np.maximum(np.linalg.norm(ref[:, a, 7:10], axis=1), 1.0)
+        assert err.max() <= 1e-5
+    # quaternions written to the state (fp32), up to sign and exactly-signed
+    assert quat_diff(out[:, 0, 3:7], ref[:, 0, 3:7]).max() <= 2e-7
+    assert quat_diff(out[:, 1, 3:7], ref[:, 1, 3:7]).max() <= 2e-7
+    assert np.abs(out[:, 0, 3:7] - ref[:, 0, 3:7]).max() <= 2e-7
+    # intermediates
+    a = aux.cpu().numpy()
+    assert (np.abs(a[:, :2] - g("pixel")) / np.maximum(np.abs(g("pixel")), 1.0)).max() < 1e-9
+    d = angle_diff_deg(a[:, 2:], g("angles"))
+    assert (d <= 1e-5 * np.maximum(np.abs(g("angles")), 1.0)).all()
+    assert d.max() < 1e-7
+    assert st.cpu()[0] == n and st.cpu()[4] == 0
+    bitexact = (out == ref).mean()
+    print(f"[{tag}] fused step: {bitexact * 100:.3f}% of state floats bit-identical to the reference")
+    assert bitexact > 0.97
+
+
+def test_fused_step_large_vs_oracle():
+    """65,536 envs (config C2 size) against the oracle, both regimes, ragged tail, (2N,13) view."""
+    for regime, n in (("reference", 65_536), ("uniform", 10_007)):
+        state = syn.servo_root_state(n, seed=13, regime=regime)
+        ref, aux_ref = osv.servo_step(state, W, H)
+        dstate = state.to(DEV).view(2 * n, 13)
+        ServoStep(W, H)(dstate)
+        out = dstate.view(n, 2, 13).cpu()
+        assert torch.equal(out[:, :, :3], ref[:, :, :3]) and torch.equal(out[:, :, 10:], ref[:, :, 10:])
+        assert quat_diff(out[:, 0, 3:7].numpy(), ref[:, 0, 3:7].numpy()).max() <= 3e-7
+        assert quat_diff(out[:, 1, 3:7].numpy(), ref[:, 1, 3:7].numpy()).max() <= 3e-7
+        for a in (0, 1):
+            r = ref[:, a, 7:10].numpy()
+            err = np.abs(out[:, a, 7:10].numpy() - r).max(axis=1) / np.maximum(np.linalg.norm(r, axis=1), 1.0)
+            assert err.max() <= 1e-5
+
+
+def test_fused_step_fast_mode_tolerance():
+    """All-fp32 mode: >= 99.9 % of envs within 1e-5 (relative to max(|ref|, 1 deg)); report the tail."""
+    n = 200_000
+    state = syn.servo_root_state(n, seed=17, regime="reference")
+    _, aux_ref = osv.servo_step(state, W, H)
+    dstate = state.to(DEV)
+    aux = torch.zeros(n, 5, dtype=torch.float64, device=DEV)
+    ServoStep(W, H, precision=PRECISION_FAST)(dstate, aux=aux)
+    d = angle_diff_deg(aux.cpu().numpy()[:, 2:], aux_ref["angles_deg"])
+    rel = d / np.maximum(np.abs(aux_ref["angles_deg"]), 1.0)
+    ok = (rel <= 1e-5).all(axis=1)
+    print(f"fast mode: {ok.mean() * 100:.3f}% of envs within 1e-5, worst rel {rel.max():.2e}")
+    assert ok.mean() >= 0.999
+    assert rel.max() < 5e-3
+    qd = quat_diff(dstate[:, 0, 3:7].cpu().numpy(), aux_ref["uav_quat"])
+    assert np.quantile(qd, 0.999) < 1e-5
+
+
+def test_fused_step_idempotent_guidance_and_host_path():
+    """Velocity commands depend on positions only: a second step (positions unchanged) rewrites identical
+    velocities; host tensors round-trip through the same kernel."""
+    state = syn.servo_root_state(4096, seed=23).to(DEV)
+    step = ServoStep(W, H)
+    step(state)
+    v1 = state[:, :, 7:10].clone()
+    step(state)
+    assert torch.equal(state[:, :, 7:10], v1)
+    host = syn.servo_root_state(1000, seed=29)
+    ref, _ = osv.servo_step(host, W, H)
+    step(host)
+    assert not host.is_cuda and quat_diff(host[:, 0, 3:7].numpy(), ref[:, 0, 3:7].numpy()).max() <= 3e-7
+
+
+def test_fused_step_errors():
+    with pytest.raises(_lib.B200CtlError, match="E_SHAPE"):
+        ServoStep(W, H)(torch.zeros(4, 2, 12, device=DEV))
+    with pytest.raises(_lib.B200CtlError, match="E_LAYOUT"):
+        ServoStep(W, H)(torch.zeros(4, 2, 26, device=DEV)[:, :, ::2])
+    ServoStep(W, H)(torch.zeros(0, 2, 13, device=DEV))
