@@ -152,75 +152,102 @@ class PdWorkload:
         self.out = [torch.empty(num_envs, NUM_DOFS, device=device) for _ in range(sets)]
         self.sets = sets
         self.window = None      # StatsWindow, set by the caller
+        self.calls = None
+
+    def bind(self, window):
+        """Marshal one call per (buffer set, statistics buffer): the per-step host cost is one foreign call."""
+        self.window = window
+        self.calls = [[self.ctl.bind(self.state[k], self.tgt[k], self.out[k], stats=b) for b in window.bufs]
+                      for k in range(self.sets)]
 
     def step(self, i=0):
-        k = i % self.sets
-        self.ctl(self.state[k], self.tgt[k], out=self.out[k], stats=self.window.current)
+        self.calls[i % self.sets][self.window.cur]()
         self.window.step_done()
 
 
 # ------------------------------------------------------------------------------------------ families (rank 0, N=1)
+def graph_time(calls, device, reps, warm=3):
+    """Capture `calls` (bound C-ABI calls, one kernel each) into one CUDA graph and time `reps` replays on the
+    launching stream.  Returns ms per kernel launch.  The graph removes the host launch cost, which at
+    64K envs is larger than the kernels themselves."""
+    stream = torch.cuda.Stream(device)
+    stream.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(stream):
+        for c in calls:
+            c()
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for c in calls:
+                c()
+        for _ in range(warm):
+            graph.replay()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream.synchronize()
+        start.record(stream)
+        for _ in range(reps):
+            graph.replay()
+        end.record(stream)
+        stream.synchronize()
+    torch.cuda.current_stream(device).wait_stream(stream)
+    return start.elapsed_time(end) / (reps * len(calls))
+
+
 def family_numbers(device, peak_gbs):
-    """Per-GPU throughput of the other laws / sizes named in BASELINE.json configs (not bench lines of their own)."""
+    """Per-GPU throughput of the other laws / sizes named in BASELINE.json configs (not bench lines of their own).
+    Every entry rotates enough buffer sets to exceed the 126 MB L2 and replays a CUDA graph of bound calls."""
     from test_isaacgym_b200 import synthetic as syn
     from test_isaacgym_b200.pd_control import PDController
     from test_isaacgym_b200.servo_step import ServoStep, PRECISION_FAST
     import test_isaacgym_b200.franka_cube_ik_osc as ctl
     out = {}
 
-    def record(name, n, bytes_per_env, fn, steps=200, flops=None):
-        ms = time_launches(fn, steps, 10, device) / steps
+    def record(name, n, bytes_per_env, calls, reps, flops=None):
+        ms = graph_time(calls, device, reps)
         rate = n / (ms * 1e-3)
         e = {"envs": n, "us_per_step": round(ms * 1e3, 3), "env_steps_per_s": rate,
-             "hbm_frac": rate * bytes_per_env / (peak_gbs * 1e9)}
+             "hbm_frac": rate * bytes_per_env / (peak_gbs * 1e9), "buffer_sets": len(calls)}
         if flops:
-            e["fp32_tflops_canonical"] = rate * flops / 1e12
+            e["tflops_canonical"] = rate * flops / 1e12
         out[name] = e
 
-    # P at C2 (65,536 x 12): L2-resident at this size unless rotated -> rotate 24 sets (302 MB)
-    n = 65_536
+    # P at C2 (65,536 x 12 = 12.6 MB per set): 24 rotating sets (302 MB)
+    n, sets = 65_536, 24
     pi = syn.pd_inputs(n, NUM_DOFS, seed=1)
     c = PDController(NUM_DOFS, pi.kp, pi.kd, tau_max=pi.tau_max, device=device)
-    sets = 24
     st = [pi.dof_state.to(device).clone() for _ in range(sets)]
     tg = [pi.q_target.to(device).clone() for _ in range(sets)]
     ou = [torch.empty(n, NUM_DOFS, device=device) for _ in range(sets)]
-    record("pd_65536x12", n, PD_BYTES_PER_ENV, lambda i=0: c(st[i % sets], tg[i % sets], out=ou[i % sets]))
+    record("pd_65536x12", n, PD_BYTES_PER_ENV, [c.bind(st[k], tg[k], ou[k]) for k in range(sets)], reps=20)
     del st, tg, ou
 
-    # S fused step at C2 and at 1M envs, both precisions
-    for n, sets in ((65_536, 24), (1_048_576, 3)):
+    # S fused step at C2 (6.8 MB per set) and at 1M envs (109 MB per set), both precisions
+    for n, sets, reps in ((65_536, 24, 10), (1_048_576, 3, 20)):
         base = syn.servo_root_state(n, seed=2).to(device)
         bufs = [base.clone() for _ in range(sets)]
         for tag, prec in (("ref", 0), ("fast", PRECISION_FAST)):
             step = ServoStep(1600, 900, precision=prec)
-            record(f"servo_step_{tag}_{n}", n, SERVO_BYTES_PER_ENV, lambda i=0: step(bufs[i % sets]), steps=100)
+            record(f"servo_step_{tag}_{n}", n, SERVO_BYTES_PER_ENV, [step.bind(b) for b in bufs], reps=reps)
         del bufs, base
 
-    # O at C3 (16,384) and at 262,144 envs
-    for n in (16_384, 262_144):
+    # O at C3 (16,384 envs: 47 MB of gym tensors per set) and at 262,144 envs (750 MB per set)
+    for n, sets, reps in ((16_384, 4, 20), (262_144, 2, 20)):
         fi = syn.franka_inputs(n, seed=3)
-        sets = 8 if n == 16_384 else 2
-        dsets = []
-        for _ in range(sets):
-            d = fi.__class__(**{k: (v.to(device).clone() if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
-            dsets.append(d)
-        outs = [torch.zeros(n, 9, device=device) for _ in range(sets)]
-
-        def osc(i=0):
-            d = dsets[i % sets]
-            ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=d.dof_pos, dof_vel=d.dof_vel,
-                     default_dof_pos_tensor=d.default_dof_pos, num_envs=n)
-            ctl.bind_hand(d.rb_states, d.hand_idxs)
-            ctl.control_osc(d.dpose, out=outs[i % sets][:, :7])
-
-        def ik(i=0):
-            d = dsets[i % sets]
-            ctl.control_ik(d.dpose, 0.05, d.j_eef, n, dof_pos=d.dof_pos, out=outs[i % sets][:, :7])
-
-        record(f"osc_{n}", n, OSC_BYTES_PER_ENV, osc, steps=100, flops=OSC_FLOPS)
-        record(f"ik_{n}", n, IK_BYTES_PER_ENV, ik, steps=100, flops=IK_FLOPS)
-        del dsets, outs
+        for prec, ptag in ((0, "fp64chain"), (1, "fp32")):
+            osc_calls, ik_calls, keep = [], [], []
+            for _ in range(sets):
+                d = fi.__class__(**{k: (v.to(device).clone() if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+                o = torch.zeros(n, 9, device=device)
+                ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=d.dof_pos, dof_vel=d.dof_vel,
+                         default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=prec)
+                ctl.bind_hand(d.rb_states, d.hand_idxs)
+                osc_calls.append(ctl.bind_control_osc(d.dpose, o[:, :7]))
+                ik_calls.append(ctl.bind_control_ik(d.dpose, o[:, :7], dof_pos=d.dof_pos))
+                keep.append((d, o))
+            record(f"osc_{ptag}_{n}", n, OSC_BYTES_PER_ENV, osc_calls, reps, flops=OSC_FLOPS)
+            record(f"ik_{ptag}_{n}", n, IK_BYTES_PER_ENV, ik_calls, reps, flops=IK_FLOPS)
+            del osc_calls, ik_calls, keep
+        ctl.bind(precision=0)
     return out
 
 
@@ -305,7 +332,7 @@ def run_b200(args):
     wl = PdWorkload(device, hi - lo, seed=1000 + rank)
     reducer = StatsReducer("torch", device) if world > 1 else None
     stats_every = max(1, args.stats_every)
-    wl.window = StatsWindow(device, reducer, stats_every)
+    wl.bind(StatsWindow(device, reducer, stats_every))
     step = wl.step
 
     with ClockSampler(local_rank) as clocks:

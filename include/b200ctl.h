@@ -172,13 +172,18 @@ B200CTL_API int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_par
 
 /* =========================== family O: OSC + damped-least-squares IK =======
  * All tensors f32, any strides (the reference passes views: j_eef strides
- * (540,9,1), mm (81,9,1), dof_pos stride-2 views, out = effort_action[:, :7]). */
+ * (540,9,1), mm (81,9,1), dof_pos stride-2 views, out = effort_action[:, :7]).
+ * precision: B200CTL_PRECISION_FP64_FACTOR (0) keeps data fp32 but runs the Cholesky /
+ * substitution chain in fp64 -- needed to hold 1e-4 against the fp64 result up to
+ * cond(J M^-1 J^T) = 1e4; B200CTL_PRECISION_FP32 (1) is the all-fp32 chain. */
+#define B200CTL_PRECISION_FP64_FACTOR 0
+#define B200CTL_PRECISION_FP32 1
 
 /* control_ik, examples/franka_cube_ik_osc.py:53-59 (explicit-arg twin franka_nut_bolt_ik_osc.py:33-38):
  * out = [dof_pos +] J^T (J J^T + lambda^2 I)^-1 dpose.
  * j_eef (N,6,D) D in {7,9}; dpose (N,6[,1]); dof_pos (N,>=D[,1]) or NULL; out (N,D). */
 B200CTL_API int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, double lambda,
-                   const DLTensor* dof_pos, DLTensor* out, b200ctl_stream_t stream);
+                   const DLTensor* dof_pos, int32_t precision, DLTensor* out, b200ctl_stream_t stream);
 
 /* control_osc, examples/franka_cube_ik_osc.py:62-79.
  * j_eef (N,6,7); mm (N,7,7); dof_pos, dof_vel (N,>=7[,1]); hand_vel (M,6) with
@@ -187,12 +192,12 @@ B200CTL_API int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, dou
 B200CTL_API int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_pos, const DLTensor* dof_vel,
                 const DLTensor* hand_vel, const DLTensor* hand_index, const DLTensor* dpose,
                 const DLTensor* q_default, double kp, double kd, double kp_null, double kd_null,
-                DLTensor* out, double* stats, b200ctl_stream_t stream);
+                int32_t precision, DLTensor* out, double* stats, b200ctl_stream_t stream);
 
 /* OSC of examples/franka_osc.py:229-241 over all D DOFs: out = J^T (J M^-1 J^T)^-1 (kp dpose) - kv M qd.
  * j_eef (N,6,D), mm (N,D,D), dof_vel (N,D[,1]), dpose (N,6[,1]), out (N,D[,1]); D in {7,9}. */
 B200CTL_API int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_vel, const DLTensor* dpose,
-                     double kp, double kv, DLTensor* out, b200ctl_stream_t stream);
+                     double kp, double kv, int32_t precision, DLTensor* out, b200ctl_stream_t stream);
 
 /* orientation_error, examples/franka_cube_ik_osc.py:34-37.  (N,4) xyzw x2 -> (N,3). */
 B200CTL_API int b200ctl_orientation_error(const DLTensor* q_desired, const DLTensor* q_current,

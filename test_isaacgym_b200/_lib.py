@@ -71,10 +71,10 @@ _SIGNATURES = {
     "b200ctl_euler_xyz_to_quat": (c_int, [_DL, _DL, c_void_p]),
     "b200ctl_quat_to_matrix": (c_int, [_DL, _DL, c_void_p]),
     "b200ctl_servo_step": (c_int, [_DL, POINTER(ServoParams), c_void_p, c_void_p, c_void_p]),
-    "b200ctl_ik_dls": (c_int, [_DL, _DL, c_double, _DL, _DL, c_void_p]),
+    "b200ctl_ik_dls": (c_int, [_DL, _DL, c_double, _DL, c_int32, _DL, c_void_p]),
     "b200ctl_osc": (c_int, [_DL, _DL, _DL, _DL, _DL, _DL, _DL, _DL, c_double, c_double, c_double, c_double,
-                            _DL, c_void_p, c_void_p]),
-    "b200ctl_osc_full": (c_int, [_DL, _DL, _DL, _DL, c_double, c_double, _DL, c_void_p]),
+                            c_int32, _DL, c_void_p, c_void_p]),
+    "b200ctl_osc_full": (c_int, [_DL, _DL, _DL, _DL, c_double, c_double, c_int32, _DL, c_void_p]),
     "b200ctl_orientation_error": (c_int, [_DL, _DL, _DL, c_void_p]),
     "b200ctl_gather_rows": (c_int, [_DL, _DL, c_int32, c_int32, _DL, c_void_p]),
     "b200ctl_nccl_unique_id": (c_int, [c_void_p]),
@@ -175,3 +175,29 @@ def to_device(x, device: torch.device, dtype: torch.dtype | None = None) -> torc
 
 def stats_buffer(device: torch.device) -> torch.Tensor:
     return torch.zeros(STATS_LEN, dtype=torch.float64, device=device)
+
+
+class BoundCall:
+    """A C-ABI call with its arguments marshalled once.
+
+    Building nine DLTensor structs per step costs tens of microseconds of Python -- more than the
+    kernels at 64K envs.  ``bind`` does it once for tensors that live as long as the simulation
+    (Isaac Gym's wrapped tensors never move); ``__call__`` only looks up the current stream.
+    Stream-ordered and allocation-free, so it can be captured into a CUDA graph.
+    """
+    __slots__ = ("fn", "args", "stream_slot", "device", "keep", "result")
+
+    def __init__(self, fn, args, stream_slot: int, device: torch.device, keep, result=None):
+        self.fn, self.args, self.stream_slot, self.device = fn, list(args), stream_slot, device
+        self.keep, self.result = keep, result
+
+    def __call__(self):
+        self.args[self.stream_slot] = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.fn(*self.args)
+        if rc:
+            check(rc)
+        return self.result
+
+
+def ptr_or_none(t):
+    return c_void_p(t.data_ptr()) if t is not None else None

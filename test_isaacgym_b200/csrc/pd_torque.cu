@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256)
 pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict__ q_tgt,
                       const float4* __restrict__ qd_tgt, PdParams pp, int num_dofs, int64_t nvec, int64_t num_envs,
                       float4* __restrict__ tau_out, double* __restrict__ stats) {
-  extern __shared__ float s_par[];   // [5][D]: kp, kd, tmax, lo, hi
+  extern __shared__ __align__(16) float s_par[];   // [5][D]: kp, kd, tmax, lo, hi
   float* s_kp = s_par;
   float* s_kd = s_par + num_dofs;
   float* s_tm = s_par + 2 * num_dofs;
@@ -178,18 +178,33 @@ struct PdLaunch {
   int num_dofs;
   int64_t num_envs;
   double* stats;
-  int grid;
+  int dev;
   cudaStream_t stream;
 };
+
+// Grid = (resident CTAs per SM for THIS instantiation) x (SM count), never more than the work:
+// every CTA is resident at once, strides over the range, and commits its statistics once.
+template <typename K>
+static int pd_grid(K kernel, size_t smem, int dev, int64_t work_items) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
+  const int64_t full = (int64_t)sm_count(dev) * per_sm;
+  const int64_t need = (work_items + 255) / 256;
+  return (int)(need < full ? (need > 0 ? need : 1) : full);
+}
 
 template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS>
 static void pd_launch_one(const PdLaunch& L) {
   if (L.vec4) {
     const size_t smem = 5 * (size_t)L.num_dofs * sizeof(float);
-    pd_torque_vec4_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS><<<L.grid, 256, smem, L.stream>>>(
+    auto kern = pd_torque_vec4_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS>;
+    const int grid = pd_grid(kern, smem, L.dev, L.num_envs * L.num_dofs / 4);
+    kern<<<grid, 256, smem, L.stream>>>(
         L.state4, L.tgt4, L.qd4, L.pp, L.num_dofs, L.num_envs * L.num_dofs / 4, L.num_envs, L.out4, L.stats);
   } else {
-    pd_torque_strided_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS><<<L.grid, 256, 0, L.stream>>>(
+    auto kern = pd_torque_strided_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS>;
+    const int grid = pd_grid(kern, 0, L.dev, L.num_envs * L.num_dofs);
+    kern<<<grid, 256, 0, L.stream>>>(
         L.state, L.tgt, L.qd, L.pp, L.num_dofs, L.num_envs, L.out, L.stats);
   }
 }
@@ -208,13 +223,6 @@ static void pd_launch(const PdLaunch& L, bool wrap, bool clamp, bool has_qd, boo
     if (clamp) { if (has_qd) pd_launch_tm<false, true, true>(L, tmax, stats); else pd_launch_tm<false, true, false>(L, tmax, stats); }
     else       { if (has_qd) pd_launch_tm<false, false, true>(L, tmax, stats); else pd_launch_tm<false, false, false>(L, tmax, stats); }
   }
-}
-
-// Grid: resident-CTA multiple of the SM count (8 CTAs of 256 threads per SM), never more than the work.
-static int pd_grid(int dev, int64_t work_items) {
-  const int64_t full = (int64_t)sm_count(dev) * 8;
-  const int64_t need = (work_items + 255) / 256;
-  return (int)(need < full ? (need > 0 ? need : 1) : full);
 }
 
 static int pd_vector_param(const DLTensor* t, const char* name, int num_dofs, int* dev, const float** p, int64_t* stride) {
@@ -276,7 +284,7 @@ extern "C" int b200ctl_pd_torque(const DLTensor* dof_state, const DLTensor* q_ta
   L.tgt4 = reinterpret_cast<const float4*>(L.tgt.p);
   L.qd4 = reinterpret_cast<const float4*>(L.qd.p);
   L.out4 = reinterpret_cast<float4*>(const_cast<void*>(L.out.p));
-  L.grid = pd_grid(dev, L.vec4 ? N * D / 4 : N * D);
+  L.dev = dev;
 
   DeviceGuard g;
   B200_TRY(g.enter(dev));
@@ -406,7 +414,7 @@ extern "C" int b200ctl_pd_torque_host(const float* dof_state, const float* q_tar
       mk(P.d_qd[slot], n, D, L.qd);
       mk(P.d_out[slot], n, D, L.out);
     }
-    L.grid = pd_grid(device, L.vec4 ? (int64_t)elems / 4 : (int64_t)elems);
+    L.dev = device;
     pd_launch(L, flags & B200CTL_PD_WRAP_ANGLE, clamp, qd_target != nullptr, tau_max != nullptr, stats_out != nullptr);
     B200_TRY(post_launch("pd_torque (host pipeline)"));
     B200_CUDA(cudaEventRecord(P.computed[slot], P.run));

@@ -16,6 +16,7 @@ template <> struct Ar<float> {
   static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
   static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
   // torch pow(x, 4) is a libm-grade pow: emulate with an fp64 product rounded once
   static __device__ __forceinline__ float pow4(float a) { const double d = (double)a * a; return (float)(d * d); }
 };
@@ -25,6 +26,7 @@ template <> struct Ar<double> {
   static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
   static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
   static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
   static __device__ __forceinline__ double pow4(double a) { return ::pow(a, 4.0); }
 };
 
@@ -51,13 +53,16 @@ __device__ __forceinline__ void cclvf_core(T px, T py, T pz, T tx, T ty, T tz, T
                                            T& vx, T& vy, T& vz) {
   using A = Ar<T>;
   const T dx = A::sub(px, tx), dy = A::sub(py, ty), dz = A::sub(pz, tz);
-  T r = A::sqrt(A::add(A::mul(dx, dx), A::mul(dy, dy)));      // :98 torch.norm over the planar pair
+  // :98 torch.norm(dim=1) over the planar pair: ATen's reduction accumulates acc = fma(x, x, acc), i.e.
+  // sqrt(fma(dy, dy, fl(dx*dx))) -- verified bit-for-bit against torch 2.11 CPU ("S parity").
+  T r = A::sqrt(A::fma(dy, dy, A::mul(dx, dx)));
   r = (r < (T)0.01) ? (T)0.01 : r;                             // :99 torch.max(r, 0.01), NaN-propagating
-  const T c = (r < rd) ? A::div(r, rd) : A::div(rd, r);       // :105
+  // :105 `rd / r` with a python scalar on the left is Tensor.__rtruediv__ = r.reciprocal() * rd
+  const T c = (r < rd) ? A::div(r, rd) : A::mul(A::div((T)1, r), rd);
   const T rr = A::mul(r, r);
   const T gap = A::sub(rr, rd2);                               // :108
   const T quart = A::add(A::add(A::pow4(r), A::mul(A::mul(A::sub(A::mul(c, c), (T)2), rd2), rr)), rd4);
-  const T factor = A::div(speed, A::sqrt(quart));              // :110
+  const T factor = A::mul(A::div((T)1, A::sqrt(quart)), speed);   // :110 speed / sqrt(..): reciprocal * speed again
   const T crd = A::mul(c, rd);
   vx = A::mul(-factor, A::add(A::div(A::mul(dx, gap), r), A::mul(crd, dy)));   // :112
   vy = A::mul(-factor, A::sub(A::div(A::mul(dy, gap), r), A::mul(crd, dx)));   // :113

@@ -41,6 +41,7 @@ dof_pos = None
 dof_vel = None
 hand_vel = None
 _hand_index = None       # optional (N,) int64: hand_vel is then the (M,6) view rb_states[:, 7:]
+precision = 0            # 0: fp32 data, fp64 factorisation chain (default); 1: all fp32
 
 
 def bind(**names) -> None:
@@ -92,7 +93,7 @@ def control_ik(dpose: torch.Tensor, damping=None, j_eef=None, num_envs=None, dof
     if out is None:
         out = torch.empty((n, d), dtype=torch.float32, device=j.device)
     a, b, c, e = _lib.dl(j), _lib.dl(dpose), _lib.dl(dof_pos), _lib.dl(out)
-    _lib.check(_lib.lib().b200ctl_ik_dls(a[0], b[0], float(lam), c[0], e[0], _lib.stream_ptr(j.device)))
+    _lib.check(_lib.lib().b200ctl_ik_dls(a[0], b[0], float(lam), c[0], int(g["precision"]), e[0], _lib.stream_ptr(j.device)))
     return out
 
 
@@ -107,7 +108,7 @@ def control_osc(dpose: torch.Tensor, out: torch.Tensor | None = None, stats: tor
                                    g["default_dof_pos_tensor"], out)]
     sp = ctypes.c_void_p(stats.data_ptr()) if stats is not None else None
     _lib.check(_lib.lib().b200ctl_osc(*(p[0] for p in packed[:8]), float(g["kp"]), float(g["kd"]), float(g["kp_null"]),
-                                      float(g["kd_null"]), packed[8][0], sp, _lib.stream_ptr(j.device)))
+                                      float(g["kd_null"]), int(g["precision"]), packed[8][0], sp, _lib.stream_ptr(j.device)))
     return out
 
 
@@ -118,5 +119,25 @@ def control_osc_full(dpose: torch.Tensor, j_eef: torch.Tensor, mm: torch.Tensor,
     if out is None:
         out = torch.empty((n, d, 1), dtype=torch.float32, device=j_eef.device)
     a, b, c, e, f = _lib.dl(j_eef), _lib.dl(mm), _lib.dl(dof_vel), _lib.dl(dpose), _lib.dl(out)
-    _lib.check(_lib.lib().b200ctl_osc_full(a[0], b[0], c[0], e[0], float(kp), float(kv), f[0], _lib.stream_ptr(j_eef.device)))
+    _lib.check(_lib.lib().b200ctl_osc_full(a[0], b[0], c[0], e[0], float(kp), float(kv), int(globals()["precision"]), f[0],
+                                           _lib.stream_ptr(j_eef.device)))
     return out
+
+
+def bind_control_osc(dpose: torch.Tensor, out: torch.Tensor, stats: torch.Tensor | None = None) -> "_lib.BoundCall":
+    """``control_osc`` with every argument marshalled once (the globals as bound NOW): a zero-argument
+    callable for the step loop; ``dpose`` / ``out`` must be persistent tensors updated in place."""
+    g = globals()
+    packed = [_lib.dl(t) for t in (g["j_eef"], g["mm"], g["dof_pos"], g["dof_vel"], g["hand_vel"], g["_hand_index"],
+                                   dpose, g["default_dof_pos_tensor"], out)]
+    args = [p[0] for p in packed[:8]] + [float(g["kp"]), float(g["kd"]), float(g["kp_null"]), float(g["kd_null"]),
+                                         int(g["precision"]), packed[8][0], _lib.ptr_or_none(stats), None]
+    return _lib.BoundCall(_lib.lib().b200ctl_osc, args, 15, out.device, (packed, stats), out)
+
+
+def bind_control_ik(dpose: torch.Tensor, out: torch.Tensor, dof_pos: torch.Tensor | None = None) -> "_lib.BoundCall":
+    """``control_ik`` (optionally fused with ``dof_pos[:, :7] +``) marshalled once."""
+    g = globals()
+    packed = [_lib.dl(t) for t in (g["j_eef"], dpose, dof_pos, out)]
+    args = [packed[0][0], packed[1][0], float(g["damping"]), packed[2][0], int(g["precision"]), packed[3][0], None]
+    return _lib.BoundCall(_lib.lib().b200ctl_ik_dls, args, 6, out.device, packed, out)

@@ -122,6 +122,16 @@ class PDController:
         if clamp_target and (self.q_lo is None or self.q_hi is None):
             raise ValueError("clamp_target needs q_lo and q_hi")
 
+    def bind(self, dof_state: torch.Tensor, q_target: torch.Tensor, out: torch.Tensor, qd_target=None,
+             stats: torch.Tensor | None = None) -> "_lib.BoundCall":
+        """Marshal the call once for tensors that persist across steps (the gym-wrapped tensors do);
+        the returned object is a zero-argument callable costing one foreign call per step."""
+        a = [_lib.dl(t) for t in (dof_state, q_target, qd_target, self.kp, self.kd, self.tau_max, self.q_lo,
+                                  self.q_hi, out)]
+        args = [a[0][0], a[1][0], a[2][0], a[3][0], a[4][0], a[5][0], a[6][0], a[7][0], int(self.flags), a[8][0],
+                _lib.ptr_or_none(stats), None]
+        return _lib.BoundCall(_lib.lib().b200ctl_pd_torque, args, 11, dof_state.device, (a, stats), out)
+
     def __call__(self, dof_state, q_target, qd_target=None, out=None, stats=None) -> torch.Tensor:
         return pd_torque(dof_state, q_target, self.kp, self.kd, qd_target, self.tau_max, self.q_lo, self.q_hi,
                          self.flags, out, stats)

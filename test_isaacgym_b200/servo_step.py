@@ -29,6 +29,13 @@ class ServoStep:
         """Per-step zoom of ``test11_servo_vecenv_camerazoom.py:409-422``."""
         self.params.zoom = float(zoom)
 
+    def bind(self, root_state: torch.Tensor, aux: torch.Tensor | None = None,
+             stats: torch.Tensor | None = None) -> "_lib.BoundCall":
+        """Marshal the in-place step once for a persistent root-state tensor (zero-argument callable)."""
+        a = _lib.dl(root_state)
+        args = [a[0], ctypes.byref(self.params), _lib.ptr_or_none(aux), _lib.ptr_or_none(stats), None]
+        return _lib.BoundCall(_lib.lib().b200ctl_servo_step, args, 4, root_state.device, (a, aux, stats, self), root_state)
+
     def __call__(self, root_state: torch.Tensor, aux: torch.Tensor | None = None,
                  stats: torch.Tensor | None = None) -> torch.Tensor:
         """In-place step.  ``aux``: optional (N,5) float64 device tensor receiving

@@ -37,8 +37,26 @@ def test_pd_matches_oracle(n, gain_set, flags):
         for tmax in (True, False):
             tau, ref32, ref64, _ = _run(pi, flags, qd, tmax)
             assert torch.equal(tau, ref32), "not bit-exact against the fp32 expression"
-            err = (tau.double() - ref64).abs() / ref64.abs().clamp_min(1.0)
-            assert err.max().item() <= 1e-5
+            # against the fp64 evaluation: 1e-5 relative to the size of the law's terms (kp|e| + kd|de| can cancel,
+            # so the output magnitude is the wrong yardstick for ANY fp32 evaluation, the reference's included);
+            # elements whose wrapped error sits on the +-pi discontinuity are excluded (fp32 and fp64 may pick
+            # opposite branches there -- again for any fp32 evaluation).
+            pos = pi.dof_state[:, 0].view(n, 12).double()
+            vel = pi.dof_state[:, 1].view(n, 12).double()
+            tgt = pi.q_target.double()
+            if flags & CLAMP_TARGET:
+                tgt = torch.max(torch.min(tgt, pi.q_hi.double()), pi.q_lo.double())
+            e = tgt - pos
+            scale = pi.kp.double() * e.abs() + pi.kd.double() * ((pi.qd_target.double() if qd else 0) - vel).abs()
+            err = (tau.double() - ref64).abs() / scale.clamp_min(1.0)
+            keep = torch.ones_like(err, dtype=torch.bool)
+            if flags & WRAP_ANGLE:
+                m = (e + np.pi) % (2 * np.pi)
+                keep = (m > 1e-4) & (m < 2 * np.pi - 1e-4)
+                scale_w = pi.kp.double() * np.pi + pi.kd.double() * vel.abs().clamp_min(1.0)
+                err = (tau.double() - ref64).abs() / scale_w.clamp_min(1.0)
+            assert err[keep].max().item() <= 1e-5
+            assert keep.double().mean() > 0.999
 
 
 def test_pd_reference_fragments(pd_fragments):
