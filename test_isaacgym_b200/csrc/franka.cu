@@ -81,14 +81,53 @@ __device__ __forceinline__ void chol_solve(const T (&L)[N][N], const T (&rdiag)[
 
 // Cooperative staging of a (N, R, C) strided view: tile[e * TS + r*C + c] for the CTA's envs.
 // Consecutive threads walk the innermost (unit-stride in the reference's views) dimension.
+//
+// The copies are 4-byte cp.async (LDGSTS): global -> shared without a register round trip, so a thread
+// issues its whole share of the tile back to back and the CTA has the full tile in flight before anyone
+// waits.  (With plain loads each warp had one request outstanding and the kernel ran at ~10 % of HBM:
+// profiles/r01_full_osc_v1.txt, long-scoreboard stalls.)
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 template <int R, int C, int TS>
 __device__ __forceinline__ void stage_tile(const TView& v, int64_t env0, int nenv, float* tile) {
+  constexpr int RC = R * C;
   const float* g = reinterpret_cast<const float*>(v.p) + env0 * v.s[0];
-  const int total = nenv * (R * C);
-  for (int f = threadIdx.x; f < total; f += blockDim.x) {
-    const int e = f / (R * C), k = f - e * (R * C);
+  // (e, k) walk the tile in steps of blockDim without a division per element
+  int e = threadIdx.x / RC, k = threadIdx.x - e * RC;
+  const int step_e = kTileEnvs / RC, step_k = kTileEnvs - step_e * RC;
+  while (e < nenv) {
     const int r = k / C, c = k - r * C;
-    tile[e * TS + k] = __ldg(g + e * v.s[0] + r * v.s[1] + c * v.s[2]);
+    cp_async_f32(tile + e * TS + k, g + e * v.s[0] + r * v.s[1] + c * v.s[2]);
+    e += step_e;
+    k += step_k;
+    if (k >= RC) { k -= RC; ++e; }
+  }
+}
+
+// (N, C) rows (optionally gathered through an int64 row index) -> tile[e * TS + c]
+template <int C, int TS>
+__device__ __forceinline__ void stage_rows(const TView& v, int64_t env0, int nenv, float* tile,
+                                           const TView* index = nullptr) {
+  if (index) {
+    // one thread per env resolves the row, then issues its C copies
+    if ((int)threadIdx.x < nenv) {
+      const int64_t row = reinterpret_cast<const int64_t*>(index->p)[(env0 + threadIdx.x) * index->s[0]];
+      const float* g = reinterpret_cast<const float*>(v.p) + row * v.s[0];
+#pragma unroll
+      for (int c = 0; c < C; ++c) cp_async_f32(tile + threadIdx.x * TS + c, g + c * v.s[1]);
+    }
+    return;
+  }
+  const float* g = reinterpret_cast<const float*>(v.p) + env0 * v.s[0];
+  for (int f = threadIdx.x; f < nenv * C; f += kTileEnvs) {
+    const int e = f / C, c = f - e * C;
+    cp_async_f32(tile + e * TS + c, g + e * v.s[0] + c * v.s[1]);
   }
 }
 
@@ -129,22 +168,26 @@ __device__ __forceinline__ void task_space_factor(const float* sJ, const float* 
 }
 
 // ------------------------------------------------------------------ a9: control_ik
+// per-env tile: [ J 6xD | dpose 6 | dof_pos D ]
 template <typename T, int D>
 __global__ void __launch_bounds__(kTileEnvs)
 ik_dls_kernel(TView j_eef, TView dpose, float lambda2, TView dof_pos, int has_pos, TView out, int64_t n) {
-  constexpr int JS = (6 * D) | 1;
-  __shared__ float tJ[kTileEnvs * JS];
+  constexpr int oDP = 6 * D, oQ = oDP + 6, TS = (oQ + D) | 1;
+  __shared__ float tile[kTileEnvs * TS];
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  stage_tile<6, D, JS>(j_eef, env0, nenv, tJ);
+  stage_tile<6, D, TS>(j_eef, env0, nenv, tile);
+  stage_rows<6, TS>(dpose, env0, nenv, tile + oDP);
+  if (has_pos) stage_rows<D, TS>(dof_pos, env0, nenv, tile + oQ);
+  cp_async_wait_all();
   __syncthreads();
   if (threadIdx.x >= nenv) return;
   const int64_t env = env0 + threadIdx.x;
-  const float* sJ = tJ + threadIdx.x * JS;
+  const float* sJ = tile + threadIdx.x * TS;
   T A[6][6], rd[6], y[6];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
-    y[r] = (T)ldf(dpose, env * dpose.s[0] + r * dpose.s[1]);
+    y[r] = (T)sJ[oDP + r];
 #pragma unroll
     for (int c = 0; c <= r; ++c) {
       T s = (r == c) ? (T)lambda2 : (T)0;     // J J^T + lambda^2 I   (:57-58)
@@ -162,55 +205,59 @@ ik_dls_kernel(TView j_eef, TView dpose, float lambda2, TView dof_pos, int has_po
 #pragma unroll
     for (int r = 0; r < 6; ++r) u = fma_t<T>((T)sJ[r * D + c], y[r], u);   // J^T y
     float uf = (float)u;
-    if (has_pos) uf = __fadd_rn(ldf(dof_pos, env * dof_pos.s[0] + c * dof_pos.s[1]), uf);   // :395
+    if (has_pos) uf = __fadd_rn(sJ[oQ + c], uf);   // dof_pos[:, :7] + control_ik(dpose)  (:395)
     o[c * out.s[1]] = uf;
   }
 }
 
 // ------------------------------------------------------------------ a10: control_osc
+// per-env tile: [ J 6x7 | M 7x7 | dof_pos 7 | dof_vel 7 | dpose 6 | hand_vel 6 ]
 template <typename T>
 __global__ void __launch_bounds__(kTileEnvs)
 osc_kernel(TView j_eef, TView mm, TView dof_pos, TView dof_vel, TView hand_vel, TView hand_index, int has_index,
            TView dpose, TView q_default, float kp, float kd, float kp_null, float kd_null, TView out, int64_t n,
            double* __restrict__ stats) {
   constexpr int D = 7;
-  constexpr int JS = (6 * D) | 1, MS = (D * D) | 1;
-  __shared__ float tJ[kTileEnvs * JS];
-  __shared__ float tM[kTileEnvs * MS];
+  constexpr int oM = 6 * D, oQ = oM + D * D, oQD = oQ + D, oDP = oQD + D, oHV = oDP + 6, TS = (oHV + 6) | 1;
+  __shared__ float tile[kTileEnvs * TS];
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  stage_tile<6, D, JS>(j_eef, env0, nenv, tJ);
-  stage_tile<D, D, MS>(mm, env0, nenv, tM);
+  stage_rows<6, TS>(hand_vel, env0, nenv, tile + oHV, has_index ? &hand_index : nullptr);   // dependent gather first
+  stage_tile<6, D, TS>(j_eef, env0, nenv, tile);
+  stage_tile<D, D, TS>(mm, env0, nenv, tile + oM);
+  stage_rows<D, TS>(dof_pos, env0, nenv, tile + oQ);
+  stage_rows<D, TS>(dof_vel, env0, nenv, tile + oQD);
+  stage_rows<6, TS>(dpose, env0, nenv, tile + oDP);
+  cp_async_wait_all();
   __syncthreads();
 
   double acc[4] = {0, 0, 0, 0};
   if (threadIdx.x < nenv) {
     const int64_t env = env0 + threadIdx.x;
-    const float* sJ = tJ + threadIdx.x * JS;
-    const float* sM = tM + threadIdx.x * MS;
+    const float* sJ = tile + threadIdx.x * TS;
+    const float* sM = sJ + oM;
+    // factor first: L is dead once chol(Lambda^-1) exists, which keeps the live register set small
+    T A[6][6], rda[6];
+    {
+      T L[D][D], rdm[D];
+      task_space_factor<T, D>(sJ, sM, L, rdm, A, rda);
+    }
     // joint-space PD term u0 (:74-76), fp32 in the reference's operand order
     float u0[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-      const float q = ldf(dof_pos, env * dof_pos.s[0] + c * dof_pos.s[1]);
-      const float qd = ldf(dof_vel, env * dof_vel.s[0] + c * dof_vel.s[1]);
       const float qdef = ldf(q_default, c * q_default.s[0]);
-      u0[c] = __fadd_rn(__fmul_rn(kd_null, -qd), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef, q))));
+      u0[c] = __fadd_rn(__fmul_rn(kd_null, -sJ[oQD + c]), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef, sJ[oQ + c]))));
     }
     // task-space target w = kp dpose - kd v_hand (:67-68) minus J u0 (null-space projector folded in)
-    const int64_t hrow = has_index ? reinterpret_cast<const int64_t*>(hand_index.p)[env * hand_index.s[0]] : env;
     T w[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      const float dp = ldf(dpose, env * dpose.s[0] + r * dpose.s[1]);
-      const float hv = ldf(hand_vel, hrow * hand_vel.s[0] + r * hand_vel.s[1]);
-      T s = (T)__fsub_rn(__fmul_rn(kp, dp), __fmul_rn(kd, hv));
+      T s = (T)__fsub_rn(__fmul_rn(kp, sJ[oDP + r]), __fmul_rn(kd, sJ[oHV + r]));
 #pragma unroll
       for (int c = 0; c < D; ++c) s = fma_t<T>(-(T)sJ[r * D + c], (T)u0[c], s);
       w[r] = s;
     }
-    T L[D][D], rdm[D], A[6][6], rda[6];
-    task_space_factor<T, D>(sJ, sM, L, rdm, A, rda);
     chol_solve<T, 6>(A, rda, w);          // w <- Lambda (w - J u0)
     float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
     bool finite = true;
@@ -239,36 +286,36 @@ osc_kernel(TView j_eef, TView mm, TView dof_pos, TView dof_vel, TView hand_vel, 
 }
 
 // ------------------------------------------------------------------ franka_osc.py:229-241
+// per-env tile: [ J 6xD | M DxD | dof_vel D | dpose 6 ]
 template <typename T, int D>
 __global__ void __launch_bounds__(kTileEnvs)
 osc_full_kernel(TView j_eef, TView mm, TView dof_vel, TView dpose, float kp, float kv, TView out, int64_t n) {
-  constexpr int JS = (6 * D) | 1, MS = (D * D) | 1;
-  __shared__ float tJ[kTileEnvs * JS];
-  __shared__ float tM[kTileEnvs * MS];
+  constexpr int oM = 6 * D, oQD = oM + D * D, oDP = oQD + D, TS = (oDP + 6) | 1;
+  __shared__ float tile[kTileEnvs * TS];
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  stage_tile<6, D, JS>(j_eef, env0, nenv, tJ);
-  stage_tile<D, D, MS>(mm, env0, nenv, tM);
+  stage_tile<6, D, TS>(j_eef, env0, nenv, tile);
+  stage_tile<D, D, TS>(mm, env0, nenv, tile + oM);
+  stage_rows<D, TS>(dof_vel, env0, nenv, tile + oQD);
+  stage_rows<6, TS>(dpose, env0, nenv, tile + oDP);
+  cp_async_wait_all();
   __syncthreads();
   if (threadIdx.x >= nenv) return;
   const int64_t env = env0 + threadIdx.x;
-  const float* sJ = tJ + threadIdx.x * JS;
-  const float* sM = tM + threadIdx.x * MS;
+  const float* sJ = tile + threadIdx.x * TS;
+  const float* sM = sJ + oM;
   T w[6];
 #pragma unroll
-  for (int r = 0; r < 6; ++r) w[r] = (T)__fmul_rn(kp, ldf(dpose, env * dpose.s[0] + r * dpose.s[1]));
+  for (int r = 0; r < 6; ++r) w[r] = (T)__fmul_rn(kp, sJ[oDP + r]);
   T L[D][D], rdm[D], A[6][6], rda[6];
   task_space_factor<T, D>(sJ, sM, L, rdm, A, rda);
   chol_solve<T, 6>(A, rda, w);            // Lambda (kp dpose)
-  float qd[D];
-#pragma unroll
-  for (int c = 0; c < D; ++c) qd[c] = ldf(dof_vel, env * dof_vel.s[0] + c * dof_vel.s[1]);
   float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
 #pragma unroll
   for (int c = 0; c < D; ++c) {
     T damp = (T)0;
 #pragma unroll
-    for (int k = 0; k < D; ++k) damp = fma_t<T>((T)sM[c * D + k], (T)qd[k], damp);
+    for (int k = 0; k < D; ++k) damp = fma_t<T>((T)sM[c * D + k], (T)sJ[oQD + k], damp);
     T u = -(T)kv * damp;                  // - kv * M qd
 #pragma unroll
     for (int r = 0; r < 6; ++r) u = fma_t<T>((T)sJ[r * D + c], w[r], u);

@@ -57,7 +57,7 @@ servo_step_kernel(float* __restrict__ state, int64_t num_envs, ServoConst k, dou
     cclvf_core<float>(ux, uy, uz, cx, cy, k.uav_height, k.uav_speed, k.uav_rd, k.uav_rd2, k.uav_rd4, uvx, uvy, uvz);
 
     float oq[4], cq[4];
-    double pu, pv, rolld, pitchd, yawd;
+    double pu, pv, rolld = 0, pitchd = 0, yawd = 0;
     bool behind;
     if (PREC == 0) {
       // torch.atan2 on fp32 (:407): correctly rounded fp32 result via fp64
@@ -77,20 +77,16 @@ servo_step_kernel(float* __restrict__ state, int64_t num_envs, ServoConst k, dou
       const double hw = k.width * 0.5, hh = k.height * 0.5;
       const double mvx = hw - pu, mvy = hh - pv;             // order_pixel_move, test10:432
       const double Kinv[9] = {1.0 / k.fx, 0.0, -k.u0 / k.fx, 0.0, 1.0 / k.fy, -k.v0 / k.fy, 0.0, 0.0, 1.0};
-      double mx, my, mz, tx, ty, tz;
+      double mx, my, mz;
       pixel_bearing<double>(Kinv, mvx + hw, mvy + hh, mx, my, mz);   // secondary_control_vecenv.py:101,107
-      pixel_bearing<double>(Kinv, hw, hh, tx, ty, tz);              // :102-103,108
-      double roll, pitch, yaw;
-      servo_angles<double, false>(mx, my, mz, tx, ty, tz, R, 0, roll, pitch, yaw);
-      constexpr double kRad2Deg = 180.0 / 3.141592653589793238462643383279502884;
-      constexpr double kDeg2Rad = 3.141592653589793238462643383279502884 / 180.0;
-      rolld = roll * 180.0 / 3.141592653589793238462643383279502884;   // :196 (x * 180 / pi)
-      pitchd = pitch * 180.0 / 3.141592653589793238462643383279502884;
-      yawd = yaw * 180.0 / 3.141592653589793238462643383279502884;
-      (void)kRad2Deg;
-      double x, y, z, w;
-      euler_xyz_to_quat<double>(rolld * kDeg2Rad, pitchd * kDeg2Rad, yawd * kDeg2Rad, x, y, z, w);   // test10:444-447
-      oq[0] = (float)x; oq[1] = (float)y; oq[2] = (float)z; oq[3] = (float)w;   // fp64 -> fp32 on assignment (:451)
+      // (the centre bearing of :102-103,108 is (1,0,0) for this K: asin(t_z) = 0)
+      double q[4], ang[3];
+      servo_quat_from_bearing<double>(mx, my, mz, R, q, aux ? ang : nullptr);   // :113-181 + test10:440-447
+      oq[0] = (float)q[0]; oq[1] = (float)q[1]; oq[2] = (float)q[2]; oq[3] = (float)q[3];   // fp64 -> fp32 (:451)
+      if (aux) {
+        constexpr double kPi = 3.141592653589793238462643383279502884;
+        rolld = ang[0] * 180.0 / kPi; pitchd = ang[1] * 180.0 / kPi; yawd = ang[2] * 180.0 / kPi;   // :196
+      }
       acc[1] = sqrt(mvx * mvx + mvy * mvy);
     } else {
       const float car_yaw = atan2f(cvy, cvx);
@@ -110,12 +106,10 @@ servo_step_kernel(float* __restrict__ state, int64_t num_envs, ServoConst k, dou
       // bearing of the moved pixel == normalised body-frame direction with the clamped depth
       const float bxc = behind ? 1e-7f : bx;
       const float inv = rsqrtf(bxc * bxc + by * by + bz * bz);
-      float roll, pitch, yaw;
-      servo_angles<float, true>(bxc * inv, by * inv, bz * inv, 1.f, 0.f, 0.f, R, 0, roll, pitch, yaw);
-      rolld = roll * 57.29577951308232f; pitchd = pitch * 57.29577951308232f; yawd = yaw * 57.29577951308232f;
-      float x, y, z, w;
-      euler_xyz_to_quat<float>(roll, pitch, yaw, x, y, z, w);
-      oq[0] = x; oq[1] = y; oq[2] = z; oq[3] = w;
+      float q[4], ang[3];
+      servo_quat_from_bearing<float>(bxc * inv, by * inv, bz * inv, R, q, aux ? ang : nullptr);
+      oq[0] = q[0]; oq[1] = q[1]; oq[2] = q[2]; oq[3] = q[3];
+      if (aux) { rolld = ang[0] * 57.29577951308232f; pitchd = ang[1] * 57.29577951308232f; yawd = ang[2] * 57.29577951308232f; }
       const float ex = (float)(k.width * 0.5) - fu, ey = (float)(k.height * 0.5) - fv;
       acc[1] = sqrtf(ex * ex + ey * ey);
     }

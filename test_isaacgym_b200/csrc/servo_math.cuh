@@ -187,3 +187,71 @@ __device__ __forceinline__ void euler_xyz_to_quat(T roll, T pitch, T yaw, T& x, 
 }
 
 }  // namespace b200ctl
+
+namespace b200ctl {
+
+// (cos a, |sin a|, a < 0) -> (cos a/2, sin a/2) for a in [-pi, pi], without cancellation.
+template <typename T>
+__device__ __forceinline__ void half_angle(T c, T s_abs, bool negative, T& ch, T& sh) {
+  if (c >= (T)0) {
+    ch = Fn<T>::sqrt(((T)1 + c) * (T)0.5);
+    sh = s_abs / ((T)2 * ch);
+  } else {
+    sh = Fn<T>::sqrt(((T)1 - c) * (T)0.5);
+    ch = s_abs / ((T)2 * sh);
+  }
+  if (negative) sh = -sh;
+}
+
+// Fused a6 + a2 for the servo step: gimbal attitude quaternion straight from the bearing.
+//
+// servo_ext_pixel (common/secondary_control_vecenv.py:99-200) returns angles through asin / acos and
+// test10:440-447 turns them back into a quaternion through sin / cos of the half angles.  Every angle
+// enters the quaternion only through its sine and cosine, and those are available in closed form:
+//   cos(yaw)   = p_x/|p_xy|,  sin(yaw)  = p_y/|p_xy|           (:125-135, negative branch iff !(p_y > 0))
+//   sin(pitch) = -p_z,        cos(pitch) = |p_xy|              (:120, centre bearing t = (1,0,0), |p| = 1)
+//   cos(roll)  = rv.mv,       |sin(roll)| = |rv x mv|          (:168-181, negative iff !(mv_z > 0))
+//   mv = C[:,1] cos(cy) - C[:,0] sin(cy),  cos(cy) = m_x/|m_xy|, sin(cy) = m_y/|m_xy|   (:143-163, C orthonormal)
+// so the step needs square roots and divisions only -- no inverse-trig / trig round trips.  Valid for the
+// orthonormal C = R(q) and pin-hole K with the principal point at the image centre, which is what the fused
+// step has; the general entry point b200ctl_servo_ext_pixel keeps the literal asin / acos evaluation.
+// `ang` (optional, radians: roll, pitch, yaw) is filled from atan2 of the same sines / cosines.
+template <typename T>
+__device__ __forceinline__ void servo_quat_from_bearing(T mx, T my, T mz, const T (&C)[9], T (&q)[4], T* ang) {
+  using F = Fn<T>;
+  const T px = C[0] * mx + C[1] * my + C[2] * mz;
+  const T py = C[3] * mx + C[4] * my + C[5] * mz;
+  const T pz = C[6] * mx + C[7] * my + C[8] * mz;
+  const T nxy = F::sqrt(px * px + py * py);
+  const T cyaw = px / nxy, syaw = py / nxy;
+  const bool yaw_neg = !(py > (T)0);
+  const T nm = F::sqrt(mx * mx + my * my);
+  const T ccy = mx / nm, scy = my / nm;
+  const T mvx = C[1] * ccy - C[0] * scy;
+  const T mvy = C[4] * ccy - C[3] * scy;
+  const T mvz = C[7] * ccy - C[6] * scy;
+  T dot = -syaw * mvx + cyaw * mvy;
+  dot = (dot > (T)1) ? (T)1 : ((dot < (T)-1) ? (T)-1 : dot);          // :179 clip
+  const T ex = cyaw * mvz, ey = syaw * mvz, ez = -syaw * mvy - cyaw * mvx;
+  const T sroll = F::sqrt(ex * ex + ey * ey + ez * ez);
+  const bool roll_neg = !(mvz > (T)0);                                  // :181
+  const T cpitch = (nxy > (T)1) ? (T)1 : nxy;
+  const T spitch_abs = (pz < (T)0) ? -pz : pz;
+  const bool pitch_neg = pz > (T)0;                                     // pitch = -asin(p_z)
+  T cr, sr, cp, sp, cy, sy;
+  half_angle<T>(dot, sroll, roll_neg, cr, sr);
+  half_angle<T>(cpitch, spitch_abs, pitch_neg, cp, sp);
+  half_angle<T>(cyaw, yaw_neg ? -syaw : syaw, yaw_neg, cy, sy);
+  q[0] = sr * cp * cy - cr * sp * sy;       // extrinsic xyz, same closed form as euler_xyz_to_quat
+  q[1] = cr * sp * cy + sr * cp * sy;
+  q[2] = cr * cp * sy - sr * sp * cy;
+  q[3] = cr * cp * cy + sr * sp * sy;
+  if (ang) {
+    ang[0] = roll_neg ? -F::atan2(sroll, dot) : F::atan2(sroll, dot);
+    ang[1] = F::atan2(-pz, nxy);
+    const T ya = F::atan2(yaw_neg ? -syaw : syaw, cyaw);
+    ang[2] = yaw_neg ? -ya : ya;
+  }
+}
+
+}  // namespace b200ctl
