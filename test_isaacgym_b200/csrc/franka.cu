@@ -131,6 +131,56 @@ __device__ __forceinline__ void stage_rows(const TView& v, int64_t env0, int nen
   }
 }
 
+// Column-owner staging: the per-env working set is a fixed list of scalars (J[r][c], M[r][c], q[c], ...).
+// Thread t owns list entries t, t+64, ...: it resolves (pointer, env stride, tile offset) ONCE and then walks
+// the tile's envs with one pointer bump per copy.  A warp's copies of one env are the consecutive entries of
+// the list, i.e. (nearly) consecutive addresses.  This replaced a per-element (env, row, col) decomposition
+// whose 64-bit index arithmetic was 60 % of all executed instructions (profiles/r01_full_osc_v2.txt).
+struct Seg {
+  const float* base;      // first env of the tile
+  int64_t s0, s1, s2;     // env / row / col strides (elements)
+  int rows, cols, toff;   // extent and offset of the segment inside the per-env tile row
+};
+__device__ __forceinline__ Seg seg_of(const TView& v, int64_t env0, int rows, int cols, int toff) {
+  Seg s;
+  s.base = reinterpret_cast<const float*>(v.p) + env0 * v.s[0];
+  s.s0 = v.s[0];
+  s.s1 = v.s[1];
+  s.s2 = rows > 1 ? v.s[2] : 0;
+  if (rows == 1) { s.s2 = v.s[1]; s.s1 = 0; }   // (N, C) vectors: the column stride is s[1]
+  s.rows = rows; s.cols = cols; s.toff = toff;
+  return s;
+}
+template <int NSEG, int TS>
+__device__ __forceinline__ void stage_columns(const Seg (&segs)[NSEG], int nenv, float* tile) {
+  int total = 0;
+#pragma unroll
+  for (int i = 0; i < NSEG; ++i) total += segs[i].rows * segs[i].cols;
+  for (int id = threadIdx.x; id < total; id += kTileEnvs) {
+    const float* g = nullptr;
+    int64_t step = 0;
+    int toff = 0, k = id;
+#pragma unroll
+    for (int i = 0; i < NSEG; ++i) {
+      const int cnt = segs[i].rows * segs[i].cols;
+      if (k >= 0 && k < cnt) {
+        const int r = k / segs[i].cols, c = k - r * segs[i].cols;
+        g = segs[i].base + r * segs[i].s1 + c * segs[i].s2;
+        step = segs[i].s0;
+        toff = segs[i].toff + k;
+      }
+      k -= cnt;
+    }
+    float* dst = tile + toff;
+#pragma unroll 4
+    for (int e = 0; e < nenv; ++e) {
+      cp_async_f32(dst, g);
+      dst += TS;
+      g += step;
+    }
+  }
+}
+
 __device__ __forceinline__ float wrap_pi(float e) {
   // ((e + pi) % (2 pi)) - pi with python floor-mod semantics (franka_cube_ik_osc.py:75)
   float m = fmodf(__fadd_rn(e, kPiF), kTwoPiF);
@@ -176,9 +226,9 @@ ik_dls_kernel(TView j_eef, TView dpose, float lambda2, TView dof_pos, int has_po
   __shared__ float tile[kTileEnvs * TS];
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  stage_tile<6, D, TS>(j_eef, env0, nenv, tile);
-  stage_rows<6, TS>(dpose, env0, nenv, tile + oDP);
-  if (has_pos) stage_rows<D, TS>(dof_pos, env0, nenv, tile + oQ);
+  const Seg segs[3] = {seg_of(j_eef, env0, 6, D, 0), seg_of(dpose, env0, 1, 6, oDP),
+                       seg_of(dof_pos, env0, 1, has_pos ? D : 0, oQ)};
+  stage_columns<3, TS>(segs, nenv, tile);
   cp_async_wait_all();
   __syncthreads();
   if (threadIdx.x >= nenv) return;
@@ -223,11 +273,9 @@ osc_kernel(TView j_eef, TView mm, TView dof_pos, TView dof_vel, TView hand_vel, 
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
   stage_rows<6, TS>(hand_vel, env0, nenv, tile + oHV, has_index ? &hand_index : nullptr);   // dependent gather first
-  stage_tile<6, D, TS>(j_eef, env0, nenv, tile);
-  stage_tile<D, D, TS>(mm, env0, nenv, tile + oM);
-  stage_rows<D, TS>(dof_pos, env0, nenv, tile + oQ);
-  stage_rows<D, TS>(dof_vel, env0, nenv, tile + oQD);
-  stage_rows<6, TS>(dpose, env0, nenv, tile + oDP);
+  const Seg segs[5] = {seg_of(j_eef, env0, 6, D, 0), seg_of(mm, env0, D, D, oM), seg_of(dof_pos, env0, 1, D, oQ),
+                       seg_of(dof_vel, env0, 1, D, oQD), seg_of(dpose, env0, 1, 6, oDP)};
+  stage_columns<5, TS>(segs, nenv, tile);
   cp_async_wait_all();
   __syncthreads();
 
@@ -294,10 +342,9 @@ osc_full_kernel(TView j_eef, TView mm, TView dof_vel, TView dpose, float kp, flo
   __shared__ float tile[kTileEnvs * TS];
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  stage_tile<6, D, TS>(j_eef, env0, nenv, tile);
-  stage_tile<D, D, TS>(mm, env0, nenv, tile + oM);
-  stage_rows<D, TS>(dof_vel, env0, nenv, tile + oQD);
-  stage_rows<6, TS>(dpose, env0, nenv, tile + oDP);
+  const Seg segs[4] = {seg_of(j_eef, env0, 6, D, 0), seg_of(mm, env0, D, D, oM), seg_of(dof_vel, env0, 1, D, oQD),
+                       seg_of(dpose, env0, 1, 6, oDP)};
+  stage_columns<4, TS>(segs, nenv, tile);
   cp_async_wait_all();
   __syncthreads();
   if (threadIdx.x >= nenv) return;

@@ -10,6 +10,8 @@
 // the fp64 "reference precision" mode is FP64-pipe bound instead.
 #include "servo_math.cuh"
 
+#include <type_traits>
+
 namespace b200ctl {
 
 constexpr int kRow = 13;            // floats per actor root-state row
@@ -50,11 +52,12 @@ servo_step_kernel(float* __restrict__ state, int64_t num_envs, ServoConst k, dou
     const float cx = row[13], cy = row[14], cz = row[15];
 
     // ---- car: velocity command, heading quaternion (test10:406-410), fp32 like the reference's torch ops
+    using CA = typename std::conditional<PREC == 0, Ar<float>, ArFast>::type;
     float cvx, cvy, cvz;
-    cclvf_core<float>(cx, cy, cz, k.car_tx, k.car_ty, k.car_tz, k.car_speed, k.car_rd, k.car_rd2, k.car_rd4, cvx, cvy, cvz);
+    cclvf_core<float, CA>(cx, cy, cz, k.car_tx, k.car_ty, k.car_tz, k.car_speed, k.car_rd, k.car_rd2, k.car_rd4, cvx, cvy, cvz);
     // ---- uav: velocity command toward (car.x, car.y, height) (test10:412-414)
     float uvx, uvy, uvz;
-    cclvf_core<float>(ux, uy, uz, cx, cy, k.uav_height, k.uav_speed, k.uav_rd, k.uav_rd2, k.uav_rd4, uvx, uvy, uvz);
+    cclvf_core<float, CA>(ux, uy, uz, cx, cy, k.uav_height, k.uav_speed, k.uav_rd, k.uav_rd2, k.uav_rd4, uvx, uvy, uvz);
 
     float oq[4], cq[4];
     double pu, pv, rolld = 0, pitchd = 0, yawd = 0;
@@ -134,9 +137,12 @@ servo_step_kernel(float* __restrict__ state, int64_t num_envs, ServoConst k, dou
   __syncthreads();
 
   // ---- write back only the columns the reference assigns: 3..9 of each actor row
+  // kTile % kRow == 12, so the column of float i = tid + kTile*j steps by -1 (mod 13): no division in the loop
+  static_assert(kTile % kRow == kRow - 1, "incremental column update assumes kTile = -1 mod kRow");
+  int col = threadIdx.x % kRow;
   for (int i = threadIdx.x; i < nfl; i += kTile) {
-    const int col = i % kRow;
     if (col >= 3 && col <= 9) gbase[i] = tile[i];
+    col = (col == 0) ? kRow - 1 : col - 1;
   }
   if (stats) {
     const int slot[5] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_SAT,

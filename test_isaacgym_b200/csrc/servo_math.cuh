@@ -30,9 +30,21 @@ template <> struct Ar<double> {
   static __device__ __forceinline__ double pow4(double a) { return ::pow(a, 4.0); }
 };
 
+// Throughput policy for the fp32 fast mode: contraction allowed, approximate division / rsqrt (<= 2 ulp).
+struct ArFast {
+  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+  static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return a * rsqrtf(a); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+  static __device__ __forceinline__ float pow4(float a) { const float q = a * a; return q * q; }
+};
+
 template <typename T> struct Fn;
 template <> struct Fn<double> {
   static __device__ __forceinline__ double sqrt(double a) { return ::sqrt(a); }
+  static __device__ __forceinline__ double rsqrt(double a) { return ::rsqrt(a); }
   static __device__ __forceinline__ double asin(double a) { return ::asin(a); }
   static __device__ __forceinline__ double acos(double a) { return ::acos(a); }
   static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
@@ -40,6 +52,7 @@ template <> struct Fn<double> {
 };
 template <> struct Fn<float> {
   static __device__ __forceinline__ float sqrt(float a) { return ::sqrtf(a); }
+  static __device__ __forceinline__ float rsqrt(float a) { return ::rsqrtf(a); }
   static __device__ __forceinline__ float asin(float a) { return ::asinf(a); }
   static __device__ __forceinline__ float acos(float a) { return ::acosf(a); }
   static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
@@ -48,10 +61,9 @@ template <> struct Fn<float> {
 
 // ------------------------------------------------------------------ a1: cclvf2
 // common/controller6.py:92-118, operand order preserved (see oracle/servo.py).
-template <typename T>
+template <typename T, typename A = Ar<T>>
 __device__ __forceinline__ void cclvf_core(T px, T py, T pz, T tx, T ty, T tz, T speed, T rd, T rd2, T rd4,
                                            T& vx, T& vy, T& vz) {
-  using A = Ar<T>;
   const T dx = A::sub(px, tx), dy = A::sub(py, ty), dz = A::sub(pz, tz);
   // :98 torch.norm(dim=1) over the planar pair: ATen's reduction accumulates acc = fma(x, x, acc), i.e.
   // sqrt(fma(dy, dy, fl(dx*dx))) -- verified bit-for-bit against torch 2.11 CPU ("S parity").
@@ -73,8 +85,8 @@ __device__ __forceinline__ void cclvf_core(T px, T py, T pz, T tx, T ty, T tz, T
 // scipy Rotation.from_quat(q).as_matrix(): q is normalised first (test10_servo_vecenv.py:423).
 template <typename T>
 __device__ __forceinline__ void quat_to_mat(T x, T y, T z, T w, T (&R)[9]) {
-  const T n = Fn<T>::sqrt(x * x + y * y + z * z + w * w);
-  x /= n; y /= n; z /= n; w /= n;
+  const T inv = Fn<T>::rsqrt(x * x + y * y + z * z + w * w);
+  x *= inv; y *= inv; z *= inv; w *= inv;
   const T x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w;
   const T xy = x * y, zw = z * w, xz = x * z, yw = y * w, yz = y * z, xw = x * w;
   R[0] = x2 - y2 - z2 + w2; R[1] = 2 * (xy - zw);      R[2] = 2 * (xz + yw);
@@ -101,8 +113,9 @@ __device__ __forceinline__ void project_body(T bx, T by, T bz, T fx, T fy, T u0,
   const T cx = -by, cy = -bz;                 // rot_coord3 :234-240
   depth_clamped = !(bx > (T)1e-7);
   const T cz = (bx > (T)1e-7) ? bx : ((bx != bx) ? bx : (T)1e-7);   // np.maximum propagates NaN
-  u = fx * (cx / cz) + u0;                    // K @ (p / p_z) :245-246
-  v = fy * (cy / cz) + v0;
+  const T rz = (T)1 / cz;
+  u = fx * (cx * rz) + u0;                    // K @ (p / p_z) :245-246
+  v = fy * (cy * rz) + v0;
 }
 
 // ------------------------------------------------------------------ a5: pixel2phy
@@ -112,8 +125,8 @@ __device__ __forceinline__ void pixel_bearing(const T (&Kinv)[9], T px, T py, T&
   const T a0 = Kinv[0] * px + Kinv[1] * py + Kinv[2];
   const T a1 = Kinv[3] * px + Kinv[4] * py + Kinv[5];
   const T a2 = Kinv[6] * px + Kinv[7] * py + Kinv[8];
-  const T n = Fn<T>::sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-  mx = a2 / n; my = a0 / n; mz = a1 / n;
+  const T inv = Fn<T>::rsqrt(a0 * a0 + a1 * a1 + a2 * a2);
+  mx = a2 * inv; my = a0 * inv; mz = a1 * inv;
 }
 
 // where(y > 0, acos(x/|xy|), -acos(x/|xy|))  (:125-135, :143-148); y == 0 takes the negative branch.
@@ -193,12 +206,15 @@ namespace b200ctl {
 // (cos a, |sin a|, a < 0) -> (cos a/2, sin a/2) for a in [-pi, pi], without cancellation.
 template <typename T>
 __device__ __forceinline__ void half_angle(T c, T s_abs, bool negative, T& ch, T& sh) {
+  // the radicand is >= 1/2 in either branch, so rsqrt never sees 0
   if (c >= (T)0) {
-    ch = Fn<T>::sqrt(((T)1 + c) * (T)0.5);
-    sh = s_abs / ((T)2 * ch);
+    const T x = ((T)1 + c) * (T)0.5, r = Fn<T>::rsqrt(x);
+    ch = x * r;
+    sh = s_abs * (T)0.5 * r;
   } else {
-    sh = Fn<T>::sqrt(((T)1 - c) * (T)0.5);
-    ch = s_abs / ((T)2 * sh);
+    const T x = ((T)1 - c) * (T)0.5, r = Fn<T>::rsqrt(x);
+    sh = x * r;
+    ch = s_abs * (T)0.5 * r;
   }
   if (negative) sh = -sh;
 }
@@ -222,18 +238,20 @@ __device__ __forceinline__ void servo_quat_from_bearing(T mx, T my, T mz, const 
   const T px = C[0] * mx + C[1] * my + C[2] * mz;
   const T py = C[3] * mx + C[4] * my + C[5] * mz;
   const T pz = C[6] * mx + C[7] * my + C[8] * mz;
-  const T nxy = F::sqrt(px * px + py * py);
-  const T cyaw = px / nxy, syaw = py / nxy;
+  const T n2 = px * px + py * py, rn = F::rsqrt(n2);      // p_xy == 0 -> 0 * inf = NaN, like the reference's 0/0
+  const T nxy = n2 * rn;
+  const T cyaw = px * rn, syaw = py * rn;
   const bool yaw_neg = !(py > (T)0);
-  const T nm = F::sqrt(mx * mx + my * my);
-  const T ccy = mx / nm, scy = my / nm;
+  const T rm = F::rsqrt(mx * mx + my * my);
+  const T ccy = mx * rm, scy = my * rm;
   const T mvx = C[1] * ccy - C[0] * scy;
   const T mvy = C[4] * ccy - C[3] * scy;
   const T mvz = C[7] * ccy - C[6] * scy;
   T dot = -syaw * mvx + cyaw * mvy;
   dot = (dot > (T)1) ? (T)1 : ((dot < (T)-1) ? (T)-1 : dot);          // :179 clip
   const T ex = cyaw * mvz, ey = syaw * mvz, ez = -syaw * mvy - cyaw * mvx;
-  const T sroll = F::sqrt(ex * ex + ey * ey + ez * ez);
+  const T e2 = ex * ex + ey * ey + ez * ez;
+  const T sroll = (e2 > (T)0) ? e2 * F::rsqrt(e2) : e2;
   const bool roll_neg = !(mvz > (T)0);                                  // :181
   const T cpitch = (nxy > (T)1) ? (T)1 : nxy;
   const T spitch_abs = (pz < (T)0) ? -pz : pz;
