@@ -15,9 +15,20 @@
 // pipe runs at half the fp32 rate, so the chain stays cheaper than the HBM time.
 // precision 1 is the all-fp32 chain (accuracy of the reference's own fp32 run).
 //
-// Kernel shape.  One thread per environment; the J (6xD) and M (DxD) views of a
-// 64-env tile are staged through shared memory by the whole CTA with coalesced
-// loads (any strides), then each thread factors its own env out of registers.
+// Kernel shape.  One thread per environment, 64-env tiles.  The per-env working set
+// (J, M, q, qd, dpose, hand velocity) is staged into shared memory first:
+//   * bulk path (TMA, cp.async.bulk + mbarrier): operands whose tile is a dense block
+//     of memory (mass matrix, dof state, dpose) arrive as ONE bulk copy per tile; the
+//     jacobian slot (216 B out of every 2,160 B) as one bulk copy per env.  Bulk copies
+//     need 16-byte alignment, so each copy starts at the aligned address below the
+//     operand and the kernel indexes past the lead-in; shared memory then holds the
+//     operand with its GLOBAL strides, which is why the compute phase addresses every
+//     operand through a runtime (offset, env, row, col) stride tuple.
+//   * LDGSTS path (4-byte cp.async, column-owner walk): anything that does not meet the
+//     bulk conditions, the index-gathered hand velocity, and the LAST tile of a launch
+//     (a bulk copy reads whole aligned blocks and must not run past the last env).
+// v2 of this kernel staged everything with 4-byte LDGSTS: at 8 cycles per warp-level
+// LDGSTS the staging alone cost ~30 us per 262,144 envs (profiles/r01_full_osc_v3.txt).
 // Roofline: HBM.  Algorithmic bytes per env: IK 248 B, OSC 496 B.
 #include "common.cuh"
 
@@ -26,6 +37,7 @@ namespace b200ctl {
 constexpr float kPiF = 3.14159265358979323846f;
 constexpr float kTwoPiF = 6.28318530717958647692f;
 constexpr int kTileEnvs = 64;
+constexpr int kMaxSeg = 6;
 
 template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
@@ -79,108 +91,6 @@ __device__ __forceinline__ void chol_solve(const T (&L)[N][N], const T (&rdiag)[
   }
 }
 
-// Cooperative staging of a (N, R, C) strided view: tile[e * TS + r*C + c] for the CTA's envs.
-// Consecutive threads walk the innermost (unit-stride in the reference's views) dimension.
-//
-// The copies are 4-byte cp.async (LDGSTS): global -> shared without a register round trip, so a thread
-// issues its whole share of the tile back to back and the CTA has the full tile in flight before anyone
-// waits.  (With plain loads each warp had one request outstanding and the kernel ran at ~10 % of HBM:
-// profiles/r01_full_osc_v1.txt, long-scoreboard stalls.)
-__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-template <int R, int C, int TS>
-__device__ __forceinline__ void stage_tile(const TView& v, int64_t env0, int nenv, float* tile) {
-  constexpr int RC = R * C;
-  const float* g = reinterpret_cast<const float*>(v.p) + env0 * v.s[0];
-  // (e, k) walk the tile in steps of blockDim without a division per element
-  int e = threadIdx.x / RC, k = threadIdx.x - e * RC;
-  const int step_e = kTileEnvs / RC, step_k = kTileEnvs - step_e * RC;
-  while (e < nenv) {
-    const int r = k / C, c = k - r * C;
-    cp_async_f32(tile + e * TS + k, g + e * v.s[0] + r * v.s[1] + c * v.s[2]);
-    e += step_e;
-    k += step_k;
-    if (k >= RC) { k -= RC; ++e; }
-  }
-}
-
-// (N, C) rows (optionally gathered through an int64 row index) -> tile[e * TS + c]
-template <int C, int TS>
-__device__ __forceinline__ void stage_rows(const TView& v, int64_t env0, int nenv, float* tile,
-                                           const TView* index = nullptr) {
-  if (index) {
-    // one thread per env resolves the row, then issues its C copies
-    if ((int)threadIdx.x < nenv) {
-      const int64_t row = reinterpret_cast<const int64_t*>(index->p)[(env0 + threadIdx.x) * index->s[0]];
-      const float* g = reinterpret_cast<const float*>(v.p) + row * v.s[0];
-#pragma unroll
-      for (int c = 0; c < C; ++c) cp_async_f32(tile + threadIdx.x * TS + c, g + c * v.s[1]);
-    }
-    return;
-  }
-  const float* g = reinterpret_cast<const float*>(v.p) + env0 * v.s[0];
-  for (int f = threadIdx.x; f < nenv * C; f += kTileEnvs) {
-    const int e = f / C, c = f - e * C;
-    cp_async_f32(tile + e * TS + c, g + e * v.s[0] + c * v.s[1]);
-  }
-}
-
-// Column-owner staging: the per-env working set is a fixed list of scalars (J[r][c], M[r][c], q[c], ...).
-// Thread t owns list entries t, t+64, ...: it resolves (pointer, env stride, tile offset) ONCE and then walks
-// the tile's envs with one pointer bump per copy.  A warp's copies of one env are the consecutive entries of
-// the list, i.e. (nearly) consecutive addresses.  This replaced a per-element (env, row, col) decomposition
-// whose 64-bit index arithmetic was 60 % of all executed instructions (profiles/r01_full_osc_v2.txt).
-struct Seg {
-  const float* base;      // first env of the tile
-  int64_t s0, s1, s2;     // env / row / col strides (elements)
-  int rows, cols, toff;   // extent and offset of the segment inside the per-env tile row
-};
-__device__ __forceinline__ Seg seg_of(const TView& v, int64_t env0, int rows, int cols, int toff) {
-  Seg s;
-  s.base = reinterpret_cast<const float*>(v.p) + env0 * v.s[0];
-  s.s0 = v.s[0];
-  s.s1 = v.s[1];
-  s.s2 = rows > 1 ? v.s[2] : 0;
-  if (rows == 1) { s.s2 = v.s[1]; s.s1 = 0; }   // (N, C) vectors: the column stride is s[1]
-  s.rows = rows; s.cols = cols; s.toff = toff;
-  return s;
-}
-template <int NSEG, int TS>
-__device__ __forceinline__ void stage_columns(const Seg (&segs)[NSEG], int nenv, float* tile) {
-  int total = 0;
-#pragma unroll
-  for (int i = 0; i < NSEG; ++i) total += segs[i].rows * segs[i].cols;
-  for (int id = threadIdx.x; id < total; id += kTileEnvs) {
-    const float* g = nullptr;
-    int64_t step = 0;
-    int toff = 0, k = id;
-#pragma unroll
-    for (int i = 0; i < NSEG; ++i) {
-      const int cnt = segs[i].rows * segs[i].cols;
-      if (k >= 0 && k < cnt) {
-        const int r = k / segs[i].cols, c = k - r * segs[i].cols;
-        g = segs[i].base + r * segs[i].s1 + c * segs[i].s2;
-        step = segs[i].s0;
-        toff = segs[i].toff + k;
-      }
-      k -= cnt;
-    }
-    float* dst = tile + toff;
-#pragma unroll 4
-    for (int e = 0; e < nenv; ++e) {
-      cp_async_f32(dst, g);
-      dst += TS;
-      g += step;
-    }
-  }
-}
-
 __device__ __forceinline__ float wrap_pi(float e) {
   // ((e + pi) % (2 pi)) - pi with python floor-mod semantics (franka_cube_ik_osc.py:75)
   float m = fmodf(__fadd_rn(e, kPiF), kTwoPiF);
@@ -190,27 +100,174 @@ __device__ __forceinline__ float wrap_pi(float e) {
 
 __device__ __forceinline__ float ldf(const TView& v, int64_t off) { return __ldg(reinterpret_cast<const float*>(v.p) + off); }
 
-// Lambda^-1 = J M^-1 J^T factored in place: on return M holds chol(M) and A holds chol(Lambda^-1).
-// sJ / sM are this thread's rows of the staged tiles.
+// ================================================================== staging engine
+// One operand of the per-env working set and how it reaches shared memory.
+struct StageSeg {
+  const float* base;      // element (env 0, row 0, col 0) of the view
+  int64_t s0, s1, s2;     // global strides in elements: env, row, col
+  int rows, cols;
+  int mode;               // bulk plan: 0 = LDGSTS, 1 = one bulk copy per tile, 2 = one per env, 3 = alias (no copy)
+  int region;             // bulk: destination offset in the tile buffer (floats, multiple of 4)
+  unsigned bytes;         // bulk: bytes per copy (multiple of 16); mode 1 counts a full 64-env tile
+  int delta;              // bulk: base address modulo 16 (bytes)
+  int b_off, b_es, b_rs, b_cs;   // bulk plan, bulk operand:   smem = b_off + e*b_es + r*b_rs + c*b_cs
+  int l_off;              // bulk plan, LDGSTS operand: smem = l_off + e*bulk_ts + r*cols + c
+  int c_off;              // canonical plan:            smem = c_off + e*canon_ts + r*cols + c
+};
+struct StagePlan {
+  StageSeg seg[kMaxSeg];
+  int nseg;
+  int canon_ts;           // canonical plan: dense row of every operand (+ extras), odd stride
+  int bulk_ts;            // bulk plan: dense row of the LDGSTS operands (+ extras) only, odd stride
+  int x_off_c, x_off_b;   // offset of the extras (gathered hand velocity) in either plan's row
+  int bulk_ok;            // 0: every tile uses the canonical LDGSTS plan
+  int smem_floats;        // dynamic shared memory, in floats (max of both plans)
+};
+struct SAddr { int off, es, rs, cs; };   // resolved smem addressing of one operand for this CTA
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Column-owner LDGSTS walk: thread t owns entries t, t+64, ... of the list of scalars (J[r][c], M[r][c], q[c] ...)
+// that are NOT bulk-staged, resolves (pointer, env stride, tile offset) once, then bumps a pointer per env.
+template <int NSEG>
+__device__ __forceinline__ void stage_ldgsts(const StagePlan& P, int64_t env0, int nenv, bool bulk, float* tile) {
+  const int ts = bulk ? P.bulk_ts : P.canon_ts;
+  int total = 0;
+#pragma unroll
+  for (int i = 0; i < NSEG; ++i) total += (bulk && P.seg[i].mode != 0) ? 0 : P.seg[i].rows * P.seg[i].cols;
+  for (int id = threadIdx.x; id < total; id += kTileEnvs) {
+    const float* g = nullptr;
+    int64_t step = 0;
+    int toff = 0, k = id;
+#pragma unroll
+    for (int i = 0; i < NSEG; ++i) {
+      const StageSeg& s = P.seg[i];
+      const int cnt = (bulk && s.mode != 0) ? 0 : s.rows * s.cols;
+      if (k >= 0 && k < cnt) {
+        const int r = k / s.cols, c = k - r * s.cols;
+        g = s.base + env0 * s.s0 + r * s.s1 + c * s.s2;
+        step = s.s0;
+        toff = (bulk ? s.l_off : s.c_off) + k;
+      }
+      k -= cnt;
+    }
+    float* dst = tile + toff;
+#pragma unroll 4
+    for (int e = 0; e < nenv; ++e) {
+      cp_async_f32(dst, g);
+      dst += ts;
+      g += step;
+    }
+  }
+}
+
+// Index-gathered (N_src, C) rows -> the extras slot of the active plan (one thread per env issues its C copies).
+template <int C>
+__device__ __forceinline__ void stage_gather(const TView& v, const TView& index, int has_index, int64_t env0, int nenv,
+                                             float* dst_row0, int ts) {
+  if ((int)threadIdx.x < nenv) {
+    const int64_t env = env0 + threadIdx.x;
+    const int64_t row = has_index ? reinterpret_cast<const int64_t*>(index.p)[env * index.s[0]] : env;
+    const float* g = reinterpret_cast<const float*>(v.p) + row * v.s[0];
+#pragma unroll
+    for (int c = 0; c < C; ++c) cp_async_f32(dst_row0 + threadIdx.x * ts + c, g + c * v.s[1]);
+  }
+}
+
+// The last tile always takes the LDGSTS plan: bulk copies fetch whole aligned blocks past the operand.
+__device__ __forceinline__ bool tile_is_bulk(const StagePlan& P) { return P.bulk_ok && (blockIdx.x + 1 < gridDim.x); }
+
+// Stage every operand of the tile and resolve the smem addressing the compute phase must use.
+// `bar` must be 8-byte aligned shared memory.  Ends with a __syncthreads(): the tile is readable on return.
+template <int NSEG>
+__device__ __forceinline__ void stage_all(const StagePlan& P, int64_t env0, int nenv, float* tile, uint64_t* bar,
+                                          SAddr (&addr)[NSEG]) {
+  const bool bulk = tile_is_bulk(P);
+#pragma unroll
+  for (int i = 0; i < NSEG; ++i) {
+    const StageSeg& s = P.seg[i];
+    if (bulk && s.mode != 0) addr[i] = SAddr{s.b_off, s.b_es, s.b_rs, s.b_cs};
+    else if (bulk) addr[i] = SAddr{s.l_off, P.bulk_ts, s.cols, 1};
+    else addr[i] = SAddr{s.c_off, P.canon_ts, s.cols, 1};
+  }
+  if (bulk) {
+    if (threadIdx.x == 0) mbar_init(bar, kTileEnvs);
+    __syncthreads();
+    unsigned my_bytes = 0;
+#pragma unroll
+    for (int i = 0; i < NSEG; ++i) {
+      const StageSeg& s = P.seg[i];
+      if (s.mode == 1 && threadIdx.x == 0) my_bytes += s.bytes;
+      if (s.mode == 2) my_bytes += s.bytes;
+    }
+    mbar_arrive_expect_tx(bar, my_bytes);     // every thread arrives; the phase completes when all bytes landed
+#pragma unroll
+    for (int i = 0; i < NSEG; ++i) {
+      const StageSeg& s = P.seg[i];
+      if (s.mode == 1 && threadIdx.x == 0) {
+        const char* src = reinterpret_cast<const char*>(s.base + env0 * s.s0) - s.delta;
+        bulk_g2s(tile + s.region, src, s.bytes, bar);
+      } else if (s.mode == 2) {
+        const char* src = reinterpret_cast<const char*>(s.base + (env0 + threadIdx.x) * s.s0) - s.delta;
+        bulk_g2s(tile + s.region + threadIdx.x * s.b_es, src, s.bytes, bar);
+      }
+    }
+  }
+  stage_ldgsts<NSEG>(P, env0, nenv, bulk, tile);
+  cp_async_wait_all();
+  if (bulk) mbar_wait(bar, 0);
+  __syncthreads();
+}
+
+#define SM(a, e, r, c) tile[(a).off + (e) * (a).es + (r) * (a).rs + (c) * (a).cs]
+
+// Lambda^-1 = J M^-1 J^T factored: on return A holds chol(Lambda^-1).  J is this thread's jacobian in registers,
+// M is read from the staged tile (lower triangle).
 template <typename T, int D>
-__device__ __forceinline__ void task_space_factor(const float* sJ, const float* sM, T (&L)[D][D], T (&rdm)[D],
+__device__ __forceinline__ void task_space_factor(const float (&J)[6][D], const float* tile, const SAddr& aM, int e,
                                                   T (&A)[6][6], T (&rda)[6]) {
+  T L[D][D], rdm[D];
 #pragma unroll
   for (int r = 0; r < D; ++r)
 #pragma unroll
-    for (int c = 0; c <= r; ++c) L[r][c] = (T)sM[r * D + c];
+    for (int c = 0; c <= r; ++c) L[r][c] = (T)SM(aM, e, r, c);
   chol_inplace<T, D>(L, rdm);
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
     T x[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) x[c] = (T)sJ[r * D + c];
+    for (int c = 0; c < D; ++c) x[c] = (T)J[r][c];
     chol_solve<T, D>(L, rdm, x);            // x = M^-1 J[r,:]^T
 #pragma unroll
     for (int c = r; c < 6; ++c) {
       T s = (T)0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) s = fma_t<T>((T)sJ[c * D + k], x[k], s);
+      for (int k = 0; k < D; ++k) s = fma_t<T>((T)J[c][k], x[k], s);
       A[c][r] = s;
     }
   }
@@ -218,31 +275,33 @@ __device__ __forceinline__ void task_space_factor(const float* sJ, const float* 
 }
 
 // ------------------------------------------------------------------ a9: control_ik
-// per-env tile: [ J 6xD | dpose 6 | dof_pos D ]
+// segments: 0 = J (6 x D), 1 = dpose (1 x 6), 2 = dof_pos (1 x D, optional)
 template <typename T, int D>
 __global__ void __launch_bounds__(kTileEnvs)
-ik_dls_kernel(TView j_eef, TView dpose, float lambda2, TView dof_pos, int has_pos, TView out, int64_t n) {
-  constexpr int oDP = 6 * D, oQ = oDP + 6, TS = (oQ + D) | 1;
-  __shared__ float tile[kTileEnvs * TS];
+ik_dls_kernel(StagePlan P, float lambda2, int has_pos, TView out, int64_t n) {
+  extern __shared__ __align__(16) float tile[];
+  __shared__ __align__(8) uint64_t bar;
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  const Seg segs[3] = {seg_of(j_eef, env0, 6, D, 0), seg_of(dpose, env0, 1, 6, oDP),
-                       seg_of(dof_pos, env0, 1, has_pos ? D : 0, oQ)};
-  stage_columns<3, TS>(segs, nenv, tile);
-  cp_async_wait_all();
-  __syncthreads();
+  SAddr a[3];
+  stage_all<3>(P, env0, nenv, tile, &bar, a);
   if (threadIdx.x >= nenv) return;
-  const int64_t env = env0 + threadIdx.x;
-  const float* sJ = tile + threadIdx.x * TS;
+  const int e = threadIdx.x;
+  const int64_t env = env0 + e;
+  float J[6][D];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) J[r][c] = SM(a[0], e, r, c);
   T A[6][6], rd[6], y[6];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
-    y[r] = (T)sJ[oDP + r];
+    y[r] = (T)SM(a[1], e, 0, r);
 #pragma unroll
     for (int c = 0; c <= r; ++c) {
       T s = (r == c) ? (T)lambda2 : (T)0;     // J J^T + lambda^2 I   (:57-58)
 #pragma unroll
-      for (int k = 0; k < D; ++k) s = fma_t<T>((T)sJ[r * D + k], (T)sJ[c * D + k], s);
+      for (int k = 0; k < D; ++k) s = fma_t<T>((T)J[r][k], (T)J[c][k], s);
       A[r][c] = s;
     }
   }
@@ -253,57 +312,59 @@ ik_dls_kernel(TView j_eef, TView dpose, float lambda2, TView dof_pos, int has_po
   for (int c = 0; c < D; ++c) {
     T u = (T)0;
 #pragma unroll
-    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)sJ[r * D + c], y[r], u);   // J^T y
+    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], y[r], u);   // J^T y
     float uf = (float)u;
-    if (has_pos) uf = __fadd_rn(sJ[oQ + c], uf);   // dof_pos[:, :7] + control_ik(dpose)  (:395)
+    if (has_pos) uf = __fadd_rn(SM(a[2], e, 0, c), uf);   // dof_pos[:, :7] + control_ik(dpose)  (:395)
     o[c * out.s[1]] = uf;
   }
 }
 
 // ------------------------------------------------------------------ a10: control_osc
-// per-env tile: [ J 6x7 | M 7x7 | dof_pos 7 | dof_vel 7 | dpose 6 | hand_vel 6 ]
+// segments: 0 = J (6x7), 1 = M (7x7), 2 = dof_pos (1x7), 3 = dof_vel (1x7), 4 = dpose (1x6);
+// the index-gathered hand velocity (1x6) goes to the extras slot of the active plan.
 template <typename T>
 __global__ void __launch_bounds__(kTileEnvs)
-osc_kernel(TView j_eef, TView mm, TView dof_pos, TView dof_vel, TView hand_vel, TView hand_index, int has_index,
-           TView dpose, TView q_default, float kp, float kd, float kp_null, float kd_null, TView out, int64_t n,
-           double* __restrict__ stats) {
+osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q_default,
+           float kp, float kd, float kp_null, float kd_null, TView out, int64_t n, double* __restrict__ stats) {
   constexpr int D = 7;
-  constexpr int oM = 6 * D, oQ = oM + D * D, oQD = oQ + D, oDP = oQD + D, oHV = oDP + 6, TS = (oHV + 6) | 1;
-  __shared__ float tile[kTileEnvs * TS];
+  extern __shared__ __align__(16) float tile[];
+  __shared__ __align__(8) uint64_t bar;
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  stage_rows<6, TS>(hand_vel, env0, nenv, tile + oHV, has_index ? &hand_index : nullptr);   // dependent gather first
-  const Seg segs[5] = {seg_of(j_eef, env0, 6, D, 0), seg_of(mm, env0, D, D, oM), seg_of(dof_pos, env0, 1, D, oQ),
-                       seg_of(dof_vel, env0, 1, D, oQD), seg_of(dpose, env0, 1, 6, oDP)};
-  stage_columns<5, TS>(segs, nenv, tile);
-  cp_async_wait_all();
-  __syncthreads();
+  const bool bulk = tile_is_bulk(P);
+  const int hv_ts = bulk ? P.bulk_ts : P.canon_ts;
+  float* hv0 = tile + (bulk ? P.x_off_b : P.x_off_c);
+  stage_gather<6>(hand_vel, hand_index, has_index, env0, nenv, hv0, hv_ts);   // dependent gather first
+  SAddr a[5];
+  stage_all<5>(P, env0, nenv, tile, &bar, a);
 
   double acc[4] = {0, 0, 0, 0};
   if (threadIdx.x < nenv) {
-    const int64_t env = env0 + threadIdx.x;
-    const float* sJ = tile + threadIdx.x * TS;
-    const float* sM = sJ + oM;
+    const int e = threadIdx.x;
+    const int64_t env = env0 + e;
+    float J[6][D];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) J[r][c] = SM(a[0], e, r, c);
     // factor first: L is dead once chol(Lambda^-1) exists, which keeps the live register set small
     T A[6][6], rda[6];
-    {
-      T L[D][D], rdm[D];
-      task_space_factor<T, D>(sJ, sM, L, rdm, A, rda);
-    }
+    task_space_factor<T, D>(J, tile, a[1], e, A, rda);
     // joint-space PD term u0 (:74-76), fp32 in the reference's operand order
     float u0[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) {
       const float qdef = ldf(q_default, c * q_default.s[0]);
-      u0[c] = __fadd_rn(__fmul_rn(kd_null, -sJ[oQD + c]), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef, sJ[oQ + c]))));
+      u0[c] = __fadd_rn(__fmul_rn(kd_null, -SM(a[3], e, 0, c)), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef, SM(a[2], e, 0, c)))));
     }
     // task-space target w = kp dpose - kd v_hand (:67-68) minus J u0 (null-space projector folded in)
+    const float* hv = hv0 + e * hv_ts;
     T w[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      T s = (T)__fsub_rn(__fmul_rn(kp, sJ[oDP + r]), __fmul_rn(kd, sJ[oHV + r]));
+      T s = (T)__fsub_rn(__fmul_rn(kp, SM(a[4], e, 0, r)), __fmul_rn(kd, hv[r]));
 #pragma unroll
-      for (int c = 0; c < D; ++c) s = fma_t<T>(-(T)sJ[r * D + c], (T)u0[c], s);
+      for (int c = 0; c < D; ++c) s = fma_t<T>(-(T)J[r][c], (T)u0[c], s);
       w[r] = s;
     }
     chol_solve<T, 6>(A, rda, w);          // w <- Lambda (w - J u0)
@@ -313,9 +374,9 @@ osc_kernel(TView j_eef, TView mm, TView dof_pos, TView dof_vel, TView hand_vel, 
     for (int c = 0; c < D; ++c) {
       T u = (T)0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) u = fma_t<T>((T)sM[c * D + k], (T)u0[k], u);    // (M u0)[c], M as given (:77)
+      for (int k = 0; k < D; ++k) u = fma_t<T>((T)SM(a[1], e, c, k), (T)u0[k], u);   // (M u0)[c], M as given (:77)
 #pragma unroll
-      for (int r = 0; r < 6; ++r) u = fma_t<T>((T)sJ[r * D + c], w[r], u);        // + J^T Lambda (...)
+      for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], w[r], u);                 // + J^T Lambda (...)
       const float uf = (float)u;
       o[c * out.s[1]] = uf;
       const bool f = isfinite(uf);
@@ -334,41 +395,43 @@ osc_kernel(TView j_eef, TView mm, TView dof_pos, TView dof_vel, TView hand_vel, 
 }
 
 // ------------------------------------------------------------------ franka_osc.py:229-241
-// per-env tile: [ J 6xD | M DxD | dof_vel D | dpose 6 ]
+// segments: 0 = J (6xD), 1 = M (DxD), 2 = dof_vel (1xD), 3 = dpose (1x6)
 template <typename T, int D>
 __global__ void __launch_bounds__(kTileEnvs)
-osc_full_kernel(TView j_eef, TView mm, TView dof_vel, TView dpose, float kp, float kv, TView out, int64_t n) {
-  constexpr int oM = 6 * D, oQD = oM + D * D, oDP = oQD + D, TS = (oDP + 6) | 1;
-  __shared__ float tile[kTileEnvs * TS];
+osc_full_kernel(StagePlan P, float kp, float kv, TView out, int64_t n) {
+  extern __shared__ __align__(16) float tile[];
+  __shared__ __align__(8) uint64_t bar;
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  const Seg segs[4] = {seg_of(j_eef, env0, 6, D, 0), seg_of(mm, env0, D, D, oM), seg_of(dof_vel, env0, 1, D, oQD),
-                       seg_of(dpose, env0, 1, 6, oDP)};
-  stage_columns<4, TS>(segs, nenv, tile);
-  cp_async_wait_all();
-  __syncthreads();
+  SAddr a[4];
+  stage_all<4>(P, env0, nenv, tile, &bar, a);
   if (threadIdx.x >= nenv) return;
-  const int64_t env = env0 + threadIdx.x;
-  const float* sJ = tile + threadIdx.x * TS;
-  const float* sM = sJ + oM;
+  const int e = threadIdx.x;
+  const int64_t env = env0 + e;
+  float J[6][D];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) J[r][c] = SM(a[0], e, r, c);
+  T A[6][6], rda[6];
+  task_space_factor<T, D>(J, tile, a[1], e, A, rda);
   T w[6];
 #pragma unroll
-  for (int r = 0; r < 6; ++r) w[r] = (T)__fmul_rn(kp, sJ[oDP + r]);
-  T L[D][D], rdm[D], A[6][6], rda[6];
-  task_space_factor<T, D>(sJ, sM, L, rdm, A, rda);
+  for (int r = 0; r < 6; ++r) w[r] = (T)__fmul_rn(kp, SM(a[3], e, 0, r));
   chol_solve<T, 6>(A, rda, w);            // Lambda (kp dpose)
   float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
 #pragma unroll
   for (int c = 0; c < D; ++c) {
     T damp = (T)0;
 #pragma unroll
-    for (int k = 0; k < D; ++k) damp = fma_t<T>((T)sM[c * D + k], (T)sJ[oQD + k], damp);
+    for (int k = 0; k < D; ++k) damp = fma_t<T>((T)SM(a[1], e, c, k), (T)SM(a[2], e, 0, k), damp);
     T u = -(T)kv * damp;                  // - kv * M qd
 #pragma unroll
-    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)sJ[r * D + c], w[r], u);
+    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], w[r], u);
     o[c * out.s[1]] = (float)u;
   }
 }
+#undef SM
 
 // ------------------------------------------------------------------ a11: orientation_error
 __global__ void orientation_error_kernel(TView qd, TView qc, TView out, int64_t n) {
@@ -393,6 +456,7 @@ __global__ void orientation_error_kernel(TView qd, TView qc, TView out, int64_t 
   o[2 * out.s[1]] = z * sg;
 }
 
+// ================================================================== host side: staging plans
 static int vec_rows(const DLTensor* t, const char* name, int64_t n, int64_t min_cols, bool exact, int* dev, TView* v) {
   B200_TRY(view_of(t, name, M_F32, 2, 3, dev, v));
   squeeze_last(*v);
@@ -405,6 +469,103 @@ static inline int tiles(int64_t n) { return (int)((n + kTileEnvs - 1) / kTileEnv
 
 static int check_precision(int precision) {
   if (precision != 0 && precision != 1) B200_FAIL(B200CTL_E_VALUE, "precision must be 0 (fp64 factorisation) or 1 (all fp32)");
+  return 0;
+}
+
+// Builds the staging plan for `nseg` operands.  (N, R, C) views use strides (s0, s1, s2); (N, C) vectors are
+// passed with rows = 1 and use (s0, -, s1).  `extras` floats per env are reserved in either plan's dense row
+// for operands staged outside the plan (the gathered hand velocity).
+struct SegSpec { const TView* v; int rows, cols; };
+static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n) {
+  StagePlan P{};
+  P.nseg = nseg;
+  int canon = 0;
+  for (int i = 0; i < nseg; ++i) {
+    StageSeg& s = P.seg[i];
+    const TView& v = *spec[i].v;
+    s.base = reinterpret_cast<const float*>(v.p);
+    s.rows = spec[i].rows;
+    s.cols = spec[i].cols;
+    s.s0 = v.s[0];
+    if (s.rows == 1) { s.s1 = 0; s.s2 = v.s[1]; }
+    else { s.s1 = v.s[1]; s.s2 = v.s[2]; }
+    s.c_off = canon;
+    canon += s.rows * s.cols;
+    s.mode = 0;
+  }
+  P.x_off_c = canon;
+  P.canon_ts = (canon + extras) | 1;                       // odd row stride: conflict-free per-thread row reads
+  const int canon_floats = kTileEnvs * P.canon_ts;
+
+  // ---- bulk plan: bulk regions first, then one dense row per env for the LDGSTS operands + extras
+  int region = 0;
+  bool any_bulk = false;
+  for (int i = 0; i < nseg && n > kTileEnvs; ++i) {
+    StageSeg& s = P.seg[i];
+    if (s.rows * s.cols == 0 || s.s0 <= 0 || s.s1 < 0 || s.s2 <= 0) continue;
+    const int64_t window = (int64_t)(s.rows - 1) * s.s1 + (int64_t)(s.cols - 1) * s.s2 + 1;   // floats spanned per env
+    if (window > s.s0) continue;                                                             // overlapping envs: not a gym layout
+    s.delta = (int)(reinterpret_cast<uintptr_t>(s.base) & 15u);
+    // an operand that lives inside the env block of an earlier tile-mode operand (dof_pos / dof_vel are two
+    // views of one dof_state tensor) aliases that region instead of copying the block twice
+    bool aliased = false;
+    for (int j = 0; j < i && !aliased; ++j) {
+      const StageSeg& t = P.seg[j];
+      if (t.mode != 1 || t.s0 != s.s0) continue;
+      const int64_t shift = s.base - t.base;      // floats
+      if (shift >= 0 && shift + window <= t.s0) {
+        s.mode = 3;
+        s.region = t.region;
+        s.bytes = 0;
+        s.b_off = t.region + t.delta / 4 + (int)shift;
+        s.b_es = (int)s.s0; s.b_rs = (int)s.s1; s.b_cs = (int)s.s2;
+        aliased = true;
+      }
+    }
+    if (aliased) { any_bulk = true; continue; }
+    if (s.s0 <= 2 * window && s.s0 <= 256) {
+      // dense enough: one bulk copy brings the whole 64-env block
+      s.mode = 1;
+      s.bytes = (unsigned)((s.delta + kTileEnvs * s.s0 * 4 + 15) & ~(int64_t)15);
+      s.region = region;
+      s.b_off = region + s.delta / 4;
+      s.b_es = (int)s.s0; s.b_rs = (int)s.s1; s.b_cs = (int)s.s2;
+      region += (int)(s.bytes / 4);
+      any_bulk = true;
+    } else if ((s.s0 * 4) % 16 == 0 && window <= 128) {
+      // sparse slot of a wide row: one bulk copy per env, same lead-in for every env
+      s.mode = 2;
+      s.bytes = (unsigned)((s.delta + window * 4 + 15) & ~(int64_t)15);
+      int es = (int)(s.bytes / 4);
+      if (((es / 4) & 1) == 0) es += 4;           // stride = 4 * odd: 4-way instead of 8-way bank conflicts
+      s.region = region;
+      s.b_es = es;
+      s.b_off = region + s.delta / 4;
+      s.b_rs = (int)s.s1; s.b_cs = (int)s.s2;
+      region += kTileEnvs * es;
+      any_bulk = true;
+    }
+  }
+  P.bulk_ok = any_bulk ? 1 : 0;
+  P.smem_floats = canon_floats;
+  if (any_bulk) {
+    int row = 0;
+    const int rows0 = (region + 3) & ~3;
+    for (int i = 0; i < nseg; ++i) {
+      StageSeg& s = P.seg[i];
+      if (s.mode == 0) { s.l_off = rows0 + row; row += s.rows * s.cols; }
+    }
+    P.x_off_b = rows0 + row;
+    P.bulk_ts = (row + extras) | 1;
+    const int bulk_floats = rows0 + kTileEnvs * P.bulk_ts;
+    if (bulk_floats > P.smem_floats) P.smem_floats = bulk_floats;
+  }
+  return P;
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  if (bytes > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return 0;
 }
 
@@ -428,16 +589,20 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
+  const SegSpec spec[3] = {{&j, 6, (int)D}, {&dp, 1, 6}, {&q, 1, has_pos ? (int)D : 0}};
+  const StagePlan P = make_plan(spec, 3, 0, n);
+  const int smem = P.smem_floats * 4;
   // lambda^2 is formed in fp32 like torch.eye(6) * damping**2 (:57)
   const float l2 = (float)(lambda * lambda);
   cudaStream_t s = (cudaStream_t)stream;
-  if (D == 7) {
-    if (precision == 0) ik_dls_kernel<double, 7><<<tiles(n), kTileEnvs, 0, s>>>(j, dp, l2, q, has_pos, o, n);
-    else ik_dls_kernel<float, 7><<<tiles(n), kTileEnvs, 0, s>>>(j, dp, l2, q, has_pos, o, n);
-  } else {
-    if (precision == 0) ik_dls_kernel<double, 9><<<tiles(n), kTileEnvs, 0, s>>>(j, dp, l2, q, has_pos, o, n);
-    else ik_dls_kernel<float, 9><<<tiles(n), kTileEnvs, 0, s>>>(j, dp, l2, q, has_pos, o, n);
-  }
+#define LAUNCH_IK(T, DD)                                                          \
+  do {                                                                            \
+    B200_TRY(set_smem(ik_dls_kernel<T, DD>, smem));                               \
+    ik_dls_kernel<T, DD><<<tiles(n), kTileEnvs, smem, s>>>(P, l2, has_pos, o, n); \
+  } while (0)
+  if (D == 7) { if (precision == 0) LAUNCH_IK(double, 7); else LAUNCH_IK(float, 7); }
+  else        { if (precision == 0) LAUNCH_IK(double, 9); else LAUNCH_IK(float, 9); }
+#undef LAUNCH_IK
   return post_launch("ik_dls_kernel");
 }
 
@@ -472,13 +637,19 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
+  const SegSpec spec[5] = {{&j, 6, 7}, {&m, 7, 7}, {&q, 1, 7}, {&qd, 1, 7}, {&dp, 1, 6}};
+  const StagePlan P = make_plan(spec, 5, 6, n);
+  const int smem = P.smem_floats * 4;
   cudaStream_t s = (cudaStream_t)stream;
-  if (precision == 0)
-    osc_kernel<double><<<tiles(n), kTileEnvs, 0, s>>>(j, m, q, qd, hv, hi, has_index, dp, qdef, (float)kp, (float)kd,
-                                                      (float)kp_null, (float)kd_null, o, n, stats);
-  else
-    osc_kernel<float><<<tiles(n), kTileEnvs, 0, s>>>(j, m, q, qd, hv, hi, has_index, dp, qdef, (float)kp, (float)kd,
-                                                     (float)kp_null, (float)kd_null, o, n, stats);
+  if (precision == 0) {
+    B200_TRY(set_smem(osc_kernel<double>, smem));
+    osc_kernel<double><<<tiles(n), kTileEnvs, smem, s>>>(P, hv, hi, has_index, qdef, (float)kp, (float)kd,
+                                                         (float)kp_null, (float)kd_null, o, n, stats);
+  } else {
+    B200_TRY(set_smem(osc_kernel<float>, smem));
+    osc_kernel<float><<<tiles(n), kTileEnvs, smem, s>>>(P, hv, hi, has_index, qdef, (float)kp, (float)kd,
+                                                        (float)kp_null, (float)kd_null, o, n, stats);
+  }
   return post_launch("osc_kernel");
 }
 
@@ -498,15 +669,19 @@ extern "C" int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
+  const SegSpec spec[4] = {{&j, 6, (int)D}, {&m, (int)D, (int)D}, {&qd, 1, (int)D}, {&dp, 1, 6}};
+  const StagePlan P = make_plan(spec, 4, 0, n);
+  const int smem = P.smem_floats * 4;
   cudaStream_t s = (cudaStream_t)stream;
   const float fkp = (float)kp, fkv = (float)kv;
-  if (D == 7) {
-    if (precision == 0) osc_full_kernel<double, 7><<<tiles(n), kTileEnvs, 0, s>>>(j, m, qd, dp, fkp, fkv, o, n);
-    else osc_full_kernel<float, 7><<<tiles(n), kTileEnvs, 0, s>>>(j, m, qd, dp, fkp, fkv, o, n);
-  } else {
-    if (precision == 0) osc_full_kernel<double, 9><<<tiles(n), kTileEnvs, 0, s>>>(j, m, qd, dp, fkp, fkv, o, n);
-    else osc_full_kernel<float, 9><<<tiles(n), kTileEnvs, 0, s>>>(j, m, qd, dp, fkp, fkv, o, n);
-  }
+#define LAUNCH_FULL(T, DD)                                                       \
+  do {                                                                           \
+    B200_TRY(set_smem(osc_full_kernel<T, DD>, smem));                            \
+    osc_full_kernel<T, DD><<<tiles(n), kTileEnvs, smem, s>>>(P, fkp, fkv, o, n); \
+  } while (0)
+  if (D == 7) { if (precision == 0) LAUNCH_FULL(double, 7); else LAUNCH_FULL(float, 7); }
+  else        { if (precision == 0) LAUNCH_FULL(double, 9); else LAUNCH_FULL(float, 9); }
+#undef LAUNCH_FULL
   return post_launch("osc_full_kernel");
 }
 
