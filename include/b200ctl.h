@@ -40,7 +40,7 @@ extern "C" {
 #ifndef DLPACK_DLPACK_H_
 typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3 } DLDeviceType;
 typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
-typedef enum { kDLInt = 0, kDLUInt = 1, kDLFloat = 2 } DLDataTypeCode;
+typedef enum { kDLInt = 0, kDLUInt = 1, kDLFloat = 2, kDLBool = 6 } DLDataTypeCode;
 typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
 typedef struct {
   void* data;
@@ -202,6 +202,25 @@ B200CTL_API int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, cons
 /* orientation_error, examples/franka_cube_ik_osc.py:34-37.  (N,4) xyzw x2 -> (N,3). */
 B200CTL_API int b200ctl_orientation_error(const DLTensor* q_desired, const DLTensor* q_current,
                               DLTensor* out, b200ctl_stream_t stream);
+
+/* Task-level goal logic of the pick loop, examples/franka_cube_ik_osc.py:348-391 and :399-406, fused:
+ * box / hand row gathers, grasp predicates, cube_grasping_yaw (:40-50), goal pose selection,
+ * orientation_error (:34-37) -> dpose, gripper targets, hand_restart latch.
+ * rb_states (M,13) f32; box_index, hand_index (N,) int64; dof_pos (N,>=9[,1]) f32; init_pos (N,3), init_rot (N,4) f32;
+ * hand_restart (N,) bool/uint8, updated IN PLACE; dpose_out (N,6[,1]); grip_out (N,2) = pos_action[:, 7:9]. */
+typedef struct {
+  double grasp_offset;       /* 0.11 for "ik", 0.10 for "osc" (:361) */
+  double box_size;           /* 0.045 (:160) */
+  double gripper_sep_closed; /* 0.045 (:365) */
+  double init_tolerance;     /* 0.02  (:375) */
+  double above_dot, yaw_dot; /* 0.99, 0.95 (:380) */
+  double lift_height;        /* 0.6   (:401) */
+  double gripper_open;       /* 0.04  (:404) */
+} b200ctl_franka_task_params;
+B200CTL_API int b200ctl_franka_task(const DLTensor* rb_states, const DLTensor* box_index, const DLTensor* hand_index,
+                        const DLTensor* dof_pos, const DLTensor* init_pos, const DLTensor* init_rot,
+                        DLTensor* hand_restart, const b200ctl_franka_task_params* params,
+                        DLTensor* dpose_out, DLTensor* grip_out, b200ctl_stream_t stream);
 
 /* Row gather / scatter of the index-list views of examples/franka_cube_ik_osc.py:348-353
  * (rb_states[hand_idxs, 7:]) -- bit-exact copies.  src (M,C) f32, index (N,) int64,

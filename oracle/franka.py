@@ -87,3 +87,77 @@ def conditioning(j_eef: torch.Tensor, mm: torch.Tensor | None, damping: float | 
     else:
         a = j @ torch.inverse(mm.double()) @ j.transpose(1, 2)
     return torch.linalg.cond(a)
+
+
+# --------------------------------------------------------------------------- task-level goal logic
+def quat_rotate(q: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """``isaacgym.torch_utils.quat_rotate`` (un-vendored -> restated from its definition, parity unpinned):
+    v (2 w^2 - 1) + 2 w (q_v x v) + 2 q_v (q_v . v), xyzw storage."""
+    q_w = q[:, -1]
+    q_vec = q[:, :3]
+    a = v * (2.0 * q_w ** 2 - 1.0).unsqueeze(-1)
+    b = torch.cross(q_vec, v, dim=-1) * q_w.unsqueeze(-1) * 2.0
+    c = q_vec * (q_vec * v).sum(-1, keepdim=True) * 2.0
+    return a + b + c
+
+
+def quat_axis(q: torch.Tensor, axis: int = 0) -> torch.Tensor:
+    """``examples/franka_cube_ik_osc.py:28-31``."""
+    basis = torch.zeros(q.shape[0], 3, dtype=q.dtype)
+    basis[:, axis] = 1
+    return quat_rotate(q, basis)
+
+
+def cube_grasping_yaw(q: torch.Tensor, corners: torch.Tensor) -> torch.Tensor:
+    """``examples/franka_cube_ik_osc.py:40-50``: horizontal rotation required to grasp the cube."""
+    rc = quat_rotate(q, corners)
+    yaw = (torch.atan2(rc[:, 1], rc[:, 0]) - 0.25 * math.pi) % (0.5 * math.pi)
+    theta = 0.5 * yaw
+    w, z = theta.cos(), theta.sin()
+    zero = torch.zeros_like(w)
+    return torch.stack([zero, zero, z, w], dim=-1)
+
+
+def task_step(rb_states, box_idxs, hand_idxs, dof_pos, init_pos, init_rot, hand_restart, box_size: float,
+              controller: str = "ik"):
+    """Goal logic of the pick loop, ``examples/franka_cube_ik_osc.py:348-391,399-406``.
+
+    Returns ``(dpose (N,6,1), grip_acts (N,2), hand_restart (N,) bool)``; ``hand_restart`` in is the state carried
+    from the previous step.  Same tensor ops in the same order as the reference loop body."""
+    n = init_pos.shape[0]
+    dt = rb_states.dtype
+    down_q = torch.tensor([1.0, 0.0, 0.0, 0.0], dtype=dt).repeat(n, 1)
+    corners = torch.full((n, 3), 0.5 * box_size, dtype=dt)
+    down_dir = torch.tensor([0.0, 0.0, -1.0], dtype=dt).view(1, 3)
+
+    box_pos, box_rot = rb_states[box_idxs, :3], rb_states[box_idxs, 3:7]
+    hand_pos, hand_rot = rb_states[hand_idxs, :3], rb_states[hand_idxs, 3:7]
+    to_box = box_pos - hand_pos
+    box_dist = torch.norm(to_box, dim=-1).unsqueeze(-1)
+    box_dir = to_box / box_dist
+    box_dot = box_dir @ down_dir.view(3, 1)
+    grasp_offset = 0.11 if controller == "ik" else 0.10
+    gripper_sep = dof_pos[:, 7] + dof_pos[:, 8]
+    gripped = (gripper_sep < 0.045) & (box_dist < grasp_offset + 0.5 * box_size)
+    yaw_q = cube_grasping_yaw(box_rot, corners)
+    box_yaw_dir = quat_axis(yaw_q, 0)
+    hand_yaw_dir = quat_axis(hand_rot, 0)
+    yaw_dot = torch.bmm(box_yaw_dir.view(n, 1, 3), hand_yaw_dir.view(n, 3, 1)).squeeze(-1)
+    to_init = init_pos - hand_pos
+    init_dist = torch.norm(to_init, dim=-1)
+    hand_restart = (hand_restart & (init_dist > 0.02)).squeeze(-1)
+    return_to_start = (hand_restart | gripped.squeeze(-1)).unsqueeze(-1)
+    above_box = ((box_dot >= 0.99) & (yaw_dot >= 0.95) & (box_dist < grasp_offset * 3)).squeeze(-1)
+    grasp_pos = box_pos.clone()
+    grasp_pos[:, 2] = torch.where(above_box, box_pos[:, 2] + grasp_offset, box_pos[:, 2] + grasp_offset * 2.5)
+    goal_pos = torch.where(return_to_start, init_pos, grasp_pos)
+    goal_rot = torch.where(return_to_start, init_rot, quat_mul(down_q, quat_conjugate(yaw_q)))
+    pos_err = goal_pos - hand_pos
+    orn_err = orientation_error(goal_rot, hand_rot)
+    dpose = torch.cat([pos_err, orn_err], -1).unsqueeze(-1)
+    close_gripper = (box_dist < grasp_offset + 0.02) | gripped
+    hand_restart = hand_restart | (box_pos[:, 2] > 0.6)
+    keep_going = torch.logical_not(hand_restart)
+    close_gripper = close_gripper & keep_going.unsqueeze(-1)
+    grip_acts = torch.where(close_gripper, torch.zeros(n, 2, dtype=dt), torch.full((n, 2), 0.04, dtype=dt))
+    return dpose, grip_acts, hand_restart

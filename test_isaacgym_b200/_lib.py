@@ -57,6 +57,13 @@ class ServoParams(ctypes.Structure):
                 ("precision", c_int32), ("reserved", c_int32)]
 
 
+class FrankaTaskParams(ctypes.Structure):
+    """``b200ctl_franka_task_params``; defaults are the constants of ``examples/franka_cube_ik_osc.py:160,361-404``."""
+    _fields_ = [("grasp_offset", c_double), ("box_size", c_double), ("gripper_sep_closed", c_double),
+                ("init_tolerance", c_double), ("above_dot", c_double), ("yaw_dot", c_double),
+                ("lift_height", c_double), ("gripper_open", c_double)]
+
+
 _DL = POINTER(DLTensor)
 _SIGNATURES = {
     "b200ctl_version": (c_int, []),
@@ -76,6 +83,7 @@ _SIGNATURES = {
                             c_int32, _DL, c_void_p, c_void_p]),
     "b200ctl_osc_full": (c_int, [_DL, _DL, _DL, _DL, c_double, c_double, c_int32, _DL, c_void_p]),
     "b200ctl_orientation_error": (c_int, [_DL, _DL, _DL, c_void_p]),
+    "b200ctl_franka_task": (c_int, [_DL, _DL, _DL, _DL, _DL, _DL, _DL, POINTER(FrankaTaskParams), _DL, _DL, c_void_p]),
     "b200ctl_gather_rows": (c_int, [_DL, _DL, c_int32, c_int32, _DL, c_void_p]),
     "b200ctl_nccl_unique_id": (c_int, [c_void_p]),
     "b200ctl_nccl_comm_init": (c_int, [POINTER(c_void_p), c_int32, c_void_p, c_int32]),
@@ -113,7 +121,7 @@ def launch_count() -> int:
 
 
 # --------------------------------------------------------------------------- tensors
-_DTYPES = {torch.float32: (2, 32), torch.float64: (2, 64), torch.int64: (0, 64)}
+_DTYPES = {torch.float32: (2, 32), torch.float64: (2, 64), torch.int64: (0, 64), torch.bool: (6, 8), torch.uint8: (1, 8)}
 
 
 class _Packed:

@@ -38,7 +38,7 @@ extern std::atomic<uint64_t> g_launch_count;
   } while (0)
 
 // ---------------------------------------------------------------- tensor views
-enum DType : int { F32 = 0, F64 = 1, I64 = 2 };
+enum DType : int { F32 = 0, F64 = 1, I64 = 2, U8 = 3 };
 
 // POD view passed to kernels by value: base pointer + element strides.
 struct TView {
@@ -49,7 +49,7 @@ struct TView {
   int dtype;
 };
 
-constexpr unsigned M_F32 = 1u << F32, M_F64 = 1u << F64, M_I64 = 1u << I64;
+constexpr unsigned M_F32 = 1u << F32, M_F64 = 1u << F64, M_I64 = 1u << I64, M_U8 = 1u << U8;
 
 // Validates a DLTensor and converts it to a TView.  `dev` is in/out: -1 accepts
 // any CUDA device and records it, otherwise the tensor must live on that device.

@@ -32,6 +32,7 @@ int view_of(const DLTensor* t, const char* name, unsigned dtype_mask, int min_nd
   if (t->dtype.lanes == 1 && t->dtype.code == kDLFloat && t->dtype.bits == 32) dt = F32;
   else if (t->dtype.lanes == 1 && t->dtype.code == kDLFloat && t->dtype.bits == 64) dt = F64;
   else if (t->dtype.lanes == 1 && t->dtype.code == kDLInt && t->dtype.bits == 64) dt = I64;
+  else if (t->dtype.lanes == 1 && (t->dtype.code == kDLUInt || t->dtype.code == 6 /* kDLBool */) && t->dtype.bits == 8) dt = U8;
   if (dt < 0 || !((1u << dt) & dtype_mask))
     B200_FAIL(B200CTL_E_DTYPE, "%s: unsupported dtype (code=%d bits=%d)", name, (int)t->dtype.code, (int)t->dtype.bits);
   if (t->ndim < min_ndim || t->ndim > max_ndim || t->ndim > 4)
@@ -47,7 +48,7 @@ int view_of(const DLTensor* t, const char* name, unsigned dtype_mask, int min_nd
     out->s[i] = t->strides ? t->strides[i] : compact;
     compact *= t->shape[i];
   }
-  const size_t esz = dt == F32 ? 4 : 8;
+  const size_t esz = dt == F32 ? 4 : (dt == U8 ? 1 : 8);
   if (t->byte_offset % esz) B200_FAIL(B200CTL_E_LAYOUT, "%s: byte_offset not element aligned", name);
   out->p = static_cast<const char*>(t->data) + t->byte_offset;
   if (!t->data && compact > 0) B200_FAIL(B200CTL_E_NULL, "%s: data pointer is NULL", name);

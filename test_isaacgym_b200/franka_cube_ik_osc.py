@@ -141,3 +141,37 @@ def bind_control_ik(dpose: torch.Tensor, out: torch.Tensor, dof_pos: torch.Tenso
     packed = [_lib.dl(t) for t in (g["j_eef"], dpose, dof_pos, out)]
     args = [packed[0][0], packed[1][0], float(g["damping"]), packed[2][0], int(g["precision"]), packed[3][0], None]
     return _lib.BoundCall(_lib.lib().b200ctl_ik_dls, args, 6, out.device, packed, out)
+
+
+class TaskStep:
+    """Fused goal logic of the pick loop (``examples/franka_cube_ik_osc.py:348-391,399-406``): one kernel replaces
+    the gathers, predicates, ``cube_grasping_yaw``, goal selection, ``orientation_error`` and gripper targets.
+
+    >>> task = TaskStep(rb_states, box_idxs, hand_idxs, dof_pos, init_pos, init_rot, hand_restart, controller="osc")  # doctest: +SKIP
+    >>> task(dpose, pos_action[:, 7:9])       # fills dpose (N,6,1) and the gripper targets, updates hand_restart     # doctest: +SKIP
+    """
+
+    def __init__(self, rb_states, box_idxs, hand_idxs, dof_pos, init_pos, init_rot, hand_restart, controller="ik",
+                 box_size=0.045):
+        dev = rb_states.device
+        self.rb_states, self.dof_pos, self.init_pos, self.init_rot = rb_states, dof_pos, init_pos, init_rot
+        self.box_idxs = torch.as_tensor(box_idxs, dtype=torch.int64, device=dev)
+        self.hand_idxs = torch.as_tensor(hand_idxs, dtype=torch.int64, device=dev)
+        self.hand_restart = hand_restart          # (N,) bool, updated in place
+        self.params = _lib.FrankaTaskParams(0.11 if controller == "ik" else 0.10, float(box_size), 0.045, 0.02,
+                                            0.99, 0.95, 0.6, 0.04)
+
+    def bind(self, dpose: torch.Tensor, grip_out: torch.Tensor) -> "_lib.BoundCall":
+        packed = [_lib.dl(t) for t in (self.rb_states, self.box_idxs, self.hand_idxs, self.dof_pos, self.init_pos,
+                                       self.init_rot, self.hand_restart, dpose, grip_out)]
+        args = [p[0] for p in packed[:7]] + [ctypes.byref(self.params), packed[7][0], packed[8][0], None]
+        return _lib.BoundCall(_lib.lib().b200ctl_franka_task, args, 10, dpose.device, (packed, self), dpose)
+
+    def __call__(self, dpose: torch.Tensor | None = None, grip_out: torch.Tensor | None = None):
+        n, dev = self.init_pos.shape[0], self.init_pos.device
+        if dpose is None:
+            dpose = torch.empty((n, 6, 1), dtype=torch.float32, device=dev)
+        if grip_out is None:
+            grip_out = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        self.bind(dpose, grip_out)()
+        return dpose, grip_out

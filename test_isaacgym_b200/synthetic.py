@@ -177,3 +177,69 @@ def franka_inputs(num_envs: int, seed: int = 0) -> FrankaInputs:
     return FrankaInputs(jacobian=jac, mass_matrix=mm.contiguous(), dof_state=dof_state, rb_states=rb,
                         hand_idxs=base + FRANKA_HAND_BODY, box_idxs=base + FRANKA_BOX_BODY,
                         dpose=dpose, default_dof_pos=torch.tensor(FRANKA_DEFAULT_DOF_POS))
+
+
+@dataclass
+class FrankaTaskInputs:
+    rb_states: torch.Tensor      # (N*13, 13) f32
+    box_idxs: torch.Tensor       # (N,) int64
+    hand_idxs: torch.Tensor      # (N,) int64
+    dof_state: torch.Tensor      # (N*9, 2) f32
+    init_pos: torch.Tensor       # (N, 3)
+    init_rot: torch.Tensor       # (N, 4)
+    hand_restart: torch.Tensor   # (N,) bool
+    box_size: float = 0.045      # examples/franka_cube_ik_osc.py:160
+
+    @property
+    def num_envs(self) -> int:
+        return self.init_pos.shape[0]
+
+    @property
+    def dof_pos(self):
+        return self.dof_state[:, 0].view(self.num_envs, FRANKA_DOF, 1)
+
+
+def franka_task_inputs(num_envs: int, seed: int = 0) -> FrankaTaskInputs:
+    """Rigid-body / dof states for the pick loop's goal logic (``examples/franka_cube_ik_osc.py:348-406``), drawn so
+    that every predicate of the loop (gripped, above_box, return_to_start, close_gripper, box lifted) fires for a
+    sizeable fraction of the envs."""
+    g = _gen(seed)
+    n = num_envs
+    rb = torch.randn(n * FRANKA_BODIES_PER_ENV, 13, generator=g) * 0.1
+    quat = torch.randn(n * FRANKA_BODIES_PER_ENV, 4, generator=g)
+    rb[:, 3:7] = quat / quat.norm(dim=1, keepdim=True)
+    base = torch.arange(n, dtype=torch.int64) * FRANKA_BODIES_PER_ENV
+    box_idxs, hand_idxs = base + FRANKA_BOX_BODY, base + FRANKA_HAND_BODY
+    u = lambda *s: torch.rand(*s, generator=g)
+    box_pos = torch.stack((0.5 + 0.2 * (u(n) - 0.5), 0.3 * (u(n) - 0.5), 0.4 + 0.0225 + 0.35 * (u(n) < 0.15).float() * u(n)), 1)
+    # box yaw about z (cube resting on the table), a few tilted
+    yaw = (u(n) - 0.5) * 2 * math.pi
+    bq = torch.stack((torch.zeros(n), torch.zeros(n), torch.sin(yaw / 2), torch.cos(yaw / 2)), 1)
+    tilt = u(n) < 0.1
+    bq[tilt] = rb[box_idxs][tilt, 3:7]
+    # hand: a third hovering right above the box pointing down with matching yaw, the rest anywhere nearby
+    above = u(n) < 0.35
+    hand_pos = box_pos + torch.stack(((u(n) - 0.5) * 0.3, (u(n) - 0.5) * 0.3, 0.05 + 0.4 * u(n)), 1)
+    close = box_pos + torch.stack(((u(n) - 0.5) * 0.004, (u(n) - 0.5) * 0.004, 0.05 + 0.2 * u(n)), 1)
+    hand_pos = torch.where(above.unsqueeze(1), close, hand_pos)
+    hq = torch.randn(n, 4, generator=g)
+    hq = hq / hq.norm(dim=1, keepdim=True)
+    # down_q * conj(yaw_q) with a small perturbation = gripper pointing down, aligned with the cube
+    gy = (yaw % (0.5 * math.pi)) * 0.5 + (u(n) - 0.5) * 0.1
+    aligned = torch.stack((torch.cos(gy), torch.sin(gy), torch.zeros(n), torch.zeros(n)), 1)
+    hq = torch.where(above.unsqueeze(1), aligned, hq)
+    rb[box_idxs, 0:3], rb[box_idxs, 3:7] = box_pos, bq
+    rb[hand_idxs, 0:3], rb[hand_idxs, 3:7] = hand_pos, hq
+    lo, hi = torch.tensor(_FRANKA_LOWER), torch.tensor(_FRANKA_UPPER)
+    pos = lo + (hi - lo) * u(n, FRANKA_DOF)
+    closed = u(n) < 0.4
+    pos[closed, 7:] = 0.02 * u(int(closed.sum()), 2)
+    vel = torch.randn(n, FRANKA_DOF, generator=g)
+    dof_state = torch.stack((pos.reshape(-1), vel.reshape(-1)), dim=1).contiguous()
+    init_pos = torch.tensor([0.3, 0.0, 0.8]) + 0.01 * torch.randn(n, 3, generator=g)
+    near_init = u(n) < 0.2
+    init_pos[near_init] = hand_pos[near_init] + 0.01 * (u(int(near_init.sum()), 3) - 0.5)
+    iq = torch.tensor([1.0, 0.0, 0.0, 0.0]) + 0.05 * torch.randn(n, 4, generator=g)
+    init_rot = iq / iq.norm(dim=1, keepdim=True)
+    return FrankaTaskInputs(rb_states=rb, box_idxs=box_idxs, hand_idxs=hand_idxs, dof_state=dof_state,
+                            init_pos=init_pos, init_rot=init_rot, hand_restart=u(n) < 0.3)

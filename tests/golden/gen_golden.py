@@ -18,6 +18,7 @@ Fixtures
   servo_edges.npz   servo_ext_pixel on hand-picked edge inputs (y == 0 branches ...)
   franka.npz        control_ik / control_osc / orientation_error, fp32 and fp64
   pd_fragments.npz  the reference's three joint-PD fragments on seeded dof_state
+  franka_task.npz   the reference's pick-loop body (examples/franka_cube_ik_osc.py:348-406) executed in place
 """
 from __future__ import annotations
 
@@ -246,6 +247,62 @@ def gen_pd_fragments():
     print("pd_fragments: u_null", tuple(u_null.shape), "effort", tuple(effort.shape))
 
 
+def _loop_body_statements():
+    """Statements of the reference's `while` loop body from `box_pos = ...` (:348) to `pos_action[:, 7:9] = ...`
+    (:406): the task logic + control deployment, compiled from the script in place."""
+    path = os.path.join(rl.REFERENCE_ROOT, "examples", "franka_cube_ik_osc.py")
+    tree = ast.parse(open(path, encoding="utf-8").read())
+    loop = next(n for n in tree.body if isinstance(n, ast.While))
+    def target_name(st):
+        if isinstance(st, ast.Assign):
+            t = st.targets[0]
+            while isinstance(t, ast.Subscript):
+                t = t.value
+            return getattr(t, "id", "")
+        return ""
+    names = [target_name(st) for st in loop.body]
+    first = names.index("box_pos")
+    last = max(i for i, (nm, st) in enumerate(zip(names, loop.body)) if nm == "pos_action" and isinstance(st, ast.Assign))
+    body = loop.body[first:last + 1]
+    return compile(ast.Module(body=body, type_ignores=[]), path, "exec")
+
+
+def gen_franka_task():
+    """Executes the reference's own loop body (task logic + control_ik / control_osc) on seeded tensors."""
+    from oracle import franka as ofr
+    code = _loop_body_statements()
+    out = {}
+    n = 512
+    ti = syn.franka_task_inputs(n, seed=7)
+    fi = syn.franka_inputs(n, seed=8)
+    for controller in ("ik", "osc"):
+        ns = rl.franka_namespace(torch.float32, damping=0.05, kp=150., kd=2.0 * np.sqrt(150.), kp_null=10.,
+                                 kd_null=2.0 * np.sqrt(10.), num_envs=n, j_eef=fi.j_eef, mm=fi.mm,
+                                 default_dof_pos_tensor=fi.default_dof_pos)
+        rl.extract_functions("examples/franka_cube_ik_osc.py", ["quat_axis", "cube_grasping_yaw"], ns)
+        dof_pos = ti.dof_pos.clone()
+        ns.update(quat_rotate=ofr.quat_rotate, controller=controller, box_size=ti.box_size,
+                  rb_states=ti.rb_states, box_idxs=ti.box_idxs.tolist(), hand_idxs=ti.hand_idxs.tolist(),
+                  dof_pos=dof_pos, dof_vel=ti.dof_state[:, 1].view(n, 9, 1), init_pos=ti.init_pos, init_rot=ti.init_rot,
+                  hand_restart=ti.hand_restart.clone(),
+                  down_q=torch.stack(n * [torch.tensor([1.0, 0.0, 0.0, 0.0])]).view((n, 4)),
+                  corners=torch.stack(n * [torch.Tensor([0.5 * ti.box_size] * 3)]),
+                  down_dir=torch.Tensor([0, 0, -1]).view(1, 3),
+                  pos_action=torch.zeros(n, 9), effort_action=torch.zeros(n, 9))
+        exec(code, ns)
+        out[f"{controller}_dpose"] = ns["dpose"].numpy()
+        out[f"{controller}_hand_restart"] = ns["hand_restart"].numpy()
+        out[f"{controller}_pos_action"] = ns["pos_action"].numpy()
+        out[f"{controller}_effort_action"] = ns["effort_action"].numpy()
+        out[f"{controller}_above_box"] = ns["above_box"].numpy()
+        out[f"{controller}_gripped"] = ns["gripped"].numpy()
+    out["seed_task"], out["seed_franka"] = np.int64(7), np.int64(8)
+    np.savez_compressed(os.path.join(HERE, "franka_task.npz"), **out)
+    print("franka_task: above_box %.3f gripped %.3f restart %.3f closed %.3f" % (
+        out["ik_above_box"].mean(), out["ik_gripped"].mean(), out["ik_hand_restart"].mean(),
+        (out["ik_pos_action"][:, 7] == 0).mean()))
+
+
 if __name__ == "__main__":
     if not rl.available():
         sys.exit("reference checkout not found at " + rl.REFERENCE_ROOT)
@@ -255,3 +312,4 @@ if __name__ == "__main__":
     gen_servo_edges()
     gen_franka()
     gen_pd_fragments()
+    gen_franka_task()

@@ -97,3 +97,18 @@ def test_pd_saturation_and_clamp():
     assert (tau.abs() <= pi_.tau_max.view(1, -1)).all()
     st = opd.pd_stats(tau, pi_.tau_max)
     assert st[0] == 256 and st[3] > 0 and st[4] == 0
+
+
+def test_task_step_oracle_matches_reference_loop_body():
+    """oracle.franka.task_step vs the fixture produced by exec-ing the reference's loop body (:348-406)."""
+    from conftest import load_golden
+    g = load_golden("franka_task.npz")
+    ti = syn.franka_task_inputs(512, seed=int(g["seed_task"]))
+    for c in ("ik", "osc"):
+        dpose, grip, hr = ofr.task_step(ti.rb_states, ti.box_idxs, ti.hand_idxs, ti.dof_pos, ti.init_pos, ti.init_rot,
+                                        ti.hand_restart, ti.box_size, c)
+        assert np.array_equal(dpose.numpy(), g[c + "_dpose"])
+        assert np.array_equal(hr.numpy(), g[c + "_hand_restart"])
+        assert np.array_equal(grip.numpy(), g[c + "_pos_action"][:, 7:9])
+    # every predicate of the loop fires for a sizeable fraction of the synthetic envs
+    assert 0.1 < g["ik_above_box"].mean() < 0.9 and 0.05 < g["ik_gripped"].mean() < 0.9
