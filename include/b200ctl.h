@@ -150,6 +150,11 @@ B200CTL_API int b200ctl_pixel2phy(const DLTensor* K, const DLTensor* pixel, DLTe
 /* euler2quaternion, common/controller6.py:46-51: extrinsic xyz (rad) -> xyzw.  (N,3) -> (N,4). */
 B200CTL_API int b200ctl_euler_xyz_to_quat(const DLTensor* euler, DLTensor* quat_out, b200ctl_stream_t stream);
 
+/* quat2euler / quaternion2euler, common/controller6.py:24-34,39-44: xyzw -> extrinsic xyz (roll, pitch, yaw) rad.
+ * normalise != 0 normalises the quaternion first (scipy from_quat); (N,4) -> (N,3).  At gimbal lock scipy zeroes the
+ * third angle; this entry point evaluates the closed form of :24-34 there. */
+B200CTL_API int b200ctl_quat_to_euler_xyz(const DLTensor* quat, int32_t normalise, DLTensor* euler_out, b200ctl_stream_t stream);
+
 /* R.from_quat(q).as_matrix(), test10_servo_vecenv.py:423.  (N,4) -> (N,3,3). */
 B200CTL_API int b200ctl_quat_to_matrix(const DLTensor* quat, DLTensor* mat_out, b200ctl_stream_t stream);
 

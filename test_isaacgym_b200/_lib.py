@@ -76,6 +76,7 @@ _SIGNATURES = {
     "b200ctl_servo_ext_pixel": (c_int, [_DL, _DL, _DL, c_double, c_double, c_int, _DL, c_void_p]),
     "b200ctl_pixel2phy": (c_int, [_DL, _DL, _DL, c_void_p]),
     "b200ctl_euler_xyz_to_quat": (c_int, [_DL, _DL, c_void_p]),
+    "b200ctl_quat_to_euler_xyz": (c_int, [_DL, c_int32, _DL, c_void_p]),
     "b200ctl_quat_to_matrix": (c_int, [_DL, _DL, c_void_p]),
     "b200ctl_servo_step": (c_int, [_DL, POINTER(ServoParams), c_void_p, c_void_p, c_void_p]),
     "b200ctl_ik_dls": (c_int, [_DL, _DL, c_double, _DL, c_int32, _DL, c_void_p]),

@@ -65,6 +65,55 @@ def quat2matrix(quat):
     return out.cpu().numpy() if host else out
 
 
+def _quat_to_euler(quaternion, normalise: bool):
+    host = _lib.is_host(quaternion)
+    dev = _lib.require_cuda() if host else quaternion.device
+    q = _lib.to_device(quaternion, dev)
+    if q.dtype not in (torch.float32, torch.float64):
+        q = q.to(torch.float64)
+    single = q.dim() == 1
+    q2 = q.reshape(-1, 4)
+    out = torch.empty((q2.shape[0], 3), dtype=torch.float64, device=dev)
+    a, b = _lib.dl(q2), _lib.dl(out)
+    _lib.check(_lib.lib().b200ctl_quat_to_euler_xyz(a[0], 1 if normalise else 0, b[0], _lib.stream_ptr(dev)))
+    if single:
+        out = out[0]
+    return out.cpu().numpy() if host else out
+
+
+def quaternion2euler(quaternion):
+    """scipy ``R.from_quat(q).as_euler('xyz')`` (``controller6.py:39-44``): xyzw -> (roll, pitch, yaw) rad."""
+    return _quat_to_euler(quaternion, True)
+
+
+def quat2euler(quaternion):
+    """Closed-form scalar helper (``controller6.py:24-34``): (x, y, z, w) -> (roll, pitch, yaw)."""
+    r = _quat_to_euler(np.asarray(quaternion, dtype=np.float64), False)
+    return float(r[0]), float(r[1]), float(r[2])
+
+
+def euler2quat(euler_angle):
+    """Closed-form scalar helper (``controller6.py:8-22``): (roll, pitch, yaw) -> (x, y, z, w)."""
+    q = euler2quaternion(np.asarray(euler_angle, dtype=np.float64))
+    return float(q[0]), float(q[1]), float(q[2]), float(q[3])
+
+
+def euler2rotation(euler):
+    """scipy ``R.from_euler('xyz', e).as_matrix()`` (``controller6.py:53-57``)."""
+    e = np.asarray(euler, dtype=np.float64) if _lib.is_host(euler) else euler
+    single = e.ndim == 1
+    m = quat2matrix(euler2quaternion(e.reshape(-1, 3)))
+    return m[0] if single else m
+
+
+def cclvf(current_pos, target_pos, speed, radius):
+    """Scalar planar ancestor of ``cclvf2`` (``controller6.py:60-90``): returns ``[vx, vy]`` (python floats, fp64)."""
+    cur = np.array([[current_pos[0], current_pos[1], 0.0]], dtype=np.float64)
+    tgt = np.array([[target_pos[0], target_pos[1], 0.0]], dtype=np.float64)
+    v = cclvf2(torch.from_numpy(cur), torch.from_numpy(tgt), speed, radius)
+    return [float(v[0, 0]), float(v[0, 1])]
+
+
 class CameraController:
     """Batched pin-hole projection of the target into the UAV camera (``controller6.py:122-253``)."""
 

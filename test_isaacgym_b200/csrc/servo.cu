@@ -252,6 +252,24 @@ __global__ void euler_to_quat_kernel(TView e, TView q, int64_t n) {
   st_as<double>(q, i * q.s[0] + 3 * q.s[1], w);
 }
 
+// quat2euler (common/controller6.py:24-34) == scipy as_euler('xyz') of quaternion2euler (:39-44) away from gimbal lock:
+// roll = atan2(2(yz + wx), w^2 - x^2 - y^2 + z^2), pitch = -asin(clip(2(xz - wy))), yaw = atan2(2(xy + wz), w^2 + x^2 - y^2 - z^2)
+__global__ void quat_to_euler_kernel(TView q, TView e, int normalise, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = ld_as<double>(q, i * q.s[0]), y = ld_as<double>(q, i * q.s[0] + q.s[1]);
+  double z = ld_as<double>(q, i * q.s[0] + 2 * q.s[1]), w = ld_as<double>(q, i * q.s[0] + 3 * q.s[1]);
+  if (normalise) {      // scipy from_quat normalises; the hand-written quat2euler does not
+    const double inv = 1.0 / sqrt(x * x + y * y + z * z + w * w);
+    x *= inv; y *= inv; z *= inv; w *= inv;
+  }
+  double sp = 2 * (x * z - w * y);
+  sp = sp > 1.0 ? 1.0 : (sp < -1.0 ? -1.0 : sp);
+  st_as<double>(e, i * e.s[0], atan2(2 * (y * z + w * x), w * w - x * x - y * y + z * z));
+  st_as<double>(e, i * e.s[0] + e.s[1], -asin(sp));
+  st_as<double>(e, i * e.s[0] + 2 * e.s[1], atan2(2 * (x * y + w * z), w * w + x * x - y * y - z * z));
+}
+
 __global__ void quat_to_matrix_kernel(TView q, TView m, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -378,6 +396,21 @@ extern "C" int b200ctl_euler_xyz_to_quat(const DLTensor* euler, DLTensor* quat_o
   B200_TRY(g.enter(dev));
   euler_to_quat_kernel<<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(e, q, n);
   return post_launch("euler_to_quat_kernel");
+}
+
+extern "C" int b200ctl_quat_to_euler_xyz(const DLTensor* quat, int32_t normalise, DLTensor* euler_out, b200ctl_stream_t stream) {
+  int dev = -1;
+  TView q, e;
+  B200_TRY(view_of(quat, "quat", M_F32 | M_F64, 2, 2, &dev, &q));
+  const int64_t n = q.n[0];
+  B200_TRY(expect_rows(q, "quat", n, 4));
+  B200_TRY(view_of(euler_out, "euler_out", M_F32 | M_F64, 2, 2, &dev, &e));
+  B200_TRY(expect_rows(e, "euler_out", n, 3));
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  quat_to_euler_kernel<<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(q, e, normalise ? 1 : 0, n);
+  return post_launch("quat_to_euler_kernel");
 }
 
 extern "C" int b200ctl_quat_to_matrix(const DLTensor* quat, DLTensor* mat_out, b200ctl_stream_t stream) {

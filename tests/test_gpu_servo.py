@@ -210,3 +210,22 @@ def test_fused_step_errors():
     with pytest.raises(_lib.B200CtlError, match="E_LAYOUT"):
         ServoStep(W, H)(torch.zeros(4, 2, 26, device=DEV)[:, :, ::2])
     ServoStep(W, H)(torch.zeros(0, 2, 13, device=DEV))
+
+
+def test_legacy_scalar_helpers():
+    """scalar / legacy helpers of controller6.py routed through the kernels with N = 1."""
+    from scipy.spatial.transform import Rotation as R
+    from test_isaacgym_b200.controller6 import cclvf, euler2quat, quat2euler, quaternion2euler, euler2rotation
+    g = np.random.default_rng(0)
+    for _ in range(8):
+        e = g.uniform(-1.4, 1.4, 3)
+        q = euler2quat(e)
+        assert np.abs(np.array(q) - R.from_euler("xyz", e).as_quat()).max() < 1e-15
+        assert np.abs(np.array(quat2euler(q)) - e).max() < 1e-13
+        assert np.abs(euler2rotation(e) - R.from_euler("xyz", e).as_matrix()).max() < 1e-15
+    qs = g.normal(size=(64, 4)) * 3.0                       # un-normalised: scipy normalises
+    assert np.abs(quaternion2euler(qs) - R.from_quat(qs).as_euler("xyz")).max() < 1e-12
+    cur, tgt = [37.0, -12.0], [1.0, 1.0]
+    ref = osv.cclvf_scalar(cur, tgt, 50, 30)
+    got = cclvf(cur, tgt, 50, 30)
+    assert abs(got[0] - ref[0]) < 1e-12 and abs(got[1] - ref[1]) < 1e-12
