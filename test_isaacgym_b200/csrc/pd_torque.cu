@@ -106,14 +106,21 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
   const int vec_per_env = num_dofs >> 2;
   PdAcc acc;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvec; v += stride) {
+  const int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  // DOF group of the current vector, advanced incrementally: a 64-bit modulo per iteration costs more
+  // instructions than the law itself
+  int dv = (int)(v0 % vec_per_env);
+  const int dstep = (int)(stride % vec_per_env);
+  for (int64_t v = v0; v < nvec; v += stride) {
     // issue every load of the iteration before the first use
     const float4 s0 = ldg_stream4(state + 2 * v);       // q0 qd0 q1 qd1
     const float4 s1 = ldg_stream4(state + 2 * v + 1);   // q2 qd2 q3 qd3
     const float4 tg = ldg_stream4(q_tgt + v);
     float4 qd = make_float4(0.f, 0.f, 0.f, 0.f);
     if (HAS_QD) qd = ldg_stream4(qd_tgt + v);
-    const int d0 = (int)(v % vec_per_env) << 2;
+    const int d0 = dv << 2;
+    dv += dstep;
+    if (dv >= vec_per_env) dv -= vec_per_env;
     const float4 kp = *reinterpret_cast<const float4*>(s_kp + d0);
     const float4 kd = *reinterpret_cast<const float4*>(s_kd + d0);
     float4 tm = make_float4(0.f, 0.f, 0.f, 0.f), lo = tm, hi = tm;
