@@ -61,21 +61,22 @@ __device__ __forceinline__ float pd_element(float pos, float vel, float tgt, flo
 }
 
 struct PdAcc {
-  float sum_abs = 0.f, sum_sq = 0.f;
+  // fp64 per-thread sums: the statistics must not depend on how envs are sliced over GPUs / CTAs beyond 1e-15
+  double sum_abs = 0.0, sum_sq = 0.0;
   unsigned n_sat = 0, n_bad = 0;
   template <bool HAS_TMAX>
   __device__ __forceinline__ void add(float tau, float tmax) {
     const bool fin = isfinite(tau);
     const float t = fin ? tau : 0.f;
-    sum_abs += fabsf(t);
-    sum_sq = fmaf(t, t, sum_sq);
+    sum_abs += (double)fabsf(t);
+    sum_sq = fma((double)t, (double)t, sum_sq);
     n_bad += fin ? 0u : 1u;
     if (HAS_TMAX) n_sat += (fin && fabsf(tau) >= tmax) ? 1u : 0u;
   }
 };
 
 __device__ __forceinline__ void pd_commit_stats(const PdAcc& a, double* stats, int64_t n_env_block0) {
-  double acc[5] = {(double)n_env_block0, (double)a.sum_abs, (double)a.sum_sq, (double)a.n_sat, (double)a.n_bad};
+  double acc[5] = {(double)n_env_block0, a.sum_abs, a.sum_sq, (double)a.n_sat, (double)a.n_bad};
   const int slot[5] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_SAT,
                        B200CTL_STAT_N_NONFINITE};
   block_stats_commit<5>(acc, stats, slot);

@@ -138,3 +138,53 @@ def test_franka_edges():
     ctl.hand_vel = torch.zeros(n, 6, device=DEV)
     u = ctl.control_osc(torch.zeros(n, 6, 1, device=DEV))
     assert u.abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("layout", ["gym", "offset4", "offset12", "odd_pitch", "transposed_mm", "compact_copies"])
+def test_franka_staging_plans(layout):
+    """Every staging plan of the O kernels gives the same torques: bulk TMA tiles with lead-ins of 0 / 4 / 8 / 12
+    bytes, per-env bulk copies, the LDGSTS fallback (env pitch not a multiple of 16 B), transposed and compact views."""
+    n = 1000                                    # 15 bulk tiles + a ragged LDGSTS tile
+    fi = syn.franka_inputs(n, seed=12)
+    f = lambda t: t.double()
+    ref = ofr.control_osc(f(fi.dpose), f(fi.j_eef), f(fi.mm), f(fi.dof_pos), f(fi.dof_vel), f(fi.hand_vel),
+                          f(fi.default_dof_pos), KP, KD, KP_NULL, KD_NULL)
+    ref_ik = ofr.control_ik(f(fi.dpose), f(fi.j_eef), DAMPING)
+
+    def shifted(t, floats):                     # same values, base address moved by `floats` * 4 bytes
+        buf = torch.zeros(t.numel() + 8, device=DEV)
+        view = buf[floats:floats + t.numel()].view(t.shape)
+        view.copy_(t.to(DEV))
+        return view
+
+    jac, mass, dofs = fi.jacobian.to(DEV), fi.mass_matrix.to(DEV), fi.dof_state.to(DEV)
+    dpose, rb = fi.dpose.to(DEV), fi.rb_states.to(DEV)
+    if layout == "offset4":
+        jac, mass, dofs, dpose = shifted(fi.jacobian, 1), shifted(fi.mass_matrix, 1), shifted(fi.dof_state, 1), shifted(fi.dpose, 1)
+    elif layout == "offset12":
+        jac, mass, dofs, dpose = shifted(fi.jacobian, 3), shifted(fi.mass_matrix, 3), shifted(fi.dof_state, 3), shifted(fi.dpose, 3)
+    j_eef = jac[:, syn.FRANKA_JACOBIAN_SLOT, :, :7]
+    mm = mass[:, :7, :7]
+    if layout == "odd_pitch":                   # env pitch 541 floats: no per-env bulk copy possible
+        wide = torch.zeros(n, 541, device=DEV)
+        wide[:, :540] = jac.view(n, 540)
+        j_eef = wide[:, :540].view(n, 10, 6, 9)[:, syn.FRANKA_JACOBIAN_SLOT, :, :7]
+        assert j_eef.stride() == (541, 9, 1)
+    elif layout == "transposed_mm":             # symmetric values, column-major view
+        mm = mass.transpose(1, 2)[:, :7, :7]
+        ref = ofr.control_osc(f(fi.dpose), f(fi.j_eef), f(fi.mm.transpose(1, 2)), f(fi.dof_pos), f(fi.dof_vel),
+                              f(fi.hand_vel), f(fi.default_dof_pos), KP, KD, KP_NULL, KD_NULL)
+    elif layout == "compact_copies":            # the views materialised: dense (N,6,7) / (N,7,7)
+        j_eef, mm = j_eef.contiguous(), mm.contiguous()
+    ctl.bind(damping=DAMPING, kp=KP, kd=KD, kp_null=KP_NULL, kd_null=KD_NULL, j_eef=j_eef, mm=mm,
+             dof_pos=dofs[:, 0].view(n, 9, 1), dof_vel=dofs[:, 1].view(n, 9, 1),
+             default_dof_pos_tensor=fi.default_dof_pos.to(DEV), num_envs=n, precision=0)
+    ctl.bind_hand(rb, fi.hand_idxs.to(DEV))
+    osc = ctl.control_osc(dpose).cpu()
+    ik = ctl.control_ik(dpose, dof_pos=None).cpu()
+    assert _rel(osc, ref).max() <= 1e-4 and np.median(_rel(osc, ref)) <= 1e-6
+    assert _rel(ik, ref_ik).max() <= 1e-5
+    ctl.bind(precision=1)
+    osc32 = ctl.control_osc(dpose).cpu()
+    ctl.bind(precision=0)
+    assert np.median(_rel(osc32, ref)) <= 1e-5
