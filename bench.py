@@ -248,6 +248,29 @@ def family_numbers(device, peak_gbs):
             record(f"ik_{ptag}_{n}", n, IK_BYTES_PER_ENV, ik_calls, reps, flops=IK_FLOPS)
             del osc_calls, ik_calls, keep
         ctl.bind(precision=0)
+
+    # the whole pick step of examples/franka_cube_ik_osc.py:348-410 at C3: goal logic + OSC as two kernels
+    n, sets = 16_384, 4
+    ti, fi = syn.franka_task_inputs(n, seed=4), syn.franka_inputs(n, seed=5)
+    task_calls, step_calls, keep = [], [], []
+    for _ in range(sets):
+        t = ti.__class__(**{k: (v.to(device).clone() if isinstance(v, torch.Tensor) else v) for k, v in ti.__dict__.items()})
+        d = fi.__class__(**{k: (v.to(device).clone() if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+        dpose = torch.zeros(n, 6, 1, device=device)
+        pos_action, effort = torch.zeros(n, 9, device=device), torch.zeros(n, 9, device=device)
+        task = ctl.TaskStep(t.rb_states, t.box_idxs, t.hand_idxs, t.dof_pos, t.init_pos, t.init_rot, t.hand_restart, "osc")
+        ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=t.dof_pos, dof_vel=t.dof_state[:, 1].view(n, 9, 1),
+                 default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=0)
+        ctl.bind_hand(t.rb_states, t.hand_idxs)
+        tc = task.bind(dpose, pos_action[:, 7:9])
+        oc = ctl.bind_control_osc(dpose, effort[:, :7])
+        task_calls.append(tc)
+        step_calls += [tc, oc]
+        keep.append((t, d, dpose, pos_action, effort, task))
+    record(f"franka_task_{n}", n, 150, task_calls, 20)
+    ms_pair = graph_time(step_calls, device, 20) * 2      # per (task + osc) pair
+    out[f"franka_pick_step_{n}"] = {"envs": n, "us_per_step": round(ms_pair * 1e3, 3), "env_steps_per_s": n / (ms_pair * 1e-3),
+                                    "kernels_per_step": 2, "note": "franka_task + osc (fp64 chain), CUDA-graph replay"}
     return out
 
 

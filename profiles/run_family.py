@@ -41,6 +41,15 @@ def main():
                 ctl.bind_control_ik(d.dpose, out[:, :7], dof_pos=d.dof_pos)
             for _ in range(a.iters):
                 call()
+    elif a.family == "task":
+        import test_isaacgym_b200.franka_cube_ik_osc as ctl
+        n = a.n or 262_144
+        ti = syn.franka_task_inputs(n, seed=4)
+        t = ti.__class__(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in ti.__dict__.items()})
+        task = ctl.TaskStep(t.rb_states, t.box_idxs, t.hand_idxs, t.dof_pos, t.init_pos, t.init_rot, t.hand_restart, "osc")
+        call = task.bind(torch.zeros(n, 6, 1, device=dev), torch.zeros(n, 2, device=dev))
+        for _ in range(a.iters):
+            call()
     elif a.family == "pd":
         from test_isaacgym_b200.pd_control import PDController
         n = a.n or 1_048_576

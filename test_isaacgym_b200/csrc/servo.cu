@@ -25,8 +25,9 @@ struct ServoConst {
 };
 
 // PREC 0: fp32 cclvf + fp64 projection / servo stages (dtype-for-dtype the reference).
-// PREC 1: everything fp32, atan2 formulations, bearing taken directly from the body-frame
+// PREC 1: everything fp32, approximate division / rsqrt, bearing taken directly from the body-frame
 //         direction (skips the project -> subtract -> unproject pixel round trip).
+// Both modes build the attitude quaternion with servo_quat_from_bearing (no inverse-trig round trips).
 template <int PREC>
 __global__ void __launch_bounds__(kTile)
 servo_step_kernel(float* __restrict__ state, int64_t num_envs, ServoConst k, double* __restrict__ aux,
@@ -221,7 +222,7 @@ __global__ void servo_ext_pixel_kernel(TView K, TView cam, TView move, double wi
   double mx, my, mz, tx, ty, tz, roll, pitch, yaw;
   pixel_bearing<double>(Kinv, px, py, mx, my, mz);
   pixel_bearing<double>(Kinv, hw, hh, tx, ty, tz);
-  servo_angles<double, false>(mx, my, mz, tx, ty, tz, C, flags, roll, pitch, yaw);
+  servo_angles<double>(mx, my, mz, tx, ty, tz, C, flags, roll, pitch, yaw);
   constexpr double kPi = 3.141592653589793238462643383279502884;
   st_as<double>(out, i * out.s[0], roll * 180 / kPi);
   st_as<double>(out, i * out.s[0] + out.s[1], pitch * 180 / kPi);

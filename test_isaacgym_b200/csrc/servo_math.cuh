@@ -1,7 +1,7 @@
 // Family S device math: circular-loiter vector field, pin-hole projection,
 // gimbal servo angles, Euler/quaternion conversions.  Templated on the compute
-// type: double reproduces the reference's fp64 numpy/scipy stages operation by
-// operation; float is the all-fp32 fast path (atan2 formulations).
+// type: double reproduces the reference's fp64 numpy/scipy stages; float is the
+// all-fp32 fast path of the fused step.
 #pragma once
 #include "common.cuh"
 
@@ -130,32 +130,28 @@ __device__ __forceinline__ void pixel_bearing(const T (&Kinv)[9], T px, T py, T&
 }
 
 // where(y > 0, acos(x/|xy|), -acos(x/|xy|))  (:125-135, :143-148); y == 0 takes the negative branch.
-template <typename T, bool ATAN_FORM>
+template <typename T>
 __device__ __forceinline__ T signed_planar_angle(T x, T y) {
-  if (ATAN_FORM) {
-    return (y > (T)0) ? Fn<T>::atan2(y, x) : -Fn<T>::atan2(-y, x);
-  } else {
-    const T n = Fn<T>::sqrt(x * x + y * y);
-    const T ux = x / n, uy = y / n;
-    const T a = Fn<T>::acos(ux);
-    return (uy > (T)0) ? a : -a;
-  }
+  const T n = Fn<T>::sqrt(x * x + y * y);
+  const T ux = x / n, uy = y / n;
+  const T a = Fn<T>::acos(ux);
+  return (uy > (T)0) ? a : -a;
 }
 
 // ------------------------------------------------------------------ a6: servo_ext_pixel
 // common/secondary_control_vecenv.py:99-200 given the two bearings m (moved pixel) and
-// t (centre pixel) and the camera rotation matrix C (row-major).  Angles in radians.
-template <typename T, bool ATAN_FORM>
+// t (centre pixel) and the camera rotation matrix C (row-major, any 3x3).  Angles in radians.  This is the literal
+// asin / acos evaluation used by the general entry point; the fused step uses servo_quat_from_bearing below.
+template <typename T>
 __device__ __forceinline__ void servo_angles(T mx, T my, T mz, T tx_, T ty_, T tz_, const T (&C)[9], int flags,
                                              T& roll, T& pitch, T& yaw) {
   using F = Fn<T>;
   const T px = C[0] * mx + C[1] * my + C[2] * mz;          // :113
   const T py = C[3] * mx + C[4] * my + C[5] * mz;
   const T pz = C[6] * mx + C[7] * my + C[8] * mz;
-  if (ATAN_FORM) pitch = F::atan2(tz_, F::sqrt(tx_ * tx_ + ty_ * ty_)) - F::atan2(pz, F::sqrt(px * px + py * py));
-  else pitch = F::asin(tz_) - F::asin(pz);                  // :120
-  yaw = signed_planar_angle<T, ATAN_FORM>(px, py);          // :125-135
-  const T cyaw = signed_planar_angle<T, ATAN_FORM>(mx, my); // :143-148
+  pitch = F::asin(tz_) - F::asin(pz);                      // :120
+  yaw = signed_planar_angle<T>(px, py);                     // :125-135
+  const T cyaw = signed_planar_angle<T>(mx, my);            // :143-148
   // mv = Rot(rotvec = cyaw * unit_z) @ unit_y   (:153-163), Rodrigues about the camera z column
   const T yx = C[1], yy = C[4], yz = C[7];
   const T zx = C[2], zy = C[5], zz = C[8];
@@ -174,13 +170,8 @@ __device__ __forceinline__ void servo_angles(T mx, T my, T mz, T tx_, T ty_, T t
   T sy, cy;
   F::sincos(yaw, &sy, &cy);
   T dot = -sy * mvx + cy * mvy;                              // :177
-  if (ATAN_FORM) {
-    const T ex = cy * mvz, ey = sy * mvz, ez = -sy * mvy - cy * mvx;
-    roll = F::atan2(F::sqrt(ex * ex + ey * ey + ez * ez), dot);
-  } else {
-    if (!(flags & B200CTL_SERVO_NO_CLIP)) dot = (dot > (T)1) ? (T)1 : ((dot < (T)-1) ? (T)-1 : dot);   // :179
-    roll = F::acos(dot);
-  }
+  if (!(flags & B200CTL_SERVO_NO_CLIP)) dot = (dot > (T)1) ? (T)1 : ((dot < (T)-1) ? (T)-1 : dot);   // :179
+  roll = F::acos(dot);
   if (flags & B200CTL_SERVO_SCALAR_ROLL_SIGN) roll = (mvz < (T)0) ? -roll : roll;   // servo_controller.py:159
   else roll = (mvz > (T)0) ? roll : -roll;                                           // :181
 }
