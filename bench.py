@@ -299,6 +299,44 @@ def cpu_baseline(budget_s=12.0):
                       "oracle/pd.py torch-CPU fp32 (the reference has no function for this law; no _ref build)"}
 
 
+def cpu_family_baselines(families):
+    """CPU oracle (the reference's numpy / scipy / torch ops, all host threads) for the other families at their
+    BASELINE config sizes, timed in the same run: adds `cpu_env_steps_per_s` / `speedup_vs_cpu` to the entries."""
+    from oracle import servo as osv, franka as ofr
+    from test_isaacgym_b200 import synthetic as syn
+    import numpy as np
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def timed(fn, reps):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return statistics.median(ts)
+
+    n = 65_536
+    state = syn.servo_root_state(n, seed=2)
+    t = timed(lambda: osv.servo_step(state, 1600, 900), 3)
+    for key in (f"servo_step_ref_{n}", f"servo_step_fast_{n}"):
+        if key in families:
+            families[key]["cpu_env_steps_per_s"] = n / t
+            families[key]["speedup_vs_cpu"] = families[key]["env_steps_per_s"] / (n / t)
+    n = 16_384
+    fi = syn.franka_inputs(n, seed=3)
+    kp, kpn = 150.0, 10.0
+    t_osc = timed(lambda: ofr.control_osc(fi.dpose, fi.j_eef, fi.mm, fi.dof_pos, fi.dof_vel, fi.hand_vel, fi.default_dof_pos,
+                                          kp, 2 * np.sqrt(kp), kpn, 2 * np.sqrt(kpn)), 10)
+    t_ik = timed(lambda: ofr.control_ik(fi.dpose, fi.j_eef, 0.05), 10)
+    for key, t in ((f"osc_fp64chain_{n}", t_osc), (f"osc_fp32_{n}", t_osc), (f"ik_fp64chain_{n}", t_ik), (f"ik_fp32_{n}", t_ik)):
+        if key in families:
+            families[key]["cpu_env_steps_per_s"] = n / t
+            families[key]["speedup_vs_cpu"] = families[key]["env_steps_per_s"] / (n / t)
+    families["_cpu_note"] = (f"cpu_env_steps_per_s: oracle (reference arithmetic: numpy/scipy fp64 for servo, torch fp32 for "
+                             f"osc/ik) on {torch.get_num_threads()} host threads, median of 3-10 steps at the same size")
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -439,6 +477,8 @@ def run_b200(args):
         line["families"] = family_numbers(device, peak)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
+        if "families" in line:
+            cpu_family_baselines(line["families"])
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

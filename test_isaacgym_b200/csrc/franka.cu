@@ -48,7 +48,7 @@ template <> __device__ __forceinline__ float rsqrt_t<float>(float d) {
   const float r = rsqrtf(d);
   return r * fmaf(-0.5f * d * r, r, 1.5f);   // one Newton step: full fp32 accuracy
 }
-template <> __device__ __forceinline__ double rsqrt_t<double>(double d) { return 1.0 / sqrt(d); }
+template <> __device__ __forceinline__ double rsqrt_t<double>(double d) { return ::rsqrt(d); }   // ~1 ulp, a third of sqrt + divide
 
 // In-place Cholesky of the lower triangle of an SPD matrix held in registers; returns the
 // reciprocal diagonal so the substitutions multiply instead of divide.
@@ -88,6 +88,27 @@ __device__ __forceinline__ void chol_solve(const T (&L)[N][N], const T (&rdiag)[
 #pragma unroll
     for (int k = i + 1; k < N; ++k) s = fma_t<T>(-L[k][i], x[k], s);
     x[i] = s * rdiag[i];
+  }
+}
+
+// two right-hand sides at once (same operation count, two interleaved dependency chains)
+template <typename T, int N>
+__device__ __forceinline__ void chol_solve2(const T (&L)[N][N], const T (&rdiag)[N], T (&x)[N], T (&y)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    T s = x[i], t = y[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) { s = fma_t<T>(-L[i][k], x[k], s); t = fma_t<T>(-L[i][k], y[k], t); }
+    x[i] = s * rdiag[i];
+    y[i] = t * rdiag[i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    T s = x[i], t = y[i];
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) { s = fma_t<T>(-L[k][i], x[k], s); t = fma_t<T>(-L[k][i], y[k], t); }
+    x[i] = s * rdiag[i];
+    y[i] = t * rdiag[i];
   }
 }
 
@@ -160,7 +181,7 @@ __device__ __forceinline__ void stage_ldgsts(const StagePlan& P, int64_t env0, i
   int total = 0;
 #pragma unroll
   for (int i = 0; i < NSEG; ++i) total += (bulk && P.seg[i].mode != 0) ? 0 : P.seg[i].rows * P.seg[i].cols;
-  for (int id = threadIdx.x; id < total; id += kTileEnvs) {
+  for (int id = threadIdx.x; id < total; id += blockDim.x) {
     const float* g = nullptr;
     int64_t step = 0;
     int toff = 0, k = id;
@@ -216,14 +237,14 @@ __device__ __forceinline__ void stage_all(const StagePlan& P, int64_t env0, int 
     else addr[i] = SAddr{s.c_off, P.canon_ts, s.cols, 1};
   }
   if (bulk) {
-    if (threadIdx.x == 0) mbar_init(bar, kTileEnvs);
+    if (threadIdx.x == 0) mbar_init(bar, blockDim.x);
     __syncthreads();
     unsigned my_bytes = 0;
 #pragma unroll
     for (int i = 0; i < NSEG; ++i) {
       const StageSeg& s = P.seg[i];
       if (s.mode == 1 && threadIdx.x == 0) my_bytes += s.bytes;
-      if (s.mode == 2) my_bytes += s.bytes;
+      if (s.mode == 2 && threadIdx.x < kTileEnvs) my_bytes += s.bytes;
     }
     mbar_arrive_expect_tx(bar, my_bytes);     // every thread arrives; the phase completes when all bytes landed
 #pragma unroll
@@ -232,7 +253,7 @@ __device__ __forceinline__ void stage_all(const StagePlan& P, int64_t env0, int 
       if (s.mode == 1 && threadIdx.x == 0) {
         const char* src = reinterpret_cast<const char*>(s.base + env0 * s.s0) - s.delta;
         bulk_g2s(tile + s.region, src, s.bytes, bar);
-      } else if (s.mode == 2) {
+      } else if (s.mode == 2 && threadIdx.x < kTileEnvs) {
         const char* src = reinterpret_cast<const char*>(s.base + (env0 + threadIdx.x) * s.s0) - s.delta;
         bulk_g2s(tile + s.region + threadIdx.x * s.b_es, src, s.bytes, bar);
       }
@@ -257,18 +278,20 @@ __device__ __forceinline__ void task_space_factor(const float (&J)[6][D], const 
 #pragma unroll
     for (int c = 0; c <= r; ++c) L[r][c] = (T)SM(aM, e, r, c);
   chol_inplace<T, D>(L, rdm);
+  // the six solves are independent: two at a time gives the scheduler two dependency chains to interleave
 #pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    T x[D];
+  for (int r = 0; r < 6; r += 2) {
+    T x[D], y[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) x[c] = (T)J[r][c];
-    chol_solve<T, D>(L, rdm, x);            // x = M^-1 J[r,:]^T
+    for (int c = 0; c < D; ++c) { x[c] = (T)J[r][c]; y[c] = (T)J[r + 1][c]; }
+    chol_solve2<T, D>(L, rdm, x, y);        // x = M^-1 J[r,:]^T, y = M^-1 J[r+1,:]^T
 #pragma unroll
     for (int c = r; c < 6; ++c) {
-      T s = (T)0;
+      T s = (T)0, t = (T)0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) s = fma_t<T>((T)J[c][k], x[k], s);
+      for (int k = 0; k < D; ++k) { s = fma_t<T>((T)J[c][k], x[k], s); t = fma_t<T>((T)J[c][k], y[k], t); }
       A[c][r] = s;
+      if (c >= r + 1) A[c][r + 1] = t;
     }
   }
   chol_inplace<T, 6>(A, rda);
@@ -323,7 +346,10 @@ ik_dls_kernel(StagePlan P, float lambda2, int has_pos, TView out, int64_t n) {
 // segments: 0 = J (6x7), 1 = M (7x7), 2 = dof_pos (1x7), 3 = dof_vel (1x7), 4 = dpose (1x6);
 // the index-gathered hand velocity (1x6) goes to the extras slot of the active plan.
 template <typename T>
-__global__ void __launch_bounds__(kTileEnvs)   // (a 168-register cap for 5 tiles/SM spills 360 B and measured 13 % slower)
+// Tried and measured slower: register caps for 5 tiles/SM (168 regs: -13 %, 200 regs: -6 %, both
+// spill); splitting one env over two warps that share Lambda^-1 through shared memory (redundant Cholesky work +
+// a CTA barrier: -70 %).
+__global__ void __launch_bounds__(kTileEnvs)
 osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q_default,
            float kp, float kd, float kp_null, float kd_null, TView out, int64_t n, double* __restrict__ stats) {
   constexpr int D = 7;
@@ -563,9 +589,18 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n)
   return P;
 }
 
+// Opt the kernel in to `bytes` of dynamic shared memory.  The 48 KB default limit counts static + dynamic
+// shared memory, so this is requested whenever dynamic memory alone exceeds 32 KB (static use is < 16 KB here);
+// the largest request per kernel and device is remembered so steady-state launches skip the driver call.
 template <typename K>
 static int set_smem(K kernel, int bytes) {
-  if (bytes > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  static int granted[64] = {};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (bytes > 32 * 1024 && dev >= 0 && dev < 64 && bytes > granted[dev]) {
+    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    granted[dev] = bytes;
+  }
   return 0;
 }
 
