@@ -103,6 +103,30 @@ inline int post_launch(const char* kernel) {
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 
+// Programmatic dependent launch (PDL).  Every kernel of the library starts with pdl_prologue(): it waits for the
+// previous kernel of the stream to complete and flush (so stream-order semantics are unchanged -- nothing is
+// read before it) and immediately allows the NEXT launch to be scheduled, so that launch's CTAs take SM slots as
+// this grid's CTAs retire instead of after a launch bubble.  Measured on the 1M-env PD step: 35.0 -> 33.4 us.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // dtype-dispatched scalar load / store of a strided element (f32 or f64 storage).
 template <typename T>
 __device__ __forceinline__ T ld_as(const TView& v, int64_t off) {

@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kTileEnvs)
 ik_dls_kernel(StagePlan P, float lambda2, int has_pos, TView out, int64_t n) {
   extern __shared__ __align__(16) float tile[];
   __shared__ __align__(8) uint64_t bar;
+  pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
   SAddr a[3];
@@ -355,6 +356,7 @@ osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q
   constexpr int D = 7;
   extern __shared__ __align__(16) float tile[];
   __shared__ __align__(8) uint64_t bar;
+  pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
   const bool bulk = tile_is_bulk(P);
@@ -427,6 +429,7 @@ __global__ void __launch_bounds__(kTileEnvs)
 osc_full_kernel(StagePlan P, float kp, float kv, TView out, int64_t n) {
   extern __shared__ __align__(16) float tile[];
   __shared__ __align__(8) uint64_t bar;
+  pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
   SAddr a[4];
@@ -633,7 +636,7 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
 #define LAUNCH_IK(T, DD)                                                          \
   do {                                                                            \
     B200_TRY(set_smem(ik_dls_kernel<T, DD>, smem));                               \
-    ik_dls_kernel<T, DD><<<tiles(n), kTileEnvs, smem, s>>>(P, l2, has_pos, o, n); \
+    launch_pdl(ik_dls_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, l2, has_pos, o, n); \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_IK(double, 7); else LAUNCH_IK(float, 7); }
   else        { if (precision == 0) LAUNCH_IK(double, 9); else LAUNCH_IK(float, 9); }
@@ -678,12 +681,12 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
   cudaStream_t s = (cudaStream_t)stream;
   if (precision == 0) {
     B200_TRY(set_smem(osc_kernel<double>, smem));
-    osc_kernel<double><<<tiles(n), kTileEnvs, smem, s>>>(P, hv, hi, has_index, qdef, (float)kp, (float)kd,
-                                                         (float)kp_null, (float)kd_null, o, n, stats);
+    launch_pdl(osc_kernel<double>, tiles(n), kTileEnvs, smem, s, P, hv, hi, has_index, qdef, (float)kp, (float)kd,
+               (float)kp_null, (float)kd_null, o, n, stats);
   } else {
     B200_TRY(set_smem(osc_kernel<float>, smem));
-    osc_kernel<float><<<tiles(n), kTileEnvs, smem, s>>>(P, hv, hi, has_index, qdef, (float)kp, (float)kd,
-                                                        (float)kp_null, (float)kd_null, o, n, stats);
+    launch_pdl(osc_kernel<float>, tiles(n), kTileEnvs, smem, s, P, hv, hi, has_index, qdef, (float)kp, (float)kd,
+               (float)kp_null, (float)kd_null, o, n, stats);
   }
   return post_launch("osc_kernel");
 }
@@ -712,7 +715,7 @@ extern "C" int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const
 #define LAUNCH_FULL(T, DD)                                                       \
   do {                                                                           \
     B200_TRY(set_smem(osc_full_kernel<T, DD>, smem));                            \
-    osc_full_kernel<T, DD><<<tiles(n), kTileEnvs, smem, s>>>(P, fkp, fkv, o, n); \
+    launch_pdl(osc_full_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, fkp, fkv, o, n); \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_FULL(double, 7); else LAUNCH_FULL(float, 7); }
   else        { if (precision == 0) LAUNCH_FULL(double, 9); else LAUNCH_FULL(float, 9); }

@@ -54,6 +54,7 @@ __device__ __forceinline__ void quat_rotate(const float (&q)[4], float vx, float
 __global__ void __launch_bounds__(128)
 franka_task_kernel(TView rb, TView box_index, TView hand_index, TView dof_pos, TView init_pos, TView init_rot,
                    uint8_t* __restrict__ hand_restart, int64_t hr_stride, TaskConst k, TView dpose, TView grip, int64_t n) {
+  pdl_prologue();
   const int64_t env = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (env >= n) return;
   const float* rbp = reinterpret_cast<const float*>(rb.p);
@@ -197,7 +198,7 @@ extern "C" int b200ctl_franka_task(const DLTensor* rb_states, const DLTensor* bo
   k.corner = (float)(0.5 * bs);
   DeviceGuard g;
   B200_TRY(g.enter(dev));
-  franka_task_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      rb, bi, hi, q, ip, iq, reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p)), hr.s[0], k, dp, gr, n);
+  launch_pdl(franka_task_kernel, (int)((n + 127) / 128), 128, 0, (cudaStream_t)stream,
+             rb, bi, hi, q, ip, iq, reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p)), hr.s[0], k, dp, gr, n);
   return post_launch("franka_task_kernel");
 }

@@ -90,6 +90,7 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
                       const float4* __restrict__ qd_tgt, PdParams pp, int num_dofs, int64_t nvec, int64_t num_envs,
                       float4* __restrict__ tau_out, double* __restrict__ stats) {
   extern __shared__ __align__(16) float s_par[];   // [5][D]: kp, kd, tmax, lo, hi
+  pdl_prologue();
   float* s_kp = s_par;
   float* s_kd = s_par + num_dofs;
   float* s_tm = s_par + 2 * num_dofs;
@@ -152,6 +153,7 @@ template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS>
 __global__ void __launch_bounds__(256)
 pd_torque_strided_kernel(TView state, TView q_tgt, TView qd_tgt, PdParams pp, int num_dofs, int64_t num_envs,
                          TView tau_out, double* __restrict__ stats) {
+  pdl_prologue();
   const float* st = reinterpret_cast<const float*>(state.p);
   const float* tg = reinterpret_cast<const float*>(q_tgt.p);
   const float* qd = reinterpret_cast<const float*>(qd_tgt.p);
@@ -207,13 +209,12 @@ static void pd_launch_one(const PdLaunch& L) {
     const size_t smem = 5 * (size_t)L.num_dofs * sizeof(float);
     auto kern = pd_torque_vec4_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS>;
     const int grid = pd_grid(kern, smem, L.dev, L.num_envs * L.num_dofs / 4);
-    kern<<<grid, 256, smem, L.stream>>>(
-        L.state4, L.tgt4, L.qd4, L.pp, L.num_dofs, L.num_envs * L.num_dofs / 4, L.num_envs, L.out4, L.stats);
+    launch_pdl(kern, grid, 256, smem, L.stream, L.state4, L.tgt4, L.qd4, L.pp, L.num_dofs,
+               L.num_envs * L.num_dofs / 4, L.num_envs, L.out4, L.stats);
   } else {
     auto kern = pd_torque_strided_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS>;
     const int grid = pd_grid(kern, 0, L.dev, L.num_envs * L.num_dofs);
-    kern<<<grid, 256, 0, L.stream>>>(
-        L.state, L.tgt, L.qd, L.pp, L.num_dofs, L.num_envs, L.out, L.stats);
+    launch_pdl(kern, grid, 256, 0, L.stream, L.state, L.tgt, L.qd, L.pp, L.num_dofs, L.num_envs, L.out, L.stats);
   }
 }
 

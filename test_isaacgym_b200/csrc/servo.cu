@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kTile)
 servo_step_kernel(float* __restrict__ state, int64_t num_envs, ServoConst k, double* __restrict__ aux,
                   double* __restrict__ stats, int vec_ok) {
   __shared__ __align__(16) float tile[kTile * kEnvRow];
+  pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTile;
   const int nenv = (int)((num_envs - env0) < kTile ? (num_envs - env0) : kTile);
   const int nfl = nenv * kEnvRow;
@@ -471,8 +472,8 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
   const int grid = grid1d(n, kTile);
   const int vec_ok = aligned16(st) ? 1 : 0;
   if (params->precision == 0)
-    servo_step_kernel<0><<<grid, kTile, 0, (cudaStream_t)stream>>>(st, n, k, aux_out, stats, vec_ok);
+    launch_pdl(servo_step_kernel<0>, grid, kTile, 0, (cudaStream_t)stream, st, n, k, aux_out, stats, vec_ok);
   else
-    servo_step_kernel<1><<<grid, kTile, 0, (cudaStream_t)stream>>>(st, n, k, aux_out, stats, vec_ok);
+    launch_pdl(servo_step_kernel<1>, grid, kTile, 0, (cudaStream_t)stream, st, n, k, aux_out, stats, vec_ok);
   return post_launch("servo_step_kernel");
 }
