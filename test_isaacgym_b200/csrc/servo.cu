@@ -5,8 +5,8 @@
 //
 // servo_step is the fused kernel: one thread per environment, the (uav, car)
 // root-state rows of a 64-env tile staged through shared memory with 128-bit
-// coalesced loads, results written back in place touching only the columns the
-// reference writes.  Roofline: HBM at 96 algorithmic B/env (read 40, write 56);
+// coalesced loads, results scattered into the staged rows, rows written back whole
+// (unchanged columns keep the bits that were read).  Roofline: HBM at 96 algorithmic B/env (read 40, write 56);
 // the fp64 "reference precision" mode is FP64-pipe bound instead.
 #include "servo_math.cuh"
 
@@ -138,14 +138,14 @@ servo_step_kernel(float* __restrict__ state, int64_t num_envs, ServoConst k, dou
   }
   __syncthreads();
 
-  // ---- write back only the columns the reference assigns: 3..9 of each actor row
-  // kTile % kRow == 12, so the column of float i = tid + kTile*j steps by -1 (mod 13): no division in the loop
-  static_assert(kTile % kRow == kRow - 1, "incremental column update assumes kTile = -1 mod kRow");
-  int col = threadIdx.x % kRow;
-  for (int i = threadIdx.x; i < nfl; i += kTile) {
-    if (col >= 3 && col <= 9) gbase[i] = tile[i];
-    col = (col == 0) ? kRow - 1 : col - 1;
-  }
+  // ---- write the staged rows back whole, 128 bits at a time.  Only columns 3..9 of each actor row changed
+  // (test10:451-454); the other columns are rewritten with the bits that were read, so the tensor handed to
+  // set_actor_root_state_tensor is bit-identical to the reference's.  A column-predicated 4-byte write-back was
+  // 21 % of all executed instructions (profiles/r01_linemix_servo_ref_v5.txt) and leaves partial sectors for L2 to
+  // merge; whole 104-byte rows are full-sector writes.
+  for (int i = threadIdx.x; i < nv4; i += kTile)
+    reinterpret_cast<float4*>(gbase)[i] = reinterpret_cast<const float4*>(tile)[i];
+  for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += kTile) gbase[i] = tile[i];
   if (stats) {
     const int slot[5] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_SAT,
                          B200CTL_STAT_N_NONFINITE};
