@@ -43,6 +43,13 @@ SERVO_BYTES_PER_ENV = 96
 IK_BYTES_PER_ENV, IK_FLOPS = 248, 480
 OSC_BYTES_PER_ENV, OSC_FLOPS = 496, 1850
 FALLBACK_HBM_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md fallback
+# measured DRAM traffic per env (ncu --set full, read + write), by family-entry prefix
+DRAM_BYTES_PER_ENV = {
+    "servo_step": (208, "profiles/r01_full_servo_v4.txt: 109.1 MB read per 1,048,576 envs; writes are the same rows"),
+    "osc_": (970, "profiles/r01_full_osc_v4.txt: 244.4 MB read + 10 MB written per 262,144 envs"),
+    "ik_": (460, "profiles/r01_full_ik_v4.txt: 115.2 MB read + 6 MB written per 262,144 envs"),
+    "franka_task": (438, "profiles/r01_full_franka_task.txt: 110.4 MB read + 4.4 MB written per 262,144 envs"),
+}
 
 
 def hbm_peak():
@@ -209,6 +216,14 @@ def family_numbers(device, peak_gbs):
              "hbm_frac": rate * bytes_per_env / (peak_gbs * 1e9), "buffer_sets": len(calls)}
         if flops:
             e["tflops_canonical"] = rate * flops / 1e12
+        # DRAM bytes per env actually moved (ncu dram__bytes_read + write at the throughput size, profiles/): the gym
+        # layouts (13-float rows, a 6x7 slot of a 10x6x9 jacobian, a 7x7 corner of a 9x9 matrix) are fetched at
+        # 64-byte granularity, so this exceeds the algorithmic bytes without any re-read
+        for key, (b, src) in DRAM_BYTES_PER_ENV.items():
+            if name.startswith(key):
+                e["dram_bytes_per_env_ncu"] = b
+                e["dram_frac"] = rate * b / (peak_gbs * 1e9)
+                e["dram_bytes_source"] = src
         out[name] = e
 
     # P at C2 (65,536 x 12 = 12.6 MB per set): 24 rotating sets (302 MB)
