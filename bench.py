@@ -174,29 +174,21 @@ class PdWorkload:
 
 # ------------------------------------------------------------------------------------------ families (rank 0, N=1)
 def graph_time(calls, device, reps, warm=3):
-    """Capture `calls` (bound C-ABI calls, one kernel each) into one CUDA graph and time `reps` replays on the
-    launching stream.  Returns ms per kernel launch.  The graph removes the host launch cost, which at
-    64K envs is larger than the kernels themselves."""
-    stream = torch.cuda.Stream(device)
-    stream.wait_stream(torch.cuda.current_stream(device))
-    with torch.cuda.stream(stream):
-        for c in calls:
-            c()
-        stream.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            for c in calls:
-                c()
-        for _ in range(warm):
-            graph.replay()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stream.synchronize()
-        start.record(stream)
-        for _ in range(reps):
-            graph.replay()
-        end.record(stream)
-        stream.synchronize()
-    torch.cuda.current_stream(device).wait_stream(stream)
+    """Capture `calls` (bound C-ABI calls, one kernel each) into one CUDA graph (`StepGraph`) and time `reps`
+    replays with CUDA events on the replaying stream.  Returns ms per kernel launch.  The graph removes the host
+    launch cost, which at 64K envs is larger than the kernels themselves."""
+    from test_isaacgym_b200.graph import StepGraph
+    g = StepGraph(calls, device)
+    stream = torch.cuda.current_stream(device)
+    for _ in range(warm):
+        g()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream.synchronize()
+    start.record(stream)
+    for _ in range(reps):
+        g()
+    end.record(stream)
+    stream.synchronize()
     return start.elapsed_time(end) / (reps * len(calls))
 
 

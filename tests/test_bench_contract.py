@@ -1,0 +1,42 @@
+"""bench.py contract checks that run without a GPU: the reference arm (CPU oracle) prints one JSON line with the
+keys the driver reads; the GPU arm refuses to run without a device instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=600)
+
+
+def test_reference_arm_json_line():
+    r = _run("--impl", "reference", "--steps", "2", "--warmup", "3")
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["steps"] == 2
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_reference_arm_non_zero_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_gpu_arm_refuses_without_a_device():
+    r = _run("--steps", "1")
+    assert r.returncode != 0
+    assert "no CPU path" in r.stdout

@@ -90,3 +90,32 @@ def test_task_step_large_vs_oracle_and_bound_call():
                                            hr_ref, ti.box_size, "osc")
     call()
     assert (restart.cpu() != hr_ref2).sum().item() <= 2
+
+
+def test_step_graph_replays_the_pick_step():
+    """StepGraph([task, osc]) == the same two calls issued eagerly; replays pick up updated inputs in place."""
+    from test_isaacgym_b200.graph import StepGraph
+    n = 2048
+    ti, fd = _dev(syn.franka_task_inputs(n, seed=9)), _dev(syn.franka_inputs(n, seed=10))
+    restart = ti.hand_restart.clone()
+    task = ctl.TaskStep(ti.rb_states, ti.box_idxs, ti.hand_idxs, ti.dof_pos, ti.init_pos, ti.init_rot, restart, "osc")
+    dpose, pos_action, effort = torch.zeros(n, 6, 1, device=DEV), torch.zeros(n, 9, device=DEV), torch.zeros(n, 9, device=DEV)
+    ctl.bind(j_eef=fd.j_eef, mm=fd.mm, dof_pos=ti.dof_pos, dof_vel=ti.dof_state[:, 1].view(n, 9, 1),
+             default_dof_pos_tensor=fd.default_dof_pos, num_envs=n, precision=0)
+    ctl.bind_hand(ti.rb_states, ti.hand_idxs)
+    calls = [task.bind(dpose, pos_action[:, 7:9]), ctl.bind_control_osc(dpose, effort[:, :7])]
+    for c in calls:
+        c()
+    want = effort.clone()
+    restart.copy_(ti.hand_restart)                 # the eager pass advanced the latch: rewind
+    effort.zero_()
+    step = StepGraph(calls)                         # (capture warm-up runs the calls once more)
+    restart.copy_(ti.hand_restart)
+    effort.zero_()
+    step()
+    torch.cuda.synchronize()
+    assert torch.equal(effort, want)
+    ti.rb_states[ti.hand_idxs, 0] += 0.05          # move every hand: the replay must see it
+    step()
+    torch.cuda.synchronize()
+    assert not torch.equal(effort, want)
