@@ -159,8 +159,9 @@ B200CTL_API int b200ctl_quat_to_euler_xyz(const DLTensor* quat, int32_t normalis
 B200CTL_API int b200ctl_quat_to_matrix(const DLTensor* quat, DLTensor* mat_out, b200ctl_stream_t stream);
 
 /* Fused control step of test10_servo_vecenv.py:403-456 (a1..a7 of SURVEY section 8):
- * reads uav pos+quat and car pos of each env, writes uav quat+linvel and car
- * quat+linvel IN PLACE; every other column keeps its bits.
+ * reads uav pos+quat and car pos of each env, computes uav quat+linvel and car
+ * quat+linvel and writes the rows back IN PLACE (whole 13-float rows: the other
+ * columns are rewritten with the bits that were read, so they keep their bits).
  * root_state: (N,2,13) or (2N,13) f32, compact (the actor root-state tensor). */
 typedef struct {
   double width, height; /* camera resolution (cam_props.width/height) */
@@ -168,7 +169,7 @@ typedef struct {
   double car_speed, car_radius;                /* test10:406  (50, 30) */
   double car_target[3];                        /* test10:406  (1,1,1)  */
   double uav_speed, uav_radius, uav_height;    /* test10:412-414 (50, 50, 260) */
-  int32_t precision;    /* 0 = fp64 stages like the reference; 1 = all-fp32 fast path (atan2 forms) */
+  int32_t precision;    /* 0 = fp64 stages like the reference; 1 = all-fp32 fast path (approximate div / rsqrt) */
   int32_t reserved;
 } b200ctl_servo_params;
 /* aux_out: optional (N,5) f64 compact device buffer [u, v, roll_deg, pitch_deg, yaw_deg] or NULL. */

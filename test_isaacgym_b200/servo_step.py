@@ -15,7 +15,7 @@ import torch
 from . import _lib
 
 PRECISION_REFERENCE = 0   # fp32 guidance + fp64 projection / servo stages, dtype-for-dtype the reference
-PRECISION_FAST = 1        # all fp32, atan2 formulations
+PRECISION_FAST = 1        # all fp32, approximate division / rsqrt, no pixel round trip
 
 
 class ServoStep:
