@@ -587,7 +587,13 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n)
     P.x_off_b = rows0 + row;
     P.bulk_ts = (row + extras) | 1;
     const int bulk_floats = rows0 + kTileEnvs * P.bulk_ts;
-    if (bulk_floats > P.smem_floats) P.smem_floats = bulk_floats;
+    if (bulk_floats * 4 > 160 * 1024) {
+      // an exotic layout whose dense blocks do not fit comfortably in shared memory: LDGSTS plan for every tile
+      P.bulk_ok = 0;
+      for (int i = 0; i < nseg; ++i) P.seg[i].mode = 0;
+    } else if (bulk_floats > P.smem_floats) {
+      P.smem_floats = bulk_floats;
+    }
   }
   return P;
 }
