@@ -85,7 +85,7 @@ __device__ __forceinline__ void pd_commit_stats(const PdAcc& a, double* stats, i
 // ---------------------------------------------------------------- fast path
 // Compact tensors, 16-byte aligned bases, D % 4 == 0.  `nvec` = N*D/4.
 template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict__ q_tgt,
                       const float4* __restrict__ qd_tgt, PdParams pp, int num_dofs, int64_t nvec, int64_t num_envs,
                       float4* __restrict__ tau_out, double* __restrict__ stats) {
