@@ -278,6 +278,14 @@ def family_numbers(device, peak_gbs):
     ms_pair = graph_time(step_calls, device, 20) * 2      # per (task + osc) pair
     out[f"franka_pick_step_{n}"] = {"envs": n, "us_per_step": round(ms_pair * 1e3, 3), "env_steps_per_s": n / (ms_pair * 1e-3),
                                     "kernels_per_step": 2, "note": "franka_task + osc (fp64 chain), CUDA-graph replay"}
+    fused = []
+    for (t, d, dpose, pos_action, effort, task) in keep:
+        ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=t.dof_pos, dof_vel=t.dof_state[:, 1].view(n, 9, 1),
+                 default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=0)
+        fused.append(ctl.bind_pick_osc(task, effort[:, :7], pos_action[:, 7:9]))
+    ms_fused = graph_time(fused, device, 20)
+    out[f"franka_pick_step_fused_{n}"] = {"envs": n, "us_per_step": round(ms_fused * 1e3, 3), "env_steps_per_s": n / (ms_fused * 1e-3),
+                                          "kernels_per_step": 1, "note": "b200ctl_franka_pick_osc (fp64 chain), CUDA-graph replay"}
     return out
 
 

@@ -228,6 +228,18 @@ B200CTL_API int b200ctl_franka_task(const DLTensor* rb_states, const DLTensor* b
                         DLTensor* hand_restart, const b200ctl_franka_task_params* params,
                         DLTensor* dpose_out, DLTensor* grip_out, b200ctl_stream_t stream);
 
+/* The whole pick step of examples/franka_cube_ik_osc.py:348-410 (--controller osc) in ONE kernel: b200ctl_franka_task's
+ * goal logic runs in the thread that then solves the env's OSC system (b200ctl_osc), dpose stays in registers.
+ * Arguments as in those two entry points (dof_pos must expose all 9 DOFs: the fingers feed gripper_sep);
+ * dpose_out (N,6[,1]) is optional (NULL = not stored); grip_out (N,2) = pos_action[:, 7:9]; out (N,7) = effort_action[:, :7]. */
+B200CTL_API int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_pos, const DLTensor* dof_vel,
+                            const DLTensor* rb_states, const DLTensor* box_index, const DLTensor* hand_index,
+                            const DLTensor* init_pos, const DLTensor* init_rot, DLTensor* hand_restart,
+                            const b200ctl_franka_task_params* task, const DLTensor* q_default,
+                            double kp, double kd, double kp_null, double kd_null, int32_t precision,
+                            DLTensor* dpose_out, DLTensor* grip_out, DLTensor* out, double* stats,
+                            b200ctl_stream_t stream);
+
 /* Row gather / scatter of the index-list views of examples/franka_cube_ik_osc.py:348-353
  * (rb_states[hand_idxs, 7:]) -- bit-exact copies.  src (M,C) f32, index (N,) int64,
  * dst (N,ncols): dst[i, j] = src[index[i], col0 + j]. */

@@ -30,7 +30,7 @@
 // v2 of this kernel staged everything with 4-byte LDGSTS: at 8 cycles per warp-level
 // LDGSTS the staging alone cost ~30 us per 262,144 envs (profiles/r01_full_osc_v3.txt).
 // Roofline: HBM.  Algorithmic bytes per env: IK 248 B, OSC 496 B.
-#include "common.cuh"
+#include "franka_task.cuh"
 
 namespace b200ctl {
 
@@ -343,6 +343,50 @@ ik_dls_kernel(StagePlan P, float lambda2, int has_pos, TView out, int64_t n) {
   }
 }
 
+// OSC torques of env `e` (examples/franka_cube_ik_osc.py:62-79) from the staged tile: J, M, q, qd are read through
+// their resolved smem addressing, the pose error `dp` and the hand velocity `hv` come in registers.
+template <typename T>
+__device__ __forceinline__ void osc_compute(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQ,
+                                            const SAddr& aQD, int e, const float (&dp)[6], const float (&hv)[6],
+                                            const TView& q_default, float kp, float kd, float kp_null, float kd_null,
+                                            float (&u_out)[7]) {
+  constexpr int D = 7;
+  float J[6][D];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) J[r][c] = SM(aJ, e, r, c);
+  // factor first: L is dead once chol(Lambda^-1) exists, which keeps the live register set small
+  T A[6][6], rda[6];
+  task_space_factor<T, D>(J, tile, aM, e, A, rda);
+  // joint-space PD term u0 (:74-76), fp32 in the reference's operand order
+  float u0[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    const float qdef = ldf(q_default, c * q_default.s[0]);
+    u0[c] = __fadd_rn(__fmul_rn(kd_null, -SM(aQD, e, 0, c)), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef, SM(aQ, e, 0, c)))));
+  }
+  // task-space target w = kp dpose - kd v_hand (:67-68) minus J u0 (null-space projector folded in)
+  T w[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    T s = (T)__fsub_rn(__fmul_rn(kp, dp[r]), __fmul_rn(kd, hv[r]));
+#pragma unroll
+    for (int c = 0; c < D; ++c) s = fma_t<T>(-(T)J[r][c], (T)u0[c], s);
+    w[r] = s;
+  }
+  chol_solve<T, 6>(A, rda, w);          // w <- Lambda (w - J u0)
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    T u = (T)0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) u = fma_t<T>((T)SM(aM, e, c, k), (T)u0[k], u);   // (M u0)[c], M as given (:77)
+#pragma unroll
+    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], w[r], u);              // + J^T Lambda (...)
+    u_out[c] = (float)u;
+  }
+}
+
 // ------------------------------------------------------------------ a10: control_osc
 // segments: 0 = J (6x7), 1 = M (7x7), 2 = dof_pos (1x7), 3 = dof_vel (1x7), 4 = dpose (1x6);
 // the index-gathered hand velocity (1x6) goes to the extras slot of the active plan.
@@ -370,48 +414,93 @@ osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q
   if (threadIdx.x < nenv) {
     const int e = threadIdx.x;
     const int64_t env = env0 + e;
-    float J[6][D];
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < D; ++c) J[r][c] = SM(a[0], e, r, c);
-    // factor first: L is dead once chol(Lambda^-1) exists, which keeps the live register set small
-    T A[6][6], rda[6];
-    task_space_factor<T, D>(J, tile, a[1], e, A, rda);
-    // joint-space PD term u0 (:74-76), fp32 in the reference's operand order
-    float u0[D];
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-      const float qdef = ldf(q_default, c * q_default.s[0]);
-      u0[c] = __fadd_rn(__fmul_rn(kd_null, -SM(a[3], e, 0, c)), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef, SM(a[2], e, 0, c)))));
-    }
-    // task-space target w = kp dpose - kd v_hand (:67-68) minus J u0 (null-space projector folded in)
+    float dp[6], hvv[6], u[D];
     const float* hv = hv0 + e * hv_ts;
-    T w[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      T s = (T)__fsub_rn(__fmul_rn(kp, SM(a[4], e, 0, r)), __fmul_rn(kd, hv[r]));
-#pragma unroll
-      for (int c = 0; c < D; ++c) s = fma_t<T>(-(T)J[r][c], (T)u0[c], s);
-      w[r] = s;
-    }
-    chol_solve<T, 6>(A, rda, w);          // w <- Lambda (w - J u0)
+    for (int r = 0; r < 6; ++r) { dp[r] = SM(a[4], e, 0, r); hvv[r] = hv[r]; }
+    osc_compute<T>(tile, a[0], a[1], a[2], a[3], e, dp, hvv, q_default, kp, kd, kp_null, kd_null, u);
     float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
     bool finite = true;
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-      T u = (T)0;
-#pragma unroll
-      for (int k = 0; k < D; ++k) u = fma_t<T>((T)SM(a[1], e, c, k), (T)u0[k], u);   // (M u0)[c], M as given (:77)
-#pragma unroll
-      for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], w[r], u);                 // + J^T Lambda (...)
-      const float uf = (float)u;
-      o[c * out.s[1]] = uf;
-      const bool f = isfinite(uf);
+      o[c * out.s[1]] = u[c];
+      const bool f = isfinite(u[c]);
       finite = finite && f;
-      const float t = f ? uf : 0.f;
+      const float t = f ? u[c] : 0.f;
       acc[1] += fabsf(t);
       acc[2] += (double)t * t;
+    }
+    acc[0] = 1.0;
+    acc[3] = finite ? 0.0 : 1.0;
+  }
+  if (stats) {
+    const int slot[4] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_NONFINITE};
+    block_stats_commit<4>(acc, stats, slot);
+  }
+}
+
+// ------------------------------------------------------------------ fused pick step: goal logic + OSC in one launch
+// examples/franka_cube_ik_osc.py:348-410 with --controller osc: the task logic of franka_task.cuh runs in the thread
+// that then solves the env's OSC system, so `dpose` never leaves registers and the step is ONE kernel.
+// segments: 0 = J (6x7), 1 = M (7x7), 2 = dof_pos (1x9: the fingers feed gripper_sep), 3 = dof_vel (1x7),
+// 4 = init_pos (1x3), 5 = init_rot (1x4); extras: box row (7) + hand row (13: pose and velocity) gathered by index.
+template <typename T>
+__global__ void __launch_bounds__(kTileEnvs)
+pick_osc_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_t* __restrict__ hand_restart,
+                int64_t hr_stride, TaskConst tk, TView q_default, float kp, float kd, float kp_null, float kd_null,
+                TView dpose_out, int has_dpose, TView grip, TView out, int64_t n, double* __restrict__ stats) {
+  constexpr int D = 7;
+  extern __shared__ __align__(16) float tile[];
+  __shared__ __align__(8) uint64_t bar;
+  pdl_prologue();
+  const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
+  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  const bool bulk = tile_is_bulk(P);
+  const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
+  float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
+  stage_gather<7>(rb, box_index, 1, env0, nenv, x0, x_ts);            // box pos + quat          (:348-349)
+  stage_gather<13>(rb, hand_index, 1, env0, nenv, x0 + 7, x_ts);      // hand pos + quat + vel   (:351-353)
+  SAddr a[6];
+  stage_all<6>(P, env0, nenv, tile, &bar, a);
+
+  double acc[4] = {0, 0, 0, 0};
+  if (threadIdx.x < nenv) {
+    const int e = threadIdx.x;
+    const int64_t env = env0 + e;
+    const float* xr = x0 + e * x_ts;
+    float box[7], hand[7], hv[6], ip[3], iq[4];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) { box[c] = xr[c]; hand[c] = xr[7 + c]; }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) hv[c] = xr[14 + c];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ip[c] = SM(a[4], e, 0, c);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) iq[c] = SM(a[5], e, 0, c);
+    const float sep = __fadd_rn(SM(a[2], e, 0, 7), SM(a[2], e, 0, 8));   // :364
+    TaskOut t;
+    task_logic(box, hand, sep, ip, iq, hand_restart[env * hr_stride] != 0, tk, t);
+    hand_restart[env * hr_stride] = t.restart ? 1 : 0;
+    float* gr = reinterpret_cast<float*>(const_cast<void*>(grip.p)) + env * grip.s[0];
+    gr[0] = t.grip;
+    gr[grip.s[1]] = t.grip;
+    if (has_dpose) {
+      float* dpo = reinterpret_cast<float*>(const_cast<void*>(dpose_out.p)) + env * dpose_out.s[0];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) dpo[c * dpose_out.s[1]] = t.dpose[c];
+    }
+    float u[D];
+    osc_compute<T>(tile, a[0], a[1], a[2], a[3], e, t.dpose, hv, q_default, kp, kd, kp_null, kd_null, u);
+    float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      o[c * out.s[1]] = u[c];
+      const bool f = isfinite(u[c]);
+      finite = finite && f;
+      const float v = f ? u[c] : 0.f;
+      acc[1] += fabsf(v);
+      acc[2] += (double)v * v;
     }
     acc[0] = 1.0;
     acc[3] = finite ? 0.0 : 1.0;
@@ -727,6 +816,64 @@ extern "C" int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const
   else        { if (precision == 0) LAUNCH_FULL(double, 9); else LAUNCH_FULL(float, 9); }
 #undef LAUNCH_FULL
   return post_launch("osc_full_kernel");
+}
+
+extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_pos, const DLTensor* dof_vel,
+                                      const DLTensor* rb_states, const DLTensor* box_index, const DLTensor* hand_index,
+                                      const DLTensor* init_pos, const DLTensor* init_rot, DLTensor* hand_restart,
+                                      const b200ctl_franka_task_params* task, const DLTensor* q_default,
+                                      double kp, double kd, double kp_null, double kd_null, int32_t precision,
+                                      DLTensor* dpose_out, DLTensor* grip_out, DLTensor* out, double* stats,
+                                      b200ctl_stream_t stream) {
+  if (!task) B200_FAIL(B200CTL_E_NULL, "task params is NULL");
+  int dev = -1;
+  TView j, m, q, qd, rb, bi, hi, ip, iq, hr, qdef, dp, gr, o;
+  B200_TRY(check_precision(precision));
+  B200_TRY(view_of(j_eef, "j_eef", M_F32, 3, 3, &dev, &j));
+  const int64_t n = j.n[0];
+  if (j.n[1] != 6 || j.n[2] != 7) B200_FAIL(B200CTL_E_SHAPE, "j_eef: expected (N,6,7)");
+  B200_TRY(view_of(mm, "mm", M_F32, 3, 3, &dev, &m));
+  if (m.n[0] != n || m.n[1] != 7 || m.n[2] != 7) B200_FAIL(B200CTL_E_SHAPE, "mm: expected (N,7,7)");
+  B200_TRY(vec_rows(dof_pos, "dof_pos", n, 9, false, &dev, &q));
+  B200_TRY(vec_rows(dof_vel, "dof_vel", n, 7, false, &dev, &qd));
+  B200_TRY(view_of(rb_states, "rb_states", M_F32, 2, 2, &dev, &rb));
+  if (rb.n[1] < 13) B200_FAIL(B200CTL_E_SHAPE, "rb_states: expected (M,13)");
+  B200_TRY(view_of(box_index, "box_index", M_I64, 1, 1, &dev, &bi));
+  B200_TRY(view_of(hand_index, "hand_index", M_I64, 1, 1, &dev, &hi));
+  if (bi.n[0] != n || hi.n[0] != n) B200_FAIL(B200CTL_E_SHAPE, "box_index / hand_index: expected (N,)");
+  B200_TRY(view_of(init_pos, "init_pos", M_F32, 2, 2, &dev, &ip));
+  if (ip.n[0] != n || ip.n[1] != 3) B200_FAIL(B200CTL_E_SHAPE, "init_pos: expected (N,3)");
+  B200_TRY(view_of(init_rot, "init_rot", M_F32, 2, 2, &dev, &iq));
+  if (iq.n[0] != n || iq.n[1] != 4) B200_FAIL(B200CTL_E_SHAPE, "init_rot: expected (N,4)");
+  B200_TRY(view_of(hand_restart, "hand_restart", M_U8, 1, 1, &dev, &hr));
+  if (hr.n[0] != n) B200_FAIL(B200CTL_E_SHAPE, "hand_restart: expected (N,) bool / uint8");
+  B200_TRY(view_of(q_default, "q_default", M_F32, 1, 1, &dev, &qdef));
+  if (qdef.n[0] < 7) B200_FAIL(B200CTL_E_SHAPE, "q_default: expected (>=7,)");
+  const int has_dpose = dpose_out != nullptr;
+  if (has_dpose) B200_TRY(vec_rows(dpose_out, "dpose_out", n, 6, true, &dev, &dp));
+  else dp = qd;
+  B200_TRY(view_of(grip_out, "grip_out", M_F32, 2, 2, &dev, &gr));
+  if (gr.n[0] != n || gr.n[1] != 2) B200_FAIL(B200CTL_E_SHAPE, "grip_out: expected (N,2)");
+  B200_TRY(vec_rows(out, "out", n, 7, true, &dev, &o));
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  const SegSpec spec[6] = {{&j, 6, 7}, {&m, 7, 7}, {&q, 1, 9}, {&qd, 1, 7}, {&ip, 1, 3}, {&iq, 1, 4}};
+  const StagePlan P = make_plan(spec, 6, 20, n);
+  const int smem = P.smem_floats * 4;
+  const TaskConst tk = make_task_const(*task);
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
+  if (precision == 0) {
+    B200_TRY(set_smem(pick_osc_kernel<double>, smem));
+    launch_pdl(pick_osc_kernel<double>, tiles(n), kTileEnvs, smem, s, P, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
+               (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
+  } else {
+    B200_TRY(set_smem(pick_osc_kernel<float>, smem));
+    launch_pdl(pick_osc_kernel<float>, tiles(n), kTileEnvs, smem, s, P, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
+               (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
+  }
+  return post_launch("pick_osc_kernel");
 }
 
 extern "C" int b200ctl_orientation_error(const DLTensor* q_desired, const DLTensor* q_current,

@@ -175,3 +175,21 @@ class TaskStep:
             grip_out = torch.empty((n, 2), dtype=torch.float32, device=dev)
         self.bind(dpose, grip_out)()
         return dpose, grip_out
+
+
+def bind_pick_osc(task: "TaskStep", out: torch.Tensor, grip_out: torch.Tensor, dpose: torch.Tensor | None = None,
+                  stats: torch.Tensor | None = None) -> "_lib.BoundCall":
+    """The whole OSC pick step (``examples/franka_cube_ik_osc.py:348-410``) as ONE kernel launch per sim step:
+    the goal logic of ``task`` runs in the thread that then solves the env's OSC system with the globals bound on
+    this module (``j_eef``, ``mm``, ``dof_vel``, gains ...); ``dpose`` stays in registers unless a tensor is given.
+
+    ``out`` = ``effort_action[:, :7]``, ``grip_out`` = ``pos_action[:, 7:9]``; ``task.hand_restart`` is updated in place.
+    """
+    g = globals()
+    tensors = (g["j_eef"], g["mm"], task.dof_pos, g["dof_vel"], task.rb_states, task.box_idxs, task.hand_idxs,
+               task.init_pos, task.init_rot, task.hand_restart)
+    packed = [_lib.dl(t) for t in tensors]
+    qd, dp, gr, o = _lib.dl(g["default_dof_pos_tensor"]), _lib.dl(dpose), _lib.dl(grip_out), _lib.dl(out)
+    args = [p[0] for p in packed] + [ctypes.byref(task.params), qd[0], float(g["kp"]), float(g["kd"]), float(g["kp_null"]),
+                                     float(g["kd_null"]), int(g["precision"]), dp[0], gr[0], o[0], _lib.ptr_or_none(stats), None]
+    return _lib.BoundCall(_lib.lib().b200ctl_franka_pick_osc, args, 21, out.device, (packed, qd, dp, gr, o, task, stats), out)

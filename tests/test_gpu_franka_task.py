@@ -119,3 +119,42 @@ def test_step_graph_replays_the_pick_step():
     step()
     torch.cuda.synchronize()
     assert not torch.equal(effort, want)
+
+
+def test_fused_pick_osc_equals_task_then_osc():
+    """b200ctl_franka_pick_osc (one launch) == b200ctl_franka_task followed by b200ctl_osc (two launches), bit for bit,
+    for both precisions, full and ragged tiles, with and without the optional dpose output."""
+    for n in (64 * 9 + 17, 2048):
+        ti, fd = _dev(syn.franka_task_inputs(n, seed=21)), _dev(syn.franka_inputs(n, seed=22))
+        for prec in (0, 1):
+            ctl.bind(damping=0.05, kp=150., kd=2.0 * np.sqrt(150.), kp_null=10., kd_null=2.0 * np.sqrt(10.), j_eef=fd.j_eef,
+                     mm=fd.mm, dof_pos=ti.dof_pos, dof_vel=ti.dof_state[:, 1].view(n, 9, 1),
+                     default_dof_pos_tensor=fd.default_dof_pos, num_envs=n, precision=prec)
+            ctl.bind_hand(ti.rb_states, ti.hand_idxs)
+            r1 = ti.hand_restart.clone()
+            t1 = ctl.TaskStep(ti.rb_states, ti.box_idxs, ti.hand_idxs, ti.dof_pos, ti.init_pos, ti.init_rot, r1, "osc")
+            pos1, eff1 = torch.zeros(n, 9, device=DEV), torch.zeros(n, 9, device=DEV)
+            dpose1, _ = t1(grip_out=pos1[:, 7:9])
+            ctl.control_osc(dpose1, out=eff1[:, :7])
+
+            r2 = ti.hand_restart.clone()
+            t2 = ctl.TaskStep(ti.rb_states, ti.box_idxs, ti.hand_idxs, ti.dof_pos, ti.init_pos, ti.init_rot, r2, "osc")
+            pos2, eff2 = torch.zeros(n, 9, device=DEV), torch.full((n, 9), 3.0, device=DEV)
+            dpose2 = torch.zeros(n, 6, 1, device=DEV)
+            st = _lib_stats()
+            ctl.bind_pick_osc(t2, eff2[:, :7], pos2[:, 7:9], dpose=dpose2, stats=st)()
+            assert torch.equal(eff2[:, :7], eff1[:, :7]) and (eff2[:, 7:] == 3.0).all()
+            assert torch.equal(pos2, pos1) and torch.equal(r2, r1) and torch.equal(dpose2, dpose1)
+            assert st.cpu()[0] == n
+            # without the dpose output
+            r3 = ti.hand_restart.clone()
+            t3 = ctl.TaskStep(ti.rb_states, ti.box_idxs, ti.hand_idxs, ti.dof_pos, ti.init_pos, ti.init_rot, r3, "osc")
+            eff3 = torch.zeros(n, 9, device=DEV)
+            ctl.bind_pick_osc(t3, eff3[:, :7], pos2[:, 7:9])()
+            assert torch.equal(eff3[:, :7], eff1[:, :7])
+    ctl.bind(precision=0)
+
+
+def _lib_stats():
+    from test_isaacgym_b200 import _lib
+    return _lib.stats_buffer(torch.device(DEV))
