@@ -286,6 +286,13 @@ def family_numbers(device, peak_gbs):
     ms_fused = graph_time(fused, device, 20)
     out[f"franka_pick_step_fused_{n}"] = {"envs": n, "us_per_step": round(ms_fused * 1e3, 3), "env_steps_per_s": n / (ms_fused * 1e-3),
                                           "kernels_per_step": 1, "note": "b200ctl_franka_pick_osc (fp64 chain), CUDA-graph replay"}
+    fused_ik = []
+    for (t, d, dpose, pos_action, effort, task) in keep:
+        ctl.bind(j_eef=d.j_eef, num_envs=n, precision=0)
+        fused_ik.append(ctl.bind_pick_ik(task, pos_action[:, :7], pos_action[:, 7:9]))
+    ms_ik = graph_time(fused_ik, device, 20)
+    out[f"franka_pick_ik_step_fused_{n}"] = {"envs": n, "us_per_step": round(ms_ik * 1e3, 3), "env_steps_per_s": n / (ms_ik * 1e-3),
+                                             "kernels_per_step": 1, "note": "b200ctl_franka_pick_ik (default controller, fp64 chain), CUDA-graph replay"}
     return out
 
 

@@ -240,6 +240,14 @@ B200CTL_API int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* m
                             DLTensor* dpose_out, DLTensor* grip_out, DLTensor* out, double* stats,
                             b200ctl_stream_t stream);
 
+/* Same fusion for the script's default controller (--controller ik): goal logic + control_ik +
+ * pos_action[:, :7] = dof_pos[:, :7] + u (:395) in one kernel.  out (N,7) = pos_action[:, :7], grip_out = pos_action[:, 7:9]. */
+B200CTL_API int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* dof_pos, const DLTensor* rb_states,
+                           const DLTensor* box_index, const DLTensor* hand_index, const DLTensor* init_pos,
+                           const DLTensor* init_rot, DLTensor* hand_restart,
+                           const b200ctl_franka_task_params* task, double lambda, int32_t precision,
+                           DLTensor* dpose_out, DLTensor* grip_out, DLTensor* out, b200ctl_stream_t stream);
+
 /* Row gather / scatter of the index-list views of examples/franka_cube_ik_osc.py:348-353
  * (rb_states[hand_idxs, 7:]) -- bit-exact copies.  src (M,C) f32, index (N,) int64,
  * dst (N,ncols): dst[i, j] = src[index[i], col0 + j]. */

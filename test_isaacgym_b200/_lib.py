@@ -87,6 +87,7 @@ _SIGNATURES = {
     "b200ctl_franka_task": (c_int, [_DL, _DL, _DL, _DL, _DL, _DL, _DL, POINTER(FrankaTaskParams), _DL, _DL, c_void_p]),
     "b200ctl_franka_pick_osc": (c_int, [_DL] * 10 + [POINTER(FrankaTaskParams), _DL, c_double, c_double, c_double, c_double,
                                         c_int32, _DL, _DL, _DL, c_void_p, c_void_p]),
+    "b200ctl_franka_pick_ik": (c_int, [_DL] * 8 + [POINTER(FrankaTaskParams), c_double, c_int32, _DL, _DL, _DL, c_void_p]),
     "b200ctl_gather_rows": (c_int, [_DL, _DL, c_int32, c_int32, _DL, c_void_p]),
     "b200ctl_nccl_unique_id": (c_int, [c_void_p]),
     "b200ctl_nccl_comm_init": (c_int, [POINTER(c_void_p), c_int32, c_void_p, c_int32]),

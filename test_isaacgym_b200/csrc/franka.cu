@@ -297,6 +297,38 @@ __device__ __forceinline__ void task_space_factor(const float (&J)[6][D], const 
   chol_inplace<T, 6>(A, rda);
 }
 
+// DLS-IK step of env `e` (examples/franka_cube_ik_osc.py:53-59) from the staged jacobian; dp = dpose in registers.
+template <typename T, int D>
+__device__ __forceinline__ void ik_compute(const float* tile, const SAddr& aJ, int e, const float (&dp)[6], float lambda2,
+                                           float (&u_out)[D]) {
+  float J[6][D];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) J[r][c] = SM(aJ, e, r, c);
+  T A[6][6], rd[6], y[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    y[r] = (T)dp[r];
+#pragma unroll
+    for (int c = 0; c <= r; ++c) {
+      T s = (r == c) ? (T)lambda2 : (T)0;     // J J^T + lambda^2 I   (:57-58)
+#pragma unroll
+      for (int k = 0; k < D; ++k) s = fma_t<T>((T)J[r][k], (T)J[c][k], s);
+      A[r][c] = s;
+    }
+  }
+  chol_inplace<T, 6>(A, rd);
+  chol_solve<T, 6>(A, rd, y);
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    T u = (T)0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], y[r], u);   // J^T y
+    u_out[c] = (float)u;
+  }
+}
+
 // ------------------------------------------------------------------ a9: control_ik
 // segments: 0 = J (6 x D), 1 = dpose (1 x 6), 2 = dof_pos (1 x D, optional)
 template <typename T, int D>
@@ -312,32 +344,14 @@ ik_dls_kernel(StagePlan P, float lambda2, int has_pos, TView out, int64_t n) {
   if (threadIdx.x >= nenv) return;
   const int e = threadIdx.x;
   const int64_t env = env0 + e;
-  float J[6][D];
+  float dp[6], u[D];
 #pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = 0; c < D; ++c) J[r][c] = SM(a[0], e, r, c);
-  T A[6][6], rd[6], y[6];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    y[r] = (T)SM(a[1], e, 0, r);
-#pragma unroll
-    for (int c = 0; c <= r; ++c) {
-      T s = (r == c) ? (T)lambda2 : (T)0;     // J J^T + lambda^2 I   (:57-58)
-#pragma unroll
-      for (int k = 0; k < D; ++k) s = fma_t<T>((T)J[r][k], (T)J[c][k], s);
-      A[r][c] = s;
-    }
-  }
-  chol_inplace<T, 6>(A, rd);
-  chol_solve<T, 6>(A, rd, y);
+  for (int r = 0; r < 6; ++r) dp[r] = SM(a[1], e, 0, r);
+  ik_compute<T, D>(tile, a[0], e, dp, lambda2, u);
   float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
 #pragma unroll
   for (int c = 0; c < D; ++c) {
-    T u = (T)0;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], y[r], u);   // J^T y
-    float uf = (float)u;
+    float uf = u[c];
     if (has_pos) uf = __fadd_rn(SM(a[2], e, 0, c), uf);   // dof_pos[:, :7] + control_ik(dpose)  (:395)
     o[c * out.s[1]] = uf;
   }
@@ -509,6 +523,57 @@ pick_osc_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_
     const int slot[4] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_NONFINITE};
     block_stats_commit<4>(acc, stats, slot);
   }
+}
+
+// ------------------------------------------------------------------ fused pick step, IK controller (the script's default)
+// examples/franka_cube_ik_osc.py:348-410 with --controller ik: goal logic, DLS-IK and
+// pos_action[:, :7] = dof_pos[:, :7] + control_ik(dpose), pos_action[:, 7:9] = grip_acts in one launch.
+// segments: 0 = J (6x7), 1 = dof_pos (1x9), 2 = init_pos (1x3), 3 = init_rot (1x4); extras: box row (7) + hand row (7).
+template <typename T>
+__global__ void __launch_bounds__(kTileEnvs)
+pick_ik_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_t* __restrict__ hand_restart,
+               int64_t hr_stride, TaskConst tk, float lambda2, TView dpose_out, int has_dpose, TView grip, TView out, int64_t n) {
+  constexpr int D = 7;
+  extern __shared__ __align__(16) float tile[];
+  __shared__ __align__(8) uint64_t bar;
+  pdl_prologue();
+  const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
+  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  const bool bulk = tile_is_bulk(P);
+  const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
+  float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
+  stage_gather<7>(rb, box_index, 1, env0, nenv, x0, x_ts);
+  stage_gather<7>(rb, hand_index, 1, env0, nenv, x0 + 7, x_ts);
+  SAddr a[4];
+  stage_all<4>(P, env0, nenv, tile, &bar, a);
+  if (threadIdx.x >= nenv) return;
+  const int e = threadIdx.x;
+  const int64_t env = env0 + e;
+  const float* xr = x0 + e * x_ts;
+  float box[7], hand[7], ip[3], iq[4];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) { box[c] = xr[c]; hand[c] = xr[7 + c]; }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) ip[c] = SM(a[2], e, 0, c);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) iq[c] = SM(a[3], e, 0, c);
+  const float sep = __fadd_rn(SM(a[1], e, 0, 7), SM(a[1], e, 0, 8));
+  TaskOut t;
+  task_logic(box, hand, sep, ip, iq, hand_restart[env * hr_stride] != 0, tk, t);
+  hand_restart[env * hr_stride] = t.restart ? 1 : 0;
+  float* gr = reinterpret_cast<float*>(const_cast<void*>(grip.p)) + env * grip.s[0];
+  gr[0] = t.grip;
+  gr[grip.s[1]] = t.grip;
+  if (has_dpose) {
+    float* dpo = reinterpret_cast<float*>(const_cast<void*>(dpose_out.p)) + env * dpose_out.s[0];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) dpo[c * dpose_out.s[1]] = t.dpose[c];
+  }
+  float u[D];
+  ik_compute<T, D>(tile, a[0], e, t.dpose, lambda2, u);
+  float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
+#pragma unroll
+  for (int c = 0; c < D; ++c) o[c * out.s[1]] = __fadd_rn(SM(a[1], e, 0, c), u[c]);   // :395
 }
 
 // ------------------------------------------------------------------ franka_osc.py:229-241
@@ -874,6 +939,56 @@ extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm
                (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
   }
   return post_launch("pick_osc_kernel");
+}
+
+extern "C" int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* dof_pos, const DLTensor* rb_states,
+                                     const DLTensor* box_index, const DLTensor* hand_index, const DLTensor* init_pos,
+                                     const DLTensor* init_rot, DLTensor* hand_restart,
+                                     const b200ctl_franka_task_params* task, double lambda, int32_t precision,
+                                     DLTensor* dpose_out, DLTensor* grip_out, DLTensor* out, b200ctl_stream_t stream) {
+  if (!task) B200_FAIL(B200CTL_E_NULL, "task params is NULL");
+  int dev = -1;
+  TView j, q, rb, bi, hi, ip, iq, hr, dp, gr, o;
+  B200_TRY(check_precision(precision));
+  B200_TRY(view_of(j_eef, "j_eef", M_F32, 3, 3, &dev, &j));
+  const int64_t n = j.n[0];
+  if (j.n[1] != 6 || j.n[2] != 7) B200_FAIL(B200CTL_E_SHAPE, "j_eef: expected (N,6,7)");
+  B200_TRY(vec_rows(dof_pos, "dof_pos", n, 9, false, &dev, &q));
+  B200_TRY(view_of(rb_states, "rb_states", M_F32, 2, 2, &dev, &rb));
+  if (rb.n[1] < 7) B200_FAIL(B200CTL_E_SHAPE, "rb_states: expected (M,13)");
+  B200_TRY(view_of(box_index, "box_index", M_I64, 1, 1, &dev, &bi));
+  B200_TRY(view_of(hand_index, "hand_index", M_I64, 1, 1, &dev, &hi));
+  if (bi.n[0] != n || hi.n[0] != n) B200_FAIL(B200CTL_E_SHAPE, "box_index / hand_index: expected (N,)");
+  B200_TRY(view_of(init_pos, "init_pos", M_F32, 2, 2, &dev, &ip));
+  if (ip.n[0] != n || ip.n[1] != 3) B200_FAIL(B200CTL_E_SHAPE, "init_pos: expected (N,3)");
+  B200_TRY(view_of(init_rot, "init_rot", M_F32, 2, 2, &dev, &iq));
+  if (iq.n[0] != n || iq.n[1] != 4) B200_FAIL(B200CTL_E_SHAPE, "init_rot: expected (N,4)");
+  B200_TRY(view_of(hand_restart, "hand_restart", M_U8, 1, 1, &dev, &hr));
+  if (hr.n[0] != n) B200_FAIL(B200CTL_E_SHAPE, "hand_restart: expected (N,) bool / uint8");
+  const int has_dpose = dpose_out != nullptr;
+  if (has_dpose) B200_TRY(vec_rows(dpose_out, "dpose_out", n, 6, true, &dev, &dp));
+  else dp = q;
+  B200_TRY(view_of(grip_out, "grip_out", M_F32, 2, 2, &dev, &gr));
+  if (gr.n[0] != n || gr.n[1] != 2) B200_FAIL(B200CTL_E_SHAPE, "grip_out: expected (N,2)");
+  B200_TRY(vec_rows(out, "out", n, 7, true, &dev, &o));
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  const SegSpec spec[4] = {{&j, 6, 7}, {&q, 1, 9}, {&ip, 1, 3}, {&iq, 1, 4}};
+  const StagePlan P = make_plan(spec, 4, 14, n);
+  const int smem = P.smem_floats * 4;
+  const TaskConst tk = make_task_const(*task);
+  const float l2 = (float)(lambda * lambda);
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
+  if (precision == 0) {
+    B200_TRY(set_smem(pick_ik_kernel<double>, smem));
+    launch_pdl(pick_ik_kernel<double>, tiles(n), kTileEnvs, smem, s, P, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+  } else {
+    B200_TRY(set_smem(pick_ik_kernel<float>, smem));
+    launch_pdl(pick_ik_kernel<float>, tiles(n), kTileEnvs, smem, s, P, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+  }
+  return post_launch("pick_ik_kernel");
 }
 
 extern "C" int b200ctl_orientation_error(const DLTensor* q_desired, const DLTensor* q_current,

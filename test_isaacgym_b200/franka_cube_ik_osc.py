@@ -193,3 +193,16 @@ def bind_pick_osc(task: "TaskStep", out: torch.Tensor, grip_out: torch.Tensor, d
     args = [p[0] for p in packed] + [ctypes.byref(task.params), qd[0], float(g["kp"]), float(g["kd"]), float(g["kp_null"]),
                                      float(g["kd_null"]), int(g["precision"]), dp[0], gr[0], o[0], _lib.ptr_or_none(stats), None]
     return _lib.BoundCall(_lib.lib().b200ctl_franka_pick_osc, args, 21, out.device, (packed, qd, dp, gr, o, task, stats), out)
+
+
+def bind_pick_ik(task: "TaskStep", out: torch.Tensor, grip_out: torch.Tensor, dpose: torch.Tensor | None = None) -> "_lib.BoundCall":
+    """The whole IK pick step (the script's default ``--controller ik``; ``examples/franka_cube_ik_osc.py:348-410``)
+    as one launch: goal logic + ``control_ik`` + ``pos_action[:, :7] = dof_pos[:, :7] + u`` (:395).
+    ``out`` = ``pos_action[:, :7]``, ``grip_out`` = ``pos_action[:, 7:9]``."""
+    g = globals()
+    tensors = (g["j_eef"], task.dof_pos, task.rb_states, task.box_idxs, task.hand_idxs, task.init_pos, task.init_rot,
+               task.hand_restart)
+    packed = [_lib.dl(t) for t in tensors]
+    dp, gr, o = _lib.dl(dpose), _lib.dl(grip_out), _lib.dl(out)
+    args = [p[0] for p in packed] + [ctypes.byref(task.params), float(g["damping"]), int(g["precision"]), dp[0], gr[0], o[0], None]
+    return _lib.BoundCall(_lib.lib().b200ctl_franka_pick_ik, args, 14, out.device, (packed, dp, gr, o, task), out)

@@ -158,3 +158,36 @@ def test_fused_pick_osc_equals_task_then_osc():
 def _lib_stats():
     from test_isaacgym_b200 import _lib
     return _lib.stats_buffer(torch.device(DEV))
+
+
+def test_fused_pick_ik_equals_task_then_ik():
+    for n in (64 * 5 + 3, 2048):
+        ti, fd = _dev(syn.franka_task_inputs(n, seed=31)), _dev(syn.franka_inputs(n, seed=32))
+        for prec in (0, 1):
+            ctl.bind(damping=0.05, j_eef=fd.j_eef, num_envs=n, precision=prec)
+            r1 = ti.hand_restart.clone()
+            t1 = ctl.TaskStep(ti.rb_states, ti.box_idxs, ti.hand_idxs, ti.dof_pos, ti.init_pos, ti.init_rot, r1, "ik")
+            pos1 = torch.zeros(n, 9, device=DEV)
+            dpose1, _ = t1(grip_out=pos1[:, 7:9])
+            ctl.control_ik(dpose1, dof_pos=ti.dof_pos, out=pos1[:, :7])
+            r2 = ti.hand_restart.clone()
+            t2 = ctl.TaskStep(ti.rb_states, ti.box_idxs, ti.hand_idxs, ti.dof_pos, ti.init_pos, ti.init_rot, r2, "ik")
+            pos2 = torch.zeros(n, 9, device=DEV)
+            dpose2 = torch.zeros(n, 6, 1, device=DEV)
+            ctl.bind_pick_ik(t2, pos2[:, :7], pos2[:, 7:9], dpose=dpose2)()
+            assert torch.equal(pos2, pos1) and torch.equal(r2, r1) and torch.equal(dpose2, dpose1)
+    ctl.bind(precision=0)
+    # against the reference loop body fixture (controller == "ik")
+    g = load_golden("franka_task.npz")
+    n = 512
+    ti, fi = _dev(syn.franka_task_inputs(n, seed=int(g["seed_task"]))), syn.franka_inputs(n, seed=int(g["seed_franka"]))
+    ctl.bind(damping=0.05, j_eef=fi.j_eef.to(DEV), num_envs=n)
+    r = ti.hand_restart.clone()
+    t = ctl.TaskStep(ti.rb_states, ti.box_idxs, ti.hand_idxs, ti.dof_pos, ti.init_pos, ti.init_rot, r, "ik")
+    pos = torch.zeros(n, 9, device=DEV)
+    ctl.bind_pick_ik(t, pos[:, :7], pos[:, 7:9])()
+    ref = g["ik_pos_action"]
+    rel = np.linalg.norm(pos.cpu().numpy()[:, :7] - ref[:, :7], axis=1) / np.linalg.norm(ref[:, :7], axis=1)
+    cond = ofr.conditioning(fi.j_eef, None, 0.05).numpy()
+    assert np.median(rel) <= 2e-6 and rel[cond <= 1e3].max() <= 5e-4      # same gate as test_full_pick_step_against_reference
+    assert np.array_equal(pos.cpu().numpy()[:, 7:], ref[:, 7:]) and np.array_equal(r.cpu().numpy(), g["ik_hand_restart"])
