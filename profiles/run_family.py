@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Run a handful of launches of one kernel family at throughput size -- the command ncu wraps.
 
-    python profiles/run_family.py servo|osc|ik|pd [--n N] [--iters K]
+    python profiles/run_family.py servo|osc|ik|task|pick|pd [--n N] [--iters K]
 """
 import argparse
 import os
@@ -50,6 +50,20 @@ def main():
         call = task.bind(torch.zeros(n, 6, 1, device=dev), torch.zeros(n, 2, device=dev))
         for _ in range(a.iters):
             call()
+    elif a.family == "pick":
+        import test_isaacgym_b200.franka_cube_ik_osc as ctl
+        n = a.n or 262_144
+        ti, fi = syn.franka_task_inputs(n, seed=4), syn.franka_inputs(n, seed=3)
+        t = ti.__class__(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in ti.__dict__.items()})
+        d = fi.__class__(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+        pos, eff = torch.zeros(n, 9, device=dev), torch.zeros(n, 9, device=dev)
+        ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=t.dof_pos, dof_vel=t.dof_state[:, 1].view(n, 9, 1),
+                 default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=0)
+        ctl.bind_hand(t.rb_states, t.hand_idxs)
+        task = ctl.TaskStep(t.rb_states, t.box_idxs, t.hand_idxs, t.dof_pos, t.init_pos, t.init_rot, t.hand_restart, "osc")
+        for call in (ctl.bind_pick_osc(task, eff[:, :7], pos[:, 7:9]), ctl.bind_pick_ik(task, pos[:, :7], pos[:, 7:9])):
+            for _ in range(a.iters):
+                call()
     elif a.family == "pd":
         from test_isaacgym_b200.pd_control import PDController
         n = a.n or 1_048_576

@@ -358,12 +358,11 @@ ik_dls_kernel(StagePlan P, float lambda2, int has_pos, TView out, int64_t n) {
 }
 
 // OSC torques of env `e` (examples/franka_cube_ik_osc.py:62-79) from the staged tile: J, M, q, qd are read through
-// their resolved smem addressing, the pose error `dp` and the hand velocity `hv` come in registers.
-template <typename T>
+// their resolved smem addressing; `target(w)` fills the fp32 task-space target kp dpose - kd v_hand (:67-68).
+template <typename T, typename TaskSpaceTarget>
 __device__ __forceinline__ void osc_compute(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQ,
-                                            const SAddr& aQD, int e, const float (&dp)[6], const float (&hv)[6],
-                                            const TView& q_default, float kp, float kd, float kp_null, float kd_null,
-                                            float (&u_out)[7]) {
+                                            const SAddr& aQD, int e, TaskSpaceTarget&& target,
+                                            const TView& q_default, float kp_null, float kd_null, float (&u_out)[7]) {
   constexpr int D = 7;
   float J[6][D];
 #pragma unroll
@@ -380,11 +379,15 @@ __device__ __forceinline__ void osc_compute(const float* tile, const SAddr& aJ, 
     const float qdef = ldf(q_default, c * q_default.s[0]);
     u0[c] = __fadd_rn(__fmul_rn(kd_null, -SM(aQD, e, 0, c)), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef, SM(aQ, e, 0, c)))));
   }
-  // task-space target w = kp dpose - kd v_hand (:67-68) minus J u0 (null-space projector folded in)
+  // task-space target w = kp dpose - kd v_hand (:67-68) minus J u0 (null-space projector folded in); the caller's
+  // target(wt) runs here, AFTER the factorisation, so whatever it needs (the pick step's goal logic) is not live
+  // across the Cholesky
+  float wt[6];
+  target(wt);
   T w[6];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
-    T s = (T)__fsub_rn(__fmul_rn(kp, dp[r]), __fmul_rn(kd, hv[r]));
+    T s = (T)wt[r];
 #pragma unroll
     for (int c = 0; c < D; ++c) s = fma_t<T>(-(T)J[r][c], (T)u0[c], s);
     w[r] = s;
@@ -428,11 +431,13 @@ osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q
   if (threadIdx.x < nenv) {
     const int e = threadIdx.x;
     const int64_t env = env0 + e;
-    float dp[6], hvv[6], u[D];
+    float u[D];
     const float* hv = hv0 + e * hv_ts;
+    const SAddr aDp = a[4];
+    osc_compute<T>(tile, a[0], a[1], a[2], a[3], e, [&](float (&w)[6]) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) { dp[r] = SM(a[4], e, 0, r); hvv[r] = hv[r]; }
-    osc_compute<T>(tile, a[0], a[1], a[2], a[3], e, dp, hvv, q_default, kp, kd, kp_null, kd_null, u);
+      for (int r = 0; r < 6; ++r) w[r] = __fsub_rn(__fmul_rn(kp, SM(aDp, e, 0, r)), __fmul_rn(kd, hv[r]));
+    }, q_default, kp_null, kd_null, u);
     float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
     bool finite = true;
 #pragma unroll
@@ -482,29 +487,31 @@ pick_osc_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_
     const int e = threadIdx.x;
     const int64_t env = env0 + e;
     const float* xr = x0 + e * x_ts;
-    float box[7], hand[7], hv[6], ip[3], iq[4];
-#pragma unroll
-    for (int c = 0; c < 7; ++c) { box[c] = xr[c]; hand[c] = xr[7 + c]; }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) hv[c] = xr[14 + c];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) ip[c] = SM(a[4], e, 0, c);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) iq[c] = SM(a[5], e, 0, c);
-    const float sep = __fadd_rn(SM(a[2], e, 0, 7), SM(a[2], e, 0, 8));   // :364
-    TaskOut t;
-    task_logic(box, hand, sep, ip, iq, hand_restart[env * hr_stride] != 0, tk, t);
-    hand_restart[env * hr_stride] = t.restart ? 1 : 0;
-    float* gr = reinterpret_cast<float*>(const_cast<void*>(grip.p)) + env * grip.s[0];
-    gr[0] = t.grip;
-    gr[grip.s[1]] = t.grip;
-    if (has_dpose) {
-      float* dpo = reinterpret_cast<float*>(const_cast<void*>(dpose_out.p)) + env * dpose_out.s[0];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) dpo[c * dpose_out.s[1]] = t.dpose[c];
-    }
+    const SAddr aQ = a[2], aIp = a[4], aIq = a[5];
     float u[D];
-    osc_compute<T>(tile, a[0], a[1], a[2], a[3], e, t.dpose, hv, q_default, kp, kd, kp_null, kd_null, u);
+    osc_compute<T>(tile, a[0], a[1], a[2], a[3], e, [&](float (&w)[6]) {
+      float box[7], hand[7], ip[3], iq[4];
+#pragma unroll
+      for (int c = 0; c < 7; ++c) { box[c] = xr[c]; hand[c] = xr[7 + c]; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ip[c] = SM(aIp, e, 0, c);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) iq[c] = SM(aIq, e, 0, c);
+      const float sep = __fadd_rn(SM(aQ, e, 0, 7), SM(aQ, e, 0, 8));   // :364
+      TaskOut t;
+      task_logic(box, hand, sep, ip, iq, hand_restart[env * hr_stride] != 0, tk, t);
+      hand_restart[env * hr_stride] = t.restart ? 1 : 0;
+      float* gr = reinterpret_cast<float*>(const_cast<void*>(grip.p)) + env * grip.s[0];
+      gr[0] = t.grip;
+      gr[grip.s[1]] = t.grip;
+      if (has_dpose) {
+        float* dpo = reinterpret_cast<float*>(const_cast<void*>(dpose_out.p)) + env * dpose_out.s[0];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dpo[c * dpose_out.s[1]] = t.dpose[c];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) w[r] = __fsub_rn(__fmul_rn(kp, t.dpose[r]), __fmul_rn(kd, xr[14 + r]));   // :67-68, hand vel :353
+    }, q_default, kp_null, kd_null, u);
     float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
     bool finite = true;
 #pragma unroll
