@@ -221,24 +221,27 @@ __device__ __forceinline__ void stage_gather(const TView& v, const TView& index,
 }
 
 // The last tile always takes the LDGSTS plan: bulk copies fetch whole aligned blocks past the operand.
-__device__ __forceinline__ bool tile_is_bulk(const StagePlan& P) { return P.bulk_ok && (blockIdx.x + 1 < gridDim.x); }
+__device__ __forceinline__ bool tile_is_bulk(const StagePlan& P, int t, int ntiles) { return P.bulk_ok && (t + 1 < ntiles); }
+__device__ __forceinline__ bool tile_is_bulk(const StagePlan& P) { return tile_is_bulk(P, blockIdx.x, gridDim.x); }
 
-// Stage every operand of the tile and resolve the smem addressing the compute phase must use.
-// `bar` must be 8-byte aligned shared memory.  Ends with a __syncthreads(): the tile is readable on return.
-template <int NSEG>
-__device__ __forceinline__ void stage_all(const StagePlan& P, int64_t env0, int nenv, float* tile, uint64_t* bar,
-                                          SAddr (&addr)[NSEG]) {
-  const bool bulk = tile_is_bulk(P);
-#pragma unroll
-  for (int i = 0; i < NSEG; ++i) {
-    const StageSeg& s = P.seg[i];
-    if (bulk && s.mode != 0) addr[i] = SAddr{s.b_off, s.b_es, s.b_rs, s.b_cs};
-    else if (bulk) addr[i] = SAddr{s.l_off, P.bulk_ts, s.cols, 1};
-    else addr[i] = SAddr{s.c_off, P.canon_ts, s.cols, 1};
-  }
-  if (bulk) {
+// Staging is split in three so a persistent CTA can refill its tile buffer while it computes:
+//   stage_begin  once per CTA (mbarrier init),
+//   stage_issue  starts every copy of tile t (bulk TMA on the mbarrier + the per-thread LDGSTS walk),
+//   stage_wait   resolves the smem addressing of tile t, waits for its copies and ends with a __syncthreads().
+// The buffer may be re-issued as soon as every thread has copied what it needs into registers and passed a
+// __syncthreads(); mbarrier phases alternate, `phase` is the caller's parity bit.
+__device__ __forceinline__ void stage_begin(const StagePlan& P, uint64_t* bar) {
+  if (P.bulk_ok) {
     if (threadIdx.x == 0) mbar_init(bar, blockDim.x);
     __syncthreads();
+  }
+}
+template <int NSEG>
+__device__ __forceinline__ void stage_issue(const StagePlan& P, int t, int ntiles, int64_t n, float* tile, uint64_t* bar) {
+  const int64_t env0 = (int64_t)t * kTileEnvs;
+  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  const bool bulk = tile_is_bulk(P, t, ntiles);
+  if (bulk) {
     unsigned my_bytes = 0;
 #pragma unroll
     for (int i = 0; i < NSEG; ++i) {
@@ -260,40 +263,64 @@ __device__ __forceinline__ void stage_all(const StagePlan& P, int64_t env0, int 
     }
   }
   stage_ldgsts<NSEG>(P, env0, nenv, bulk, tile);
+}
+template <int NSEG>
+__device__ __forceinline__ void stage_wait(const StagePlan& P, int t, int ntiles, uint64_t* bar, unsigned& phase,
+                                           SAddr (&addr)[NSEG]) {
+  const bool bulk = tile_is_bulk(P, t, ntiles);
+#pragma unroll
+  for (int i = 0; i < NSEG; ++i) {
+    const StageSeg& s = P.seg[i];
+    if (bulk && s.mode != 0) addr[i] = SAddr{s.b_off, s.b_es, s.b_rs, s.b_cs};
+    else if (bulk) addr[i] = SAddr{s.l_off, P.bulk_ts, s.cols, 1};
+    else addr[i] = SAddr{s.c_off, P.canon_ts, s.cols, 1};
+  }
   cp_async_wait_all();
-  if (bulk) mbar_wait(bar, 0);
+  if (bulk) { mbar_wait(bar, phase); phase ^= 1u; }
   __syncthreads();
+}
+
+// One-tile-per-CTA form: stage tile blockIdx.x and return when it is readable.
+template <int NSEG>
+__device__ __forceinline__ void stage_all(const StagePlan& P, int64_t env0, int nenv, float* tile, uint64_t* bar,
+                                          SAddr (&addr)[NSEG]) {
+  unsigned phase = 0;
+  const int64_t n = env0 + nenv;      // only the last tile is ragged, so this clamps exactly like the true n
+  stage_begin(P, bar);
+  stage_issue<NSEG>(P, blockIdx.x, gridDim.x, n, tile, bar);
+  stage_wait<NSEG>(P, blockIdx.x, gridDim.x, bar, phase, addr);
 }
 
 #define SM(a, e, r, c) tile[(a).off + (e) * (a).es + (r) * (a).rs + (c) * (a).cs]
 
-// Lambda^-1 = J M^-1 J^T factored: on return A holds chol(Lambda^-1).  J is this thread's jacobian in registers,
-// M is read from the staged tile (lower triangle).
+// Lambda^-1 = J M^-1 J^T factored: on return A holds chol(Lambda^-1).  J is this thread's jacobian and L the lower
+// triangle of its mass matrix, both in registers (L is overwritten by chol(M)).
 template <typename T, int D>
-__device__ __forceinline__ void task_space_factor(const float (&J)[6][D], const float* tile, const SAddr& aM, int e,
-                                                  T (&A)[6][6], T (&rda)[6]) {
-  T L[D][D], rdm[D];
-#pragma unroll
-  for (int r = 0; r < D; ++r)
-#pragma unroll
-    for (int c = 0; c <= r; ++c) L[r][c] = (T)SM(aM, e, r, c);
+__device__ __forceinline__ void task_space_factor(const float (&J)[6][D], T (&L)[D][D], T (&A)[6][6], T (&rda)[6]) {
+  T rdm[D];
   chol_inplace<T, D>(L, rdm);
-  // the six solves are independent: two at a time gives the scheduler two dependency chains to interleave
+  // J M^-1 J^T = Y^T Y with Y = L^-1 J^T: six independent forward substitutions (no back substitution, no M^-1),
+  // written column-interleaved so the scheduler sees six dependency chains at once
+  T Y[6][D];
 #pragma unroll
-  for (int r = 0; r < 6; r += 2) {
-    T x[D], y[D];
+  for (int i = 0; i < D; ++i) {
 #pragma unroll
-    for (int c = 0; c < D; ++c) { x[c] = (T)J[r][c]; y[c] = (T)J[r + 1][c]; }
-    chol_solve2<T, D>(L, rdm, x, y);        // x = M^-1 J[r,:]^T, y = M^-1 J[r+1,:]^T
+    for (int r = 0; r < 6; ++r) {
+      T s = (T)J[r][i];
 #pragma unroll
-    for (int c = r; c < 6; ++c) {
-      T s = (T)0, t = (T)0;
-#pragma unroll
-      for (int k = 0; k < D; ++k) { s = fma_t<T>((T)J[c][k], x[k], s); t = fma_t<T>((T)J[c][k], y[k], t); }
-      A[c][r] = s;
-      if (c >= r + 1) A[c][r + 1] = t;
+      for (int k = 0; k < i; ++k) s = fma_t<T>(-L[i][k], Y[r][k], s);
+      Y[r][i] = s * rdm[i];
     }
   }
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) {
+      T s = (T)0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) s = fma_t<T>(Y[r][k], Y[c][k], s);
+      A[r][c] = s;
+    }
   chol_inplace<T, 6>(A, rda);
 }
 
@@ -357,21 +384,26 @@ ik_dls_kernel(StagePlan P, float lambda2, int has_pos, TView out, int64_t n) {
   }
 }
 
-// OSC torques of env `e` (examples/franka_cube_ik_osc.py:62-79) from the staged tile: J, M, q, qd are read through
-// their resolved smem addressing; `target(w)` fills the fp32 task-space target kp dpose - kd v_hand (:67-68).
+// OSC torques (examples/franka_cube_ik_osc.py:62-79) in two phases.  osc_gather copies everything the env needs
+// out of the staged tile into registers -- J, the lower triangle of M, M u0 and the task-space right-hand side --
+// after which the tile buffer is dead and can be refilled; osc_solve is pure register arithmetic.
+// `target(w)` fills the fp32 task-space target kp dpose - kd v_hand (:67-68).
+template <typename T>
+struct OscRegs {
+  float J[6][7];
+  T L[7][7];      // lower triangle of M (:63), overwritten by its Cholesky factor
+  T Mu0[7];       // M u0 with M as given (:77)
+  T w[6];         // kp dpose - kd v_hand - J u0
+};
 template <typename T, typename TaskSpaceTarget>
-__device__ __forceinline__ void osc_compute(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQ,
-                                            const SAddr& aQD, int e, TaskSpaceTarget&& target,
-                                            const TView& q_default, float kp_null, float kd_null, float (&u_out)[7]) {
+__device__ __forceinline__ void osc_gather(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQ,
+                                           const SAddr& aQD, int e, TaskSpaceTarget&& target, const TView& q_default,
+                                           float kp_null, float kd_null, OscRegs<T>& R) {
   constexpr int D = 7;
-  float J[6][D];
 #pragma unroll
   for (int r = 0; r < 6; ++r)
 #pragma unroll
-    for (int c = 0; c < D; ++c) J[r][c] = SM(aJ, e, r, c);
-  // factor first: L is dead once chol(Lambda^-1) exists, which keeps the live register set small
-  T A[6][6], rda[6];
-  task_space_factor<T, D>(J, tile, aM, e, A, rda);
+    for (int c = 0; c < D; ++c) R.J[r][c] = SM(aJ, e, r, c);
   // joint-space PD term u0 (:74-76), fp32 in the reference's operand order
   float u0[D];
 #pragma unroll
@@ -379,29 +411,49 @@ __device__ __forceinline__ void osc_compute(const float* tile, const SAddr& aJ, 
     const float qdef = ldf(q_default, c * q_default.s[0]);
     u0[c] = __fadd_rn(__fmul_rn(kd_null, -SM(aQD, e, 0, c)), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef, SM(aQ, e, 0, c)))));
   }
-  // task-space target w = kp dpose - kd v_hand (:67-68) minus J u0 (null-space projector folded in); the caller's
-  // target(wt) runs here, AFTER the factorisation, so whatever it needs (the pick step's goal logic) is not live
-  // across the Cholesky
+  // task-space target minus J u0 (the null-space projector folded in)
   float wt[6];
   target(wt);
-  T w[6];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
     T s = (T)wt[r];
 #pragma unroll
-    for (int c = 0; c < D; ++c) s = fma_t<T>(-(T)J[r][c], (T)u0[c], s);
-    w[r] = s;
+    for (int c = 0; c < D; ++c) s = fma_t<T>(-(T)R.J[r][c], (T)u0[c], s);
+    R.w[r] = s;
   }
-  chol_solve<T, 6>(A, rda, w);          // w <- Lambda (w - J u0)
 #pragma unroll
   for (int c = 0; c < D; ++c) {
     T u = (T)0;
 #pragma unroll
-    for (int k = 0; k < D; ++k) u = fma_t<T>((T)SM(aM, e, c, k), (T)u0[k], u);   // (M u0)[c], M as given (:77)
+    for (int k = 0; k < D; ++k) {
+      const T m = (T)SM(aM, e, c, k);
+      if (k <= c) R.L[c][k] = m;
+      u = fma_t<T>(m, (T)u0[k], u);
+    }
+    R.Mu0[c] = u;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void osc_solve(OscRegs<T>& R, float (&u_out)[7]) {
+  constexpr int D = 7;
+  T A[6][6], rda[6];
+  task_space_factor<T, D>(R.J, R.L, A, rda);
+  chol_solve<T, 6>(A, rda, R.w);          // w <- Lambda (w - J u0)
 #pragma unroll
-    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], w[r], u);              // + J^T Lambda (...)
+  for (int c = 0; c < D; ++c) {
+    T u = R.Mu0[c];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)R.J[r][c], R.w[r], u);          // + J^T Lambda (...)
     u_out[c] = (float)u;
   }
+}
+template <typename T, typename TaskSpaceTarget>
+__device__ __forceinline__ void osc_compute(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQ,
+                                            const SAddr& aQD, int e, TaskSpaceTarget&& target,
+                                            const TView& q_default, float kp_null, float kd_null, float (&u_out)[7]) {
+  OscRegs<T> R;
+  osc_gather<T>(tile, aJ, aM, aQ, aQD, e, target, q_default, kp_null, kd_null, R);
+  osc_solve<T>(R, u_out);
 }
 
 // ------------------------------------------------------------------ a10: control_osc
@@ -418,39 +470,58 @@ osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q
   extern __shared__ __align__(16) float tile[];
   __shared__ __align__(8) uint64_t bar;
   pdl_prologue();
-  const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
-  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  const bool bulk = tile_is_bulk(P);
-  const int hv_ts = bulk ? P.bulk_ts : P.canon_ts;
-  float* hv0 = tile + (bulk ? P.x_off_b : P.x_off_c);
-  stage_gather<6>(hand_vel, hand_index, has_index, env0, nenv, hv0, hv_ts);   // dependent gather first
-  SAddr a[5];
-  stage_all<5>(P, env0, nenv, tile, &bar, a);
-
+  // persistent CTA: tiles blockIdx.x, + gridDim.x, ...; the tile buffer is refilled while the previous tile's
+  // factorisation runs out of registers
+  const int ntiles = (int)((n + kTileEnvs - 1) / kTileEnvs);
+  auto issue = [&](int t) {
+    const int64_t env0 = (int64_t)t * kTileEnvs;
+    const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+    const bool bulk = tile_is_bulk(P, t, ntiles);
+    stage_gather<6>(hand_vel, hand_index, has_index, env0, nenv, tile + (bulk ? P.x_off_b : P.x_off_c),
+                    bulk ? P.bulk_ts : P.canon_ts);                            // dependent gather first
+    stage_issue<5>(P, t, ntiles, n, tile, &bar);
+  };
+  unsigned phase = 0;
+  stage_begin(P, &bar);
+  int t = blockIdx.x;
+  if (t < ntiles) issue(t);
   double acc[4] = {0, 0, 0, 0};
-  if (threadIdx.x < nenv) {
+  for (; t < ntiles; t += gridDim.x) {
+    const int64_t env0 = (int64_t)t * kTileEnvs;
+    const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+    const bool bulk = tile_is_bulk(P, t, ntiles);
+    SAddr a[5];
+    stage_wait<5>(P, t, ntiles, &bar, phase, a);
+    const bool live = (int)threadIdx.x < nenv;
     const int e = threadIdx.x;
-    const int64_t env = env0 + e;
-    float u[D];
-    const float* hv = hv0 + e * hv_ts;
-    const SAddr aDp = a[4];
-    osc_compute<T>(tile, a[0], a[1], a[2], a[3], e, [&](float (&w)[6]) {
+    OscRegs<T> R;
+    if (live) {
+      const float* hv = tile + (bulk ? P.x_off_b : P.x_off_c) + e * (bulk ? P.bulk_ts : P.canon_ts);
+      const SAddr aDp = a[4];
+      osc_gather<T>(tile, a[0], a[1], a[2], a[3], e, [&](float (&w)[6]) {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) w[r] = __fsub_rn(__fmul_rn(kp, SM(aDp, e, 0, r)), __fmul_rn(kd, hv[r]));
-    }, q_default, kp_null, kd_null, u);
-    float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
-    bool finite = true;
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-      o[c * out.s[1]] = u[c];
-      const bool f = isfinite(u[c]);
-      finite = finite && f;
-      const float t = f ? u[c] : 0.f;
-      acc[1] += fabsf(t);
-      acc[2] += (double)t * t;
+        for (int r = 0; r < 6; ++r) w[r] = __fsub_rn(__fmul_rn(kp, SM(aDp, e, 0, r)), __fmul_rn(kd, hv[r]));
+      }, q_default, kp_null, kd_null, R);
     }
-    acc[0] = 1.0;
-    acc[3] = finite ? 0.0 : 1.0;
+    __syncthreads();                      // every thread has its operands in registers: the buffer is free
+    if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
+    if (live) {
+      float u[D];
+      osc_solve<T>(R, u);
+      float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + (env0 + e) * out.s[0];
+      bool finite = true;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        o[c * out.s[1]] = u[c];
+        const bool f = isfinite(u[c]);
+        finite = finite && f;
+        const float v = f ? u[c] : 0.f;
+        acc[1] += fabsf(v);
+        acc[2] += (double)v * v;
+      }
+      acc[0] += 1.0;
+      acc[3] += finite ? 0.0 : 1.0;
+    }
   }
   if (stats) {
     const int slot[4] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_NONFINITE};
@@ -603,8 +674,12 @@ osc_full_kernel(StagePlan P, float kp, float kv, TView out, int64_t n) {
   for (int r = 0; r < 6; ++r)
 #pragma unroll
     for (int c = 0; c < D; ++c) J[r][c] = SM(a[0], e, r, c);
-  T A[6][6], rda[6];
-  task_space_factor<T, D>(J, tile, a[1], e, A, rda);
+  T A[6][6], rda[6], L[D][D];
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) L[r][c] = (T)SM(a[1], e, r, c);
+  task_space_factor<T, D>(J, L, A, rda);
   T w[6];
 #pragma unroll
   for (int r = 0; r < 6; ++r) w[r] = (T)__fmul_rn(kp, SM(a[3], e, 0, r));
@@ -774,6 +849,19 @@ static int set_smem(K kernel, int bytes) {
   return 0;
 }
 
+// Grid of a persistent tile kernel: every CTA slot of the device (occupancy x SM count), or one CTA per tile when
+// there are fewer tiles than slots.
+template <typename K>
+static int persistent_grid(K kernel, int smem, int ntiles, int* grid) {
+  int dev = 0, sms = 0, occ = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTileEnvs, smem));
+  const int slots = sms * (occ > 0 ? occ : 1);
+  *grid = ntiles < slots ? ntiles : slots;
+  return 0;
+}
+
 }  // namespace b200ctl
 
 using namespace b200ctl;
@@ -845,14 +933,17 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
   const SegSpec spec[5] = {{&j, 6, 7}, {&m, 7, 7}, {&q, 1, 7}, {&qd, 1, 7}, {&dp, 1, 6}};
   const StagePlan P = make_plan(spec, 5, 6, n);
   const int smem = P.smem_floats * 4;
+  int grid = 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (precision == 0) {
     B200_TRY(set_smem(osc_kernel<double>, smem));
-    launch_pdl(osc_kernel<double>, tiles(n), kTileEnvs, smem, s, P, hv, hi, has_index, qdef, (float)kp, (float)kd,
+    B200_TRY(persistent_grid(osc_kernel<double>, smem, tiles(n), &grid));
+    launch_pdl(osc_kernel<double>, grid, kTileEnvs, smem, s, P, hv, hi, has_index, qdef, (float)kp, (float)kd,
                (float)kp_null, (float)kd_null, o, n, stats);
   } else {
     B200_TRY(set_smem(osc_kernel<float>, smem));
-    launch_pdl(osc_kernel<float>, tiles(n), kTileEnvs, smem, s, P, hv, hi, has_index, qdef, (float)kp, (float)kd,
+    B200_TRY(persistent_grid(osc_kernel<float>, smem, tiles(n), &grid));
+    launch_pdl(osc_kernel<float>, grid, kTileEnvs, smem, s, P, hv, hi, has_index, qdef, (float)kp, (float)kd,
                (float)kp_null, (float)kd_null, o, n, stats);
   }
   return post_launch("osc_kernel");
