@@ -81,6 +81,42 @@ def test_franka_c3_size_vs_oracle():
     assert st.cpu()[0] == n and st.cpu()[4] == 0
 
 
+def test_osc_persistent_many_tiles_per_cta():
+    """More tiles than CTA slots (148 SMs x 4 resident CTAs x 64 envs = 37,888): every persistent CTA of
+    ``osc_kernel`` refills its tile buffer at least twice, the last tile is ragged.  Same gate as C3, both chains,
+    plus: the result must not depend on how tiles were spread over CTAs (bit-identical to slices run alone)."""
+    n = 148 * 4 * 64 * 2 + 64 * 37 + 29
+    fi = syn.franka_inputs(n, seed=7)
+    d = _bind(fi)
+    ctl.bind_hand(d.rb_states, d.hand_idxs)
+    f = lambda t: t.double()
+    ref = ofr.control_osc(f(fi.dpose), f(fi.j_eef), f(fi.mm), f(fi.dof_pos), f(fi.dof_vel), f(fi.hand_vel),
+                          f(fi.default_dof_pos), KP, KD, KP_NULL, KD_NULL)
+    cond = ofr.conditioning(fi.j_eef, fi.mm).numpy()
+    outs = {}
+    for prec, tol in ((0, 1e-4), (1, 2e-2)):
+        ctl.bind(precision=prec)
+        st = _lib.stats_buffer(torch.device(DEV))
+        osc = ctl.control_osc(d.dpose, stats=st)
+        outs[prec] = osc
+        r = _rel(osc.cpu(), ref)
+        print(f"precision {prec}: rel err median {np.median(r):.2e} gated max {r[cond <= 1e4].max():.2e}")
+        assert r[cond <= 1e4].max() <= tol
+        st = st.cpu()
+        assert st[0] == n and st[4] == 0
+        assert abs(st[1].item() - osc.abs().double().sum().item()) <= 1e-9 * st[1].item()
+    # a 4,096-env slice starting at a tile boundary, run as its own launch (one tile per CTA), must match bit for bit
+    lo, m = 64 * 700, 4096
+    ctl.bind(j_eef=d.j_eef[lo:lo + m], mm=d.mm[lo:lo + m], dof_pos=d.dof_pos[lo:lo + m], dof_vel=d.dof_vel[lo:lo + m],
+             num_envs=m)
+    ctl.bind_hand(d.rb_states, d.hand_idxs[lo:lo + m])
+    for prec in (0, 1):
+        ctl.bind(precision=prec)
+        small = ctl.control_osc(d.dpose[lo:lo + m])
+        assert torch.equal(small, outs[prec][lo:lo + m])
+    ctl.bind(precision=0)
+
+
 def test_franka_gather_scatter_bit_exact():
     n = 1000
     fi = syn.franka_inputs(n, seed=4)
