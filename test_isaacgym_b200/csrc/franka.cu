@@ -6,8 +6,8 @@
 //     Lambda^-1 = J M^-1 J^T,   u0 = joint-space PD term (:74-76),
 //     u = J^T Lambda (kp dpose - kd v_hand) + (I - J^T Lambda J M^-1) M u0
 //       = J^T Lambda (w - J u0) + M u0
-// so one 7x7 Cholesky, six two-sided substitutions, one 6x6 Cholesky and ONE 6x6
-// solve replace them (M and Lambda^-1 are SPD for a physical arm).
+// so one 7x7 Cholesky with its triangular inverse X (Lambda^-1 = (X J^T)^T (X J^T)), one
+// 6x6 Cholesky and ONE 6x6 solve replace them (M and Lambda^-1 are SPD for a physical arm).
 //
 // Precision.  Data is fp32 in and out.  precision 0 (default) runs the
 // factorisation chain in fp64: with cond(Lambda^-1) up to 1e4 an fp32 chain -- the
@@ -19,7 +19,10 @@
 // (J, M, q, qd, dpose, hand velocity) is staged into shared memory first:
 //   * bulk path (TMA, cp.async.bulk + mbarrier): operands whose tile is a dense block
 //     of memory (mass matrix, dof state, dpose) arrive as ONE bulk copy per tile; the
-//     jacobian slot (216 B out of every 2,160 B) as one bulk copy per env.  Bulk copies
+//     jacobian slot (216 B out of every 2,160 B) as ONE 2-D tensor-map copy per tile
+//     (cp.async.bulk.tensor.2d: a 64-env x 60-float box of an (N, slot) tensor whose row
+//     pitch is the env stride; rows past N are zero-filled by the TMA unit), or, where
+//     no tensor map can be encoded, as one 1-D bulk copy per env.  Bulk copies
 //     need 16-byte alignment, so each copy starts at the aligned address below the
 //     operand and the kernel indexes past the lead-in; shared memory then holds the
 //     operand with its GLOBAL strides, which is why the compute phase addresses every
@@ -31,6 +34,8 @@
 // LDGSTS the staging alone cost ~30 us per 262,144 envs (profiles/r01_full_osc_v3.txt).
 // Roofline: HBM.  Algorithmic bytes per env: IK 248 B, OSC 496 B.
 #include "franka_task.cuh"
+
+#include <cuda.h>   // CUtensorMap + enums only: cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint
 
 namespace b200ctl {
 
@@ -127,7 +132,8 @@ struct StageSeg {
   const float* base;      // element (env 0, row 0, col 0) of the view
   int64_t s0, s1, s2;     // global strides in elements: env, row, col
   int rows, cols;
-  int mode;               // bulk plan: 0 = LDGSTS, 1 = one bulk copy per tile, 2 = one per env, 3 = alias (no copy)
+  int mode;               // bulk plan: 0 = LDGSTS, 1 = one bulk copy per tile, 3 = alias (no copy),
+                          //            4 = one 2-D tensor-map copy per tile (the kernel's CUtensorMap parameter)
   int region;             // bulk: destination offset in the tile buffer (floats, multiple of 4)
   unsigned bytes;         // bulk: bytes per copy (multiple of 16); mode 1 counts a full 64-env tile
   int delta;              // bulk: base address modulo 16 (bytes)
@@ -141,6 +147,8 @@ struct StagePlan {
   int canon_ts;           // canonical plan: dense row of every operand (+ extras), odd stride
   int bulk_ts;            // bulk plan: dense row of the LDGSTS operands (+ extras) only, odd stride
   int x_off_c, x_off_b;   // offset of the extras (gathered hand velocity) in either plan's row
+  int tmap_region;        // bulk plan: destination offset (floats) and bytes of the mode-4 tensor-map copy (0 = none)
+  unsigned tmap_bytes;
   int bulk_ok;            // 0: every tile uses the canonical LDGSTS plan
   int smem_floats;        // dynamic shared memory, in floats (max of both plans)
 };
@@ -171,6 +179,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// TMA 2-D tiled copy global -> shared through a tensor map (SASS: UTMALDG); coordinates are (element in row, row)
+__device__ __forceinline__ void tensor2d_g2s(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
 // Column-owner LDGSTS walk: thread t owns entries t, t+64, ... of the list of scalars (J[r][c], M[r][c], q[c] ...)
@@ -237,28 +251,26 @@ __device__ __forceinline__ void stage_begin(const StagePlan& P, uint64_t* bar) {
   }
 }
 template <int NSEG>
-__device__ __forceinline__ void stage_issue(const StagePlan& P, int t, int ntiles, int64_t n, float* tile, uint64_t* bar) {
+__device__ __forceinline__ void stage_issue(const StagePlan& P, const CUtensorMap* tmap, int t, int ntiles, int64_t n,
+                                            float* tile, uint64_t* bar) {
   const int64_t env0 = (int64_t)t * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
   const bool bulk = tile_is_bulk(P, t, ntiles);
   if (bulk) {
-    unsigned my_bytes = 0;
+    unsigned my_bytes = threadIdx.x == 0 ? P.tmap_bytes : 0u;
 #pragma unroll
     for (int i = 0; i < NSEG; ++i) {
       const StageSeg& s = P.seg[i];
       if (s.mode == 1 && threadIdx.x == 0) my_bytes += s.bytes;
-      if (s.mode == 2 && threadIdx.x < kTileEnvs) my_bytes += s.bytes;
     }
     mbar_arrive_expect_tx(bar, my_bytes);     // every thread arrives; the phase completes when all bytes landed
+    if (threadIdx.x == 0 && P.tmap_bytes) tensor2d_g2s(tile + P.tmap_region, tmap, 0, (int)env0, bar);
 #pragma unroll
     for (int i = 0; i < NSEG; ++i) {
       const StageSeg& s = P.seg[i];
       if (s.mode == 1 && threadIdx.x == 0) {
         const char* src = reinterpret_cast<const char*>(s.base + env0 * s.s0) - s.delta;
         bulk_g2s(tile + s.region, src, s.bytes, bar);
-      } else if (s.mode == 2 && threadIdx.x < kTileEnvs) {
-        const char* src = reinterpret_cast<const char*>(s.base + (env0 + threadIdx.x) * s.s0) - s.delta;
-        bulk_g2s(tile + s.region + threadIdx.x * s.b_es, src, s.bytes, bar);
       }
     }
   }
@@ -282,45 +294,54 @@ __device__ __forceinline__ void stage_wait(const StagePlan& P, int t, int ntiles
 
 // One-tile-per-CTA form: stage tile blockIdx.x and return when it is readable.
 template <int NSEG>
-__device__ __forceinline__ void stage_all(const StagePlan& P, int64_t env0, int nenv, float* tile, uint64_t* bar,
-                                          SAddr (&addr)[NSEG]) {
+__device__ __forceinline__ void stage_all(const StagePlan& P, const CUtensorMap* tmap, int64_t env0, int nenv, float* tile,
+                                          uint64_t* bar, SAddr (&addr)[NSEG]) {
   unsigned phase = 0;
   const int64_t n = env0 + nenv;      // only the last tile is ragged, so this clamps exactly like the true n
   stage_begin(P, bar);
-  stage_issue<NSEG>(P, blockIdx.x, gridDim.x, n, tile, bar);
+  stage_issue<NSEG>(P, tmap, blockIdx.x, gridDim.x, n, tile, bar);
   stage_wait<NSEG>(P, blockIdx.x, gridDim.x, bar, phase, addr);
 }
 
 #define SM(a, e, r, c) tile[(a).off + (e) * (a).es + (r) * (a).rs + (c) * (a).cs]
 
 // Lambda^-1 = J M^-1 J^T factored: on return A holds chol(Lambda^-1).  J is this thread's jacobian and L the lower
-// triangle of its mass matrix, both in registers (L is overwritten by chol(M)).
+// triangle of its mass matrix, both in registers (L is overwritten by the INVERSE of chol(M)).
+//   J M^-1 J^T = Y^T Y,  Y = X J^T,  X = chol(M)^-1  (lower triangular, formed in place: 56 FMAs for D = 7).
+// Row k of Y is X[k][0..k] . J[:, 0..k]: the rows are independent of each other (six forward substitutions would be
+// a 7-step serial chain with all of Y -- 84 registers at fp64 -- live at once), and each row is folded into
+// Lambda^-1 += y y^T as soon as it exists, so Y is never stored.  Peak live set 178 registers at fp64 instead of 208.
 template <typename T, int D>
 __device__ __forceinline__ void task_space_factor(const float (&J)[6][D], T (&L)[D][D], T (&A)[6][6], T (&rda)[6]) {
   T rdm[D];
   chol_inplace<T, D>(L, rdm);
-  // J M^-1 J^T = Y^T Y with Y = L^-1 J^T: six independent forward substitutions (no back substitution, no M^-1),
-  // written column-interleaved so the scheduler sees six dependency chains at once
-  T Y[6][D];
+  // X = L^-1 in place, column by column: X[j][j] = 1 / L[j][j], X[i][j] = -(sum_{k=j}^{i-1} L[i][k] X[k][j]) / L[i][i]
 #pragma unroll
-  for (int i = 0; i < D; ++i) {
+  for (int j = 0; j < D; ++j) {
+    L[j][j] = rdm[j];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      T s = (T)J[r][i];
+    for (int i = j + 1; i < D; ++i) {
+      T s = (T)0;
 #pragma unroll
-      for (int k = 0; k < i; ++k) s = fma_t<T>(-L[i][k], Y[r][k], s);
-      Y[r][i] = s * rdm[i];
+      for (int k = j; k < i; ++k) s = fma_t<T>(L[i][k], L[k][j], s);
+      L[i][j] = -s * rdm[i];
     }
   }
 #pragma unroll
-  for (int r = 0; r < 6; ++r)
+  for (int k = 0; k < D; ++k) {
+    T y[6];
 #pragma unroll
-    for (int c = 0; c <= r; ++c) {
+    for (int r = 0; r < 6; ++r) {
       T s = (T)0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) s = fma_t<T>(Y[r][k], Y[c][k], s);
-      A[r][c] = s;
+      for (int j = 0; j <= k; ++j) s = fma_t<T>(L[k][j], (T)J[r][j], s);
+      y[r] = s;
     }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) A[r][c] = (k == 0) ? y[r] * y[c] : fma_t<T>(y[r], y[c], A[r][c]);
+  }
   chol_inplace<T, 6>(A, rda);
 }
 
@@ -360,14 +381,14 @@ __device__ __forceinline__ void ik_compute(const float* tile, const SAddr& aJ, i
 // segments: 0 = J (6 x D), 1 = dpose (1 x 6), 2 = dof_pos (1 x D, optional)
 template <typename T, int D>
 __global__ void __launch_bounds__(kTileEnvs)
-ik_dls_kernel(StagePlan P, float lambda2, int has_pos, TView out, int64_t n) {
-  extern __shared__ __align__(16) float tile[];
+ik_dls_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float lambda2, int has_pos, TView out, int64_t n) {
+  extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
   SAddr a[3];
-  stage_all<3>(P, env0, nenv, tile, &bar, a);
+  stage_all<3>(P, &tmap, env0, nenv, tile, &bar, a);
   if (threadIdx.x >= nenv) return;
   const int e = threadIdx.x;
   const int64_t env = env0 + e;
@@ -464,10 +485,10 @@ template <typename T>
 // spill); splitting one env over two warps that share Lambda^-1 through shared memory (redundant Cholesky work +
 // a CTA barrier: -70 %).
 __global__ void __launch_bounds__(kTileEnvs)
-osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q_default,
+osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel, TView hand_index, int has_index, TView q_default,
            float kp, float kd, float kp_null, float kd_null, TView out, int64_t n, double* __restrict__ stats) {
   constexpr int D = 7;
-  extern __shared__ __align__(16) float tile[];
+  extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   pdl_prologue();
   // persistent CTA: tiles blockIdx.x, + gridDim.x, ...; the tile buffer is refilled while the previous tile's
@@ -479,13 +500,17 @@ osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q
     const bool bulk = tile_is_bulk(P, t, ntiles);
     stage_gather<6>(hand_vel, hand_index, has_index, env0, nenv, tile + (bulk ? P.x_off_b : P.x_off_c),
                     bulk ? P.bulk_ts : P.canon_ts);                            // dependent gather first
-    stage_issue<5>(P, t, ntiles, n, tile, &bar);
+    stage_issue<5>(P, &tmap, t, ntiles, n, tile, &bar);
   };
   unsigned phase = 0;
   stage_begin(P, &bar);
   int t = blockIdx.x;
   if (t < ntiles) issue(t);
-  double acc[4] = {0, 0, 0, 0};
+  // statistics live in shared memory between tiles: four fp64 accumulators are eight registers this kernel does not
+  // have (the fp64 chain sits at the 255-register limit)
+  __shared__ double s_acc[4][kTileEnvs];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s_acc[k][threadIdx.x] = 0.0;
   for (; t < ntiles; t += gridDim.x) {
     const int64_t env0 = (int64_t)t * kTileEnvs;
     const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
@@ -510,20 +535,26 @@ osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q
       osc_solve<T>(R, u);
       float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + (env0 + e) * out.s[0];
       bool finite = true;
+      double sum_abs = 0.0, sum_sq = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
         o[c * out.s[1]] = u[c];
         const bool f = isfinite(u[c]);
         finite = finite && f;
         const float v = f ? u[c] : 0.f;
-        acc[1] += fabsf(v);
-        acc[2] += (double)v * v;
+        sum_abs += fabsf(v);
+        sum_sq += (double)v * v;
       }
-      acc[0] += 1.0;
-      acc[3] += finite ? 0.0 : 1.0;
+      s_acc[0][e] += 1.0;
+      s_acc[1][e] += sum_abs;
+      s_acc[2][e] += sum_sq;
+      s_acc[3][e] += finite ? 0.0 : 1.0;
     }
   }
   if (stats) {
+    double acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = s_acc[k][threadIdx.x];
     const int slot[4] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_NONFINITE};
     block_stats_commit<4>(acc, stats, slot);
   }
@@ -536,11 +567,11 @@ osc_kernel(StagePlan P, TView hand_vel, TView hand_index, int has_index, TView q
 // 4 = init_pos (1x3), 5 = init_rot (1x4); extras: box row (7) + hand row (13: pose and velocity) gathered by index.
 template <typename T>
 __global__ void __launch_bounds__(kTileEnvs)
-pick_osc_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_t* __restrict__ hand_restart,
+pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, TView box_index, TView hand_index, uint8_t* __restrict__ hand_restart,
                 int64_t hr_stride, TaskConst tk, TView q_default, float kp, float kd, float kp_null, float kd_null,
                 TView dpose_out, int has_dpose, TView grip, TView out, int64_t n, double* __restrict__ stats) {
   constexpr int D = 7;
-  extern __shared__ __align__(16) float tile[];
+  extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
@@ -551,7 +582,7 @@ pick_osc_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_
   stage_gather<7>(rb, box_index, 1, env0, nenv, x0, x_ts);            // box pos + quat          (:348-349)
   stage_gather<13>(rb, hand_index, 1, env0, nenv, x0 + 7, x_ts);      // hand pos + quat + vel   (:351-353)
   SAddr a[6];
-  stage_all<6>(P, env0, nenv, tile, &bar, a);
+  stage_all<6>(P, &tmap, env0, nenv, tile, &bar, a);
 
   double acc[4] = {0, 0, 0, 0};
   if (threadIdx.x < nenv) {
@@ -609,10 +640,10 @@ pick_osc_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_
 // segments: 0 = J (6x7), 1 = dof_pos (1x9), 2 = init_pos (1x3), 3 = init_rot (1x4); extras: box row (7) + hand row (7).
 template <typename T>
 __global__ void __launch_bounds__(kTileEnvs)
-pick_ik_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_t* __restrict__ hand_restart,
+pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, TView box_index, TView hand_index, uint8_t* __restrict__ hand_restart,
                int64_t hr_stride, TaskConst tk, float lambda2, TView dpose_out, int has_dpose, TView grip, TView out, int64_t n) {
   constexpr int D = 7;
-  extern __shared__ __align__(16) float tile[];
+  extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
@@ -623,7 +654,7 @@ pick_ik_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_t
   stage_gather<7>(rb, box_index, 1, env0, nenv, x0, x_ts);
   stage_gather<7>(rb, hand_index, 1, env0, nenv, x0 + 7, x_ts);
   SAddr a[4];
-  stage_all<4>(P, env0, nenv, tile, &bar, a);
+  stage_all<4>(P, &tmap, env0, nenv, tile, &bar, a);
   if (threadIdx.x >= nenv) return;
   const int e = threadIdx.x;
   const int64_t env = env0 + e;
@@ -658,14 +689,14 @@ pick_ik_kernel(StagePlan P, TView rb, TView box_index, TView hand_index, uint8_t
 // segments: 0 = J (6xD), 1 = M (DxD), 2 = dof_vel (1xD), 3 = dpose (1x6)
 template <typename T, int D>
 __global__ void __launch_bounds__(kTileEnvs)
-osc_full_kernel(StagePlan P, float kp, float kv, TView out, int64_t n) {
-  extern __shared__ __align__(16) float tile[];
+osc_full_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float kp, float kv, TView out, int64_t n) {
+  extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
   SAddr a[4];
-  stage_all<4>(P, env0, nenv, tile, &bar, a);
+  stage_all<4>(P, &tmap, env0, nenv, tile, &bar, a);
   if (threadIdx.x >= nenv) return;
   const int e = threadIdx.x;
   const int64_t env = env0 + e;
@@ -737,12 +768,54 @@ static int check_precision(int precision) {
   return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (getenv("B200CTL_NO_TENSORMAP")) return (EncodeTiledFn) nullptr;      // A/B switch for profiles/
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// Tensor map of a sparse per-env slot: rows = envs at pitch `env_stride` floats, `valid` floats per row starting at
+// the 16-byte aligned address `base`; box = kTileEnvs rows x (4 * odd) floats so per-thread row reads stay 4-way
+// bank-conflicted at worst (as in the per-env plan).  Fills seg->b_es / seg->bytes.  Returns false if unavailable.
+static bool encode_slot_map(CUtensorMap* map, const void* base, int valid, int64_t env_stride, int64_t n, StageSeg* seg) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || n > 0x7fffffff || valid <= 0 || valid > 252) return false;
+  int box = (valid + 3) & ~3;
+  if (((box / 4) & 1) == 0) box += 4;
+  if (box > 256) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)valid, (cuuint64_t)n};
+  const cuuint64_t gstride[1] = {(cuuint64_t)env_stride * 4};
+  const cuuint32_t bdim[2] = {(cuuint32_t)box, (cuuint32_t)kTileEnvs};
+  const cuuint32_t estride[2] = {1, 1};
+  if (enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, bdim, estride,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  seg->b_es = box;
+  seg->bytes = (unsigned)(kTileEnvs * box * 4);
+  return true;
+}
+
 // Builds the staging plan for `nseg` operands.  (N, R, C) views use strides (s0, s1, s2); (N, C) vectors are
 // passed with rows = 1 and use (s0, -, s1).  `extras` floats per env are reserved in either plan's dense row
 // for operands staged outside the plan (the gathered hand velocity).
 struct SegSpec { const TView* v; int rows, cols; };
-static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n) {
+static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n, CUtensorMap* tmap) {
   StagePlan P{};
+  memset(tmap, 0, sizeof(*tmap));
+  bool tmap_used = false;
   P.nseg = nseg;
   int canon = 0;
   for (int i = 0; i < nseg; ++i) {
@@ -797,17 +870,19 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n)
       s.b_es = (int)s.s0; s.b_rs = (int)s.s1; s.b_cs = (int)s.s2;
       region += (int)(s.bytes / 4);
       any_bulk = true;
-    } else if ((s.s0 * 4) % 16 == 0 && window <= 128) {
-      // sparse slot of a wide row: one bulk copy per env, same lead-in for every env
-      s.mode = 2;
-      s.bytes = (unsigned)((s.delta + window * 4 + 15) & ~(int64_t)15);
-      int es = (int)(s.bytes / 4);
-      if (((es / 4) & 1) == 0) es += 4;           // stride = 4 * odd: 4-way instead of 8-way bank conflicts
+    } else if ((s.s0 * 4) % 16 == 0 && window <= 128 && !tmap_used &&
+               encode_slot_map(tmap, reinterpret_cast<const char*>(s.base) - s.delta, s.delta / 4 + (int)window, s.s0, n, &s)) {
+      // sparse slot of a wide row, as a 2-D tensor (element in slot, env) with the env stride as row pitch: ONE
+      // tensor-map copy per tile.  Elements past the window and rows past N are zero-filled, never read.
+      tmap_used = true;
+      s.mode = 4;
+      region = (region + 31) & ~31;               // TMA tensor destinations are 128-byte aligned
       s.region = region;
-      s.b_es = es;
       s.b_off = region + s.delta / 4;
-      s.b_rs = (int)s.s1; s.b_cs = (int)s.s2;
-      region += kTileEnvs * es;
+      s.b_rs = (int)s.s1; s.b_cs = (int)s.s2;     // b_es / bytes set by encode_slot_map (box row = 4 * odd floats)
+      region += kTileEnvs * s.b_es;
+      P.tmap_region = s.region;
+      P.tmap_bytes = s.bytes;
       any_bulk = true;
     }
   }
@@ -826,6 +901,7 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n)
     if (bulk_floats * 4 > 160 * 1024) {
       // an exotic layout whose dense blocks do not fit comfortably in shared memory: LDGSTS plan for every tile
       P.bulk_ok = 0;
+      P.tmap_bytes = 0;
       for (int i = 0; i < nseg; ++i) P.seg[i].mode = 0;
     } else if (bulk_floats > P.smem_floats) {
       P.smem_floats = bulk_floats;
@@ -883,7 +959,8 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
   DeviceGuard g;
   B200_TRY(g.enter(dev));
   const SegSpec spec[3] = {{&j, 6, (int)D}, {&dp, 1, 6}, {&q, 1, has_pos ? (int)D : 0}};
-  const StagePlan P = make_plan(spec, 3, 0, n);
+  CUtensorMap tmap;
+  const StagePlan P = make_plan(spec, 3, 0, n, &tmap);
   const int smem = P.smem_floats * 4;
   // lambda^2 is formed in fp32 like torch.eye(6) * damping**2 (:57)
   const float l2 = (float)(lambda * lambda);
@@ -891,7 +968,7 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
 #define LAUNCH_IK(T, DD)                                                          \
   do {                                                                            \
     B200_TRY(set_smem(ik_dls_kernel<T, DD>, smem));                               \
-    launch_pdl(ik_dls_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, l2, has_pos, o, n); \
+    launch_pdl(ik_dls_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, tmap, l2, has_pos, o, n); \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_IK(double, 7); else LAUNCH_IK(float, 7); }
   else        { if (precision == 0) LAUNCH_IK(double, 9); else LAUNCH_IK(float, 9); }
@@ -931,19 +1008,20 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
   DeviceGuard g;
   B200_TRY(g.enter(dev));
   const SegSpec spec[5] = {{&j, 6, 7}, {&m, 7, 7}, {&q, 1, 7}, {&qd, 1, 7}, {&dp, 1, 6}};
-  const StagePlan P = make_plan(spec, 5, 6, n);
+  CUtensorMap tmap;
+  const StagePlan P = make_plan(spec, 5, 6, n, &tmap);
   const int smem = P.smem_floats * 4;
   int grid = 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (precision == 0) {
     B200_TRY(set_smem(osc_kernel<double>, smem));
     B200_TRY(persistent_grid(osc_kernel<double>, smem, tiles(n), &grid));
-    launch_pdl(osc_kernel<double>, grid, kTileEnvs, smem, s, P, hv, hi, has_index, qdef, (float)kp, (float)kd,
+    launch_pdl(osc_kernel<double>, grid, kTileEnvs, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, (float)kd,
                (float)kp_null, (float)kd_null, o, n, stats);
   } else {
     B200_TRY(set_smem(osc_kernel<float>, smem));
     B200_TRY(persistent_grid(osc_kernel<float>, smem, tiles(n), &grid));
-    launch_pdl(osc_kernel<float>, grid, kTileEnvs, smem, s, P, hv, hi, has_index, qdef, (float)kp, (float)kd,
+    launch_pdl(osc_kernel<float>, grid, kTileEnvs, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, (float)kd,
                (float)kp_null, (float)kd_null, o, n, stats);
   }
   return post_launch("osc_kernel");
@@ -966,14 +1044,15 @@ extern "C" int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const
   DeviceGuard g;
   B200_TRY(g.enter(dev));
   const SegSpec spec[4] = {{&j, 6, (int)D}, {&m, (int)D, (int)D}, {&qd, 1, (int)D}, {&dp, 1, 6}};
-  const StagePlan P = make_plan(spec, 4, 0, n);
+  CUtensorMap tmap;
+  const StagePlan P = make_plan(spec, 4, 0, n, &tmap);
   const int smem = P.smem_floats * 4;
   cudaStream_t s = (cudaStream_t)stream;
   const float fkp = (float)kp, fkv = (float)kv;
 #define LAUNCH_FULL(T, DD)                                                       \
   do {                                                                           \
     B200_TRY(set_smem(osc_full_kernel<T, DD>, smem));                            \
-    launch_pdl(osc_full_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, fkp, fkv, o, n); \
+    launch_pdl(osc_full_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, tmap, fkp, fkv, o, n); \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_FULL(double, 7); else LAUNCH_FULL(float, 7); }
   else        { if (precision == 0) LAUNCH_FULL(double, 9); else LAUNCH_FULL(float, 9); }
@@ -1022,18 +1101,19 @@ extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm
   DeviceGuard g;
   B200_TRY(g.enter(dev));
   const SegSpec spec[6] = {{&j, 6, 7}, {&m, 7, 7}, {&q, 1, 9}, {&qd, 1, 7}, {&ip, 1, 3}, {&iq, 1, 4}};
-  const StagePlan P = make_plan(spec, 6, 20, n);
+  CUtensorMap tmap;
+  const StagePlan P = make_plan(spec, 6, 20, n, &tmap);
   const int smem = P.smem_floats * 4;
   const TaskConst tk = make_task_const(*task);
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
   if (precision == 0) {
     B200_TRY(set_smem(pick_osc_kernel<double>, smem));
-    launch_pdl(pick_osc_kernel<double>, tiles(n), kTileEnvs, smem, s, P, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
+    launch_pdl(pick_osc_kernel<double>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
                (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
   } else {
     B200_TRY(set_smem(pick_osc_kernel<float>, smem));
-    launch_pdl(pick_osc_kernel<float>, tiles(n), kTileEnvs, smem, s, P, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
+    launch_pdl(pick_osc_kernel<float>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
                (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
   }
   return post_launch("pick_osc_kernel");
@@ -1073,7 +1153,8 @@ extern "C" int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* dof
   DeviceGuard g;
   B200_TRY(g.enter(dev));
   const SegSpec spec[4] = {{&j, 6, 7}, {&q, 1, 9}, {&ip, 1, 3}, {&iq, 1, 4}};
-  const StagePlan P = make_plan(spec, 4, 14, n);
+  CUtensorMap tmap;
+  const StagePlan P = make_plan(spec, 4, 14, n, &tmap);
   const int smem = P.smem_floats * 4;
   const TaskConst tk = make_task_const(*task);
   const float l2 = (float)(lambda * lambda);
@@ -1081,10 +1162,10 @@ extern "C" int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* dof
   uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
   if (precision == 0) {
     B200_TRY(set_smem(pick_ik_kernel<double>, smem));
-    launch_pdl(pick_ik_kernel<double>, tiles(n), kTileEnvs, smem, s, P, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+    launch_pdl(pick_ik_kernel<double>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
   } else {
     B200_TRY(set_smem(pick_ik_kernel<float>, smem));
-    launch_pdl(pick_ik_kernel<float>, tiles(n), kTileEnvs, smem, s, P, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+    launch_pdl(pick_ik_kernel<float>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
   }
   return post_launch("pick_ik_kernel");
 }
