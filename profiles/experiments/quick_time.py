@@ -1,0 +1,67 @@
+#!/usr/bin/env python3
+"""Quick A/B timing of one kernel family (CUDA-graph replays of bound calls, rotating buffers > L2).
+
+    python profiles/experiments/quick_time.py servo|osc|ik|pd [--sizes 65536,1048576]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import bench  # noqa: E402
+from test_isaacgym_b200 import synthetic as syn  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("family")
+    ap.add_argument("--sizes", default="")
+    ap.add_argument("--reps", type=int, default=20)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    if a.family == "servo":
+        from test_isaacgym_b200.servo_step import ServoStep, PRECISION_FAST
+        for n in [int(x) for x in (a.sizes or "65536,1048576").split(",")]:
+            sets = max(3, (300 << 20) // (n * 104))
+            base = syn.servo_root_state(n, seed=2).to(dev)
+            bufs = [base.clone() for _ in range(min(sets, 24))]
+            for tag, prec in (("ref", 0), ("fast", PRECISION_FAST)):
+                step = ServoStep(1600, 900, precision=prec)
+                ts = [bench.graph_time([step.bind(b) for b in bufs], dev, a.reps) * 1e3 for _ in range(3)]
+                print(f"servo_{tag} n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
+    elif a.family in ("osc", "ik"):
+        import test_isaacgym_b200.franka_cube_ik_osc as ctl
+        for n in [int(x) for x in (a.sizes or "16384,262144").split(",")]:
+            sets = 4 if n <= 32768 else 2
+            fi = syn.franka_inputs(n, seed=3)
+            for prec, ptag in ((0, "fp64"), (1, "fp32")):
+                calls, keep = [], []
+                for _ in range(sets):
+                    d = fi.__class__(**{k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+                    o = torch.zeros(n, 9, device=dev)
+                    ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=d.dof_pos, dof_vel=d.dof_vel,
+                             default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=prec)
+                    ctl.bind_hand(d.rb_states, d.hand_idxs)
+                    calls.append(ctl.bind_control_osc(d.dpose, o[:, :7]) if a.family == "osc"
+                                 else ctl.bind_control_ik(d.dpose, o[:, :7], dof_pos=d.dof_pos))
+                    keep.append((d, o))
+                ts = [bench.graph_time(calls, dev, a.reps) * 1e3 for _ in range(3)]
+                print(f"{a.family}_{ptag} n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
+    elif a.family == "pd":
+        from test_isaacgym_b200.pd_control import PDController
+        for n in [int(x) for x in (a.sizes or "65536,1048576").split(",")]:
+            sets = max(3, min(24, (400 << 20) // (n * 192)))
+            pi = syn.pd_inputs(n, 12, seed=1)
+            c = PDController(12, pi.kp, pi.kd, tau_max=pi.tau_max, device=dev)
+            st = [pi.dof_state.to(dev).clone() for _ in range(sets)]
+            tg = [pi.q_target.to(dev).clone() for _ in range(sets)]
+            ou = [torch.empty(n, 12, device=dev) for _ in range(sets)]
+            ts = [bench.graph_time([c.bind(st[k], tg[k], ou[k]) for k in range(sets)], dev, a.reps) * 1e3 for _ in range(3)]
+            print(f"pd n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
+
+
+if __name__ == "__main__":
+    main()

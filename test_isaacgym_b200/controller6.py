@@ -145,6 +145,11 @@ class CameraController:
         self._fy = self._fx
         self.camera_matrix = np.asarray([[self._fx, 0., self._u0], [0., self._fy, self._v0], [0., 0., 1.]])
 
+    def get_rot_uav2world(self):
+        """Identity: the reference hard-codes roll = pitch = yaw = 0 (``controller6.py:188-197``), which is why
+        ``world2pixel`` uses ``car - uav`` unrotated (:221)."""
+        return np.identity(3)
+
     def world2pixel(self):
         """-> (N,3) float64 ``[u, v, 1]`` (numpy for host inputs, CUDA tensor for CUDA inputs)."""
         host = _lib.is_host(self.uav_location)

@@ -31,19 +31,35 @@ struct ServoConst {
 template <int PREC>
 __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64_t num_envs, const ServoConst& k,
                                                 double* __restrict__ aux, double* __restrict__ stats, int vec_ok) {
-  __shared__ __align__(16) float tile[kTile * kEnvRow];
+  __shared__ __align__(128) float tile[kTile * kEnvRow];
+  __shared__ __align__(8) uint64_t bar;
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTile;
   const int nenv = (int)((num_envs - env0) < kTile ? (num_envs - env0) : kTile);
   const int nfl = nenv * kEnvRow;
   float* gbase = state + env0 * kEnvRow;
 
-  // ---- stage the tile: 128-bit coalesced loads (tile base is 16-byte aligned: 64*104 B)
-  const int nv4 = vec_ok ? (nfl >> 2) : 0;
-  for (int i = threadIdx.x; i < nv4; i += kTile)
-    reinterpret_cast<float4*>(tile)[i] = __ldg(reinterpret_cast<const float4*>(gbase) + i);
-  for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += kTile) tile[i] = __ldg(gbase + i);
-  __syncthreads();
+  // ---- stage the tile.  A full tile of a 16-byte aligned state tensor is one dense 6,656-byte block: ONE TMA bulk
+  // copy brings it in and ONE bulk copy writes it back (the tile base stays 16-byte aligned: 64 * 104 B), so the
+  // staging / write-back loops -- 25-31 % of all executed instructions in profiles/r01_linemix_servo_*_v5.txt --
+  // disappear from the instruction stream.  The ragged last tile and unaligned tensors take the loops.
+  const bool bulk = vec_ok && nenv == kTile;
+  constexpr unsigned kTileBytes = kTile * kEnvRow * sizeof(float);
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      mbar_arrive_expect_tx(&bar, kTileBytes);
+      bulk_g2s(tile, gbase, kTileBytes, &bar);
+    }
+    __syncthreads();              // the initialised barrier is visible to every waiter
+    mbar_wait(&bar, 0);
+  } else {
+    const int nv4 = vec_ok ? (nfl >> 2) : 0;
+    for (int i = threadIdx.x; i < nv4; i += kTile)
+      reinterpret_cast<float4*>(tile)[i] = __ldg(reinterpret_cast<const float4*>(gbase) + i);
+    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += kTile) tile[i] = __ldg(gbase + i);
+    __syncthreads();
+  }
 
   double acc[5] = {0, 0, 0, 0, 0};
   if (threadIdx.x < nenv) {
@@ -135,16 +151,24 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
     acc[3] = behind ? 1.0 : 0.0;
     acc[4] = finite ? 0.0 : 1.0;
   }
-  __syncthreads();
-
-  // ---- write the staged rows back whole, 128 bits at a time.  Only columns 3..9 of each actor row changed
-  // (test10:451-454); the other columns are rewritten with the bits that were read, so the tensor handed to
-  // set_actor_root_state_tensor is bit-identical to the reference's.  A column-predicated 4-byte write-back was
-  // 21 % of all executed instructions (profiles/r01_linemix_servo_ref_v5.txt) and leaves partial sectors for L2 to
-  // merge; whole 104-byte rows are full-sector writes.
-  for (int i = threadIdx.x; i < nv4; i += kTile)
-    reinterpret_cast<float4*>(gbase)[i] = reinterpret_cast<const float4*>(tile)[i];
-  for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += kTile) gbase[i] = tile[i];
+  // ---- write the staged rows back whole.  Only columns 3..9 of each actor row changed (test10:451-454); the other
+  // columns are rewritten with the bits that were read, so the tensor handed to set_actor_root_state_tensor is
+  // bit-identical to the reference's.  (A column-predicated 4-byte write-back was 21 % of all executed instructions
+  // and leaves partial sectors for L2 to merge; whole 104-byte rows are full-sector writes.)
+  if (bulk) {
+    fence_proxy_async_smem();     // this thread's row updates -> visible to the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_s2g(gbase, tile, kTileBytes);
+      bulk_commit_wait_read();    // the tile must stay allocated until the TMA unit has read it
+    }
+  } else {
+    __syncthreads();
+    const int nv4 = vec_ok ? (nfl >> 2) : 0;
+    for (int i = threadIdx.x; i < nv4; i += kTile)
+      reinterpret_cast<float4*>(gbase)[i] = reinterpret_cast<const float4*>(tile)[i];
+    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += kTile) gbase[i] = tile[i];
+  }
   if (stats) {
     const int slot[5] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_SAT,
                          B200CTL_STAT_N_NONFINITE};

@@ -45,6 +45,18 @@ def getSimCameraMatrix(width, height, widthMeter, focalDis):
     return np.array([[fxy, 0, width / 2 + 0.5], [0, fxy, height / 2 + 0.5], [0, 0, 1]])
 
 
+def convertPixelToPhy(aRoi, aCameraMatrix):
+    """ROI centre -> unit bearing (fwd, right, down), numpy (3,) (``servo_controller.py:49-61``);
+    evaluated by ``b200ctl_pixel2phy`` with N = 1."""
+    pixel = np.array([[aRoi.x + aRoi.width / 2, aRoi.y + aRoi.height / 2]], dtype=np.float64)
+    return np.asarray(SecondaryControl(1, 1, 1).pixel2phy(pixel, np.asarray(aCameraMatrix, dtype=np.float64))).reshape(3)
+
+
+def convertPhyToPixel(aUnitVector, aCameraMatrix):
+    """Bearing -> ``[u, v, 0, 0]`` (``servo_controller.py:64-72``)."""
+    return SecondaryControl(1, 1, 1).phy2pixel(aUnitVector, aCameraMatrix)
+
+
 def getRotMatrix(aCamAngleRad):
     """Rz(yaw) @ Rx(roll) @ Ry(pitch) (``servo_controller.py:75-86``)."""
     return _rz(aCamAngleRad[2]) @ _rx(aCamAngleRad[0]) @ _ry(aCamAngleRad[1])

@@ -229,3 +229,29 @@ def test_legacy_scalar_helpers():
     ref = osv.cclvf_scalar(cur, tgt, 50, 30)
     got = cclvf(cur, tgt, 50, 30)
     assert abs(got[0] - ref[0]) < 1e-12 and abs(got[1] - ref[1]) < 1e-12
+
+
+def test_scalar_class_and_roi_helpers(servo_kat):
+    """common/secondary_control.py (scalar class, Rect ROI) and servo_controller.py's convert helpers."""
+    from test_isaacgym_b200.secondary_control import SecondaryControl as ScalarControl, Rect as ScRect
+    from test_isaacgym_b200.servo_controller import convertPixelToPhy, convertPhyToPixel, Rect
+    from test_isaacgym_b200.controller6 import CameraController
+    from scipy.spatial.transform import Rotation as R
+    sc = ScalarControl(W, H)
+    cam = R.from_euler("xyz", [-10, 90, 45], degrees=True).as_matrix()      # secondary_control.py:196
+    out = sc.servo_ext_pixel(servo_kat["K"], cam, 25, 46)
+    assert out.shape == (3,) and np.abs(out - servo_kat["class_out"]).max() < 1e-9
+    K = servo_kat["K"]
+    for roi in (Rect(825, 496, 0, 0), Rect(10, 20, 30, 40)):
+        px = np.array([roi.x + roi.width / 2, roi.y + roi.height / 2, 1.0])
+        a = np.linalg.inv(K) @ px
+        want = np.array([a[2], a[0], a[1]]) / np.linalg.norm(a)            # servo_controller.py:49-61
+        got = convertPixelToPhy(roi, K)
+        assert got.shape == (3,) and np.abs(got - want).max() < 1e-15
+        assert np.abs(sc.pixel2phy(ScRect(roi.x, roi.y, roi.width, roi.height), K) - want).max() < 1e-15
+        back = convertPhyToPixel(got, K)
+        assert abs(back[0] - px[0]) < 1e-9 and abs(back[1] - px[1]) < 1e-9 and back[2:] == [0, 0]
+
+    class Props:
+        width, height = W, H
+    assert np.array_equal(CameraController(Props, 4).get_rot_uav2world(), np.identity(3))
