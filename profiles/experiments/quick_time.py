@@ -19,7 +19,12 @@ def main():
     ap.add_argument("family")
     ap.add_argument("--sizes", default="")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--lib", default="", help="time an A/B variant built by build_variant.sh instead of the in-tree library")
     a = ap.parse_args()
+    if a.lib:
+        from test_isaacgym_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(a.lib)
+        print("library:", _lib.LIB_PATH, flush=True)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     if a.family == "servo":

@@ -43,6 +43,9 @@ constexpr float kPiF = 3.14159265358979323846f;
 constexpr float kTwoPiF = 6.28318530717958647692f;
 constexpr int kTileEnvs = 64;
 constexpr int kMaxSeg = 6;
+#ifndef B200_OSC_F64_MAXREG
+#define B200_OSC_F64_MAXREG 255   // register cap of the fp64-chain OSC kernel (A/B knob, profiles/): 200 = 5 tiles per SM
+#endif
 
 template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
@@ -463,7 +466,7 @@ template <typename T>
 // Tried and measured slower: register caps for 5 tiles/SM (168 regs: -13 %, 200 regs: -6 %, both
 // spill); splitting one env over two warps that share Lambda^-1 through shared memory (redundant Cholesky work +
 // a CTA barrier: -70 %).
-__global__ void __launch_bounds__(kTileEnvs)
+__global__ void __launch_bounds__(kTileEnvs) __maxnreg__(sizeof(T) == 8 ? B200_OSC_F64_MAXREG : 255)
 osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel, TView hand_index, int has_index, TView q_default,
            float kp, float kd, float kp_null, float kd_null, TView out, int64_t n, double* __restrict__ stats) {
   constexpr int D = 7;

@@ -370,7 +370,12 @@ extern "C" int b200ctl_pd_torque_host(const float* dof_state, const float* q_tar
 
   const int D = num_dofs;
   // chunk: ~8 MB of state per slot keeps the copy engines busy while bounding the first-chunk latency
-  int64_t chunk_envs = (int64_t)(1 << 20) / D;
+  static const int64_t chunk_elems = [] {          // A/B knob for profiles/: elements (env x dof) per pipeline slot
+    const char* e = getenv("B200CTL_HOST_CHUNK_ELEMS");
+    const long long v = e ? atoll(e) : 0;
+    return (int64_t)(v >= 1024 ? v : (1 << 20));
+  }();
+  int64_t chunk_envs = chunk_elems / D;
   if (chunk_envs < 1) chunk_envs = 1;
   if (D % 4 == 0 && chunk_envs >= 4) chunk_envs &= ~(int64_t)3;
   if (chunk_envs > num_envs) chunk_envs = num_envs;
