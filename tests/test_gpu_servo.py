@@ -212,6 +212,31 @@ def test_fused_step_errors():
     ServoStep(W, H)(torch.zeros(0, 2, 13, device=DEV))
 
 
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 128, 200])
+@pytest.mark.parametrize("precision", [0, PRECISION_FAST])
+def test_fused_step_tma_tiles_equal_loop_tiles(n, precision):
+    """Full 64-env tiles go through TMA bulk copies (in and out), the ragged last tile and tensors whose base is not
+    16-byte aligned through copy loops: same bits either way, and nothing outside the tensor is touched."""
+    state = syn.servo_root_state(n, seed=11)
+    step = ServoStep(W, H, precision=precision)
+    aligned = state.to(DEV)
+    step(aligned)
+    guard = 7.25
+    pad = torch.full((n * 26 + 5,), guard, device=DEV)
+    shifted = pad[1:1 + n * 26].view(n, 2, 13)            # base pointer 4 bytes past a 16-byte boundary
+    shifted.copy_(state.to(DEV))
+    step(shifted)
+    assert torch.equal(aligned, shifted)
+    assert pad[0].item() == guard and bool((pad[1 + n * 26:] == guard).all())
+    # tensor followed by a guard region: the bulk write-back of the last full tile ends exactly at the tile
+    buf = torch.full(((n + 4) * 26,), guard, device=DEV)
+    view = buf[:n * 26].view(n, 2, 13)
+    view.copy_(state.to(DEV))
+    step(view)
+    assert torch.equal(view, aligned) and bool((buf[n * 26:] == guard).all())
+    assert torch.equal(aligned.cpu()[:, :, :3], state[:, :, :3]) and torch.equal(aligned.cpu()[:, :, 10:], state[:, :, 10:])
+
+
 def test_legacy_scalar_helpers():
     """scalar / legacy helpers of controller6.py routed through the kernels with N = 1."""
     from scipy.spatial.transform import Rotation as R
