@@ -20,6 +20,7 @@ constexpr int kTile = 64;           // envs per CTA
 
 struct ServoConst {
   double width, height, fx, fy, u0, v0;
+  double kinv00, kinv02, kinv11, kinv12;   // inv(K) entries 1/fx, -u0/fx, 1/fy, -v0/fy, formed on the host
   float car_speed, car_rd, car_rd2, car_rd4, car_tx, car_ty, car_tz;
   float uav_speed, uav_rd, uav_rd2, uav_rd4, uav_height;
 };
@@ -81,13 +82,13 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
     bool behind;
     if (PREC == 0) {
       // torch.atan2 on fp32 (:407): correctly rounded fp32 result via fp64
-      const float car_yaw = (float)atan2((double)cvy, (double)cvx);
+      const float car_yaw = (float)atan2_f32grade((double)cvy, (double)cvx);
       double s, c;
-      sincos((double)car_yaw * 0.5, &s, &c);     // scipy from_euler('xyz', [0,0,yaw]) in fp64 (:410)
+      sincos_halfpi((double)car_yaw * 0.5, &s, &c);     // scipy from_euler('xyz', [0,0,yaw]) in fp64 (:410)
       cq[0] = 0.f; cq[1] = 0.f; cq[2] = (float)s; cq[3] = (float)c;
 
       double R[9];
-      quat_to_mat<double>(qx, qy, qz, qw, R);    // :423
+      quat_to_mat<double, FnStep64>(qx, qy, qz, qw, R);    // :423
       // the difference car - uav is formed in the state dtype (fp32) before promotion (controller6.py:172-173,221)
       const double dx = (double)__fsub_rn(cx, ux), dy = (double)__fsub_rn(cy, uy), dz = (double)__fsub_rn(cz, uz);
       const double bx = R[0] * dx + R[3] * dy + R[6] * dz;   // inv(R) = R^T for the normalised quaternion
@@ -96,18 +97,18 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       project_body<double>(bx, by, bz, k.fx, k.fy, k.u0, k.v0, pu, pv, behind);   // :226-246
       const double hw = k.width * 0.5, hh = k.height * 0.5;
       const double mvx = hw - pu, mvy = hh - pv;             // order_pixel_move, test10:432
-      const double Kinv[9] = {1.0 / k.fx, 0.0, -k.u0 / k.fx, 0.0, 1.0 / k.fy, -k.v0 / k.fy, 0.0, 0.0, 1.0};
+      const double Kinv[9] = {k.kinv00, 0.0, k.kinv02, 0.0, k.kinv11, k.kinv12, 0.0, 0.0, 1.0};
       double mx, my, mz;
-      pixel_bearing<double>(Kinv, mvx + hw, mvy + hh, mx, my, mz);   // secondary_control_vecenv.py:101,107
+      pixel_bearing<double, FnStep64>(Kinv, mvx + hw, mvy + hh, mx, my, mz);   // secondary_control_vecenv.py:101,107
       // (the centre bearing of :102-103,108 is (1,0,0) for this K: asin(t_z) = 0)
       double q[4], ang[3];
-      servo_quat_from_bearing<double>(mx, my, mz, R, q, aux ? ang : nullptr);   // :113-181 + test10:440-447
+      servo_quat_from_bearing<double, FnStep64>(mx, my, mz, R, q, aux ? ang : nullptr);   // :113-181 + test10:440-447
       oq[0] = (float)q[0]; oq[1] = (float)q[1]; oq[2] = (float)q[2]; oq[3] = (float)q[3];   // fp64 -> fp32 (:451)
       if (aux) {
         constexpr double kPi = 3.141592653589793238462643383279502884;
         rolld = ang[0] * 180.0 / kPi; pitchd = ang[1] * 180.0 / kPi; yawd = ang[2] * 180.0 / kPi;   // :196
       }
-      acc[1] = sqrt(mvx * mvx + mvy * mvy);
+      if (stats) acc[1] = sqrt(mvx * mvx + mvy * mvy);
     } else {
       const float car_yaw = atan2f(cvy, cvx);
       float s, c;
@@ -131,7 +132,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       oq[0] = q[0]; oq[1] = q[1]; oq[2] = q[2]; oq[3] = q[3];
       if (aux) { rolld = ang[0] * 57.29577951308232f; pitchd = ang[1] * 57.29577951308232f; yawd = ang[2] * 57.29577951308232f; }
       const float ex = (float)(k.width * 0.5) - fu, ey = (float)(k.height * 0.5) - fv;
-      acc[1] = sqrtf(ex * ex + ey * ey);
+      if (stats) acc[1] = sqrtf(ex * ex + ey * ey);
     }
 
     // ---- scatter into the staged rows (test10:451-454)
@@ -144,12 +145,14 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       double* a = aux + (env0 + threadIdx.x) * 5;
       a[0] = pu; a[1] = pv; a[2] = rolld; a[3] = pitchd; a[4] = yawd;
     }
-    const bool finite = isfinite(oq[0]) && isfinite(oq[1]) && isfinite(oq[2]) && isfinite(oq[3]);
-    acc[0] = 1.0;
-    if (!isfinite(acc[1])) acc[1] = 0.0;
-    acc[2] = acc[1] * acc[1];
-    acc[3] = behind ? 1.0 : 0.0;
-    acc[4] = finite ? 0.0 : 1.0;
+    if (stats) {
+      const bool finite = isfinite(oq[0]) && isfinite(oq[1]) && isfinite(oq[2]) && isfinite(oq[3]);
+      acc[0] = 1.0;
+      if (!isfinite(acc[1])) acc[1] = 0.0;
+      acc[2] = acc[1] * acc[1];
+      acc[3] = behind ? 1.0 : 0.0;
+      acc[4] = finite ? 0.0 : 1.0;
+    }
   }
   // ---- write the staged rows back whole.  Only columns 3..9 of each actor row changed (test10:451-454); the other
   // columns are rewritten with the bits that were read, so the tensor handed to set_actor_root_state_tensor is
@@ -494,6 +497,7 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
   k.fx = alpha * (params->zoom * 18) * 0.001;
   k.fy = k.fx;
   k.u0 = params->width / 2; k.v0 = params->height / 2;
+  k.kinv00 = 1.0 / k.fx; k.kinv02 = -k.u0 / k.fx; k.kinv11 = 1.0 / k.fy; k.kinv12 = -k.v0 / k.fy;
   auto f = [](double x) { return (float)x; };
   k.car_speed = f(params->car_speed); k.car_rd = f(params->car_radius);
   k.car_rd2 = f(params->car_radius * params->car_radius);

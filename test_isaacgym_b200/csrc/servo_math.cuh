@@ -59,6 +59,72 @@ template <> struct Fn<float> {
   static __device__ __forceinline__ void sincos(float a, float* s, float* c) { ::sincosf(a, s, c); }
 };
 
+// ---- reduced-cost fp64 functions of the fused reference-precision step -----------------------------------------
+// The fused step rounds everything it stores to fp32 (test10_servo_vecenv.py:451-454), so its fp64 stages need
+// ~1e-13, not libdevice's last ulp; libdevice's rsqrt / atan2 / sincos were 13.7 % + 12.3 % + 7.5 % of all executed
+// instructions of the step (profiles/r01_linemix_servo_ref_v6.txt).  Coefficients: csrc/tools/fit_poly.py.
+// The standalone entry points (b200ctl_quat_to_matrix, b200ctl_pixel2phy, ...) keep Fn<double>.
+
+// 1/sqrt(x): MUFU.RSQ64H seed (2^-22) + two Newton steps, no special-case code: ~2 ulp for normal x > 0;
+// x = 0 / inf / NaN / x < 0 all end in NaN (libdevice returns inf for 0) -- every use in the step either guards
+// the operand or multiplies the result by the zero operand, which is NaN either way.
+__device__ __forceinline__ double rsqrt_seeded(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  y = fma(y, fma(-h, y * y, 0.5), y);
+  y = fma(y, fma(-h, y * y, 0.5), y);
+  return y;
+}
+// sin and cos of |a| <= pi/2 (half of an fp32 yaw): two Horner chains, no range reduction.
+__device__ __forceinline__ void sincos_halfpi(double a, double* s, double* c) {
+  constexpr double kSinP[7] = {     // sin(a) = a P(a^2), |a| <= pi/2 + 1e-6: max rel err 7.9e-14
+      +9.99999999999949596e-01, -1.66666666664664759e-01, +8.33333332035067313e-03, -1.98412666819711126e-04,
+      +2.75569528317734083e-06, -2.50302655426415775e-08, +1.54111870971544081e-10};
+  constexpr double kCosP[8] = {     // cos(a) = P(a^2), |a| <= pi/2 + 1e-6: max abs err 2.1e-15
+      +9.99999999999998113e-01, -4.99999999999897748e-01, +4.16666666657989210e-02, -1.38888888608197821e-03,
+      +2.48015828383639587e-05, -2.75569334492936956e-07, +2.08582570650177641e-09, -1.10072215909754479e-11};
+  const double u = a * a;
+  double ps = kSinP[6], pc = kCosP[7];
+#pragma unroll
+  for (int i = 5; i >= 0; --i) ps = fma(ps, u, kSinP[i]);
+#pragma unroll
+  for (int i = 6; i >= 0; --i) pc = fma(pc, u, kCosP[i]);
+  *s = a * ps;
+  *c = pc;
+}
+// atan2 of two fp32-valued operands, good to ~3e-13: octant reduction, reciprocal from the MUFU.RCP64H seed + two
+// Newton steps, degree-14 polynomial in t^2.  Zeros, infinities, NaNs and magnitudes outside [1e-30, 1e30] take
+// libdevice's atan2 (never in a running simulation: the operands are the car's commanded velocity).
+__device__ __forceinline__ double atan2_f32grade(double y, double x) {
+  constexpr double kAtanP[15] = {   // atan(t) = t P(t^2), t in [0,1]: max rel err 2.9e-13
+      +9.99999999999710010e-01, -3.33333333202547766e-01, +1.99999990134476779e-01, -1.42856846620934341e-01,
+      +1.11106408020913983e-01, -9.08636074921461007e-02, +7.66317779457992565e-02, -6.53623027598632111e-02,
+      +5.45824289519867140e-02, -4.23246742159247014e-02, +2.84106798948627476e-02, -1.52325472569444249e-02,
+      +5.93640633896713472e-03, -1.46667809518313016e-03, +1.70461754426792420e-04};
+  const double ax = fabs(x), ay = fabs(y);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  if (!(mx > 1e-30 && mx < 1e30)) return ::atan2(y, x);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
+  r = fma(fma(-mx, r, 1.0), r, r);
+  r = fma(fma(-mx, r, 1.0), r, r);
+  const double t = mn * r, u = t * t;
+  double p = kAtanP[14];
+#pragma unroll
+  for (int i = 13; i >= 0; --i) p = fma(p, u, kAtanP[i]);
+  double a = t * p;
+  if (ay > ax) a = 1.57079632679489661923 - a;
+  if (x < 0.0) a = 3.14159265358979323846 - a;
+  return copysign(a, y);
+}
+// Fn<double> with the seeded rsqrt: the function policy of the fused step's fp64 stages.
+struct FnStep64 : Fn<double> {
+  static __device__ __forceinline__ double rsqrt(double a) { return rsqrt_seeded(a); }
+};
+template <typename T> struct FnStep { using type = Fn<T>; };
+template <> struct FnStep<double> { using type = FnStep64; };
+
 // ------------------------------------------------------------------ a1: cclvf2
 // common/controller6.py:92-118, operand order preserved (see oracle/servo.py).
 template <typename T, typename A = Ar<T>>
@@ -70,7 +136,10 @@ __device__ __forceinline__ void cclvf_core(T px, T py, T pz, T tx, T ty, T tz, T
   T r = A::sqrt(A::fma(dy, dy, A::mul(dx, dx)));
   r = (r < (T)0.01) ? (T)0.01 : r;                             // :99 torch.max(r, 0.01), NaN-propagating
   // :105 `rd / r` with a python scalar on the left is Tensor.__rtruediv__ = r.reciprocal() * rd
-  const T c = (r < rd) ? A::div(r, rd) : A::mul(A::div((T)1, r), rd);
+  // (one division either way: r / rd inside the circle, (1 / r) * rd outside)
+  const bool inside = r < rd;
+  const T q = A::div(inside ? r : (T)1, inside ? rd : r);
+  const T c = inside ? q : A::mul(q, rd);
   const T rr = A::mul(r, r);
   const T gap = A::sub(rr, rd2);                               // :108
   const T quart = A::add(A::add(A::pow4(r), A::mul(A::mul(A::sub(A::mul(c, c), (T)2), rd2), rr)), rd4);
@@ -83,9 +152,9 @@ __device__ __forceinline__ void cclvf_core(T px, T py, T pz, T tx, T ty, T tz, T
 
 // ------------------------------------------------------------------ a3: quaternion -> matrix
 // scipy Rotation.from_quat(q).as_matrix(): q is normalised first (test10_servo_vecenv.py:423).
-template <typename T>
+template <typename T, typename F = Fn<T>>
 __device__ __forceinline__ void quat_to_mat(T x, T y, T z, T w, T (&R)[9]) {
-  const T inv = Fn<T>::rsqrt(x * x + y * y + z * z + w * w);
+  const T inv = F::rsqrt(x * x + y * y + z * z + w * w);
   x *= inv; y *= inv; z *= inv; w *= inv;
   const T x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w;
   const T xy = x * y, zw = z * w, xz = x * z, yw = y * w, yz = y * z, xw = x * w;
@@ -120,12 +189,12 @@ __device__ __forceinline__ void project_body(T bx, T by, T bz, T fx, T fy, T u0,
 
 // ------------------------------------------------------------------ a5: pixel2phy
 // common/secondary_control_vecenv.py:35-51: unit bearing, axes (fwd, right, down).
-template <typename T>
+template <typename T, typename F = Fn<T>>
 __device__ __forceinline__ void pixel_bearing(const T (&Kinv)[9], T px, T py, T& mx, T& my, T& mz) {
   const T a0 = Kinv[0] * px + Kinv[1] * py + Kinv[2];
   const T a1 = Kinv[3] * px + Kinv[4] * py + Kinv[5];
   const T a2 = Kinv[6] * px + Kinv[7] * py + Kinv[8];
-  const T inv = Fn<T>::rsqrt(a0 * a0 + a1 * a1 + a2 * a2);
+  const T inv = F::rsqrt(a0 * a0 + a1 * a1 + a2 * a2);
   mx = a2 * inv; my = a0 * inv; mz = a1 * inv;
 }
 
@@ -195,15 +264,15 @@ __device__ __forceinline__ void euler_xyz_to_quat(T roll, T pitch, T yaw, T& x, 
 namespace b200ctl {
 
 // (cos a, |sin a|, a < 0) -> (cos a/2, sin a/2) for a in [-pi, pi], without cancellation.
-template <typename T>
+template <typename T, typename F = Fn<T>>
 __device__ __forceinline__ void half_angle(T c, T s_abs, bool negative, T& ch, T& sh) {
   // the radicand is >= 1/2 in either branch, so rsqrt never sees 0
   if (c >= (T)0) {
-    const T x = ((T)1 + c) * (T)0.5, r = Fn<T>::rsqrt(x);
+    const T x = ((T)1 + c) * (T)0.5, r = F::rsqrt(x);
     ch = x * r;
     sh = s_abs * (T)0.5 * r;
   } else {
-    const T x = ((T)1 - c) * (T)0.5, r = Fn<T>::rsqrt(x);
+    const T x = ((T)1 - c) * (T)0.5, r = F::rsqrt(x);
     sh = x * r;
     ch = s_abs * (T)0.5 * r;
   }
@@ -223,9 +292,8 @@ __device__ __forceinline__ void half_angle(T c, T s_abs, bool negative, T& ch, T
 // orthonormal C = R(q) and pin-hole K with the principal point at the image centre, which is what the fused
 // step has; the general entry point b200ctl_servo_ext_pixel keeps the literal asin / acos evaluation.
 // `ang` (optional, radians: roll, pitch, yaw) is filled from atan2 of the same sines / cosines.
-template <typename T>
+template <typename T, typename F = Fn<T>>
 __device__ __forceinline__ void servo_quat_from_bearing(T mx, T my, T mz, const T (&C)[9], T (&q)[4], T* ang) {
-  using F = Fn<T>;
   const T px = C[0] * mx + C[1] * my + C[2] * mz;
   const T py = C[3] * mx + C[4] * my + C[5] * mz;
   const T pz = C[6] * mx + C[7] * my + C[8] * mz;
@@ -248,9 +316,9 @@ __device__ __forceinline__ void servo_quat_from_bearing(T mx, T my, T mz, const 
   const T spitch_abs = (pz < (T)0) ? -pz : pz;
   const bool pitch_neg = pz > (T)0;                                     // pitch = -asin(p_z)
   T cr, sr, cp, sp, cy, sy;
-  half_angle<T>(dot, sroll, roll_neg, cr, sr);
-  half_angle<T>(cpitch, spitch_abs, pitch_neg, cp, sp);
-  half_angle<T>(cyaw, yaw_neg ? -syaw : syaw, yaw_neg, cy, sy);
+  half_angle<T, F>(dot, sroll, roll_neg, cr, sr);
+  half_angle<T, F>(cpitch, spitch_abs, pitch_neg, cp, sp);
+  half_angle<T, F>(cyaw, yaw_neg ? -syaw : syaw, yaw_neg, cy, sy);
   q[0] = sr * cp * cy - cr * sp * sy;       // extrinsic xyz, same closed form as euler_xyz_to_quat
   q[1] = cr * sp * cy + sr * cp * sy;
   q[2] = cr * cp * sy - sr * sp * cy;
