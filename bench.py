@@ -228,6 +228,19 @@ def family_numbers(device, peak_gbs):
     record("pd_65536x12", n, PD_BYTES_PER_ENV, [c.bind(st[k], tg[k], ou[k]) for k in range(sets)], reps=20)
     del st, tg, ou
 
+    # P at C1 (1,024 x 12, BASELINE configs[0]: 197 KB per set, L2-resident whatever the rotation): one CTA wave of
+    # 12 CTAs, so this is the floor of ONE graph-replayed, programmatically-serialised launch on this box -- the
+    # yardstick for every C2 / C3 entry below
+    n, sets = 1_024, 24
+    pi = syn.pd_inputs(n, NUM_DOFS, seed=1)
+    c1 = PDController(NUM_DOFS, pi.kp, pi.kd, tau_max=pi.tau_max, device=device)
+    st = [pi.dof_state.to(device).clone() for _ in range(sets)]
+    tg = [pi.q_target.to(device).clone() for _ in range(sets)]
+    ou = [torch.empty(n, NUM_DOFS, device=device) for _ in range(sets)]
+    record("pd_1024x12", n, PD_BYTES_PER_ENV, [c1.bind(st[k], tg[k], ou[k]) for k in range(sets)], reps=20)
+    out["pd_1024x12"]["note"] = "launch floor: L2-resident, 12 CTAs"
+    del st, tg, ou
+
     # S fused step at C2 (6.8 MB per set) and at 1M envs (109 MB per set), both precisions
     for n, sets, reps in ((65_536, 24, 10), (1_048_576, 3, 20)):
         base = syn.servo_root_state(n, seed=2).to(device)

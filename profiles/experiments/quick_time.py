@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Quick A/B timing of one kernel family (CUDA-graph replays of bound calls, rotating buffers > L2).
 
-    python profiles/experiments/quick_time.py servo|osc|ik|pd [--sizes 65536,1048576]
+    python profiles/experiments/quick_time.py servo|osc|ik|pick|pd [--sizes 65536,1048576]
 """
 import argparse
 import os
@@ -55,6 +55,25 @@ def main():
                     keep.append((d, o))
                 ts = [bench.graph_time(calls, dev, a.reps) * 1e3 for _ in range(3)]
                 print(f"{a.family}_{ptag} n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
+    elif a.family == "pick":
+        import test_isaacgym_b200.franka_cube_ik_osc as ctl
+        for n in [int(x) for x in (a.sizes or "16384").split(",")]:
+            ti, fi = syn.franka_task_inputs(n, seed=4), syn.franka_inputs(n, seed=5)
+            osc, ik, keep = [], [], []
+            for _ in range(4 if n <= 32768 else 2):
+                t = ti.__class__(**{k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in ti.__dict__.items()})
+                d = fi.__class__(**{k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+                pos_action, effort = torch.zeros(n, 9, device=dev), torch.zeros(n, 9, device=dev)
+                task = ctl.TaskStep(t.rb_states, t.box_idxs, t.hand_idxs, t.dof_pos, t.init_pos, t.init_rot, t.hand_restart, "osc")
+                ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=t.dof_pos, dof_vel=t.dof_state[:, 1].view(n, 9, 1),
+                         default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=0)
+                ctl.bind_hand(t.rb_states, t.hand_idxs)
+                osc.append(ctl.bind_pick_osc(task, effort[:, :7], pos_action[:, 7:9]))
+                ik.append(ctl.bind_pick_ik(task, pos_action[:, :7], pos_action[:, 7:9]))
+                keep.append((t, d, pos_action, effort, task))
+            for tag, calls in (("pick_osc_fp64", osc), ("pick_ik_fp64", ik)):
+                ts = [bench.graph_time(calls, dev, a.reps) * 1e3 for _ in range(3)]
+                print(f"{tag} n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
     elif a.family == "pd":
         from test_isaacgym_b200.pd_control import PDController
         for n in [int(x) for x in (a.sizes or "65536,1048576").split(",")]:

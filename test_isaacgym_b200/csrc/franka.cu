@@ -56,7 +56,31 @@ template <> __device__ __forceinline__ float rsqrt_t<float>(float d) {
   const float r = rsqrtf(d);
   return r * fmaf(-0.5f * d * r, r, 1.5f);   // one Newton step: full fp32 accuracy
 }
-template <> __device__ __forceinline__ double rsqrt_t<double>(double d) { return ::rsqrt(d); }   // ~1 ulp, a third of sqrt + divide
+// fp64 reciprocal square root of the Cholesky pivots.  Thirteen of them sit on the serial critical path of every env
+// (7 + 6 pivots), so their LATENCY counts, not their throughput: libdevice's rsqrt (special-case code, ~1 ulp) ->
+// MUFU.RSQ64H seed + two Newton steps (2 ulp, profiles/experiments/rsqrt_ulp.cu) took the fp64-chain OSC from
+// 55.5 to 51.0 us per 262,144 envs and from 7.20 to 6.69 us at 16,384.  Pivots of an SPD matrix are positive normal
+// numbers; a non-positive pivot (not SPD) gives NaN either way.
+#ifndef B200_OSC_RSQRT
+#define B200_OSC_RSQRT 1      // A/B knob (profiles/): 0 libdevice, 1 seed + two Newton steps, 2 seed + one cubic step
+#endif
+template <> __device__ __forceinline__ double rsqrt_t<double>(double d) {
+#if B200_OSC_RSQRT == 0
+  return ::rsqrt(d);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#if B200_OSC_RSQRT == 1
+  const double h = 0.5 * d;
+  y = fma(y, fma(-h, y * y, 0.5), y);
+  y = fma(y, fma(-h, y * y, 0.5), y);
+  return y;
+#else
+  const double e = fma(-(d * y), y, 1.0);           // e = 1 - d y^2;  1/sqrt(1 - e) = 1 + e/2 + 3 e^2 / 8 + O(e^3)
+  return fma(y * e, fma(e, 0.375, 0.5), y);
+#endif
+#endif
+}
 
 // In-place Cholesky of the lower triangle of an SPD matrix held in registers; returns the
 // reciprocal diagonal so the substitutions multiply instead of divide.
@@ -203,13 +227,19 @@ __device__ __forceinline__ void stage_ldgsts(const StagePlan& P, int64_t env0, i
   }
 }
 
-// Index-gathered (N_src, C) rows -> the extras slot of the active plan (one thread per env issues its C copies).
+// Index-gathered (N_src, C) rows -> the extras slot of the active plan, in two steps so the index load is in flight
+// while the thread issues everything that does not depend on it (the TMA copies of thread 0 above all: a warp issues
+// in order, and the first use of the index stalls it for a full memory latency):
+//   gather_row   loads this thread's source row number (the load only, nothing consumes it yet),
+//   gather_copy  issues the C 4-byte copies of that row.
+__device__ __forceinline__ int64_t gather_row(const TView& index, int has_index, int64_t env0, int nenv) {
+  if ((int)threadIdx.x >= nenv) return 0;
+  const int64_t env = env0 + threadIdx.x;
+  return has_index ? __ldg(reinterpret_cast<const int64_t*>(index.p) + env * index.s[0]) : env;
+}
 template <int C>
-__device__ __forceinline__ void stage_gather(const TView& v, const TView& index, int has_index, int64_t env0, int nenv,
-                                             float* dst_row0, int ts) {
+__device__ __forceinline__ void gather_copy(const TView& v, int64_t row, int nenv, float* dst_row0, int ts) {
   if ((int)threadIdx.x < nenv) {
-    const int64_t env = env0 + threadIdx.x;
-    const int64_t row = has_index ? reinterpret_cast<const int64_t*>(index.p)[env * index.s[0]] : env;
     const float* g = reinterpret_cast<const float*>(v.p) + row * v.s[0];
 #pragma unroll
     for (int c = 0; c < C; ++c) cp_async_f32(dst_row0 + threadIdx.x * ts + c, g + c * v.s[1]);
@@ -400,7 +430,7 @@ struct OscRegs {
 };
 template <typename T, typename TaskSpaceTarget>
 __device__ __forceinline__ void osc_gather(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQ,
-                                           const SAddr& aQD, int e, TaskSpaceTarget&& target, const TView& q_default,
+                                           const SAddr& aQD, int e, TaskSpaceTarget&& target, const float* q_default,
                                            float kp_null, float kd_null, OscRegs<T>& R) {
   constexpr int D = 7;
 #pragma unroll
@@ -411,8 +441,7 @@ __device__ __forceinline__ void osc_gather(const float* tile, const SAddr& aJ, c
   float u0[D];
 #pragma unroll
   for (int c = 0; c < D; ++c) {
-    const float qdef = ldf(q_default, c * q_default.s[0]);
-    u0[c] = __fadd_rn(__fmul_rn(kd_null, -SM(aQD, e, 0, c)), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef, SM(aQ, e, 0, c)))));
+    u0[c] = __fadd_rn(__fmul_rn(kd_null, -SM(aQD, e, 0, c)), __fmul_rn(kp_null, wrap_pi(__fsub_rn(q_default[c], SM(aQ, e, 0, c)))));
   }
   // task-space target minus J u0 (the null-space projector folded in)
   float wt[6];
@@ -453,7 +482,7 @@ __device__ __forceinline__ void osc_solve(OscRegs<T>& R, float (&u_out)[7]) {
 template <typename T, typename TaskSpaceTarget>
 __device__ __forceinline__ void osc_compute(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQ,
                                             const SAddr& aQD, int e, TaskSpaceTarget&& target,
-                                            const TView& q_default, float kp_null, float kd_null, float (&u_out)[7]) {
+                                            const float* q_default, float kp_null, float kd_null, float (&u_out)[7]) {
   OscRegs<T> R;
   osc_gather<T>(tile, aJ, aM, aQ, aQD, e, target, q_default, kp_null, kd_null, R);
   osc_solve<T>(R, u_out);
@@ -476,18 +505,28 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   // persistent CTA: tiles blockIdx.x, + gridDim.x, ...; the tile buffer is refilled while the previous tile's
   // factorisation runs out of registers
   const int ntiles = (int)((n + kTileEnvs - 1) / kTileEnvs);
-  auto issue = [&](int t) {
-    const int64_t env0 = (int64_t)t * kTileEnvs;
-    const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  auto tile_envs = [&](int t) { const int64_t left = n - (int64_t)t * kTileEnvs; return (int)(left < kTileEnvs ? left : kTileEnvs); };
+  // the hand-velocity row number of tile t is loaded one tile ahead of its use (row_of), so the gather copies -- the
+  // longest latency of the staging, issued first -- do not wait for the index (profiles/: 6.6 % of the stall samples
+  // of the fp64 chain sat on that first use).  Issuing the first tile's TMA copies ahead of its gather instead
+  // measured the same.
+  auto row_of = [&](int t) { return gather_row(hand_index, has_index, (int64_t)t * kTileEnvs, tile_envs(t)); };
+  auto issue = [&](int t, int64_t row) {
     const bool bulk = tile_is_bulk(P, t, ntiles);
-    stage_gather<6>(hand_vel, hand_index, has_index, env0, nenv, tile + (bulk ? P.x_off_b : P.x_off_c),
-                    bulk ? P.bulk_ts : P.canon_ts);                            // dependent gather first
+    gather_copy<6>(hand_vel, row, tile_envs(t), tile + (bulk ? P.x_off_b : P.x_off_c), bulk ? P.bulk_ts : P.canon_ts);
     stage_issue<5>(P, &tmap, t, ntiles, n, tile, &bar);
   };
   unsigned phase = 0;
-  stage_begin(P, &bar);
+  // default joint positions (:74-76): one global read per CTA instead of seven per env.  Loaded into a register here
+  // and stored only after the first tile's copies are on their way: a store right behind the load would hold warp 0
+  // -- the warp that issues the TMA copies -- for a memory latency (measured: +0.3 us at 16,384 envs)
+  __shared__ float s_qdef[8];
+  const float qdef_mine = threadIdx.x < 7 ? ldf(q_default, threadIdx.x * q_default.s[0]) : 0.f;
   int t = blockIdx.x;
-  if (t < ntiles) issue(t);
+  int64_t row = t < ntiles ? row_of(t) : 0;
+  stage_begin(P, &bar);
+  if (t < ntiles) issue(t, row);
+  if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;      // published by the barrier that ends stage_wait
   // statistics live in shared memory between tiles: four fp64 accumulators are eight registers this kernel does not
   // have (the fp64 chain sits at the 255-register limit)
   __shared__ double s_acc[4][kTileEnvs];
@@ -495,8 +534,10 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   for (int k = 0; k < 4; ++k) s_acc[k][threadIdx.x] = 0.0;
   for (; t < ntiles; t += gridDim.x) {
     const int64_t env0 = (int64_t)t * kTileEnvs;
-    const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+    const int nenv = tile_envs(t);
     const bool bulk = tile_is_bulk(P, t, ntiles);
+    const int t_next = t + (int)gridDim.x;
+    if (t_next < ntiles) row = row_of(t_next);     // in flight across the wait and the gather
     SAddr a[5];
     stage_wait<5>(P, t, ntiles, &bar, phase, a);
     const bool live = (int)threadIdx.x < nenv;
@@ -508,10 +549,10 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
       osc_gather<T>(tile, a[0], a[1], a[2], a[3], e, [&](float (&w)[6]) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) w[r] = __fsub_rn(__fmul_rn(kp, SM(aDp, e, 0, r)), __fmul_rn(kd, hv[r]));
-      }, q_default, kp_null, kd_null, R);
+      }, s_qdef, kp_null, kd_null, R);
     }
     __syncthreads();                      // every thread has its operands in registers: the buffer is free
-    if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
+    if (t_next < ntiles) issue(t_next, row);
     if (live) {
       float u[D];
       osc_solve<T>(R, u);
@@ -561,10 +602,18 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   const bool bulk = tile_is_bulk(P);
   const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
   float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
-  stage_gather<7>(rb, box_index, 1, env0, nenv, x0, x_ts);            // box pos + quat          (:348-349)
-  stage_gather<13>(rb, hand_index, 1, env0, nenv, x0 + 7, x_ts);      // hand pos + quat + vel   (:351-353)
+  // index loads first, then the TMA / LDGSTS issue, then the copies that need the indices (see gather_row)
+  const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
+  __shared__ float s_qdef[8];
+  const float qdef_mine = threadIdx.x < 7 ? ldf(q_default, threadIdx.x * q_default.s[0]) : 0.f;
   SAddr a[6];
-  stage_all<6>(P, &tmap, env0, nenv, tile, &bar, a);
+  unsigned phase = 0;
+  stage_begin(P, &bar);
+  stage_issue<6>(P, &tmap, blockIdx.x, gridDim.x, n, tile, &bar);
+  gather_copy<7>(rb, box_row, nenv, x0, x_ts);              // box pos + quat          (:348-349)
+  gather_copy<13>(rb, hand_row, nenv, x0 + 7, x_ts);        // hand pos + quat + vel   (:351-353)
+  if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;     // stored after the issue, see osc_kernel
+  stage_wait<6>(P, blockIdx.x, gridDim.x, &bar, phase, a);
 
   double acc[4] = {0, 0, 0, 0};
   if (threadIdx.x < nenv) {
@@ -595,7 +644,7 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
       }
 #pragma unroll
       for (int r = 0; r < 6; ++r) w[r] = __fsub_rn(__fmul_rn(kp, t.dpose[r]), __fmul_rn(kd, xr[14 + r]));   // :67-68, hand vel :353
-    }, q_default, kp_null, kd_null, u);
+    }, s_qdef, kp_null, kd_null, u);
     float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
     bool finite = true;
 #pragma unroll
@@ -633,10 +682,14 @@ pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, 
   const bool bulk = tile_is_bulk(P);
   const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
   float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
-  stage_gather<7>(rb, box_index, 1, env0, nenv, x0, x_ts);
-  stage_gather<7>(rb, hand_index, 1, env0, nenv, x0 + 7, x_ts);
+  const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
   SAddr a[4];
-  stage_all<4>(P, &tmap, env0, nenv, tile, &bar, a);
+  unsigned phase = 0;
+  stage_begin(P, &bar);
+  stage_issue<4>(P, &tmap, blockIdx.x, gridDim.x, n, tile, &bar);
+  gather_copy<7>(rb, box_row, nenv, x0, x_ts);
+  gather_copy<7>(rb, hand_row, nenv, x0 + 7, x_ts);
+  stage_wait<4>(P, blockIdx.x, gridDim.x, &bar, phase, a);
   if (threadIdx.x >= nenv) return;
   const int e = threadIdx.x;
   const int64_t env = env0 + e;
