@@ -35,8 +35,11 @@ def main():
             bufs = [base.clone() for _ in range(min(sets, 24))]
             for tag, prec in (("ref", 0), ("fast", PRECISION_FAST)):
                 step = ServoStep(1600, 900, precision=prec)
-                ts = [bench.graph_time([step.bind(b) for b in bufs], dev, a.reps) * 1e3 for _ in range(3)]
-                print(f"servo_{tag} n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
+                from test_isaacgym_b200 import _lib as L
+                sb = L.stats_buffer(dev)
+                for stag, kw in (("", {}), ("+stats", {"stats": sb})):
+                    ts = [bench.graph_time([step.bind(b, **kw) for b in bufs], dev, a.reps) * 1e3 for _ in range(3)]
+                    print(f"servo_{tag}{stag} n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
     elif a.family in ("osc", "ik"):
         import test_isaacgym_b200.franka_cube_ik_osc as ctl
         for n in [int(x) for x in (a.sizes or "16384,262144").split(",")]:
@@ -55,6 +58,17 @@ def main():
                     keep.append((d, o))
                 ts = [bench.graph_time(calls, dev, a.reps) * 1e3 for _ in range(3)]
                 print(f"{a.family}_{ptag} n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
+                if a.family == "osc":
+                    from test_isaacgym_b200 import _lib as L
+                    sb = L.stats_buffer(dev)
+                    scalls = []
+                    for d, o in keep:
+                        ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=d.dof_pos, dof_vel=d.dof_vel,
+                                 default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=prec)
+                        ctl.bind_hand(d.rb_states, d.hand_idxs)
+                        scalls.append(ctl.bind_control_osc(d.dpose, o[:, :7], stats=sb))
+                    ts = [bench.graph_time(scalls, dev, a.reps) * 1e3 for _ in range(3)]
+                    print(f"osc_{ptag}+stats n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
     elif a.family == "pick":
         import test_isaacgym_b200.franka_cube_ik_osc as ctl
         for n in [int(x) for x in (a.sizes or "16384").split(",")]:
@@ -83,8 +97,11 @@ def main():
             st = [pi.dof_state.to(dev).clone() for _ in range(sets)]
             tg = [pi.q_target.to(dev).clone() for _ in range(sets)]
             ou = [torch.empty(n, 12, device=dev) for _ in range(sets)]
-            ts = [bench.graph_time([c.bind(st[k], tg[k], ou[k]) for k in range(sets)], dev, a.reps) * 1e3 for _ in range(3)]
-            print(f"pd n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
+            from test_isaacgym_b200 import _lib as L
+            sb = L.stats_buffer(dev)
+            for tag, kw in (("", {}), ("+stats", {"stats": sb})):
+                ts = [bench.graph_time([c.bind(st[k], tg[k], ou[k], **kw) for k in range(sets)], dev, a.reps) * 1e3 for _ in range(3)]
+                print(f"pd{tag} n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
 
 
 if __name__ == "__main__":

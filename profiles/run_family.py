@@ -17,6 +17,7 @@ def main():
     ap.add_argument("family")
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--stats", action="store_true", help="servo: pass a statistics buffer")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     if a.family == "servo":
@@ -24,7 +25,9 @@ def main():
         n = a.n or 1_048_576
         bufs = [syn.servo_root_state(n, seed=2).to(dev) for _ in range(2)]
         for prec in (0, 1):
-            call = [ServoStep(1600, 900, precision=prec).bind(b) for b in bufs]
+            from test_isaacgym_b200 import _lib
+            sb = _lib.stats_buffer(dev) if a.stats else None
+            call = [ServoStep(1600, 900, precision=prec).bind(b, stats=sb) for b in bufs]
             for i in range(a.iters):
                 call[i % 2]()
     elif a.family in ("osc", "ik"):

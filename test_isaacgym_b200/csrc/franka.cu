@@ -35,6 +35,8 @@
 // Roofline: HBM.  Algorithmic bytes per env: IK 248 B, OSC 496 B.
 #include "franka_task.cuh"
 
+#include <mutex>
+
 #include <cuda.h>   // CUtensorMap + enums only: cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint
 
 namespace b200ctl {
@@ -248,7 +250,7 @@ __device__ __forceinline__ void gather_copy(const TView& v, int64_t row, int nen
 
 // The last tile always takes the LDGSTS plan: bulk copies fetch whole aligned blocks past the operand.
 __device__ __forceinline__ bool tile_is_bulk(const StagePlan& P, int t, int ntiles) { return P.bulk_ok && (t + 1 < ntiles); }
-__device__ __forceinline__ bool tile_is_bulk(const StagePlan& P) { return tile_is_bulk(P, blockIdx.x, gridDim.x); }
+__device__ __forceinline__ int tile_count(int64_t n) { return (int)((n + kTileEnvs - 1) / kTileEnvs); }
 
 // Staging is split in three so a persistent CTA can refill its tile buffer while it computes:
 //   stage_begin  once per CTA (mbarrier init),
@@ -529,9 +531,10 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;      // published by the barrier that ends stage_wait
   // statistics live in shared memory between tiles: four fp64 accumulators are eight registers this kernel does not
   // have (the fp64 chain sits at the 255-register limit)
-  __shared__ double s_acc[4][kTileEnvs];
+  __shared__ double s_acc[2][kTileEnvs];        // sum |u|, sum u^2
+  __shared__ unsigned s_cnt[2][kTileEnvs];      // envs, envs with a non-finite torque
 #pragma unroll
-  for (int k = 0; k < 4; ++k) s_acc[k][threadIdx.x] = 0.0;
+  for (int k = 0; k < 2; ++k) { s_acc[k][threadIdx.x] = 0.0; s_cnt[k][threadIdx.x] = 0u; }
   for (; t < ntiles; t += gridDim.x) {
     const int64_t env0 = (int64_t)t * kTileEnvs;
     const int nenv = tile_envs(t);
@@ -568,18 +571,17 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
         sum_abs += fabsf(v);
         sum_sq += (double)v * v;
       }
-      s_acc[0][e] += 1.0;
-      s_acc[1][e] += sum_abs;
-      s_acc[2][e] += sum_sq;
-      s_acc[3][e] += finite ? 0.0 : 1.0;
+      s_acc[0][e] += sum_abs;
+      s_acc[1][e] += sum_sq;
+      s_cnt[0][e] += 1u;
+      s_cnt[1][e] += finite ? 0u : 1u;
     }
   }
   if (stats) {
-    double acc[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = s_acc[k][threadIdx.x];
-    const int slot[4] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_NONFINITE};
-    block_stats_commit<4>(acc, stats, slot);
+    double acc[2] = {s_acc[0][threadIdx.x], s_acc[1][threadIdx.x]};
+    unsigned cnt[2] = {s_cnt[0][threadIdx.x], s_cnt[1][threadIdx.x]};
+    const int slots[4] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_NONFINITE};
+    block_stats_commit<2, 2>(acc, cnt, stats, slots);
   }
 }
 
@@ -597,9 +599,10 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   pdl_prologue();
+  const int ntiles = tile_count(n);
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
-  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  const bool bulk = tile_is_bulk(P);
+  const int nenv = (int)((n - env0) < kTileEnvs ? ((n - env0) > 0 ? (n - env0) : 0) : kTileEnvs);
+  const bool bulk = tile_is_bulk(P, blockIdx.x, ntiles);
   const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
   float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
   // index loads first, then the TMA / LDGSTS issue, then the copies that need the indices (see gather_row)
@@ -609,13 +612,14 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   SAddr a[6];
   unsigned phase = 0;
   stage_begin(P, &bar);
-  stage_issue<6>(P, &tmap, blockIdx.x, gridDim.x, n, tile, &bar);
+  stage_issue<6>(P, &tmap, blockIdx.x, ntiles, n, tile, &bar);
   gather_copy<7>(rb, box_row, nenv, x0, x_ts);              // box pos + quat          (:348-349)
   gather_copy<13>(rb, hand_row, nenv, x0 + 7, x_ts);        // hand pos + quat + vel   (:351-353)
   if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;     // stored after the issue, see osc_kernel
-  stage_wait<6>(P, blockIdx.x, gridDim.x, &bar, phase, a);
+  stage_wait<6>(P, blockIdx.x, ntiles, &bar, phase, a);
 
-  double acc[4] = {0, 0, 0, 0};
+  double acc[2] = {0, 0};        // sum |u|, sum u^2
+  unsigned cnt[2] = {0, 0};      // envs, envs with a non-finite torque
   if (threadIdx.x < nenv) {
     const int e = threadIdx.x;
     const int64_t env = env0 + e;
@@ -653,15 +657,15 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
       const bool f = isfinite(u[c]);
       finite = finite && f;
       const float v = f ? u[c] : 0.f;
-      acc[1] += fabsf(v);
-      acc[2] += (double)v * v;
+      acc[0] += fabsf(v);
+      acc[1] += (double)v * v;
     }
-    acc[0] = 1.0;
-    acc[3] = finite ? 0.0 : 1.0;
+    cnt[0] = 1u;
+    cnt[1] = finite ? 0u : 1u;
   }
   if (stats) {
-    const int slot[4] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_NONFINITE};
-    block_stats_commit<4>(acc, stats, slot);
+    const int slots[4] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_NONFINITE};
+    block_stats_commit<2, 2>(acc, cnt, stats, slots);
   }
 }
 
@@ -679,7 +683,7 @@ pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, 
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  const bool bulk = tile_is_bulk(P);
+  const bool bulk = tile_is_bulk(P, blockIdx.x, gridDim.x);
   const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
   float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
   const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
@@ -947,15 +951,27 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
 
 // Opt the kernel in to `bytes` of dynamic shared memory.  The 48 KB default limit counts static + dynamic
 // shared memory, so this is requested whenever dynamic memory alone exceeds 32 KB (static use is < 16 KB here);
-// the largest request per kernel and device is remembered so steady-state launches skip the driver call.
+// the largest request per kernel FUNCTION and device is remembered so steady-state launches skip the driver call.
+// (Keyed by the function's address: two instantiations of one template share the pointer TYPE, and a table per
+// type let the fp32 instantiation ride on the fp64 one's grant.)
 template <typename K>
 static int set_smem(K kernel, int bytes) {
-  static int granted[64] = {};
+  struct Entry { const void* fn; int granted[64]; };
+  static Entry table[64] = {};
+  static std::mutex mu;
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
-  if (bytes > 32 * 1024 && dev >= 0 && dev < 64 && bytes > granted[dev]) {
+  if (bytes <= 32 * 1024 || dev < 0 || dev >= 64) return 0;
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  std::lock_guard<std::mutex> lock(mu);
+  Entry* e = nullptr;
+  for (Entry& t : table) {
+    if (t.fn == fn || t.fn == nullptr) { e = &t; break; }
+  }
+  if (e) e->fn = fn;
+  if (!e || bytes > e->granted[dev]) {
     B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    granted[dev] = bytes;
+    if (e) e->granted[dev] = bytes;
   }
   return 0;
 }

@@ -60,6 +60,9 @@ __device__ __forceinline__ float pd_element(float pos, float vel, float tgt, flo
   return tau;
 }
 
+#ifndef B200_PD_STATS_MODE
+#define B200_PD_STATS_MODE 1      // A/B knob (profiles/): 0 = fp64 accumulation per element, 1 = fp32 partials per vector
+#endif
 struct PdAcc {
   // fp64 per-thread sums: the statistics must not depend on how envs are sliced over GPUs / CTAs beyond 1e-15
   double sum_abs = 0.0, sum_sq = 0.0;
@@ -73,24 +76,105 @@ struct PdAcc {
     n_bad += fin ? 0u : 1u;
     if (HAS_TMAX) n_sat += (fin && fabsf(tau) >= tmax) ? 1u : 0u;
   }
+  // One 4-element vector of the fast path.  The four elements are summed in fp32 first, in a fixed order, and the
+  // partials are accumulated in fp64: a vector is a fixed group of the flattened (env, dof) index whatever the env
+  // slice, so the statistics stay slice-invariant to fp64 summation order, at a quarter of the fp64 conversions /
+  // additions per element (the fp64 epilogue arithmetic was 16 of ~140 loop instructions and 2 us of a 33.6 us step).
+  template <bool HAS_TMAX>
+  __device__ __forceinline__ void add4(const float4& o, const float4& tm) {
+#if B200_PD_STATS_MODE == 0
+    add<HAS_TMAX>(o.x, tm.x); add<HAS_TMAX>(o.y, tm.y); add<HAS_TMAX>(o.z, tm.z); add<HAS_TMAX>(o.w, tm.w);
+#else
+    // fast path: one finiteness test per vector (a finite sum of magnitudes means four finite elements; the test on q
+    // catches an fp32 overflow of the squares); anything else takes the per-element fp64 path
+    const float a = __fadd_rn(__fadd_rn(__fadd_rn(fabsf(o.x), fabsf(o.y)), fabsf(o.z)), fabsf(o.w));
+    const float q = __fmaf_rn(o.w, o.w, __fmaf_rn(o.z, o.z, __fmaf_rn(o.y, o.y, __fmul_rn(o.x, o.x))));
+    if (isfinite(a) && isfinite(q)) {
+      sum_abs += (double)a;
+      sum_sq += (double)q;
+      if (HAS_TMAX)
+        n_sat += (fabsf(o.x) >= tm.x ? 1u : 0u) + (fabsf(o.y) >= tm.y ? 1u : 0u) + (fabsf(o.z) >= tm.z ? 1u : 0u) +
+                 (fabsf(o.w) >= tm.w ? 1u : 0u);
+    } else {
+      add<HAS_TMAX>(o.x, tm.x); add<HAS_TMAX>(o.y, tm.y); add<HAS_TMAX>(o.z, tm.z); add<HAS_TMAX>(o.w, tm.w);
+    }
+#endif
+  }
 };
 
+// End-of-CTA commit of the PD statistics: the two fp64 sums ride one interleaved shuffle butterfly, the two counters
+// take the integer REDUX unit, and after the cross-warp stage lanes 0..4 of warp 0 each own one entry of the vector,
+// so the whole CTA issues ONE predicated RED instruction.  All CTAs of the persistent grid finish together, so this
+// tail is exposed time: the generic five-chain block_stats_commit was ~1.3 us of a 33.5 us step.
 __device__ __forceinline__ void pd_commit_stats(const PdAcc& a, double* stats, int64_t n_env_block0) {
-  double acc[5] = {(double)n_env_block0, a.sum_abs, a.sum_sq, (double)a.n_sat, (double)a.n_bad};
-  const int slot[5] = {B200CTL_STAT_N_ENV, B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_SAT,
-                       B200CTL_STAT_N_NONFINITE};
-  block_stats_commit<5>(acc, stats, slot);
+  __shared__ double s_d[2][32];
+  __shared__ unsigned s_u[2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double x = a.sum_abs, y = a.sum_sq;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, o);
+    y += __shfl_xor_sync(0xffffffffu, y, o);
+  }
+  unsigned ns = __reduce_add_sync(0xffffffffu, a.n_sat), nb = __reduce_add_sync(0xffffffffu, a.n_bad);
+  if (lane == 0) { s_d[0][warp] = x; s_d[1][warp] = y; s_u[0][warp] = ns; s_u[1][warp] = nb; }
+  __syncthreads();
+  if (warp != 0) return;
+  const int nwarp = (blockDim.x + 31) >> 5;
+  x = lane < nwarp ? s_d[0][lane] : 0.0;
+  y = lane < nwarp ? s_d[1][lane] : 0.0;
+  ns = lane < nwarp ? s_u[0][lane] : 0u;
+  nb = lane < nwarp ? s_u[1][lane] : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, o);
+    y += __shfl_xor_sync(0xffffffffu, y, o);
+  }
+  ns = __reduce_add_sync(0xffffffffu, ns);
+  nb = __reduce_add_sync(0xffffffffu, nb);
+  // every lane now holds the CTA totals; n_env_block0 is non-zero in thread 0 of block 0 only
+  const double n_env = (double)__shfl_sync(0xffffffffu, (long long)n_env_block0, 0);
+  const double val = lane == 0 ? n_env : lane == 1 ? x : lane == 2 ? y : lane == 3 ? (double)ns : (double)nb;
+  const int slot = lane == 0 ? B200CTL_STAT_N_ENV : lane == 1 ? B200CTL_STAT_SUM_ABS : lane == 2 ? B200CTL_STAT_SUM_SQ
+                 : lane == 3 ? B200CTL_STAT_N_SAT : B200CTL_STAT_N_NONFINITE;
+  if (lane < 5 && val != 0.0) atomicAdd(stats + slot, val);
 }
 
 // ---------------------------------------------------------------- fast path
 // Compact tensors, 16-byte aligned bases, D % 4 == 0.  `nvec` = N*D/4.
+// CTA shape: 256 threads; 6 resident CTAs per SM (40 registers) without statistics.  The statistics variant keeps
+// the NEXT iteration's loads in flight while it accumulates, which needs ~10 more registers: 5 CTAs per SM (48).
+// (Measured and rejected: 512 / 768 / 1024-thread CTAs to cut the number of end-of-kernel REDs on the one line that
+// holds the statistics vector -- no change at 1M envs, slower at 1,024; profiles/README.md.)
+#ifndef B200_PD_STATS_BLOCK
+#define B200_PD_STATS_BLOCK 256     // A/B knobs (profiles/)
+#endif
+#ifndef B200_PD_STATS_CTAS
+#define B200_PD_STATS_CTAS 5
+#endif
+constexpr int pd_block(bool stats) { return stats ? B200_PD_STATS_BLOCK : 256; }
+constexpr int pd_ctas(bool stats) { return stats ? B200_PD_STATS_CTAS : 6; }
 template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(pd_block(STATS), pd_ctas(STATS))
 pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict__ q_tgt,
                       const float4* __restrict__ qd_tgt, PdParams pp, int num_dofs, int64_t nvec, int64_t num_envs,
                       float4* __restrict__ tau_out, double* __restrict__ stats) {
   extern __shared__ __align__(16) float s_par[];   // [5][D]: kp, kd, tmax, lo, hi
   pdl_prologue();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  // The loop is rotated: the streaming loads of an iteration are issued at the end of the previous one, and those of
+  // the first iteration HERE, ahead of the per-DOF parameter staging -- otherwise every CTA spends one L2 round trip
+  // (parameter load -> shared store -> barrier) before its first byte of dof_state is requested, which is 8 % of a
+  // 65,536-env launch.
+  int64_t v = v0;
+  float4 s0, s1, tg, qd = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (v < nvec) {
+    s0 = ldg_stream4(state + 2 * v);       // q0 qd0 q1 qd1
+    s1 = ldg_stream4(state + 2 * v + 1);   // q2 qd2 q3 qd3
+    tg = ldg_stream4(q_tgt + v);
+    if (HAS_QD) qd = ldg_stream4(qd_tgt + v);
+  }
   float* s_kp = s_par;
   float* s_kd = s_par + num_dofs;
   float* s_tm = s_par + 2 * num_dofs;
@@ -107,19 +191,11 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
 
   const int vec_per_env = num_dofs >> 2;
   PdAcc acc;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   // DOF group of the current vector, advanced incrementally: a 64-bit modulo per iteration costs more
   // instructions than the law itself
   int dv = (int)(v0 % vec_per_env);
   const int dstep = (int)(stride % vec_per_env);
-  for (int64_t v = v0; v < nvec; v += stride) {
-    // issue every load of the iteration before the first use
-    const float4 s0 = ldg_stream4(state + 2 * v);       // q0 qd0 q1 qd1
-    const float4 s1 = ldg_stream4(state + 2 * v + 1);   // q2 qd2 q3 qd3
-    const float4 tg = ldg_stream4(q_tgt + v);
-    float4 qd = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (HAS_QD) qd = ldg_stream4(qd_tgt + v);
+  while (v < nvec) {
     const int d0 = dv << 2;
     dv += dstep;
     if (dv >= vec_per_env) dv -= vec_per_env;
@@ -137,14 +213,20 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
     o.z = pd_element<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX>(s1.x, s1.y, tg.z, qd.z, kp.z, kd.z, tm.z, lo.z, hi.z);
     o.w = pd_element<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX>(s1.z, s1.w, tg.w, qd.w, kp.w, kd.w, tm.w, lo.w, hi.w);
     stg_stream4(tau_out + v, o);
-    if (STATS) {
-      acc.add<HAS_TMAX>(o.x, tm.x);
-      acc.add<HAS_TMAX>(o.y, tm.y);
-      acc.add<HAS_TMAX>(o.z, tm.z);
-      acc.add<HAS_TMAX>(o.w, tm.w);
+    v += stride;
+    if (v < nvec) {                        // next iteration's loads, all issued before their first use
+      s0 = ldg_stream4(state + 2 * v);
+      s1 = ldg_stream4(state + 2 * v + 1);
+      tg = ldg_stream4(q_tgt + v);
+      if (HAS_QD) qd = ldg_stream4(qd_tgt + v);
     }
+    if (STATS) acc.add4<HAS_TMAX>(o, tm);  // under the loads just issued
   }
+#ifdef B200_PD_STATS_NOCOMMIT      // diagnostic: the accumulation without the reduction / atomics (results unusable)
+  if (STATS && acc.sum_abs == -1.0) stats[0] = acc.sum_sq + acc.n_sat + acc.n_bad;
+#else
   if (STATS) pd_commit_stats(acc, stats, (blockIdx.x == 0 && threadIdx.x == 0) ? num_envs : 0);
+#endif
 }
 
 // ---------------------------------------------------------------- generic path
@@ -195,11 +277,11 @@ struct PdLaunch {
 // Grid = (resident CTAs per SM for THIS instantiation) x (SM count), never more than the work:
 // every CTA is resident at once, strides over the range, and commits its statistics once.
 template <typename K>
-static int pd_grid(K kernel, size_t smem, int dev, int64_t work_items) {
+static int pd_grid(K kernel, size_t smem, int dev, int64_t work_items, int block) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t full = (int64_t)sm_count(dev) * per_sm;
-  const int64_t need = (work_items + 255) / 256;
+  const int64_t need = (work_items + block - 1) / block;
   return (int)(need < full ? (need > 0 ? need : 1) : full);
 }
 
@@ -208,12 +290,13 @@ static void pd_launch_one(const PdLaunch& L) {
   if (L.vec4) {
     const size_t smem = 5 * (size_t)L.num_dofs * sizeof(float);
     auto kern = pd_torque_vec4_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS>;
-    const int grid = pd_grid(kern, smem, L.dev, L.num_envs * L.num_dofs / 4);
-    launch_pdl(kern, grid, 256, smem, L.stream, L.state4, L.tgt4, L.qd4, L.pp, L.num_dofs,
+    constexpr int block = pd_block(STATS);
+    const int grid = pd_grid(kern, smem, L.dev, L.num_envs * L.num_dofs / 4, block);
+    launch_pdl(kern, grid, block, smem, L.stream, L.state4, L.tgt4, L.qd4, L.pp, L.num_dofs,
                L.num_envs * L.num_dofs / 4, L.num_envs, L.out4, L.stats);
   } else {
     auto kern = pd_torque_strided_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS>;
-    const int grid = pd_grid(kern, 0, L.dev, L.num_envs * L.num_dofs);
+    const int grid = pd_grid(kern, 0, L.dev, L.num_envs * L.num_dofs, 256);
     launch_pdl(kern, grid, 256, 0, L.stream, L.state, L.tgt, L.qd, L.pp, L.num_dofs, L.num_envs, L.out, L.stats);
   }
 }
