@@ -241,13 +241,28 @@ def family_numbers(device, peak_gbs):
     out["pd_1024x12"]["note"] = "launch floor: L2-resident, 12 CTAs"
     del st, tg, ou
 
-    # S fused step at C2 (6.8 MB per set) and at 1M envs (109 MB per set), both precisions
+    # P at the headline size WITHOUT the fused statistics epilogue (the headline loop accumulates them): what the
+    # statistics cost, and how close the plain law runs to the measured copy bandwidth
+    n, sets = 1_048_576, 4
+    pi = syn.pd_inputs(n, NUM_DOFS, seed=1)
+    c4 = PDController(NUM_DOFS, pi.kp, pi.kd, tau_max=pi.tau_max, device=device)
+    st = [pi.dof_state.to(device).clone() for _ in range(sets)]
+    tg = [pi.q_target.to(device).clone() for _ in range(sets)]
+    ou = [torch.empty(n, NUM_DOFS, device=device) for _ in range(sets)]
+    record("pd_1048576x12_nostats", n, PD_BYTES_PER_ENV, [c4.bind(st[k], tg[k], ou[k]) for k in range(sets)], reps=20)
+    del st, tg, ou
+
+    # S fused step at C2 (6.8 MB per set) and at 1M envs (109 MB per set), both precisions; "_stats" = with the
+    # statistics vector the rollout harness passes (persistent CTAs, one commit per CTA)
+    from test_isaacgym_b200 import _lib
+    sbuf = _lib.stats_buffer(device)
     for n, sets, reps in ((65_536, 24, 10), (1_048_576, 3, 20)):
         base = syn.servo_root_state(n, seed=2).to(device)
         bufs = [base.clone() for _ in range(sets)]
         for tag, prec in (("ref", 0), ("fast", PRECISION_FAST)):
             step = ServoStep(1600, 900, precision=prec)
             record(f"servo_step_{tag}_{n}", n, SERVO_BYTES_PER_ENV, [step.bind(b) for b in bufs], reps=reps)
+            record(f"servo_step_{tag}_{n}_stats", n, SERVO_BYTES_PER_ENV, [step.bind(b, stats=sbuf) for b in bufs], reps=reps)
         del bufs, base
 
     # O at C3 (16,384 envs: 47 MB of gym tensors per set) and at 262,144 envs (750 MB per set)
@@ -509,6 +524,8 @@ def run_b200(args):
         except Exception:
             pass
     if rank == 0 and world == 1 and not args.no_families:
+        time.sleep(2.0)     # the headline and e2e loops leave the GPU power-capped (SM clock ~1.7 GHz); the family
+        # entries are latency-bound kernels timed in isolation, so let the clocks recover first
         line["families"] = family_numbers(device, peak)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()

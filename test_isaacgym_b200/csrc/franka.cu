@@ -306,13 +306,12 @@ __device__ __forceinline__ void stage_wait(const StagePlan& P, int t, int ntiles
   __syncthreads();
 }
 
-// One-tile-per-CTA form: stage tile blockIdx.x and return when it is readable.
+// One-tile-per-CTA form: stage tile blockIdx.x and return when it is readable (after the kernel's stage_begin).
 template <int NSEG>
 __device__ __forceinline__ void stage_all(const StagePlan& P, const CUtensorMap* tmap, int64_t env0, int nenv, float* tile,
                                           uint64_t* bar, SAddr (&addr)[NSEG]) {
   unsigned phase = 0;
   const int64_t n = env0 + nenv;      // only the last tile is ragged, so this clamps exactly like the true n
-  stage_begin(P, bar);
   stage_issue<NSEG>(P, tmap, blockIdx.x, gridDim.x, n, tile, bar);
   stage_wait<NSEG>(P, blockIdx.x, gridDim.x, bar, phase, addr);
 }
@@ -398,6 +397,7 @@ __global__ void __launch_bounds__(kTileEnvs)
 ik_dls_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float lambda2, int has_pos, TView out, int64_t n) {
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
+  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
@@ -503,6 +503,7 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   constexpr int D = 7;
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
+  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   pdl_prologue();
   // persistent CTA: tiles blockIdx.x, + gridDim.x, ...; the tile buffer is refilled while the previous tile's
   // factorisation runs out of registers
@@ -526,7 +527,6 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   const float qdef_mine = threadIdx.x < 7 ? ldf(q_default, threadIdx.x * q_default.s[0]) : 0.f;
   int t = blockIdx.x;
   int64_t row = t < ntiles ? row_of(t) : 0;
-  stage_begin(P, &bar);
   if (t < ntiles) issue(t, row);
   if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;      // published by the barrier that ends stage_wait
   // statistics live in shared memory between tiles: four fp64 accumulators are eight registers this kernel does not
@@ -598,6 +598,7 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   constexpr int D = 7;
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
+  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   pdl_prologue();
   const int ntiles = tile_count(n);
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
@@ -611,7 +612,6 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   const float qdef_mine = threadIdx.x < 7 ? ldf(q_default, threadIdx.x * q_default.s[0]) : 0.f;
   SAddr a[6];
   unsigned phase = 0;
-  stage_begin(P, &bar);
   stage_issue<6>(P, &tmap, blockIdx.x, ntiles, n, tile, &bar);
   gather_copy<7>(rb, box_row, nenv, x0, x_ts);              // box pos + quat          (:348-349)
   gather_copy<13>(rb, hand_row, nenv, x0 + 7, x_ts);        // hand pos + quat + vel   (:351-353)
@@ -680,6 +680,7 @@ pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, 
   constexpr int D = 7;
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
+  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
@@ -689,7 +690,6 @@ pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, 
   const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
   SAddr a[4];
   unsigned phase = 0;
-  stage_begin(P, &bar);
   stage_issue<4>(P, &tmap, blockIdx.x, gridDim.x, n, tile, &bar);
   gather_copy<7>(rb, box_row, nenv, x0, x_ts);
   gather_copy<7>(rb, hand_row, nenv, x0 + 7, x_ts);
@@ -731,6 +731,7 @@ __global__ void __launch_bounds__(kTileEnvs)
 osc_full_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float kp, float kv, TView out, int64_t n) {
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
+  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);

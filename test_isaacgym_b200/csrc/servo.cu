@@ -16,7 +16,6 @@ namespace b200ctl {
 
 constexpr int kRow = 13;            // floats per actor root-state row
 constexpr int kEnvRow = 2 * kRow;   // [uav, car]
-constexpr int kTile = 64;           // envs per tile (= threads per CTA)
 
 struct ServoConst {
   double width, height, fx, fy, u0, v0;
@@ -29,10 +28,10 @@ struct ServoConst {
 // PREC 1: everything fp32, approximate division / rsqrt, bearing taken directly from the body-frame
 //         direction (skips the project -> subtract -> unproject pixel round trip).
 // Both modes build the attitude quaternion with servo_quat_from_bearing (no inverse-trig round trips).
-template <int PREC, bool STATS>
+template <int PREC, bool STATS, int TILE>
 __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64_t num_envs, const ServoConst& k,
                                                 double* __restrict__ aux, double* __restrict__ stats, int vec_ok) {
-  __shared__ __align__(128) float tile[kTile * kEnvRow];
+  __shared__ __align__(128) float tile[TILE * kEnvRow];
   __shared__ __align__(8) uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);     // touches no global memory: done ahead of the dependency wait
   pdl_prologue();
@@ -41,14 +40,14 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   // statistics and a persistent grid with them: the statistics are accumulated in registers across tiles and
   // committed once per CTA -- a commit per 64-env tile (16,384 CTAs per 1M envs, each ending in atomics it has to see
   // acknowledged before its SM slot frees) made the step 82 us instead of 37.7.
-  const int ntiles = (int)((num_envs + kTile - 1) / kTile);
-  constexpr unsigned kTileBytes = kTile * kEnvRow * sizeof(float);
+  const int ntiles = (int)((num_envs + TILE - 1) / TILE);
+  constexpr unsigned kBytes = TILE * kEnvRow * sizeof(float);
   unsigned phase = 0;
   double acc_d[2] = {0, 0};          // sum |pixel error|, sum error^2
   unsigned acc_u[3] = {0, 0, 0};     // envs, envs with the target behind the camera, non-finite attitudes
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-  const int64_t env0 = (int64_t)t * kTile;
-  const int nenv = (int)((num_envs - env0) < kTile ? (num_envs - env0) : kTile);
+  const int64_t env0 = (int64_t)t * TILE;
+  const int nenv = (int)((num_envs - env0) < TILE ? (num_envs - env0) : TILE);
   const int nfl = nenv * kEnvRow;
   float* gbase = state + env0 * kEnvRow;
 
@@ -56,20 +55,20 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   // copy brings it in and ONE bulk copy writes it back (the tile base stays 16-byte aligned: 64 * 104 B), so the
   // staging / write-back loops -- 25-31 % of all executed instructions in profiles/r01_linemix_servo_*_v5.txt --
   // disappear from the instruction stream.  The ragged last tile and unaligned tensors take the loops.
-  const bool bulk = vec_ok && nenv == kTile;
+  const bool bulk = vec_ok && nenv == TILE;
   if (bulk) {
     if (threadIdx.x == 0) {
       // the buffer is free: this thread waited for the previous tile's write-back to have read it (below)
-      mbar_arrive_expect_tx(&bar, kTileBytes);
-      bulk_g2s(tile, gbase, kTileBytes, &bar);
+      mbar_arrive_expect_tx(&bar, kBytes);
+      bulk_g2s(tile, gbase, kBytes, &bar);
     }
     mbar_wait(&bar, phase);
     phase ^= 1u;
   } else {
     const int nv4 = vec_ok ? (nfl >> 2) : 0;
-    for (int i = threadIdx.x; i < nv4; i += kTile)
+    for (int i = threadIdx.x; i < nv4; i += TILE)
       reinterpret_cast<float4*>(tile)[i] = __ldg(reinterpret_cast<const float4*>(gbase) + i);
-    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += kTile) tile[i] = __ldg(gbase + i);
+    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += TILE) tile[i] = __ldg(gbase + i);
     __syncthreads();
   }
 
@@ -173,15 +172,15 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
     fence_proxy_async_smem();     // this thread's row updates -> visible to the async proxy
     __syncthreads();
     if (threadIdx.x == 0) {
-      bulk_s2g(gbase, tile, kTileBytes);
+      bulk_s2g(gbase, tile, kBytes);
       bulk_commit_wait_read();    // the buffer may be refilled / freed only after the TMA unit has read it
     }
   } else {
     __syncthreads();
     const int nv4 = vec_ok ? (nfl >> 2) : 0;
-    for (int i = threadIdx.x; i < nv4; i += kTile)
+    for (int i = threadIdx.x; i < nv4; i += TILE)
       reinterpret_cast<float4*>(gbase)[i] = reinterpret_cast<const float4*>(tile)[i];
-    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += kTile) gbase[i] = tile[i];
+    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += TILE) gbase[i] = tile[i];
     __syncthreads();              // every row is out before the next tile's loads overwrite the buffer
   }
   }   // tile loop
@@ -193,20 +192,23 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
 }
 
 // Entry kernels per (precision, statistics) so each gets its own register budget: the fp64-stage kernel is latency
-// bound and gains from 16 resident tiles per SM (64 registers: 57 -> 52 us per 1M envs at the time); the fp32 kernel
-// is left to the compiler's default -- any explicit minimum made it slower.  STATS is a template parameter so the
-// five fp64 accumulators that live across the tile loop cost the plain step nothing.
+// bound and gains from 1,024 resident threads per SM (64 registers: 57 -> 52 us per 1M envs at the time); the fp32
+// kernel is left to the compiler's default -- any explicit minimum made it slower.  STATS is a template parameter so
+// the accumulators that live across the tile loop cost the plain step nothing.  Tile size (= CTA size): 64 envs;
+// 128 for the fp32 statistics variant (measured per 1M envs with statistics, tiles of 64 / 128 / 256:
+// reference precision 43.3 / 44.2 / 47.6 us, fast 40.6 / 39.0 / 38.9 us).
+template <int PREC, bool STATS> struct ServoTile { static constexpr int value = (STATS && PREC == 1) ? 128 : 64; };
 template <int PREC, bool STATS> __global__ void servo_step_kernel(float*, int64_t, ServoConst, double*, double*, int);
-#define B200_SERVO_KERNEL(PREC, STATS, BOUNDS)                                                                         \
+#define B200_SERVO_KERNEL(PREC, STATS, ...)                                                                            \
   template <>                                                                                                          \
-  __global__ void BOUNDS servo_step_kernel<PREC, STATS>(float* state, int64_t num_envs, ServoConst k, double* aux,     \
-                                                        double* stats, int vec_ok) {                                   \
-    servo_step_body<PREC, STATS>(state, num_envs, k, aux, stats, vec_ok);                                              \
+  __global__ void __VA_ARGS__ servo_step_kernel<PREC, STATS>(float* state, int64_t num_envs, ServoConst k,             \
+                                                             double* aux, double* stats, int vec_ok) {                 \
+    servo_step_body<PREC, STATS, ServoTile<PREC, STATS>::value>(state, num_envs, k, aux, stats, vec_ok);               \
   }
-B200_SERVO_KERNEL(0, false, __launch_bounds__(kTile, 16))
-B200_SERVO_KERNEL(0, true, __launch_bounds__(kTile, 16))
-B200_SERVO_KERNEL(1, false, __launch_bounds__(kTile))
-B200_SERVO_KERNEL(1, true, __launch_bounds__(kTile))
+B200_SERVO_KERNEL(0, false, __launch_bounds__(64, 16))
+B200_SERVO_KERNEL(0, true, __launch_bounds__(64, 16))
+B200_SERVO_KERNEL(1, false, __launch_bounds__(64))
+B200_SERVO_KERNEL(1, true, __launch_bounds__(128))
 #undef B200_SERVO_KERNEL
 
 // ---------------------------------------------------------------- standalone entry points
@@ -526,18 +528,18 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
   DeviceGuard g;
   B200_TRY(g.enter(dev));
   float* st = reinterpret_cast<float*>(const_cast<void*>(s.p));
-  // persistent grid: every resident CTA slot of the device (occupancy x SM count), or one CTA per tile if fewer
-  const int ntiles = grid1d(n, kTile);
   void (*kern)(float*, int64_t, ServoConst, double*, double*, int) =
       params->precision == 0 ? (stats ? servo_step_kernel<0, true> : servo_step_kernel<0, false>)
                              : (stats ? servo_step_kernel<1, true> : servo_step_kernel<1, false>);
-  int occ = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTile, 0));
   // with statistics: persistent CTAs (one commit per CTA); without: one CTA per tile -- the hardware's dynamic CTA
-  // scheduling balances the SMs better than a static tile stride (1M envs: 37.7 vs 39.9 us, fast mode 34.8 vs 40.6)
+  // scheduling balances the SMs better than a static tile stride (1M envs: 37.0 vs 39.9 us, fast mode 35.0 vs 40.6)
+  const int tile = (stats && params->precision == 1) ? ServoTile<1, true>::value : 64;
+  const int ntiles = grid1d(n, tile);
+  int occ = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, tile, 0));
   const int slots = sm_count(dev) * (occ > 0 ? occ : 1);
   const int grid = (stats && ntiles > slots) ? slots : ntiles;
   const int vec_ok = aligned16(st) ? 1 : 0;
-  launch_pdl(kern, grid, kTile, 0, (cudaStream_t)stream, st, n, k, aux_out, stats, vec_ok);
+  launch_pdl(kern, grid, tile, 0, (cudaStream_t)stream, st, n, k, aux_out, stats, vec_ok);
   return post_launch("servo_step_kernel");
 }
