@@ -432,7 +432,12 @@ def run_b200(args):
     torch.cuda.set_device(device)
     import torch.distributed as dist
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL on a HIGH-PRIORITY stream: the control kernels are persistent grids chained by programmatic dependent
+        # launch, so a normal-priority collective kernel is starved of an SM slot until the control stream itself
+        # blocks on the window's event -- and then waits for the peer to reach the same point (measured at N=2:
+        # 47.8 us/step instead of 32.6)
+        from test_isaacgym_b200.sharding import nccl_options
+        dist.init_process_group("nccl", device_id=device, pg_options=nccl_options())
     from test_isaacgym_b200 import _lib
     from test_isaacgym_b200.sharding import StatsReducer, StatsWindow, env_slice
     from test_isaacgym_b200.pd_control import pd_torque
@@ -443,14 +448,22 @@ def run_b200(args):
     wl = PdWorkload(device, hi - lo, seed=1000 + rank)
     reducer = StatsReducer("torch", device) if world > 1 else None
     stats_every = max(1, args.stats_every)
-    wl.bind(StatsWindow(device, reducer, stats_every))
+    wl.bind(StatsWindow(device, reducer, stats_every, overlap=args.stats_overlap))
     step = wl.step
 
     with ClockSampler(local_rank) as clocks:
         # sustained warm-up so the clock samples describe the loaded state of this very kernel
+        # (every rank must run the SAME number of steps: the statistics all-reduce fires every k-th step, and ranks
+        # whose clocks disagree on when the warm-up ends would enqueue different numbers of collectives and deadlock;
+        # the continue / stop decision is therefore itself reduced over the ranks)
         t_end = time.perf_counter() + args.sustain_s
         it = 0
-        while time.perf_counter() < t_end:
+        while True:
+            go = torch.tensor([1 if time.perf_counter() < t_end else 0], device=device, dtype=torch.int32)
+            if world > 1:
+                dist.all_reduce(go, op=dist.ReduceOp.MIN)
+            if int(go.item()) == 0:
+                break
             for _ in range(200):
                 wl.step(it)
                 it += 1
@@ -506,6 +519,7 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(), "envs_per_gpu": hi - lo, "num_dofs": NUM_DOFS, "global_envs": total_envs,
                    "parallelism": f"env-slices x{world}", "stats_allreduce_every": stats_every if world > 1 else None,
+                   "stats_allreduce": ("side stream" if args.stats_overlap else "in order on the control stream") if world > 1 else None,
                    "l2_policy": f"inputs > L2: {wl.sets} rotating buffer sets of 201 MB (151 MB in + 50 MB out each)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "pd_torque_vec4_kernel", "bytes_per_launch": (hi - lo) * PD_BYTES_PER_ENV,
@@ -546,6 +560,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--stats-every", type=int, default=16, help="all-reduce the statistics vector every k steps (N > 1)")
+    ap.add_argument("--stats-overlap", action="store_true", help="all-reduce on a side stream instead of in order (N > 1)")
     ap.add_argument("--sustain-s", type=float, default=1.0, help="seconds of pre-load before the timed region (clock sampling)")
     ap.add_argument("--no-families", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

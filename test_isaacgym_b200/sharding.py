@@ -34,6 +34,19 @@ def rebase_index(index: torch.Tensor, rows_per_env: int, start: int) -> torch.Te
     return index - start * rows_per_env
 
 
+def nccl_options():
+    """``pg_options`` for ``dist.init_process_group("nccl", ...)`` in a process that runs b200ctl step loops: the
+    collectives go to a high-priority CUDA stream.  The control kernels are persistent grids chained by programmatic
+    dependent launch -- the next step's CTAs take every SM slot the moment the previous step's CTAs retire -- so a
+    normal-priority all-reduce kernel does not get a slot until the control stream blocks on the statistics window's
+    event, and then still waits for the peer ranks to reach the same point.  (A non-torch host does the same by
+    calling ``b200ctl_stats_allreduce`` on a stream created with ``cudaStreamCreateWithPriority``.)"""
+    from torch.distributed import ProcessGroupNCCL
+    opts = ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return opts
+
+
 class StatsReducer:
     """Sum all-reduce of statistics vectors across ranks.
 
@@ -49,7 +62,7 @@ class StatsReducer:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self._comm = ctypes.c_void_p()
-        self._side = torch.cuda.Stream(device) if (device is not None and device.type == "cuda") else None
+        self._side = torch.cuda.Stream(device, priority=-1) if (device is not None and device.type == "cuda") else None
         if backend == "abi" and self.world > 1:
             L = _lib.lib()
             uid = torch.zeros(128, dtype=torch.uint8)
@@ -63,15 +76,23 @@ class StatsReducer:
             with torch.cuda.device(device):
                 _lib.check(L.b200ctl_nccl_comm_init(ctypes.byref(self._comm), self.world, raw, self.rank))
 
-    def all_reduce(self, stats: torch.Tensor):
-        """In-place sum over ranks.  On GPUs the reduction is enqueued on the side stream (ordered after
-        everything already on the current stream) and a ``torch.cuda.Event`` marking its completion is
-        returned: wait on it (``current_stream().wait_event(ev)`` / ``ev.synchronize()``) before reading or
-        re-zeroing ``stats``.  Kernels of later steps must accumulate into a DIFFERENT buffer meanwhile
-        (see ``StatsWindow``).  Returns None on CPU / single rank (already complete)."""
+    def all_reduce(self, stats: torch.Tensor, overlap: bool = False):
+        """In-place sum over ranks.
+
+        ``overlap=False`` (default): the reduction is enqueued IN ORDER on the current stream, between two control
+        steps; returns None.  ``overlap=True``: it is enqueued on the side stream (ordered after everything already on
+        the current stream) and a ``torch.cuda.Event`` marking its completion is returned: wait on it
+        (``current_stream().wait_event(ev)`` / ``ev.synchronize()``) before reading or re-zeroing ``stats``; kernels
+        of later steps must accumulate into a DIFFERENT buffer meanwhile (see ``StatsWindow``).
+
+        In order is the default because the control kernels are ONE-WAVE persistent grids: a collective kernel that
+        is resident next to them (waiting for its peers, which may lag by up to a window) displaces a few of their CTAs
+        into a second wave and every step it overlaps takes ~1.6x as long -- measured at N=2, k=16: 46.5 us/step
+        overlapped vs 31.6 us/step without any collective (``profiles/experiments/host_cost.py``).  In order, the
+        ranks re-synchronise every window and the cost is the collective's own latency once per k steps."""
         if self.world == 1:
             return None
-        if self._side is not None:
+        if overlap and self._side is not None:
             self._side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self._side):
                 self._reduce(stats)
@@ -105,14 +126,15 @@ class StatsReducer:
 
 class StatsWindow:
     """Double-buffered statistics accumulator: kernels add into the current buffer; every ``every`` steps the
-    finished buffer is all-reduced on the side stream while the next steps accumulate into the other one, so
-    the collective never sits on the critical path of the control step."""
+    finished buffer is all-reduced -- in order on the control stream by default, or on the reducer's side stream with
+    ``overlap=True`` while the next steps accumulate into the other buffer (see ``StatsReducer.all_reduce`` for why
+    overlapping is not the default) -- and stays readable as ``last_reduced`` for a whole window."""
 
-    def __init__(self, device: torch.device, reducer: StatsReducer | None, every: int = 16):
+    def __init__(self, device: torch.device, reducer: StatsReducer | None, every: int = 16, overlap: bool = False):
         self.bufs = [_lib.stats_buffer(device), _lib.stats_buffer(device)]
         self.events = [None, None]
         self.cur = 0
-        self.reducer, self.every, self.device = reducer, max(1, every), device
+        self.reducer, self.every, self.device, self.overlap = reducer, max(1, every), device, overlap
         self.last_reduced = None      # most recent globally-reduced window (device tensor)
         self._steps = 0
 
@@ -127,7 +149,7 @@ class StatsWindow:
             return
         done = self.cur
         if self.reducer is not None:
-            self.events[done] = self.reducer.all_reduce(self.bufs[done])
+            self.events[done] = self.reducer.all_reduce(self.bufs[done], overlap=self.overlap)
         self.last_reduced = self.bufs[done]
         self.cur ^= 1
         ev = self.events[self.cur]

@@ -23,7 +23,8 @@ def main():
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", device_id=dev)
+    from test_isaacgym_b200.sharding import nccl_options
+    dist.init_process_group("nccl", device_id=dev, pg_options=nccl_options())
     n, d = 100_003, 12
     full = syn.pd_inputs(n, d, seed=5)
     ctl = PDController(d, full.kp, full.kd, tau_max=full.tau_max, device=dev)
