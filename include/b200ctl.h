@@ -257,7 +257,9 @@ B200CTL_API int b200ctl_gather_rows(const DLTensor* src, const DLTensor* index, 
 /* =========================== multi-GPU: statistics all-reduce ==============
  * ncclAllReduce(sum, double) of `n` stats entries in place.  `comm` is an
  * ncclComm_t; NCCL is resolved at run time from the already-loaded libnccl
- * (no link-time dependency).  The control step itself moves no bytes between GPUs. */
+ * (no link-time dependency).  The control step itself moves no bytes between GPUs.
+ * Enqueue it on the SAME stream as the control kernels, between two steps: those kernels are one-wave persistent
+ * grids, and a collective kernel resident next to them pushes part of every overlapped step into a second wave. */
 B200CTL_API int b200ctl_nccl_unique_id(void* id_out_128_bytes);
 B200CTL_API int b200ctl_nccl_comm_init(void** comm_out, int32_t world_size, const void* id_128_bytes, int32_t rank);
 B200CTL_API int b200ctl_nccl_comm_destroy(void* comm);
