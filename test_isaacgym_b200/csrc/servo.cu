@@ -65,6 +65,9 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
     mbar_wait(&bar, phase);
     phase ^= 1u;
   } else {
+    // a persistent CTA may come here from a bulk tile: thread 0 reaches this barrier only after that tile's
+    // write-back has READ the buffer, so nobody overwrites it early
+    __syncthreads();
     const int nv4 = vec_ok ? (nfl >> 2) : 0;
     for (int i = threadIdx.x; i < nv4; i += TILE)
       reinterpret_cast<float4*>(tile)[i] = __ldg(reinterpret_cast<const float4*>(gbase) + i);

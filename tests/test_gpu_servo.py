@@ -280,3 +280,36 @@ def test_scalar_class_and_roi_helpers(servo_kat):
     class Props:
         width, height = W, H
     assert np.array_equal(CameraController(Props, 4).get_rot_uav2world(), np.identity(3))
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_statistics_variant_is_the_same_step(precision):
+    """With a statistics vector the step runs as a PERSISTENT grid (several tiles per CTA through one tile buffer,
+    128-env tiles in fast mode, one commit per CTA): the state it writes must be bit-identical to the plain
+    one-CTA-per-tile step, for a size with many tiles per CTA and a ragged last tile, aligned and unaligned; the
+    vector must hold the env count, the mean pixel error of the aux output and no non-finite attitudes, and add up
+    over calls."""
+    from test_isaacgym_b200 import _lib
+    n = 400_003                                   # > 16 x 148 tiles of 64: several tiles per persistent CTA
+    state = syn.servo_root_state(n, seed=23, regime="reference")
+    step = ServoStep(W, H, precision=precision)
+    for unaligned in (False, True):
+        if unaligned:                             # base pointer 4 bytes off a 16-byte boundary: loop-staged tiles
+            ba, bb = (torch.zeros(n * 26 + 1, device=DEV) for _ in range(2))
+            a, b = ba[1:].view(n, 2, 13), bb[1:].view(n, 2, 13)
+            a.copy_(state), b.copy_(state)
+        else:
+            a, b = state.to(DEV), state.to(DEV)
+        aux = torch.zeros(n, 5, dtype=torch.float64, device=DEV)
+        st = _lib.stats_buffer(torch.device(DEV))
+        step(a)
+        step(b, aux=aux, stats=st)
+        assert torch.equal(a, b)
+        s = st.cpu()
+        err = torch.linalg.vector_norm(torch.tensor([W / 2, H / 2], dtype=torch.float64) - aux[:, :2].cpu(), dim=1)
+        fin = torch.isfinite(err)
+        assert s[0] == n and s[4] == 0
+        assert abs(float(s[1]) - float(err[fin].sum())) <= 1e-6 * float(err[fin].sum())
+        assert abs(float(s[2]) - float((err[fin] ** 2).sum())) <= 1e-6 * float((err[fin] ** 2).sum())
+        step(b, stats=st)                         # a second step adds to the same vector
+        assert st.cpu()[0] == 2 * n
