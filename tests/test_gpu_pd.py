@@ -177,3 +177,24 @@ def test_pd_host_buffer_path():
     pi = syn.pd_inputs(4096, 12, seed=2)
     tau = pd_torque(pi.dof_state, pi.q_target, pi.kp, pi.kd)
     assert torch.equal(tau, opd.pd_torque(pi.dof_state, pi.q_target, pi.kp, pi.kd))
+
+
+def test_pd_stats_are_slice_invariant():
+    """The statistics of env slices computed separately add up to the statistics of the whole (counts exactly, sums to
+    fp64 summation order): the per-vector fp32 partial sums group the same four elements whatever the slice, and a
+    vector holding a non-finite torque takes the per-element fp64 path in either case."""
+    n, d = 50_001, 12
+    pi = syn.pd_inputs(n, d, seed=29)
+    state = pi.dof_state.clone()
+    state[5 * d + 3, 0] = float("nan")            # one NaN position and one Inf velocity: non-finite torques
+    state[40_000 * d + 7, 1] = float("inf")
+    ctl = PDController(d, pi.kp, pi.kd, tau_max=pi.tau_max, device=DEV)
+    ds, tg = state.to(DEV), pi.q_target.to(DEV)
+    whole = _lib.stats_buffer(torch.device(DEV))
+    ctl(ds, tg, stats=whole)
+    parts = _lib.stats_buffer(torch.device(DEV))
+    for s, e in ((0, 7), (7, 20_000), (20_000, 20_001), (20_001, n)):
+        ctl(ds[s * d:e * d], tg[s:e], stats=parts)
+    w, p = whole.cpu(), parts.cpu()
+    assert w[0] == n and p[0] == n and w[4] == p[4] and w[4] >= 1 and w[3] == p[3]
+    assert torch.allclose(w[1:3], p[1:3], rtol=1e-13, atol=0)
