@@ -13,8 +13,10 @@
 // Kernel shape: one thread owns 4 consecutive (env,dof) elements per iteration:
 // two 128-bit streaming loads of interleaved (q, qd) pairs, one 128-bit load of
 // targets, one 128-bit store.  Per-DOF gains / limits sit in shared memory.  The
-// grid is a multiple of the SM count and strides over the element range, so
-// the per-block statistics epilogue costs one atomic per block per entry.
+// loop is rotated (the loads of iteration i+1 are issued at the end of iteration i,
+// those of the first iteration ahead of the parameter staging).  The grid is a
+// multiple of the SM count and strides over the element range -- one wave with the
+// statistics epilogue (one RED instruction per CTA), four without.
 // Arithmetic is fp32 with explicit round-to-nearest intrinsics (no FMA
 // contraction): bit-identical to the torch expression of the reference.
 #include "common.cuh"

@@ -4,10 +4,13 @@
 // euler2quaternion (controller6.py:46-51) and the root-state scatter (test10:451-454).
 //
 // servo_step is the fused kernel: one thread per environment, the (uav, car)
-// root-state rows of a 64-env tile staged through shared memory with 128-bit
-// coalesced loads, results scattered into the staged rows, rows written back whole
-// (unchanged columns keep the bits that were read).  Roofline: HBM at 96 algorithmic B/env (read 40, write 56);
-// the fp64 "reference precision" mode is FP64-pipe bound instead.
+// root-state rows of a 64-env tile staged through shared memory by ONE TMA bulk copy
+// (128-bit / scalar loops for ragged or unaligned tiles), results scattered into the
+// staged rows, rows written back whole by ONE bulk copy (unchanged columns keep the
+// bits that were read).  One CTA per tile; a persistent grid with one statistics
+// commit per CTA when a statistics vector is passed.  Roofline: HBM at 96 algorithmic
+// B/env (read 40, write 56), 208 B/env of real DRAM traffic for 13-float rows; the
+// fp64 "reference precision" mode is issue / FP64-pipe bound on top of that.
 #include "servo_math.cuh"
 
 #include <type_traits>
