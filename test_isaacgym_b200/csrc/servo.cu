@@ -31,9 +31,15 @@ struct ServoConst {
 // PREC 1: everything fp32, approximate division / rsqrt, bearing taken directly from the body-frame
 //         direction (skips the project -> subtract -> unproject pixel round trip).
 // Both modes build the attitude quaternion with servo_quat_from_bearing (no inverse-trig round trips).
-template <int PREC, bool STATS, int TILE>
+// SPLIT: two threads per env -- threads [0, TILE) evaluate the attitude chain (projection, servo angles, gimbal
+// quaternion), threads [TILE, 2 TILE) the guidance (both vector fields, the car heading).  The two halves read the
+// staged inputs and write disjoint columns, so they never exchange anything; the arithmetic per env is the same as in
+// the one-thread form (same bits).  It halves the serial chain of a tile: the small-N step is one wave of CTAs whose
+// time IS that chain (65,536 envs), while at 1M envs the step is issue bound and the form does not matter.
+template <int PREC, bool STATS, int TILE, bool SPLIT>
 __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64_t num_envs, const ServoConst& k,
                                                 double* __restrict__ aux, double* __restrict__ stats, int vec_ok) {
+  constexpr int NT = SPLIT ? 2 * TILE : TILE;      // threads per CTA
   __shared__ __align__(128) float tile[TILE * kEnvRow];
   __shared__ __align__(8) uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);     // touches no global memory: done ahead of the dependency wait
@@ -72,36 +78,51 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
     // write-back has READ the buffer, so nobody overwrites it early
     __syncthreads();
     const int nv4 = vec_ok ? (nfl >> 2) : 0;
-    for (int i = threadIdx.x; i < nv4; i += TILE)
+    for (int i = threadIdx.x; i < nv4; i += NT)
       reinterpret_cast<float4*>(tile)[i] = __ldg(reinterpret_cast<const float4*>(gbase) + i);
-    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += TILE) tile[i] = __ldg(gbase + i);
+    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += NT) tile[i] = __ldg(gbase + i);
     __syncthreads();
   }
 
-  if (threadIdx.x < nenv) {
-    float* row = tile + threadIdx.x * kEnvRow;
+  const int e = SPLIT ? (int)threadIdx.x % TILE : (int)threadIdx.x;     // env of this thread within the tile
+  const bool do_attitude = !SPLIT || (int)threadIdx.x < TILE;
+  const bool do_guidance = !SPLIT || (int)threadIdx.x >= TILE;
+  if (e < nenv) {
+    float* row = tile + e * kEnvRow;
     const float ux = row[0], uy = row[1], uz = row[2];
-    const float qx = row[3], qy = row[4], qz = row[5], qw = row[6];
     const float cx = row[13], cy = row[14], cz = row[15];
 
-    // ---- car: velocity command, heading quaternion (test10:406-410), fp32 like the reference's torch ops
-    using CA = typename std::conditional<PREC == 0, Ar<float>, ArFast>::type;
-    float cvx, cvy, cvz;
-    cclvf_core<float, CA>(cx, cy, cz, k.car_tx, k.car_ty, k.car_tz, k.car_speed, k.car_rd, k.car_rd2, k.car_rd4, cvx, cvy, cvz);
-    // ---- uav: velocity command toward (car.x, car.y, height) (test10:412-414)
-    float uvx, uvy, uvz;
-    cclvf_core<float, CA>(ux, uy, uz, cx, cy, k.uav_height, k.uav_speed, k.uav_rd, k.uav_rd2, k.uav_rd4, uvx, uvy, uvz);
+    if (do_guidance) {
+      // ---- car: velocity command, heading quaternion (test10:406-410), fp32 like the reference's torch ops
+      using CA = typename std::conditional<PREC == 0, Ar<float>, ArFast>::type;
+      float cvx, cvy, cvz;
+      cclvf_core<float, CA>(cx, cy, cz, k.car_tx, k.car_ty, k.car_tz, k.car_speed, k.car_rd, k.car_rd2, k.car_rd4, cvx, cvy, cvz);
+      // ---- uav: velocity command toward (car.x, car.y, height) (test10:412-414)
+      float uvx, uvy, uvz;
+      cclvf_core<float, CA>(ux, uy, uz, cx, cy, k.uav_height, k.uav_speed, k.uav_rd, k.uav_rd2, k.uav_rd4, uvx, uvy, uvz);
+      float cqz, cqw;
+      if (PREC == 0) {
+        // torch.atan2 on fp32 (:407): correctly rounded fp32 result via fp64
+        const float car_yaw = (float)atan2_f32grade((double)cvy, (double)cvx);
+        double sn, cs;
+        sincos_halfpi((double)car_yaw * 0.5, &sn, &cs);     // scipy from_euler('xyz', [0,0,yaw]) in fp64 (:410)
+        cqz = (float)sn; cqw = (float)cs;
+      } else {
+        const float car_yaw = atan2f(cvy, cvx);
+        sincosf(car_yaw * 0.5f, &cqz, &cqw);
+      }
+      // scatter into the staged rows (test10:452-454)
+      row[7] = uvx; row[8] = uvy; row[9] = uvz;
+      row[16] = 0.f; row[17] = 0.f; row[18] = cqz; row[19] = cqw;
+      row[20] = cvx; row[21] = cvy; row[22] = cvz;
+    }
 
-    float oq[4], cq[4];
+    if (do_attitude) {
+    const float qx = row[3], qy = row[4], qz = row[5], qw = row[6];
+    float oq[4];
     double pu, pv, rolld = 0, pitchd = 0, yawd = 0, err = 0;   // err = |order_pixel_move| (test10:432), statistics only
     bool behind;
     if (PREC == 0) {
-      // torch.atan2 on fp32 (:407): correctly rounded fp32 result via fp64
-      const float car_yaw = (float)atan2_f32grade((double)cvy, (double)cvx);
-      double s, c;
-      sincos_halfpi((double)car_yaw * 0.5, &s, &c);     // scipy from_euler('xyz', [0,0,yaw]) in fp64 (:410)
-      cq[0] = 0.f; cq[1] = 0.f; cq[2] = (float)s; cq[3] = (float)c;
-
       double R[9];
       quat_to_mat<double, FnStep64>(qx, qy, qz, qw, R);    // :423
       // the difference car - uav is formed in the state dtype (fp32) before promotion (controller6.py:172-173,221)
@@ -125,11 +146,6 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       }
       if (STATS) err = sqrt(mvx * mvx + mvy * mvy);
     } else {
-      const float car_yaw = atan2f(cvy, cvx);
-      float s, c;
-      sincosf(car_yaw * 0.5f, &s, &c);
-      cq[0] = 0.f; cq[1] = 0.f; cq[2] = s; cq[3] = c;
-
       float R[9];
       quat_to_mat<float>(qx, qy, qz, qw, R);
       const float dx = cx - ux, dy = cy - uy, dz = cz - uz;
@@ -150,14 +166,11 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       if (STATS) err = sqrtf(ex * ex + ey * ey);
     }
 
-    // ---- scatter into the staged rows (test10:451-454)
+    // ---- scatter into the staged row (test10:451)
     row[3] = oq[0]; row[4] = oq[1]; row[5] = oq[2]; row[6] = oq[3];
-    row[7] = uvx; row[8] = uvy; row[9] = uvz;
-    row[16] = cq[0]; row[17] = cq[1]; row[18] = cq[2]; row[19] = cq[3];
-    row[20] = cvx; row[21] = cvy; row[22] = cvz;
 
     if (aux) {
-      double* a = aux + (env0 + threadIdx.x) * 5;
+      double* a = aux + (env0 + e) * 5;
       a[0] = pu; a[1] = pv; a[2] = rolld; a[3] = pitchd; a[4] = yawd;
     }
     if (STATS) {
@@ -169,6 +182,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       acc_u[1] += behind ? 1u : 0u;
       acc_u[2] += finite ? 0u : 1u;
     }
+    }   // attitude
   }
   // ---- write the staged rows back whole.  Only columns 3..9 of each actor row changed (test10:451-454); the other
   // columns are rewritten with the bits that were read, so the tensor handed to set_actor_root_state_tensor is
@@ -184,9 +198,9 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   } else {
     __syncthreads();
     const int nv4 = vec_ok ? (nfl >> 2) : 0;
-    for (int i = threadIdx.x; i < nv4; i += TILE)
+    for (int i = threadIdx.x; i < nv4; i += NT)
       reinterpret_cast<float4*>(gbase)[i] = reinterpret_cast<const float4*>(tile)[i];
-    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += TILE) gbase[i] = tile[i];
+    for (int i = (nv4 << 2) + threadIdx.x; i < nfl; i += NT) gbase[i] = tile[i];
     __syncthreads();              // every row is out before the next tile's loads overwrite the buffer
   }
   }   // tile loop
@@ -204,17 +218,21 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
 // 128 for the fp32 statistics variant (measured per 1M envs with statistics, tiles of 64 / 128 / 256:
 // reference precision 43.3 / 44.2 / 47.6 us, fast 40.6 / 39.0 / 38.9 us).
 template <int PREC, bool STATS> struct ServoTile { static constexpr int value = (STATS && PREC == 1) ? 128 : 64; };
-template <int PREC, bool STATS> __global__ void servo_step_kernel(float*, int64_t, ServoConst, double*, double*, int);
-#define B200_SERVO_KERNEL(PREC, STATS, ...)                                                                            \
+template <int PREC, bool STATS, bool SPLIT>
+__global__ void servo_step_kernel(float*, int64_t, ServoConst, double*, double*, int);
+#define B200_SERVO_KERNEL(PREC, STATS, SPLIT, ...)                                                                     \
   template <>                                                                                                          \
-  __global__ void __VA_ARGS__ servo_step_kernel<PREC, STATS>(float* state, int64_t num_envs, ServoConst k,             \
-                                                             double* aux, double* stats, int vec_ok) {                 \
-    servo_step_body<PREC, STATS, ServoTile<PREC, STATS>::value>(state, num_envs, k, aux, stats, vec_ok);               \
+  __global__ void __VA_ARGS__ servo_step_kernel<PREC, STATS, SPLIT>(float* state, int64_t num_envs, ServoConst k,      \
+                                                                    double* aux, double* stats, int vec_ok) {          \
+    servo_step_body<PREC, STATS, ServoTile<PREC, STATS>::value, SPLIT>(state, num_envs, k, aux, stats, vec_ok);        \
   }
-B200_SERVO_KERNEL(0, false, __launch_bounds__(64, 16))
-B200_SERVO_KERNEL(0, true, __launch_bounds__(64, 16))
-B200_SERVO_KERNEL(1, false, __launch_bounds__(64))
-B200_SERVO_KERNEL(1, true, __launch_bounds__(128))
+B200_SERVO_KERNEL(0, false, false, __launch_bounds__(64, 16))
+B200_SERVO_KERNEL(0, true, false, __launch_bounds__(64, 16))
+B200_SERVO_KERNEL(1, false, false, __launch_bounds__(64))
+B200_SERVO_KERNEL(1, true, false, __launch_bounds__(128))
+B200_SERVO_KERNEL(0, false, true, __launch_bounds__(128, 8))
+B200_SERVO_KERNEL(0, true, true, __launch_bounds__(128, 8))
+B200_SERVO_KERNEL(1, false, true, __launch_bounds__(128))
 #undef B200_SERVO_KERNEL
 
 // ---------------------------------------------------------------- standalone entry points
@@ -534,18 +552,35 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
   DeviceGuard g;
   B200_TRY(g.enter(dev));
   float* st = reinterpret_cast<float*>(const_cast<void*>(s.p));
-  void (*kern)(float*, int64_t, ServoConst, double*, double*, int) =
-      params->precision == 0 ? (stats ? servo_step_kernel<0, true> : servo_step_kernel<0, false>)
-                             : (stats ? servo_step_kernel<1, true> : servo_step_kernel<1, false>);
   // with statistics: persistent CTAs (one commit per CTA); without: one CTA per tile -- the hardware's dynamic CTA
-  // scheduling balances the SMs better than a static tile stride (1M envs: 37.0 vs 39.9 us, fast mode 35.0 vs 40.6)
+  // scheduling balances the SMs better than a static tile stride (1M envs: 37.0 vs 39.9 us, fast mode 35.0 vs 40.6).
+  // Two threads per env (SPLIT) while all tiles fit the device in one wave of the one-thread form: the step is then a
+  // single latency chain per tile and the split halves it; beyond that the step is issue bound and one thread per env
+  // keeps more tiles resident.
   const int tile = (stats && params->precision == 1) ? ServoTile<1, true>::value : 64;
   const int ntiles = grid1d(n, tile);
+  typedef void (*Kern)(float*, int64_t, ServoConst, double*, double*, int);
+  auto pick = [&](bool split) -> Kern {
+    if (params->precision == 0) {
+      if (stats) return split ? servo_step_kernel<0, true, true> : servo_step_kernel<0, true, false>;
+      return split ? servo_step_kernel<0, false, true> : servo_step_kernel<0, false, false>;
+    }
+    if (stats) return servo_step_kernel<1, true, false>;
+    return split ? servo_step_kernel<1, false, true> : servo_step_kernel<1, false, false>;
+  };
   int occ = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, tile, 0));
-  const int slots = sm_count(dev) * (occ > 0 ? occ : 1);
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick(false), tile, 0));
+  int slots = sm_count(dev) * (occ > 0 ? occ : 1);
+  // (measured, us per step at 16,384 / 65,536 envs: reference precision 3.08 -> 2.39 / 5.66 -> 5.36, fast 2.31 -> 2.05 /
+  // 4.74 -> 4.70; forced at 1M envs 36.2 -> 44.6; the fast statistics variant with its 128-env tiles loses: 5.55 -> 6.06)
+  const bool split = ntiles <= slots && !(stats && params->precision == 1);
+  Kern kern = pick(split);
+  if (split) {
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 2 * tile, 0));
+    slots = sm_count(dev) * (occ > 0 ? occ : 1);
+  }
   const int grid = (stats && ntiles > slots) ? slots : ntiles;
   const int vec_ok = aligned16(st) ? 1 : 0;
-  launch_pdl(kern, grid, tile, 0, (cudaStream_t)stream, st, n, k, aux_out, stats, vec_ok);
+  launch_pdl(kern, grid, split ? 2 * tile : tile, 0, (cudaStream_t)stream, st, n, k, aux_out, stats, vec_ok);
   return post_launch("servo_step_kernel");
 }

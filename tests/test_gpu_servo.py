@@ -313,3 +313,19 @@ def test_statistics_variant_is_the_same_step(precision):
         assert abs(float(s[2]) - float((err[fin] ** 2).sum())) <= 1e-6 * float((err[fin] ** 2).sum())
         step(b, stats=st)                         # a second step adds to the same vector
         assert st.cpu()[0] == 2 * n
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_two_threads_per_env_form_gives_the_same_bits(precision):
+    """Below one wave of tiles the step runs with two threads per env (attitude chain / guidance), above it with one:
+    a large tensor stepped whole (one thread per env) must equal the same tensor stepped in slices small enough to take
+    the two-thread form, bit for bit."""
+    n = 400_000
+    state = syn.servo_root_state(n, seed=31, regime="reference")
+    step = ServoStep(W, H, precision=precision)
+    whole = state.to(DEV)
+    step(whole)
+    parts = state.to(DEV)
+    for s in range(0, n, 50_000):                 # 782 tiles each: far below 16 x 148 resident tiles
+        step(parts[s:s + 50_000])
+    assert torch.equal(whole, parts)
