@@ -156,7 +156,12 @@ __device__ __forceinline__ void pd_commit_stats(const PdAcc& a, double* stats, i
 #endif
 constexpr int pd_block(bool stats) { return stats ? B200_PD_STATS_BLOCK : 256; }
 constexpr int pd_ctas(bool stats) { return stats ? B200_PD_STATS_CTAS : 6; }
-template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS>
+// DANY = false: D % 4 == 0, the four elements of a vector are four consecutive DOFs of ONE env and the per-DOF
+// parameters are read as float4.  DANY = true: any D >= 4 with N * D % 4 == 0 (Franka: D = 9) -- a vector may straddle
+// two envs, so each element carries its own DOF index ((4 v + i) mod D, advanced incrementally) and the parameters are
+// read as scalars; the streaming accesses are the same 128-bit ones.  (Before, D = 9 / D = 7 fell to the
+// one-element-per-thread kernel: 3.7 / 3.5 TB/s against 6.6 TB/s at D = 12, profiles/experiments/pd_dof_sweep.py.)
+template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS, bool DANY>
 __global__ void __launch_bounds__(pd_block(STATS), pd_ctas(STATS))
 pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict__ q_tgt,
                       const float4* __restrict__ qd_tgt, PdParams pp, int num_dofs, int64_t nvec, int64_t num_envs,
@@ -191,23 +196,36 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
   }
   __syncthreads();
 
-  const int vec_per_env = num_dofs >> 2;
   PdAcc acc;
-  // DOF group of the current vector, advanced incrementally: a 64-bit modulo per iteration costs more
+  // DOF of the vector's first element, advanced incrementally: a 64-bit modulo per iteration costs more
   // instructions than the law itself
-  int dv = (int)(v0 % vec_per_env);
-  const int dstep = (int)(stride % vec_per_env);
+  int dfirst = (int)((4 * v0) % num_dofs);
+  const int dstep = (int)((4 * stride) % num_dofs);
   while (v < nvec) {
-    const int d0 = dv << 2;
-    dv += dstep;
-    if (dv >= vec_per_env) dv -= vec_per_env;
-    const float4 kp = *reinterpret_cast<const float4*>(s_kp + d0);
-    const float4 kd = *reinterpret_cast<const float4*>(s_kd + d0);
-    float4 tm = make_float4(0.f, 0.f, 0.f, 0.f), lo = tm, hi = tm;
-    if (HAS_TMAX) tm = *reinterpret_cast<const float4*>(s_tm + d0);
-    if (CLAMP_TGT) {
-      lo = *reinterpret_cast<const float4*>(s_lo + d0);
-      hi = *reinterpret_cast<const float4*>(s_hi + d0);
+    const int d0 = dfirst;
+    dfirst += dstep;
+    if (dfirst >= num_dofs) dfirst -= num_dofs;
+    float4 kp, kd, tm = make_float4(0.f, 0.f, 0.f, 0.f), lo = tm, hi = tm;
+    if (!DANY) {
+      kp = *reinterpret_cast<const float4*>(s_kp + d0);
+      kd = *reinterpret_cast<const float4*>(s_kd + d0);
+      if (HAS_TMAX) tm = *reinterpret_cast<const float4*>(s_tm + d0);
+      if (CLAMP_TGT) {
+        lo = *reinterpret_cast<const float4*>(s_lo + d0);
+        hi = *reinterpret_cast<const float4*>(s_hi + d0);
+      }
+    } else {
+      int d1 = d0 + 1, d2 = d0 + 2, d3 = d0 + 3;          // D >= 4: at most one wrap
+      if (d1 >= num_dofs) d1 -= num_dofs;
+      if (d2 >= num_dofs) d2 -= num_dofs;
+      if (d3 >= num_dofs) d3 -= num_dofs;
+      kp = make_float4(s_kp[d0], s_kp[d1], s_kp[d2], s_kp[d3]);
+      kd = make_float4(s_kd[d0], s_kd[d1], s_kd[d2], s_kd[d3]);
+      if (HAS_TMAX) tm = make_float4(s_tm[d0], s_tm[d1], s_tm[d2], s_tm[d3]);
+      if (CLAMP_TGT) {
+        lo = make_float4(s_lo[d0], s_lo[d1], s_lo[d2], s_lo[d3]);
+        hi = make_float4(s_hi[d0], s_hi[d1], s_hi[d2], s_hi[d3]);
+      }
     }
     float4 o;
     o.x = pd_element<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX>(s0.x, s0.y, tg.x, qd.x, kp.x, kd.x, tm.x, lo.x, hi.x);
@@ -263,6 +281,9 @@ pd_torque_strided_kernel(TView state, TView q_tgt, TView qd_tgt, PdParams pp, in
 }
 
 // ---------------------------------------------------------------- dispatch
+// 128-bit path: four flattened (env, dof) elements per thread iteration.
+static inline bool pd_vectorisable(int64_t n, int64_t D) { return D >= 4 && (n * D) % 4 == 0; }
+
 struct PdLaunch {
   bool vec4;
   const float4 *state4, *tgt4, *qd4;
@@ -291,7 +312,8 @@ template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS>
 static void pd_launch_one(const PdLaunch& L) {
   if (L.vec4) {
     const size_t smem = 5 * (size_t)L.num_dofs * sizeof(float);
-    auto kern = pd_torque_vec4_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS>;
+    auto kern = (L.num_dofs % 4 == 0) ? pd_torque_vec4_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS, false>
+                                      : pd_torque_vec4_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS, true>;
     constexpr int block = pd_block(STATS);
     // One wave of CTAs with statistics (one commit per CTA: 2 / 4 waves cost +0.7 / +1.4 us per 1M envs); four
     // without -- same speed, and a co-resident kernel of another stream then costs its share of the SM slots instead
@@ -374,7 +396,7 @@ extern "C" int b200ctl_pd_torque(const DLTensor* dof_state, const DLTensor* q_ta
   L.num_envs = N;
   L.stats = stats;
   L.stream = (cudaStream_t)stream;
-  L.vec4 = (D % 4 == 0) && is_compact(L.state) && is_compact(L.tgt) && is_compact(L.out) &&
+  L.vec4 = pd_vectorisable(N, D) && is_compact(L.state) && is_compact(L.tgt) && is_compact(L.out) &&
            (!has_qd || is_compact(L.qd)) && aligned16(L.state.p) && aligned16(L.tgt.p) && aligned16(L.out.p) &&
            (!has_qd || aligned16(L.qd.p));
   L.state4 = reinterpret_cast<const float4*>(L.state.p);
@@ -502,7 +524,7 @@ extern "C" int b200ctl_pd_torque_host(const float* dof_state, const float* q_tar
 
     B200_CUDA(cudaStreamWaitEvent(P.run, P.uploaded[slot], 0));
     L.num_envs = n;
-    L.vec4 = (D % 4 == 0);
+    L.vec4 = pd_vectorisable(n, D);
     L.state4 = reinterpret_cast<const float4*>(P.d_state[slot]);
     L.tgt4 = reinterpret_cast<const float4*>(P.d_tgt[slot]);
     L.qd4 = reinterpret_cast<const float4*>(P.d_qd[slot]);

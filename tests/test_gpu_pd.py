@@ -198,3 +198,22 @@ def test_pd_stats_are_slice_invariant():
     w, p = whole.cpu(), parts.cpu()
     assert w[0] == n and p[0] == n and w[4] == p[4] and w[4] >= 1 and w[3] == p[3]
     assert torch.allclose(w[1:3], p[1:3], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("d", [4, 5, 6, 7, 9, 10, 13, 31])
+@pytest.mark.parametrize("flags", [0, WRAP_ANGLE | CLAMP_TARGET])
+def test_pd_vector_path_for_any_dof_count(d, flags):
+    """D not a multiple of 4 (Franka: 9) takes the 128-bit path too when N * D is: a vector then straddles two envs and
+    every element carries its own DOF index.  Bit-exact against the oracle, with and without a velocity target and the
+    torque limit, statistics included; the host-buffer pipeline goes the same way."""
+    n = 4100                                      # n * d % 4 == 0 for every d; several grid-stride iterations per thread
+    pi = syn.pd_inputs(n, d, seed=100 + d)
+    for qd, tmax in ((False, True), (True, False)):
+        tau, ref32, _, st = _run(pi, flags, qd, tmax, stats=True)
+        assert torch.equal(tau, ref32)
+        ref = opd.pd_stats(ref32, pi.tau_max if tmax else None)
+        s = st.cpu()
+        assert s[0] == n and s[3] == ref[3] and s[4] == ref[4]
+        assert torch.allclose(s[1:3], ref[1:3], rtol=1e-6)
+    host = pd_torque(pi.dof_state, pi.q_target, pi.kp, pi.kd, None, pi.tau_max, pi.q_lo, pi.q_hi, flags)
+    assert torch.equal(host, opd.pd_torque(pi.dof_state, pi.q_target, pi.kp, pi.kd, None, pi.tau_max, pi.q_lo, pi.q_hi, flags))
