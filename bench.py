@@ -265,6 +265,16 @@ def family_numbers(device, peak_gbs):
     record("pd_1048576x12_nostats", n, PD_BYTES_PER_ENV, [c4.bind(st[k], tg[k], ou[k]) for k in range(sets)], reps=20)
     del st, tg, ou
 
+    # P on the Franka's own DOF count (D = 9: a 128-bit vector straddles two envs, per-element DOF indices)
+    n, sets, d9 = 1_048_576, 4, 9
+    pi = syn.pd_inputs(n, d9, seed=1)
+    c9 = PDController(d9, pi.kp, pi.kd, tau_max=pi.tau_max, device=device)
+    st = [pi.dof_state.to(device).clone() for _ in range(sets)]
+    tg = [pi.q_target.to(device).clone() for _ in range(sets)]
+    ou = [torch.empty(n, d9, device=device) for _ in range(sets)]
+    record("pd_1048576x9_nostats", n, 16 * d9, [c9.bind(st[k], tg[k], ou[k]) for k in range(sets)], reps=20)
+    del st, tg, ou
+
     # S fused step at C2 (6.8 MB per set) and at 1M envs (109 MB per set), both precisions; "_stats" = with the
     # statistics vector the rollout harness passes (persistent CTAs, one commit per CTA)
     from test_isaacgym_b200 import _lib

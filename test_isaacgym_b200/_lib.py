@@ -129,31 +129,48 @@ _DTYPES = {torch.float32: (2, 32), torch.float64: (2, 64), torch.int64: (0, 64),
 
 
 class _Packed:
-    """A DLTensor plus the ctypes arrays it points into (kept alive for the call)."""
-    __slots__ = ("dl", "_shape", "_strides", "_tensor")
+    """A DLTensor plus the ctypes arrays it points into.  Describes memory, not a tensor object: two tensors with the
+    same pointer, shape, strides and dtype share one."""
+    __slots__ = ("dl", "_shape", "_strides", "ref")
 
-    def __init__(self, t: torch.Tensor):
-        if not isinstance(t, torch.Tensor):
-            raise TypeError(f"expected a torch.Tensor, got {type(t).__name__}")
-        if not t.is_cuda:
-            raise B200CtlError(-2, "tensor is not on a CUDA device; b200ctl has no CPU path")
-        if t.dtype not in _DTYPES:
-            raise B200CtlError(-3, f"unsupported dtype {t.dtype}")
-        nd = t.dim()
-        self._shape = (c_int64 * max(nd, 1))(*t.shape)
-        self._strides = (c_int64 * max(nd, 1))(*t.stride())
-        code, bits = _DTYPES[t.dtype]
-        self.dl = DLTensor(c_void_p(t.data_ptr()), DLDevice(2, t.device.index or 0), nd, DLDataType(code, bits, 1),
+    def __init__(self, ptr: int, shape, strides, dtype, index: int):
+        nd = len(shape)
+        self._shape = (c_int64 * max(nd, 1))(*shape)
+        self._strides = (c_int64 * max(nd, 1))(*strides)
+        code, bits = _DTYPES[dtype]
+        self.dl = DLTensor(c_void_p(ptr), DLDevice(2, index), nd, DLDataType(code, bits, 1),
                            ctypes.cast(self._shape, POINTER(c_int64)), ctypes.cast(self._strides, POINTER(c_int64)), 0)
-        self._tensor = t
+        self.ref = ctypes.byref(self.dl)
+
+
+# Descriptor cache: the reference-style entry points (``control_osc(dpose)``, ``cclvf2(...)`` ...) marshal up to nine
+# tensors per call, and building the ctypes structs costs ~10 us per tensor -- an order of magnitude more than the
+# kernels at 16,384 envs.  The step loop passes the same persistent gym tensors every step, so descriptors are cached
+# by what they describe (pointer, shape, strides, dtype, device); the cache holds no reference to any tensor.
+_DL_CACHE: dict = {}
+_DL_CACHE_MAX = 0 if os.environ.get("B200CTL_NO_DL_CACHE") else 1024      # 0: every call builds its descriptors (A/B)
 
 
 def dl(t):
-    """torch CUDA tensor -> (pointer-to-DLTensor, keep-alive); None -> (NULL, None)."""
+    """torch CUDA tensor -> (pointer-to-DLTensor, keep-alive); None -> (NULL, None).  The keep-alive holds the
+    descriptor AND the tensor (a ``BoundCall`` keeps its operands' memory alive through it)."""
     if t is None:
         return None, None
-    p = _Packed(t)
-    return ctypes.byref(p.dl), p
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise B200CtlError(-2, "tensor is not on a CUDA device; b200ctl has no CPU path")
+    if t.dtype not in _DTYPES:
+        raise B200CtlError(-3, f"unsupported dtype {t.dtype}")
+    key = (t.data_ptr(), t.shape, t.stride(), t.dtype, t.device.index)
+    p = _DL_CACHE.get(key)
+    if p is None:
+        if len(_DL_CACHE) >= _DL_CACHE_MAX:
+            _DL_CACHE.clear()
+        p = _Packed(key[0], key[1], key[2], key[3], key[4] or 0)
+        if _DL_CACHE_MAX:
+            _DL_CACHE[key] = p
+    return p.ref, (p, t)
 
 
 def stream_ptr(device: torch.device) -> c_void_p:
