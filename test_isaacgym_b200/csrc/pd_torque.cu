@@ -148,6 +148,9 @@ __device__ __forceinline__ void pd_commit_stats(const PdAcc& a, double* stats, i
 // the NEXT iteration's loads in flight while it accumulates, which needs ~10 more registers: 5 CTAs per SM (48).
 // (Measured and rejected: 512 / 768 / 1024-thread CTAs to cut the number of end-of-kernel REDs on the one line that
 // holds the statistics vector -- no change at 1M envs, slower at 1,024; profiles/README.md.)
+#ifndef B200_PD_INDEX_T
+#define B200_PD_INDEX_T unsigned    // A/B knob (profiles/): int64_t = the 64-bit index arithmetic of the first version
+#endif
 #ifndef B200_PD_STATS_BLOCK
 #define B200_PD_STATS_BLOCK 256     // A/B knobs (profiles/)
 #endif
@@ -168,13 +171,16 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
                       float4* __restrict__ tau_out, double* __restrict__ stats) {
   extern __shared__ __align__(16) float s_par[];   // [5][D]: kp, kd, tmax, lo, hi
   pdl_prologue();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  // 32-bit vector indices (the host routes nvec >= 2^31 to the strided kernel): one IMAD.WIDE per address instead of a
+  // 64-bit multiply-add chain
+  typedef B200_PD_INDEX_T idx_t;
+  const idx_t stride = (idx_t)(gridDim.x * blockDim.x);
+  const idx_t v0 = (idx_t)(blockIdx.x * blockDim.x + threadIdx.x);
   // The loop is rotated: the streaming loads of an iteration are issued at the end of the previous one, and those of
   // the first iteration HERE, ahead of the per-DOF parameter staging -- otherwise every CTA spends one L2 round trip
   // (parameter load -> shared store -> barrier) before its first byte of dof_state is requested, which is 8 % of a
   // 65,536-env launch.
-  int64_t v = v0;
+  idx_t v = v0;
   float4 s0, s1, tg, qd = make_float4(0.f, 0.f, 0.f, 0.f);
   if (v < nvec) {
     s0 = ldg_stream4(state + 2 * v);       // q0 qd0 q1 qd1
@@ -199,8 +205,8 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
   PdAcc acc;
   // DOF of the vector's first element, advanced incrementally: a 64-bit modulo per iteration costs more
   // instructions than the law itself
-  int dfirst = (int)((4 * v0) % num_dofs);
-  const int dstep = (int)((4 * stride) % num_dofs);
+  int dfirst = (int)((4 * (uint64_t)v0) % (unsigned)num_dofs);
+  const int dstep = (int)((4 * (uint64_t)stride) % (unsigned)num_dofs);
   while (v < nvec) {
     const int d0 = dfirst;
     dfirst += dstep;
@@ -282,7 +288,7 @@ pd_torque_strided_kernel(TView state, TView q_tgt, TView qd_tgt, PdParams pp, in
 
 // ---------------------------------------------------------------- dispatch
 // 128-bit path: four flattened (env, dof) elements per thread iteration.
-static inline bool pd_vectorisable(int64_t n, int64_t D) { return D >= 4 && (n * D) % 4 == 0; }
+static inline bool pd_vectorisable(int64_t n, int64_t D) { return D >= 4 && (n * D) % 4 == 0 && n * D / 4 < (int64_t(1) << 31); }
 
 struct PdLaunch {
   bool vec4;
