@@ -579,7 +579,10 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 2 * tile, 0));
     slots = sm_count(dev) * (occ > 0 ? occ : 1);
   }
-  const int grid = (stats && ntiles > slots) ? slots : ntiles;
+#ifndef B200_SERVO_STATS_WAVES
+#define B200_SERVO_STATS_WAVES 4
+#endif
+  const int grid = (stats && ntiles > slots * B200_SERVO_STATS_WAVES) ? slots * B200_SERVO_STATS_WAVES : ntiles;
   const int vec_ok = aligned16(st) ? 1 : 0;
   launch_pdl(kern, grid, split ? 2 * tile : tile, 0, (cudaStream_t)stream, st, n, k, aux_out, stats, vec_ok);
   return post_launch("servo_step_kernel");

@@ -282,15 +282,18 @@ def test_scalar_class_and_roi_helpers(servo_kat):
     assert np.array_equal(CameraController(Props, 4).get_rot_uav2world(), np.identity(3))
 
 
+@pytest.mark.parametrize("n", [400_003, 1_300_003])
 @pytest.mark.parametrize("precision", [0, 1])
-def test_statistics_variant_is_the_same_step(precision):
-    """With a statistics vector the step runs as a PERSISTENT grid (several tiles per CTA through one tile buffer,
-    128-env tiles in fast mode, one commit per CTA): the state it writes must be bit-identical to the plain
+def test_statistics_variant_is_the_same_step(precision, n):
+    """With a statistics vector the step runs as a PERSISTENT grid once the tiles exceed four waves of resident CTAs
+    (several tiles per CTA through one tile buffer, 128-env tiles in fast mode, one commit per CTA; below that, one
+    tile per CTA): the state it writes must be bit-identical to the plain
     one-CTA-per-tile step, for a size with many tiles per CTA and a ragged last tile, aligned and unaligned; the
     vector must hold the env count, the mean pixel error of the aux output and no non-finite attitudes, and add up
     over calls."""
     from test_isaacgym_b200 import _lib
-    n = 400_003                                   # > 16 x 148 tiles of 64: several tiles per persistent CTA
+    # 400,003 envs: 6,251 / 3,126 tiles, at most four waves -> one tile per CTA with a statistics commit each;
+    # 1,300,003 envs: 20,313 / 10,157 tiles > 4 x 148 x resident CTAs -> several tiles per persistent CTA
     state = syn.servo_root_state(n, seed=23, regime="reference")
     step = ServoStep(W, H, precision=precision)
     for unaligned in (False, True):
