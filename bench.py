@@ -441,7 +441,7 @@ def run_reference(args):
                                        f"{torch.get_num_threads()} threads); the reference has no single function for this law"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -449,7 +449,7 @@ def run_reference(args):
 def run_b200(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: b200ctl has no CPU path"}))
+        emit({"error": "no CUDA device: b200ctl has no CPU path"})
         return 1
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
@@ -571,14 +571,39 @@ def run_b200(args):
         if "families" in line:
             cpu_family_baselines(line["families"])
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep file descriptor 1 for the JSON line alone: native libraries write there too (NCCL prints its version banner
+    to stdout under NCCL_DEBUG=VERSION, ahead of the line), so fd 1 is pointed at stderr for the rest of the run and the
+    line goes to a duplicate of the original."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+        return
+    while data:
+        data = data[os.write(_JSON_FD, data):]
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
