@@ -40,3 +40,16 @@ def test_gpu_arm_refuses_without_a_device():
     r = _run("--steps", "1")
     assert r.returncode != 0
     assert "no CPU path" in r.stdout
+
+
+def test_stdout_carries_the_json_line_only():
+    """Native libraries write to file descriptor 1 behind Python's back (NCCL's version banner under
+    NCCL_DEBUG=VERSION preceded the JSON line of the N > 1 runs): after ``claim_stdout`` such output lands on stderr
+    and the line alone on the original stdout."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); "
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('python-level noise'); "
+            "bench.emit({'metric': 'm', 'value': 1.0})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.count("\n") == 1 and json.loads(r.stdout) == {"metric": "m", "value": 1.0}
+    assert "NCCL version" in r.stderr and "python-level noise" in r.stderr
