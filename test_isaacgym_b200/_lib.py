@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ctl.so")
+# B200CTL_LIB: an A/B build of the same ABI (profiles/experiments/build_variant.sh), e.g. to run the GPU tests against it
+LIB_PATH = os.environ.get("B200CTL_LIB") or os.path.join(_HERE, "libb200ctl.so")
 
 STATS_LEN = 8
 PD_WRAP_ANGLE = 1

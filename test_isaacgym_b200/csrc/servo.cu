@@ -36,13 +36,23 @@ struct ServoConst {
 // staged inputs and write disjoint columns, so they never exchange anything; the arithmetic per env is the same as in
 // the one-thread form (same bits).  It halves the serial chain of a tile: the small-N step is one wave of CTAs whose
 // time IS that chain (65,536 envs), while at 1M envs the step is issue bound and the form does not matter.
+#ifndef B200_SERVO_STATS_NBUF
+#define B200_SERVO_STATS_NBUF 1      // A/B knob: 2 = double-buffered tiles in the persistent (statistics) form
+#endif
 template <int PREC, bool STATS, int TILE, bool SPLIT>
 __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64_t num_envs, const ServoConst& k,
                                                 double* __restrict__ aux, double* __restrict__ stats, int vec_ok) {
   constexpr int NT = SPLIT ? 2 * TILE : TILE;      // threads per CTA
-  __shared__ __align__(128) float tile[TILE * kEnvRow];
-  __shared__ __align__(8) uint64_t bar;
-  if (threadIdx.x == 0) mbar_init(&bar, 1);     // touches no global memory: done ahead of the dependency wait
+  // Tile buffers of a persistent CTA.  NBUF == 2 (A/B knob B200_SERVO_STATS_NBUF, not the default: unmeasured) lets the
+  // bulk load of the CTA's NEXT tile run under the arithmetic of the current one -- the CTAs of a persistent grid move
+  // in step, so with one buffer the SM alternates between a load phase and an arithmetic phase.
+  constexpr int NBUF = (STATS && !SPLIT) ? B200_SERVO_STATS_NBUF : 1;
+  __shared__ __align__(128) float tiles[NBUF][TILE * kEnvRow];
+  __shared__ __align__(8) uint64_t bars[NBUF];
+  if (threadIdx.x == 0) {                       // touches no global memory: done ahead of the dependency wait
+#pragma unroll
+    for (int b = 0; b < NBUF; ++b) mbar_init(&bars[b], 1);
+  }
   pdl_prologue();
   __syncthreads();                              // the initialised barrier is visible to every waiter
   // Tiles blockIdx.x, + gridDim.x, ... through ONE tile buffer.  The host launches one CTA per tile without
@@ -51,10 +61,20 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   // acknowledged before its SM slot frees) made the step 82 us instead of 37.7.
   const int ntiles = (int)((num_envs + TILE - 1) / TILE);
   constexpr unsigned kBytes = TILE * kEnvRow * sizeof(float);
-  unsigned phase = 0;
+  unsigned phases = 0;               // bit b: phase parity of bars[b]
   double acc_d[2] = {0, 0};          // sum |pixel error|, sum error^2
   unsigned acc_u[3] = {0, 0, 0};     // envs, envs with the target behind the camera, non-finite attitudes
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  auto full_tile = [&](int t) { return vec_ok && (num_envs - (int64_t)t * TILE) >= TILE; };
+  auto fetch = [&](int t, int b) {   // thread 0: one bulk copy of tile t into buffer b
+    mbar_arrive_expect_tx(&bars[b], kBytes);
+    bulk_g2s(tiles[b], state + (int64_t)t * TILE * kEnvRow, kBytes, &bars[b]);
+  };
+  if (NBUF == 2 && threadIdx.x == 0 && (int)blockIdx.x < ntiles && full_tile((int)blockIdx.x)) fetch((int)blockIdx.x, 0);
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+  const int buf = NBUF == 2 ? (it & 1) : 0;
+  float* const tile = tiles[buf];
+  uint64_t* const bar = &bars[buf];
   const int64_t env0 = (int64_t)t * TILE;
   const int nenv = (int)((num_envs - env0) < TILE ? (num_envs - env0) : TILE);
   const int nfl = nenv * kEnvRow;
@@ -65,17 +85,27 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   // staging / write-back loops -- 25-31 % of all executed instructions in profiles/r01_linemix_servo_*_v5.txt --
   // disappear from the instruction stream.  The ragged last tile and unaligned tensors take the loops.
   const bool bulk = vec_ok && nenv == TILE;
-  if (bulk) {
-    if (threadIdx.x == 0) {
-      // the buffer is free: this thread waited for the previous tile's write-back to have read it (below)
-      mbar_arrive_expect_tx(&bar, kBytes);
-      bulk_g2s(tile, gbase, kBytes, &bar);
+  if (NBUF == 2) {
+    // the CTA's next tile into the other buffer: its last reader is the write-back committed at the end of the
+    // previous iteration (and this buffer's, one iteration earlier) -- wait until both have READ shared memory
+    const int tn = t + (int)gridDim.x;
+    if (threadIdx.x == 0 && tn < ntiles && full_tile(tn)) {
+      bulk_wait_read();
+      fetch(tn, buf ^ 1);
     }
-    mbar_wait(&bar, phase);
-    phase ^= 1u;
+  }
+  if (bulk) {
+    if (NBUF == 1 && threadIdx.x == 0) {
+      // the buffer is free: this thread waited for the previous tile's write-back to have read it (below)
+      mbar_arrive_expect_tx(bar, kBytes);
+      bulk_g2s(tile, gbase, kBytes, bar);
+    }
+    mbar_wait(bar, NBUF == 1 ? phases : ((phases >> buf) & 1u));
+    phases ^= NBUF == 1 ? 1u : (1u << buf);
   } else {
     // a persistent CTA may come here from a bulk tile: thread 0 reaches this barrier only after that tile's
     // write-back has READ the buffer, so nobody overwrites it early
+    if (NBUF == 2 && threadIdx.x == 0) bulk_wait_read();
     __syncthreads();
     const int nv4 = vec_ok ? (nfl >> 2) : 0;
     for (int i = threadIdx.x; i < nv4; i += NT)
@@ -193,7 +223,8 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
     __syncthreads();
     if (threadIdx.x == 0) {
       bulk_s2g(gbase, tile, kBytes);
-      bulk_commit_wait_read();    // the buffer may be refilled / freed only after the TMA unit has read it
+      // the buffer may be refilled / freed only after the TMA unit has read it
+      if (NBUF == 1) bulk_commit_wait_read(); else bulk_commit();     // two buffers: waited for before the next fetch
     }
   } else {
     __syncthreads();
@@ -204,6 +235,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
     __syncthreads();              // every row is out before the next tile's loads overwrite the buffer
   }
   }   // tile loop
+  if (NBUF == 2 && threadIdx.x == 0) bulk_wait_read();   // shared memory outlives the last write-back's read
   if (STATS) {
     const int slots[5] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_SAT,
                           B200CTL_STAT_N_NONFINITE};
@@ -227,7 +259,7 @@ __global__ void servo_step_kernel(float*, int64_t, ServoConst, double*, double*,
     servo_step_body<PREC, STATS, ServoTile<PREC, STATS>::value, SPLIT>(state, num_envs, k, aux, stats, vec_ok);        \
   }
 B200_SERVO_KERNEL(0, false, false, __launch_bounds__(64, 16))
-B200_SERVO_KERNEL(0, true, false, __launch_bounds__(64, 16))
+B200_SERVO_KERNEL(0, true, false, __launch_bounds__(64, B200_SERVO_STATS_NBUF == 2 ? 14 : 16))   // 2 x 6.6 KB x 16 > one SM
 B200_SERVO_KERNEL(1, false, false, __launch_bounds__(64))
 B200_SERVO_KERNEL(1, true, false, __launch_bounds__(128))
 B200_SERVO_KERNEL(0, false, true, __launch_bounds__(128, 8))
