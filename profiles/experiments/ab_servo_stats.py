@@ -24,15 +24,24 @@ def main():
     sb = L.stats_buffer(dev)
     libs = [("in-tree", L.LIB_PATH)] + [(os.path.basename(p), os.path.abspath(p)) for p in sys.argv[1:]]
     calls = {}
+    want = {}
     for name, path in libs:
         L.LIB_PATH, L._lib = path, None          # bind this variant's entry point
         for tag, prec in (("ref", 0), ("fast", PRECISION_FAST)):
             step = ServoStep(1600, 900, precision=prec)
+            # same bits as the in-tree build (state and statistics vector), ragged size: bulk and loop-staged tiles
+            chk, st = base[: n - 37].clone(), L.stats_buffer(dev)
+            step(chk, stats=st)
+            if name == "in-tree":
+                want[tag] = (chk, st)
+            else:
+                same = torch.equal(chk, want[tag][0]) and torch.allclose(st, want[tag][1], rtol=1e-12, atol=0)
+                print(f"{name:28s} servo_{tag}+stats == in-tree: {same}", flush=True)
             calls[name, tag + "+stats"] = [step.bind(b, stats=sb) for b in bufs]
             if tag == "ref":
                 calls[name, tag] = [step.bind(b) for b in bufs]
     best = {k: 1e9 for k in calls}
-    for _ in range(3):
+    for _ in range(2):
         for k, c in calls.items():
             best[k] = min(best[k], bench.graph_time(c, dev, 20, runs=2, warm_ms=10.0) * 1e3)
     for (name, tag), t in best.items():
