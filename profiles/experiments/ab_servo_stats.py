@@ -29,17 +29,17 @@ def main():
         L.LIB_PATH, L._lib = path, None          # bind this variant's entry point
         for tag, prec in (("ref", 0), ("fast", PRECISION_FAST)):
             step = ServoStep(1600, 900, precision=prec)
-            # same bits as the in-tree build (state and statistics vector), ragged size: bulk and loop-staged tiles
-            chk, st = base[: n - 37].clone(), L.stats_buffer(dev)
-            step(chk, stats=st)
-            if name == "in-tree":
-                want[tag] = (chk, st)
-            else:
-                same = torch.equal(chk, want[tag][0]) and torch.allclose(st, want[tag][1], rtol=1e-12, atol=0)
-                print(f"{name:28s} servo_{tag}+stats == in-tree: {same}", flush=True)
-            calls[name, tag + "+stats"] = [step.bind(b, stats=sb) for b in bufs]
-            if tag == "ref":
-                calls[name, tag] = [step.bind(b) for b in bufs]
+            for stag in ("", "+stats"):
+                # same bits as the in-tree build (state and statistics vector); ragged size: bulk and loop-staged tiles
+                chk, st = base[: n - 37].clone(), L.stats_buffer(dev)
+                step(chk, stats=st if stag else None)
+                if name == "in-tree":
+                    want[tag + stag] = (chk, st)
+                else:
+                    w = want[tag + stag]
+                    same = torch.equal(chk, w[0]) and torch.allclose(st, w[1], rtol=1e-12, atol=0)
+                    print(f"{name:28s} servo_{tag + stag:10s} == in-tree: {same}", flush=True)
+                calls[name, tag + stag] = [step.bind(b, **({"stats": sb} if stag else {})) for b in bufs]
     best = {k: 1e9 for k in calls}
     for _ in range(2):
         for k, c in calls.items():

@@ -39,6 +39,9 @@ struct ServoConst {
 #ifndef B200_SERVO_STATS_NBUF
 #define B200_SERVO_STATS_NBUF 1      // A/B knob: 2 = double-buffered tiles in the persistent (statistics) form
 #endif
+#ifndef B200_SERVO_PERSIST_ALL
+#define B200_SERVO_PERSIST_ALL 0     // A/B knob: 1 = the persistent grid (and its tile buffers) without statistics too
+#endif
 template <int PREC, bool STATS, int TILE, bool SPLIT>
 __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64_t num_envs, const ServoConst& k,
                                                 double* __restrict__ aux, double* __restrict__ stats, int vec_ok) {
@@ -46,7 +49,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   // Tile buffers of a persistent CTA.  NBUF == 2 (A/B knob B200_SERVO_STATS_NBUF, not the default: unmeasured) lets the
   // bulk load of the CTA's NEXT tile run under the arithmetic of the current one -- the CTAs of a persistent grid move
   // in step, so with one buffer the SM alternates between a load phase and an arithmetic phase.
-  constexpr int NBUF = (STATS && !SPLIT) ? B200_SERVO_STATS_NBUF : 1;
+  constexpr int NBUF = ((STATS || B200_SERVO_PERSIST_ALL) && !SPLIT) ? B200_SERVO_STATS_NBUF : 1;
   __shared__ __align__(128) float tiles[NBUF][TILE * kEnvRow];
   __shared__ __align__(8) uint64_t bars[NBUF];
   if (threadIdx.x == 0) {                       // touches no global memory: done ahead of the dependency wait
@@ -258,7 +261,7 @@ __global__ void servo_step_kernel(float*, int64_t, ServoConst, double*, double*,
                                                                     double* aux, double* stats, int vec_ok) {          \
     servo_step_body<PREC, STATS, ServoTile<PREC, STATS>::value, SPLIT>(state, num_envs, k, aux, stats, vec_ok);        \
   }
-B200_SERVO_KERNEL(0, false, false, __launch_bounds__(64, 16))
+B200_SERVO_KERNEL(0, false, false, __launch_bounds__(64, (B200_SERVO_PERSIST_ALL && B200_SERVO_STATS_NBUF == 2) ? 14 : 16))
 B200_SERVO_KERNEL(0, true, false, __launch_bounds__(64, B200_SERVO_STATS_NBUF == 2 ? 14 : 16))   // 2 x 6.6 KB x 16 > one SM
 B200_SERVO_KERNEL(1, false, false, __launch_bounds__(64))
 B200_SERVO_KERNEL(1, true, false, __launch_bounds__(128))
@@ -618,7 +621,8 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
 #ifndef B200_SERVO_STATS_WAVES
 #define B200_SERVO_STATS_WAVES 4
 #endif
-  const int grid = (stats && ntiles > slots * B200_SERVO_STATS_WAVES) ? slots * B200_SERVO_STATS_WAVES : ntiles;
+  const bool persist = stats != nullptr || B200_SERVO_PERSIST_ALL;
+  const int grid = (persist && ntiles > slots * B200_SERVO_STATS_WAVES) ? slots * B200_SERVO_STATS_WAVES : ntiles;
   const int vec_ok = aligned16(st) ? 1 : 0;
   launch_pdl(kern, grid, split ? 2 * tile : tile, 0, (cudaStream_t)stream, st, n, k, aux_out, stats, vec_ok);
   return post_launch("servo_step_kernel");
