@@ -99,7 +99,12 @@ enum {
  * q_lo,q_hi : (D,) f32, required iff B200CTL_PD_CLAMP_TARGET
  * tau_out   : (N, D) f32         stats     : device double[8] or NULL
  * fp32 arithmetic in the operand order of franka_cube_ik_osc.py:74-75 without
- * FMA contraction, so results are bit-identical to the torch-fp32 expression. */
+ * FMA contraction, so results are bit-identical to the torch-fp32 expression.
+ * In place: tau_out may be exactly q_target or qd_target (same pointer, shape, strides).  Any other overlap of
+ * tau_out with an input returns B200CTL_E_ALIAS.  num_dofs up to 4096 (above 2048 the per-DOF parameters are
+ * not staged in shared memory).  stats / aux pointers anywhere in this header must be float64 device memory of
+ * the operands' device (checked: B200CTL_E_DEVICE / B200CTL_E_LAYOUT); their LENGTH cannot be checked -- stats
+ * must hold B200CTL_STATS_LEN doubles. */
 #define B200CTL_PD_WRAP_ANGLE 1   /* e = ((q* - q + pi) mod 2pi) - pi, floor-mod (franka_cube_ik_osc.py:75) */
 #define B200CTL_PD_CLAMP_TARGET 2 /* q* <- clamp(q*, q_lo, q_hi) first (joint_monkey.py:121-150 limits) */
 B200CTL_API int b200ctl_pd_torque(const DLTensor* dof_state, const DLTensor* q_target, const DLTensor* qd_target,
@@ -204,6 +209,19 @@ B200CTL_API int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLT
  * j_eef (N,6,D), mm (N,D,D), dof_vel (N,D[,1]), dpose (N,6[,1]), out (N,D[,1]); D in {7,9}. */
 B200CTL_API int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_vel, const DLTensor* dpose,
                      double kp, double kv, int32_t precision, DLTensor* out, b200ctl_stream_t stream);
+
+/* The whole control law of the loop of examples/franka_osc.py:221-241 in ONE kernel:
+ *   pos_cur, orn_cur = rb_states[hand_index, :3], rb_states[hand_index, 3:7]            (:221-222)
+ *   orn_cur /= |orn_cur| (:231);  orn_err = orientation_error(orn_des, orn_cur)           (:232, def. :25-28)
+ *   pos_err = kp (pos_des - pos_cur), multiplied by 0 unless pos_control                  (:234-237)
+ *   dpose = [pos_err ; orn_err] (:239);  out = J^T (J M^-1 J^T)^-1 (kp dpose) - kv M qd   (:229-230, :241)
+ * j_eef (N,6,D), mm (N,D,D), dof_vel (N,D[,1]), D in {7,9}; rb_states (M,>=7) f32 (not modified: the reference
+ * normalises a gathered copy); hand_index (N,) int64; pos_des (N,3); orn_des (N,4) xyzw; dpose_out (N,6[,1]) or NULL;
+ * out (N,D[,1]).  A hand_index entry outside [0, M) is never dereferenced: that env's outputs are NaN. */
+B200CTL_API int b200ctl_franka_osc_step(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_vel,
+                            const DLTensor* rb_states, const DLTensor* hand_index, const DLTensor* pos_des,
+                            const DLTensor* orn_des, double kp, double kv, int32_t pos_control, int32_t precision,
+                            DLTensor* dpose_out, DLTensor* out, b200ctl_stream_t stream);
 
 /* orientation_error, examples/franka_cube_ik_osc.py:34-37.  (N,4) xyzw x2 -> (N,3). */
 B200CTL_API int b200ctl_orientation_error(const DLTensor* q_desired, const DLTensor* q_current,

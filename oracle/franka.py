@@ -79,6 +79,34 @@ def control_osc_full(dpose, j_eef, mm, dof_vel, kp: float, kv: float) -> torch.T
     return jt @ m_eef @ (kp * dpose).unsqueeze(-1) - kv * mm @ dof_vel
 
 
+def franka_osc_step(rb_states, hand_idxs, pos_des, orn_des, j_eef, mm, dof_vel, kp: float, kv: float,
+                    pos_control: bool = True):
+    """The loop body of ``examples/franka_osc.py:221-241`` -> ``(dpose (N,6), u (N,D,1))``.
+
+    Pinned by ``tests/golden/franka_full.npz`` (the script's own statements executed in place)."""
+    pos_cur = rb_states[hand_idxs, :3]
+    orn_cur = rb_states[hand_idxs, 3:7]
+    jt = j_eef.transpose(1, 2)
+    m_eef = torch.inverse(j_eef @ torch.inverse(mm) @ jt)
+    orn_cur = orn_cur / torch.norm(orn_cur, dim=-1).unsqueeze(-1)
+    orn_err = orientation_error(orn_des, orn_cur)
+    pos_err = kp * (pos_des - pos_cur)
+    if not pos_control:
+        pos_err = pos_err * 0
+    dpose = torch.cat([pos_err, orn_err], -1)
+    u = jt @ m_eef @ (kp * dpose).unsqueeze(-1) - kv * mm @ dof_vel
+    return dpose, u
+
+
+def franka_osc_pos_des(init_pos: torch.Tensor, itr: int) -> torch.Tensor:
+    """``examples/franka_osc.py:224-227``."""
+    pos_des = init_pos.clone()
+    pos_des[:, 0] = init_pos[:, 0] - 0.1
+    pos_des[:, 1] = math.sin(itr / 50) * 0.2
+    pos_des[:, 2] = init_pos[:, 2] + math.cos(itr / 50) * 0.2
+    return pos_des
+
+
 def conditioning(j_eef: torch.Tensor, mm: torch.Tensor | None, damping: float | None = None) -> torch.Tensor:
     """cond(J M^-1 J^T) (OSC) or cond(J J^T + lambda^2 I) (IK) per env, fp64 -- the gate of SURVEY.md section 8d."""
     j = j_eef.double()

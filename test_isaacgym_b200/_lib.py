@@ -84,6 +84,7 @@ _SIGNATURES = {
     "b200ctl_osc": (c_int, [_DL, _DL, _DL, _DL, _DL, _DL, _DL, _DL, c_double, c_double, c_double, c_double,
                             c_int32, _DL, c_void_p, c_void_p]),
     "b200ctl_osc_full": (c_int, [_DL, _DL, _DL, _DL, c_double, c_double, c_int32, _DL, c_void_p]),
+    "b200ctl_franka_osc_step": (c_int, [_DL] * 7 + [c_double, c_double, c_int32, c_int32, _DL, _DL, c_void_p]),
     "b200ctl_orientation_error": (c_int, [_DL, _DL, _DL, c_void_p]),
     "b200ctl_franka_task": (c_int, [_DL, _DL, _DL, _DL, _DL, _DL, _DL, POINTER(FrankaTaskParams), _DL, _DL, c_void_p]),
     "b200ctl_franka_pick_osc": (c_int, [_DL] * 10 + [POINTER(FrankaTaskParams), _DL, c_double, c_double, c_double, c_double,
@@ -231,3 +232,27 @@ class BoundCall:
 
 def ptr_or_none(t):
     return c_void_p(t.data_ptr()) if t is not None else None
+
+
+def f64_arg(t, device: torch.device, min_numel: int, name: str):
+    """``stats`` / ``aux`` cross the ABI as raw ``double*`` (no descriptor): every ``__call__`` / ``bind`` path checks
+    the tensor here first -- a float64, contiguous CUDA tensor on the operands' device with at least ``min_numel``
+    elements -- so a CPU / fp32 / short / wrong-GPU buffer raises ``B200CtlError`` instead of becoming a stray
+    ``atomicAdd``.  (The library re-checks the pointer's memory type and device on its side.)"""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise B200CtlError(-2, f"{name}: tensor is not on a CUDA device; b200ctl has no CPU path")
+    if device is not None and t.device != device:
+        raise B200CtlError(-2, f"{name}: on {t.device}, the operands are on {device}")
+    if t.dtype != torch.float64:
+        raise B200CtlError(-3, f"{name}: expected float64, got {t.dtype}")
+    if not t.is_contiguous() or t.numel() < min_numel:
+        raise B200CtlError(-4, f"{name}: expected a contiguous tensor of at least {min_numel} elements, got shape {tuple(t.shape)}")
+    return c_void_p(t.data_ptr())
+
+
+def stats_arg(stats, device: torch.device):
+    return f64_arg(stats, device, STATS_LEN, "stats")

@@ -74,6 +74,11 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int sm_count(int dev);
 
+// Raw device pointers of the ABI (`stats`, `aux`: float64 accumulators that carry no DLTensor descriptor) are checked
+// against the driver's own record before a kernel may atomicAdd / store through them: device (or managed) memory of
+// device `dev`, 8-byte aligned.  NULL is accepted (the argument is optional).  Verdicts are cached per pointer.
+int check_f64_device_ptr(const void* p, const char* name, int dev);
+
 struct DeviceGuard {
   int prev = -1;
   bool switched = false;

@@ -234,17 +234,26 @@ __device__ __forceinline__ void stage_ldgsts(const StagePlan& P, int64_t env0, i
 // in order, and the first use of the index stalls it for a full memory latency):
 //   gather_row   loads this thread's source row number (the load only, nothing consumes it yet),
 //   gather_copy  issues the C 4-byte copies of that row.
-__device__ __forceinline__ int64_t gather_row(const TView& index, int has_index, int64_t env0, int nenv) {
+__device__ __forceinline__ int64_t gather_row(const TView& index, int has_index, int64_t env0, int nenv, int64_t nrows) {
   if ((int)threadIdx.x >= nenv) return 0;
   const int64_t env = env0 + threadIdx.x;
-  return has_index ? __ldg(reinterpret_cast<const int64_t*>(index.p) + env * index.s[0]) : env;
+  const int64_t row = has_index ? __ldg(reinterpret_cast<const int64_t*>(index.p) + env * index.s[0]) : env;
+  // device-side index lists are not visible to the host-side validation: a row outside the source tensor is never
+  // dereferenced -- the env's gathered operand becomes NaN, so do its outputs, and N_NONFINITE counts it
+  return (row >= 0 && row < nrows) ? row : -1;
 }
 template <int C>
 __device__ __forceinline__ void gather_copy(const TView& v, int64_t row, int nenv, float* dst_row0, int ts) {
   if ((int)threadIdx.x < nenv) {
+    float* d = dst_row0 + threadIdx.x * ts;
+    if (row < 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) d[c] = __int_as_float(0x7fc00000);
+      return;
+    }
     const float* g = reinterpret_cast<const float*>(v.p) + row * v.s[0];
 #pragma unroll
-    for (int c = 0; c < C; ++c) cp_async_f32(dst_row0 + threadIdx.x * ts + c, g + c * v.s[1]);
+    for (int c = 0; c < C; ++c) cp_async_f32(d + c, g + c * v.s[1]);
   }
 }
 
@@ -513,7 +522,7 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   // longest latency of the staging, issued first -- do not wait for the index (profiles/: 6.6 % of the stall samples
   // of the fp64 chain sat on that first use).  Issuing the first tile's TMA copies ahead of its gather instead
   // measured the same.
-  auto row_of = [&](int t) { return gather_row(hand_index, has_index, (int64_t)t * kTileEnvs, tile_envs(t)); };
+  auto row_of = [&](int t) { return gather_row(hand_index, has_index, (int64_t)t * kTileEnvs, tile_envs(t), hand_vel.n[0]); };
   auto issue = [&](int t, int64_t row) {
     const bool bulk = tile_is_bulk(P, t, ntiles);
     gather_copy<6>(hand_vel, row, tile_envs(t), tile + (bulk ? P.x_off_b : P.x_off_c), bulk ? P.bulk_ts : P.canon_ts);
@@ -607,7 +616,7 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
   float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
   // index loads first, then the TMA / LDGSTS issue, then the copies that need the indices (see gather_row)
-  const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
+  const int64_t box_row = gather_row(box_index, 1, env0, nenv, rb.n[0]), hand_row = gather_row(hand_index, 1, env0, nenv, rb.n[0]);
   __shared__ float s_qdef[8];
   const float qdef_mine = threadIdx.x < 7 ? ldf(q_default, threadIdx.x * q_default.s[0]) : 0.f;
   SAddr a[6];
@@ -687,7 +696,7 @@ pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, 
   const bool bulk = tile_is_bulk(P, blockIdx.x, gridDim.x);
   const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
   float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
-  const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
+  const int64_t box_row = gather_row(box_index, 1, env0, nenv, rb.n[0]), hand_row = gather_row(hand_index, 1, env0, nenv, rb.n[0]);
   SAddr a[4];
   unsigned phase = 0;
   stage_issue<4>(P, &tmap, blockIdx.x, gridDim.x, n, tile, &bar);
@@ -725,6 +734,39 @@ pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, 
 }
 
 // ------------------------------------------------------------------ franka_osc.py:229-241
+// u = J^T Lambda (kp dpose) - kv M qd over all D DOFs, from the staged J / M / dof_vel of env `e`; `kd` = kp * dpose
+// as the reference rounds it in fp32.
+template <typename T, int D>
+__device__ __forceinline__ void osc_full_solve(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQD, int e,
+                                               const float (&kd)[6], float kv, const TView& out, int64_t env) {
+  float J[6][D];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) J[r][c] = SM(aJ, e, r, c);
+  T A[6][6], rda[6], L[D][D];
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) L[r][c] = (T)SM(aM, e, r, c);
+  task_space_factor<T, D>(J, L, A, rda);
+  T w[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) w[r] = (T)kd[r];
+  chol_solve<T, 6>(A, rda, w);            // Lambda (kp dpose)
+  float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    T damp = (T)0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) damp = fma_t<T>((T)SM(aM, e, c, k), (T)SM(aQD, e, 0, k), damp);
+    T u = -(T)kv * damp;                  // - kv * M qd
+#pragma unroll
+    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], w[r], u);
+    o[c * out.s[1]] = (float)u;
+  }
+}
+
 // segments: 0 = J (6xD), 1 = M (DxD), 2 = dof_vel (1xD), 3 = dpose (1x6)
 template <typename T, int D>
 __global__ void __launch_bounds__(kTileEnvs)
@@ -739,33 +781,74 @@ osc_full_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float kp,
   stage_all<4>(P, &tmap, env0, nenv, tile, &bar, a);
   if (threadIdx.x >= nenv) return;
   const int e = threadIdx.x;
+  float kd[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) kd[r] = __fmul_rn(kp, SM(a[3], e, 0, r));
+  osc_full_solve<T, D>(tile, a[0], a[1], a[2], e, kd, kv, out, env0 + e);
+}
+
+// ------------------------------------------------------------------ franka_osc.py:221-241, the whole loop law in one launch
+// pos_cur / orn_cur = rb_states[hand_idxs, :3] / [.., 3:7] (:221-222); orn_cur /= |orn_cur| (:231);
+// orn_err = orientation_error(orn_des, orn_cur) (:232); pos_err = kp (pos_des - pos_cur), times 0 without --pos_control
+// (:234-237); dpose = [pos_err ; orn_err] (:239); u = J^T M_eef (kp dpose) - kv M qd (:241).  fp32 un-contracted in the
+// reference's operand order up to dpose, which never leaves registers unless a tensor is given.
+// segments: 0 = J (6xD), 1 = M (DxD), 2 = dof_vel (1xD), 3 = pos_des (1x3), 4 = orn_des (1x4); extras: hand row (7).
+template <typename T, int D>
+__global__ void __launch_bounds__(kTileEnvs)
+franka_osc_step_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, TView hand_index, float kp, float kv,
+                       int pos_control, TView dpose_out, int has_dpose, TView out, int64_t n) {
+  extern __shared__ __align__(128) float tile[];
+  __shared__ __align__(8) uint64_t bar;
+  stage_begin(P, &bar);
+  pdl_prologue();
+  const int ntiles = tile_count(n);
+  const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
+  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  const bool bulk = tile_is_bulk(P, blockIdx.x, ntiles);
+  const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
+  float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
+  const int64_t hand_row = gather_row(hand_index, 1, env0, nenv, rb.n[0]);
+  SAddr a[5];
+  unsigned phase = 0;
+  stage_issue<5>(P, &tmap, blockIdx.x, ntiles, n, tile, &bar);
+  gather_copy<7>(rb, hand_row, nenv, x0, x_ts);
+  stage_wait<5>(P, blockIdx.x, ntiles, &bar, phase, a);
+  if (threadIdx.x >= nenv) return;
+  const int e = threadIdx.x;
   const int64_t env = env0 + e;
-  float J[6][D];
+  const float* xr = x0 + e * x_ts;
+  float dp[6];
 #pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = 0; c < D; ++c) J[r][c] = SM(a[0], e, r, c);
-  T A[6][6], rda[6], L[D][D];
-#pragma unroll
-  for (int r = 0; r < D; ++r)
-#pragma unroll
-    for (int c = 0; c <= r; ++c) L[r][c] = (T)SM(a[1], e, r, c);
-  task_space_factor<T, D>(J, L, A, rda);
-  T w[6];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) w[r] = (T)__fmul_rn(kp, SM(a[3], e, 0, r));
-  chol_solve<T, 6>(A, rda, w);            // Lambda (kp dpose)
-  float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
-#pragma unroll
-  for (int c = 0; c < D; ++c) {
-    T damp = (T)0;
-#pragma unroll
-    for (int k = 0; k < D; ++k) damp = fma_t<T>((T)SM(a[1], e, c, k), (T)SM(a[2], e, 0, k), damp);
-    T u = -(T)kv * damp;                  // - kv * M qd
-#pragma unroll
-    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], w[r], u);
-    o[c * out.s[1]] = (float)u;
+  for (int c = 0; c < 3; ++c) {
+    float pe = __fmul_rn(kp, __fsub_rn(SM(a[3], e, 0, c), xr[c]));      // :234
+    if (!pos_control) pe = __fmul_rn(pe, 0.0f);                         // :236-237 (keeps the sign of zero, NaN / Inf -> NaN)
+    dp[c] = pe;
   }
+  {
+    // torch.norm(dim=-1) over the four components of the gathered (contiguous) copy: squares rounded, summed in storage
+    // order, then sqrt (:231) -- bit-identical to torch-CPU on every env of tests/golden/franka_full.npz
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(xr[3], xr[3]), __fmul_rn(xr[4], xr[4])), __fmul_rn(xr[5], xr[5])),
+                                           __fmul_rn(xr[6], xr[6])));
+    const float cx = __fdiv_rn(xr[3], nrm), cy = __fdiv_rn(xr[4], nrm), cz = __fdiv_rn(xr[5], nrm), cw = __fdiv_rn(xr[6], nrm);
+    const float ax = SM(a[4], e, 0, 0), ay = SM(a[4], e, 0, 1), az = SM(a[4], e, 0, 2), aw = SM(a[4], e, 0, 3);
+    const float bx = -cx, by = -cy, bz = -cz, bw = cw;                  // conj(current)
+    auto dot4 = [](float p0, float p1, float p2, float p3) { return __fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3); };
+    const float x = dot4(__fmul_rn(aw, bx), __fmul_rn(ax, bw), __fmul_rn(ay, bz), -__fmul_rn(az, by));
+    const float y = dot4(__fmul_rn(aw, by), -__fmul_rn(ax, bz), __fmul_rn(ay, bw), __fmul_rn(az, bx));
+    const float z = dot4(__fmul_rn(aw, bz), __fmul_rn(ax, by), -__fmul_rn(ay, bx), __fmul_rn(az, bw));
+    const float w = dot4(__fmul_rn(aw, bw), -__fmul_rn(ax, bx), -__fmul_rn(ay, by), -__fmul_rn(az, bz));
+    const float sg = (w > 0.f) ? 1.f : ((w < 0.f) ? -1.f : ((w == 0.f) ? 0.f : w));
+    dp[3] = x * sg; dp[4] = y * sg; dp[5] = z * sg;
+  }
+  if (has_dpose) {
+    float* dpo = reinterpret_cast<float*>(const_cast<void*>(dpose_out.p)) + env * dpose_out.s[0];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) dpo[c * dpose_out.s[1]] = dp[c];
+  }
+  float kd[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) kd[r] = __fmul_rn(kp, dp[r]);             // (kp * dpose) of :241
+  osc_full_solve<T, D>(tile, a[0], a[1], a[2], e, kd, kv, out, env);
 }
 #undef SM
 
@@ -1056,6 +1139,7 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
     if (hv.n[0] != n) B200_FAIL(B200CTL_E_SHAPE, "hand_vel: expected (N,6) without hand_index");
     hi = hv;
   }
+  B200_TRY(check_f64_device_ptr(stats, "stats", dev));
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
@@ -1112,6 +1196,52 @@ extern "C" int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const
   return post_launch("osc_full_kernel");
 }
 
+extern "C" int b200ctl_franka_osc_step(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_vel,
+                                       const DLTensor* rb_states, const DLTensor* hand_index, const DLTensor* pos_des,
+                                       const DLTensor* orn_des, double kp, double kv, int32_t pos_control,
+                                       int32_t precision, DLTensor* dpose_out, DLTensor* out, b200ctl_stream_t stream) {
+  int dev = -1;
+  TView j, m, qd, rb, hi, pd, od, dp, o;
+  B200_TRY(check_precision(precision));
+  B200_TRY(view_of(j_eef, "j_eef", M_F32, 3, 3, &dev, &j));
+  const int64_t n = j.n[0], D = j.n[2];
+  if (j.n[1] != 6 || (D != 7 && D != 9)) B200_FAIL(B200CTL_E_SHAPE, "j_eef: expected (N,6,7) or (N,6,9)");
+  B200_TRY(view_of(mm, "mm", M_F32, 3, 3, &dev, &m));
+  if (m.n[0] != n || m.n[1] != D || m.n[2] != D) B200_FAIL(B200CTL_E_SHAPE, "mm: expected (N,D,D)");
+  B200_TRY(vec_rows(dof_vel, "dof_vel", n, D, true, &dev, &qd));
+  B200_TRY(view_of(rb_states, "rb_states", M_F32, 2, 2, &dev, &rb));
+  if (rb.n[1] < 7) B200_FAIL(B200CTL_E_SHAPE, "rb_states: expected (M,13)");
+  B200_TRY(view_of(hand_index, "hand_index", M_I64, 1, 1, &dev, &hi));
+  if (hi.n[0] != n) B200_FAIL(B200CTL_E_SHAPE, "hand_index: expected (N,)");
+  B200_TRY(view_of(pos_des, "pos_des", M_F32, 2, 2, &dev, &pd));
+  if (pd.n[0] != n || pd.n[1] != 3) B200_FAIL(B200CTL_E_SHAPE, "pos_des: expected (N,3)");
+  B200_TRY(view_of(orn_des, "orn_des", M_F32, 2, 2, &dev, &od));
+  if (od.n[0] != n || od.n[1] != 4) B200_FAIL(B200CTL_E_SHAPE, "orn_des: expected (N,4)");
+  const int has_dpose = dpose_out != nullptr;
+  if (has_dpose) B200_TRY(vec_rows(dpose_out, "dpose_out", n, 6, true, &dev, &dp));
+  else dp = qd;
+  B200_TRY(vec_rows(out, "out", n, D, true, &dev, &o));
+  if (n == 0) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(dev));
+  const SegSpec spec[5] = {{&j, 6, (int)D}, {&m, (int)D, (int)D}, {&qd, 1, (int)D}, {&pd, 1, 3}, {&od, 1, 4}};
+  CUtensorMap tmap;
+  const StagePlan P = make_plan(spec, 5, 7, n, &tmap);
+  const int smem = P.smem_floats * 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  const float fkp = (float)kp, fkv = (float)kv;
+#define LAUNCH_STEP(T, DD)                                                              \
+  do {                                                                                  \
+    B200_TRY(set_smem(franka_osc_step_kernel<T, DD>, smem));                            \
+    launch_pdl(franka_osc_step_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, hi, fkp, fkv, pos_control ? 1 : 0, \
+               dp, has_dpose, o, n);                                                    \
+  } while (0)
+  if (D == 7) { if (precision == 0) LAUNCH_STEP(double, 7); else LAUNCH_STEP(float, 7); }
+  else        { if (precision == 0) LAUNCH_STEP(double, 9); else LAUNCH_STEP(float, 9); }
+#undef LAUNCH_STEP
+  return post_launch("franka_osc_step_kernel");
+}
+
 extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_pos, const DLTensor* dof_vel,
                                       const DLTensor* rb_states, const DLTensor* box_index, const DLTensor* hand_index,
                                       const DLTensor* init_pos, const DLTensor* init_rot, DLTensor* hand_restart,
@@ -1149,6 +1279,7 @@ extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm
   B200_TRY(view_of(grip_out, "grip_out", M_F32, 2, 2, &dev, &gr));
   if (gr.n[0] != n || gr.n[1] != 2) B200_FAIL(B200CTL_E_SHAPE, "grip_out: expected (N,2)");
   B200_TRY(vec_rows(out, "out", n, 7, true, &dev, &o));
+  B200_TRY(check_f64_device_ptr(stats, "stats", dev));
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));

@@ -24,10 +24,13 @@ franka_task_kernel(TView rb, TView box_index, TView hand_index, TView dof_pos, T
   const int64_t brow = reinterpret_cast<const int64_t*>(box_index.p)[env * box_index.s[0]];
   const int64_t hrow = reinterpret_cast<const int64_t*>(hand_index.p)[env * hand_index.s[0]];
   float box[7], hand[7];
+  // an index outside the rigid-body tensor is never dereferenced: the row reads as NaN and so does the env's dpose
+  const bool bok = brow >= 0 && brow < rb.n[0], hok = hrow >= 0 && hrow < rb.n[0];
+  const float nanf_ = __int_as_float(0x7fc00000);
 #pragma unroll
   for (int c = 0; c < 7; ++c) {
-    box[c] = __ldg(rbp + brow * rb.s[0] + c * rb.s[1]);       // box_pos, box_rot    :348-349
-    hand[c] = __ldg(rbp + hrow * rb.s[0] + c * rb.s[1]);      // hand_pos, hand_rot  :351-352
+    box[c] = bok ? __ldg(rbp + brow * rb.s[0] + c * rb.s[1]) : nanf_;       // box_pos, box_rot    :348-349
+    hand[c] = hok ? __ldg(rbp + hrow * rb.s[0] + c * rb.s[1]) : nanf_;      // hand_pos, hand_rot  :351-352
   }
   const float* qp = reinterpret_cast<const float*>(dof_pos.p) + env * dof_pos.s[0];
   const float sep = __fadd_rn(__ldg(qp + 7 * dof_pos.s[1]), __ldg(qp + 8 * dof_pos.s[1]));   // :364

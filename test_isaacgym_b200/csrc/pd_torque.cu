@@ -288,6 +288,9 @@ pd_torque_strided_kernel(TView state, TView q_tgt, TView qd_tgt, PdParams pp, in
 
 // ---------------------------------------------------------------- dispatch
 // 128-bit path: four flattened (env, dof) elements per thread iteration.
+// The vector kernel stages 5 per-DOF parameter arrays in 20 D bytes of dynamic shared memory; beyond the 48 KB a kernel
+// gets without opting in, the call takes the strided kernel (parameters read through L1/L2) instead of failing to launch.
+constexpr int kPdVecMaxDofs = 2048;
 static inline bool pd_vectorisable(int64_t n, int64_t D) { return D >= 4 && (n * D) % 4 == 0 && n * D / 4 < (int64_t(1) << 31); }
 
 struct PdLaunch {
@@ -350,6 +353,30 @@ static void pd_launch(const PdLaunch& L, bool wrap, bool clamp, bool has_qd, boo
   }
 }
 
+// Byte range [lo, hi) spanned by a view (any strides, negative included).
+static void view_span(const TView& v, uintptr_t* lo, uintptr_t* hi) {
+  int64_t mn = 0, mx = 0;
+  for (int i = 0; i < v.ndim; ++i) {
+    if (v.n[i] == 0) { *lo = *hi = reinterpret_cast<uintptr_t>(v.p); return; }
+    const int64_t ext = (v.n[i] - 1) * v.s[i];
+    if (ext < 0) mn += ext; else mx += ext;
+  }
+  *lo = reinterpret_cast<uintptr_t>(v.p) + mn * 4;
+  *hi = reinterpret_cast<uintptr_t>(v.p) + (mx + 1) * 4;
+}
+static bool views_overlap(const TView& a, const TView& b) {
+  uintptr_t al, ah, bl, bh;
+  view_span(a, &al, &ah);
+  view_span(b, &bl, &bh);
+  return al < bh && bl < ah;
+}
+static bool same_view(const TView& a, const TView& b) {
+  if (a.p != b.p || a.ndim != b.ndim) return false;
+  for (int i = 0; i < a.ndim; ++i)
+    if (a.n[i] != b.n[i] || (a.n[i] > 1 && a.s[i] != b.s[i])) return false;
+  return true;
+}
+
 static int pd_vector_param(const DLTensor* t, const char* name, int num_dofs, int* dev, const float** p, int64_t* stride) {
   TView v;
   B200_TRY(view_of(t, name, M_F32, 1, 1, dev, &v));
@@ -396,13 +423,29 @@ extern "C" int b200ctl_pd_torque(const DLTensor* dof_state, const DLTensor* q_ta
     B200_TRY(pd_vector_param(q_lo, "q_lo", (int)D, &dev, &L.pp.q_lo, &L.pp.s_lo));
     B200_TRY(pd_vector_param(q_hi, "q_hi", (int)D, &dev, &L.pp.q_hi, &L.pp.s_hi));
   }
+  B200_TRY(check_f64_device_ptr(stats, "stats", dev));
   if (N == 0) return 0;
+
+  // In-place use.  tau_out may BE q_target or qd_target (same pointer, shape and strides: every element is read and
+  // then written by the one thread that owns it) -- that call takes the strided kernel, whose loads are plain and whose
+  // pointers are not `restrict`.  Any other overlap of the output with an input (a shifted or partial alias, or the
+  // dof_state tensor itself) would let one thread's store race another thread's load: refused.
+  bool in_place = false;
+  if (views_overlap(L.out, L.state)) B200_FAIL(B200CTL_E_ALIAS, "tau_out overlaps dof_state");
+  if (views_overlap(L.out, L.tgt)) {
+    if (!same_view(L.out, L.tgt)) B200_FAIL(B200CTL_E_ALIAS, "tau_out partially overlaps q_target (only tau_out == q_target is allowed)");
+    in_place = true;
+  }
+  if (has_qd && views_overlap(L.out, L.qd)) {
+    if (!same_view(L.out, L.qd)) B200_FAIL(B200CTL_E_ALIAS, "tau_out partially overlaps qd_target (only tau_out == qd_target is allowed)");
+    in_place = true;
+  }
 
   L.num_dofs = (int)D;
   L.num_envs = N;
   L.stats = stats;
   L.stream = (cudaStream_t)stream;
-  L.vec4 = pd_vectorisable(N, D) && is_compact(L.state) && is_compact(L.tgt) && is_compact(L.out) &&
+  L.vec4 = !in_place && pd_vectorisable(N, D) && D <= kPdVecMaxDofs && is_compact(L.state) && is_compact(L.tgt) && is_compact(L.out) &&
            (!has_qd || is_compact(L.qd)) && aligned16(L.state.p) && aligned16(L.tgt.p) && aligned16(L.out.p) &&
            (!has_qd || aligned16(L.qd.p));
   L.state4 = reinterpret_cast<const float4*>(L.state.p);
@@ -530,7 +573,7 @@ extern "C" int b200ctl_pd_torque_host(const float* dof_state, const float* q_tar
 
     B200_CUDA(cudaStreamWaitEvent(P.run, P.uploaded[slot], 0));
     L.num_envs = n;
-    L.vec4 = pd_vectorisable(n, D);
+    L.vec4 = pd_vectorisable(n, D) && D <= kPdVecMaxDofs;
     L.state4 = reinterpret_cast<const float4*>(P.d_state[slot]);
     L.tgt4 = reinterpret_cast<const float4*>(P.d_tgt[slot]);
     L.qd4 = reinterpret_cast<const float4*>(P.d_qd[slot]);

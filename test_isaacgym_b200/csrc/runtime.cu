@@ -69,6 +69,31 @@ int sm_count(int dev) {
   return cache[dev];
 }
 
+int check_f64_device_ptr(const void* p, const char* name, int dev) {
+  if (!p) return 0;
+  if (reinterpret_cast<uintptr_t>(p) & 7u) B200_FAIL(B200CTL_E_LAYOUT, "%s: pointer is not 8-byte aligned (float64 expected)", name);
+  // small direct-mapped cache of pointers already vouched for: the step loop passes the same two or three buffers
+  // forever, and a hit also keeps the driver query out of CUDA-graph capture (the warm-up call populates it)
+  struct Slot { std::atomic<uintptr_t> key{0}; };
+  static Slot cache[64];
+  const uintptr_t key = reinterpret_cast<uintptr_t>(p) ^ ((uintptr_t)(dev + 1) << 56);
+  Slot& slot = cache[(reinterpret_cast<uintptr_t>(p) >> 6) & 63];
+  if (slot.key.load(std::memory_order_relaxed) == key) return 0;
+  cudaPointerAttributes a{};
+  const cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    B200_FAIL(B200CTL_E_DEVICE, "%s: not a CUDA pointer (%s); b200ctl has no CPU path", name, cudaGetErrorString(e));
+  }
+  if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
+    B200_FAIL(B200CTL_E_DEVICE, "%s: expected device memory (a float64 CUDA tensor), got %s memory", name,
+              a.type == cudaMemoryTypeHost ? "pinned host" : "unregistered host");
+  if (a.type == cudaMemoryTypeDevice && a.device != dev)
+    B200_FAIL(B200CTL_E_DEVICE, "%s: on cuda:%d, expected cuda:%d", name, a.device, dev);
+  slot.key.store(key, std::memory_order_relaxed);
+  return 0;
+}
+
 // ---------------------------------------------------------------- gather_rows
 __global__ void gather_rows_kernel(TView src, TView idx, int col0, int ncols, TView dst, int64_t n) {
   const int64_t total = n * ncols;
@@ -76,8 +101,9 @@ __global__ void gather_rows_kernel(TView src, TView idx, int col0, int ncols, TV
     const int64_t i = e / ncols;
     const int j = (int)(e - i * ncols);
     const int64_t row = reinterpret_cast<const int64_t*>(idx.p)[i * idx.s[0]];
-    // bit-exact copy: move the 32-bit pattern, no arithmetic
-    const uint32_t bits = reinterpret_cast<const uint32_t*>(src.p)[row * src.s[0] + (col0 + j) * src.s[1]];
+    // bit-exact copy: move the 32-bit pattern, no arithmetic.  A row outside the source is not dereferenced (NaN).
+    const uint32_t bits = (row >= 0 && row < src.n[0])
+        ? reinterpret_cast<const uint32_t*>(src.p)[row * src.s[0] + (col0 + j) * src.s[1]] : 0x7fc00000u;
     reinterpret_cast<uint32_t*>(const_cast<void*>(dst.p))[i * dst.s[0] + j * dst.s[1]] = bits;
   }
 }

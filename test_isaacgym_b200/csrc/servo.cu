@@ -42,6 +42,12 @@ struct ServoConst {
 #ifndef B200_SERVO_PERSIST_ALL
 #define B200_SERVO_PERSIST_ALL 0     // A/B knob: 1 = the persistent grid (and its tile buffers) without statistics too
 #endif
+#ifndef B200_SERVO_STATS_F32ERR
+#define B200_SERVO_STATS_F32ERR 0    // A/B knob: 1 = the statistics' pixel-error norm is formed in fp32 from the fp64 pixel move
+#endif
+#ifndef B200_SERVO_STATS_SMEM
+#define B200_SERVO_STATS_SMEM 0      // A/B knob: 1 = the per-thread statistics accumulators live in shared memory between tiles
+#endif
 template <int PREC, bool STATS, int TILE, bool SPLIT>
 __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64_t num_envs, const ServoConst& k,
                                                 double* __restrict__ aux, double* __restrict__ stats, int vec_ok) {
@@ -67,6 +73,15 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   unsigned phases = 0;               // bit b: phase parity of bars[b]
   double acc_d[2] = {0, 0};          // sum |pixel error|, sum error^2
   unsigned acc_u[3] = {0, 0, 0};     // envs, envs with the target behind the camera, non-finite attitudes
+  // B200_SERVO_STATS_SMEM: the accumulators cross the tile loop in shared memory instead of seven registers the
+  // reference-precision kernel does not have (64-register cap for 16 resident tiles per SM: 52 bytes spilled)
+  constexpr bool ACC_SMEM = STATS && B200_SERVO_STATS_SMEM && PREC == 0;
+  __shared__ double s_accd[ACC_SMEM ? 2 : 1][ACC_SMEM ? NT : 1];
+  __shared__ unsigned s_accu[ACC_SMEM ? 3 : 1][ACC_SMEM ? NT : 1];
+  if (ACC_SMEM) {
+    s_accd[0][threadIdx.x] = 0.0; s_accd[1][threadIdx.x] = 0.0;
+    s_accu[0][threadIdx.x] = 0u; s_accu[1][threadIdx.x] = 0u; s_accu[2][threadIdx.x] = 0u;
+  }
   auto full_tile = [&](int t) { return vec_ok && (num_envs - (int64_t)t * TILE) >= TILE; };
   auto fetch = [&](int t, int b) {   // thread 0: one bulk copy of tile t into buffer b
     mbar_arrive_expect_tx(&bars[b], kBytes);
@@ -177,7 +192,10 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
         constexpr double kPi = 3.141592653589793238462643383279502884;
         rolld = ang[0] * 180.0 / kPi; pitchd = ang[1] * 180.0 / kPi; yawd = ang[2] * 180.0 / kPi;   // :196
       }
-      if (STATS) err = sqrt(mvx * mvx + mvy * mvy);
+      if (STATS) {
+        if (B200_SERVO_STATS_F32ERR) { const float ex = (float)mvx, ey = (float)mvy; err = (double)sqrtf(fmaf(ex, ex, ey * ey)); }
+        else err = sqrt(mvx * mvx + mvy * mvy);
+      }
     } else {
       float R[9];
       quat_to_mat<float>(qx, qy, qz, qw, R);
@@ -206,14 +224,25 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       double* a = aux + (env0 + e) * 5;
       a[0] = pu; a[1] = pv; a[2] = rolld; a[3] = pitchd; a[4] = yawd;
     }
+#ifdef B200_SERVO_STATS_DEBUG
+    if (B200_SERVO_STATS_DEBUG == 2) { acc_d[0] = 1.0; acc_d[1] = 1.0; acc_u[0] = 1u; acc_u[1] = 1u; acc_u[2] = 1u; } else
+#endif
     if (STATS) {
       const bool finite = isfinite(oq[0]) && isfinite(oq[1]) && isfinite(oq[2]) && isfinite(oq[3]);
       if (!isfinite(err)) err = 0.0;
-      acc_d[0] += err;
-      acc_d[1] = fma(err, err, acc_d[1]);
-      acc_u[0] += 1u;
-      acc_u[1] += behind ? 1u : 0u;
-      acc_u[2] += finite ? 0u : 1u;
+      if (ACC_SMEM) {
+        s_accd[0][threadIdx.x] += err;
+        s_accd[1][threadIdx.x] = fma(err, err, s_accd[1][threadIdx.x]);
+        s_accu[0][threadIdx.x] += 1u;
+        s_accu[1][threadIdx.x] += behind ? 1u : 0u;
+        s_accu[2][threadIdx.x] += finite ? 0u : 1u;
+      } else {
+        acc_d[0] += err;
+        acc_d[1] = fma(err, err, acc_d[1]);
+        acc_u[0] += 1u;
+        acc_u[1] += behind ? 1u : 0u;
+        acc_u[2] += finite ? 0u : 1u;
+      }
     }
     }   // attitude
   }
@@ -239,7 +268,14 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   }
   }   // tile loop
   if (NBUF == 2 && threadIdx.x == 0) bulk_wait_read();   // shared memory outlives the last write-back's read
+#ifdef B200_SERVO_STATS_DEBUG      // A/B only: 1 = accumulate but never commit, 2 = commit constants without accumulating
+  if (B200_SERVO_STATS_DEBUG == 1) { if (acc_d[0] == 12345.678) stats[7] = acc_d[1] + acc_u[0] + acc_u[1] + acc_u[2]; return; }
+#endif
   if (STATS) {
+    if (ACC_SMEM) {
+      acc_d[0] = s_accd[0][threadIdx.x]; acc_d[1] = s_accd[1][threadIdx.x];
+      acc_u[0] = s_accu[0][threadIdx.x]; acc_u[1] = s_accu[1][threadIdx.x]; acc_u[2] = s_accu[2][threadIdx.x];
+    }
     const int slots[5] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_SAT,
                           B200CTL_STAT_N_NONFINITE};
     block_stats_commit<2, 3>(acc_d, acc_u, stats, slots);
@@ -564,6 +600,8 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
   if (!is_compact(s)) B200_FAIL(B200CTL_E_LAYOUT, "root_state must be the compact actor root-state tensor");
   if (params->precision != 0 && params->precision != 1) B200_FAIL(B200CTL_E_VALUE, "precision must be 0 or 1");
   if (!(params->width > 0) || !(params->height > 0) || !(params->zoom > 0)) B200_FAIL(B200CTL_E_VALUE, "width / height / zoom must be positive");
+  B200_TRY(check_f64_device_ptr(stats, "stats", dev));
+  B200_TRY(check_f64_device_ptr(aux_out, "aux_out", dev));
   if (n == 0) return 0;
 
   ServoConst k;

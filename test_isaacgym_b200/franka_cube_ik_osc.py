@@ -22,6 +22,8 @@ from __future__ import annotations
 
 import ctypes
 import math
+import sys
+import types
 
 import torch
 
@@ -45,20 +47,43 @@ precision = 0            # 0: fp32 data, fp64 factorisation chain (default); 1: 
 
 
 def bind(**names) -> None:
-    """Assign controller globals by name (same names as the reference script)."""
+    """Assign controller globals by name (same names as the reference script).  ``hand_index=`` (an (N,) index list or
+    tensor, or None) may accompany ``hand_vel=``: the pair is what ``bind_hand`` sets.  Rebinding ``hand_vel`` alone
+    drops any index bound earlier -- ``hand_vel`` is then the already gathered (N,6) tensor of the reference (:353)."""
     g = globals()
+    index = names.pop("hand_index", _KEEP)
     for k, v in names.items():
         if k not in g or k.startswith("_"):
             raise KeyError(f"{k!r} is not a controller global of franka_cube_ik_osc")
-        g[k] = v
+        setattr(sys.modules[__name__], k, v)
+    if index is not _KEEP:
+        hv = g["hand_vel"]
+        g["_hand_index"] = None if index is None else torch.as_tensor(
+            index, dtype=torch.int64, device=hv.device if isinstance(hv, torch.Tensor) else None)
+
+
+_KEEP = object()
 
 
 def bind_hand(rb_states: torch.Tensor, hand_idxs) -> None:
     """Fuse ``hand_vel = rb_states[hand_idxs, 7:]`` (:353) into the OSC kernel: bind the live
     rigid-body-state tensor and the index list once instead of gathering every step."""
-    global hand_vel, _hand_index
-    hand_vel = rb_states[:, 7:13]
-    _hand_index = torch.as_tensor(hand_idxs, dtype=torch.int64, device=rb_states.device)
+    bind(hand_vel=rb_states[:, 7:13], hand_index=hand_idxs)
+
+
+class _ControllerModule(types.ModuleType):
+    """``hand_vel`` and the optional gather index are a PAIR: the documented assignment ``ctl.hand_vel = rb_states[hand_idxs, 7:]``
+    rebinds an (N,6) tensor, and an index list left over from an earlier ``bind_hand`` would then address rows that do
+    not exist.  Assigning ``hand_vel`` on the module therefore clears the index (``bind_hand`` / ``bind(hand_index=)``
+    set it again afterwards)."""
+
+    def __setattr__(self, name, value):
+        if name == "hand_vel":
+            super().__setattr__("_hand_index", None)
+        super().__setattr__(name, value)
+
+
+sys.modules[__name__].__class__ = _ControllerModule
 
 
 def gather_rows(src: torch.Tensor, index, col0: int = 0, ncols: int | None = None) -> torch.Tensor:
@@ -106,7 +131,7 @@ def control_osc(dpose: torch.Tensor, out: torch.Tensor | None = None, stats: tor
         out = torch.empty((n, 7), dtype=torch.float32, device=j.device)
     packed = [_lib.dl(t) for t in (j, m, g["dof_pos"], g["dof_vel"], g["hand_vel"], g["_hand_index"], dpose,
                                    g["default_dof_pos_tensor"], out)]
-    sp = ctypes.c_void_p(stats.data_ptr()) if stats is not None else None
+    sp = _lib.stats_arg(stats, j.device)
     _lib.check(_lib.lib().b200ctl_osc(*(p[0] for p in packed[:8]), float(g["kp"]), float(g["kd"]), float(g["kp_null"]),
                                       float(g["kd_null"]), int(g["precision"]), packed[8][0], sp, _lib.stream_ptr(j.device)))
     return out
@@ -131,7 +156,7 @@ def bind_control_osc(dpose: torch.Tensor, out: torch.Tensor, stats: torch.Tensor
     packed = [_lib.dl(t) for t in (g["j_eef"], g["mm"], g["dof_pos"], g["dof_vel"], g["hand_vel"], g["_hand_index"],
                                    dpose, g["default_dof_pos_tensor"], out)]
     args = [p[0] for p in packed[:8]] + [float(g["kp"]), float(g["kd"]), float(g["kp_null"]), float(g["kd_null"]),
-                                         int(g["precision"]), packed[8][0], _lib.ptr_or_none(stats), None]
+                                         int(g["precision"]), packed[8][0], _lib.stats_arg(stats, out.device), None]
     return _lib.BoundCall(_lib.lib().b200ctl_osc, args, 15, out.device, (packed, stats), out)
 
 
@@ -191,7 +216,7 @@ def bind_pick_osc(task: "TaskStep", out: torch.Tensor, grip_out: torch.Tensor, d
     packed = [_lib.dl(t) for t in tensors]
     qd, dp, gr, o = _lib.dl(g["default_dof_pos_tensor"]), _lib.dl(dpose), _lib.dl(grip_out), _lib.dl(out)
     args = [p[0] for p in packed] + [ctypes.byref(task.params), qd[0], float(g["kp"]), float(g["kd"]), float(g["kp_null"]),
-                                     float(g["kd_null"]), int(g["precision"]), dp[0], gr[0], o[0], _lib.ptr_or_none(stats), None]
+                                     float(g["kd_null"]), int(g["precision"]), dp[0], gr[0], o[0], _lib.stats_arg(stats, out.device), None]
     return _lib.BoundCall(_lib.lib().b200ctl_franka_pick_osc, args, 21, out.device, (packed, qd, dp, gr, o, task, stats), out)
 
 

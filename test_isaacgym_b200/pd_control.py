@@ -58,7 +58,7 @@ def pd_torque(dof_state: torch.Tensor, q_target: torch.Tensor, kp, kd, qd_target
     if out is None:
         out = torch.empty((n, d), dtype=torch.float32, device=dev)
     a = [_lib.dl(t) for t in (dof_state, q_target, qd_target, kp_t, kd_t, tm_t, lo_t, hi_t, out)]
-    sp = ctypes.c_void_p(stats.data_ptr()) if stats is not None else None
+    sp = _lib.stats_arg(stats, dev)
     _lib.check(L.b200ctl_pd_torque(a[0][0], a[1][0], a[2][0], a[3][0], a[4][0], a[5][0], a[6][0], a[7][0],
                                    int(flags), a[8][0], sp, _lib.stream_ptr(dev)))
     return out
@@ -129,7 +129,7 @@ class PDController:
         a = [_lib.dl(t) for t in (dof_state, q_target, qd_target, self.kp, self.kd, self.tau_max, self.q_lo,
                                   self.q_hi, out)]
         args = [a[0][0], a[1][0], a[2][0], a[3][0], a[4][0], a[5][0], a[6][0], a[7][0], int(self.flags), a[8][0],
-                _lib.ptr_or_none(stats), None]
+                _lib.stats_arg(stats, dof_state.device), None]
         return _lib.BoundCall(_lib.lib().b200ctl_pd_torque, args, 11, dof_state.device, (a, stats), out)
 
     def __call__(self, dof_state, q_target, qd_target=None, out=None, stats=None) -> torch.Tensor:

@@ -33,7 +33,9 @@ class ServoStep:
              stats: torch.Tensor | None = None) -> "_lib.BoundCall":
         """Marshal the in-place step once for a persistent root-state tensor (zero-argument callable)."""
         a = _lib.dl(root_state)
-        args = [a[0], ctypes.byref(self.params), _lib.ptr_or_none(aux), _lib.ptr_or_none(stats), None]
+        dev = root_state.device
+        args = [a[0], ctypes.byref(self.params), _lib.f64_arg(aux, dev, 5 * (root_state.numel() // 26), "aux"),
+                _lib.stats_arg(stats, dev), None]
         return _lib.BoundCall(_lib.lib().b200ctl_servo_step, args, 4, root_state.device, (a, aux, stats, self), root_state)
 
     def __call__(self, root_state: torch.Tensor, aux: torch.Tensor | None = None,
@@ -46,13 +48,9 @@ class ServoStep:
             self(staged, aux, stats)
             root_state.copy_(staged.cpu())
             return root_state
-        if aux is not None:
-            n = root_state.numel() // 26
-            if aux.dtype != torch.float64 or not aux.is_contiguous() or aux.numel() != 5 * n:
-                raise ValueError("aux: expected a contiguous float64 (N,5) device tensor")
         a = _lib.dl(root_state)
-        ap = ctypes.c_void_p(aux.data_ptr()) if aux is not None else None
-        sp = ctypes.c_void_p(stats.data_ptr()) if stats is not None else None
+        ap = _lib.f64_arg(aux, root_state.device, 5 * (root_state.numel() // 26), "aux")
+        sp = _lib.stats_arg(stats, root_state.device)
         _lib.check(_lib.lib().b200ctl_servo_step(a[0], ctypes.byref(self.params), ap, sp, _lib.stream_ptr(root_state.device)))
         return root_state
 

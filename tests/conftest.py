@@ -56,6 +56,11 @@ def franka_golden():
 
 
 @pytest.fixture(scope="session")
+def franka_full():
+    return load_golden("franka_full.npz")
+
+
+@pytest.fixture(scope="session")
 def pd_fragments():
     return load_golden("pd_fragments.npz")
 

@@ -19,6 +19,9 @@ Fixtures
   franka.npz        control_ik / control_osc / orientation_error, fp32 and fp64
   pd_fragments.npz  the reference's three joint-PD fragments on seeded dof_state
   franka_task.npz   the reference's pick-loop body (examples/franka_cube_ik_osc.py:348-406) executed in place
+  franka_full.npz   the reference's all-DOF OSC loop body (examples/franka_osc.py:221-241) executed in place, fp32 and
+                    fp64, and the explicit-argument control_ik / scalar orientation_error of
+                    examples/franka_nut_bolt_ik_osc.py:27-38
 """
 from __future__ import annotations
 
@@ -303,6 +306,75 @@ def gen_franka_task():
         (out["ik_pos_action"][:, 7] == 0).mean()))
 
 
+def _franka_osc_loop_statements():
+    """Statements of the `while` loop body of examples/franka_osc.py from `pos_cur = ...` (:221) to `u = ...` (:241):
+    hand-pose gather, desired-position update, the OSC solve and the dpose assembly, compiled from the script in place."""
+    path = os.path.join(rl.REFERENCE_ROOT, "examples", "franka_osc.py")
+    tree = ast.parse(open(path, encoding="utf-8").read())
+    loop = next(n for n in tree.body if isinstance(n, ast.While))
+
+    def target_name(st):
+        return getattr(st.targets[0], "id", "") if isinstance(st, ast.Assign) else ""
+    names = [target_name(st) for st in loop.body]
+    first, last = names.index("pos_cur"), names.index("u")
+    return compile(ast.Module(body=loop.body[first:last + 1], type_ignores=[]), path, "exec")
+
+
+def gen_franka_full():
+    """the reference's own statements for the all-DOF OSC (franka_osc.py) and the explicit-argument
+    IK (franka_nut_bolt_ik_osc.py), executed on seeded 9-DOF inputs."""
+    import types
+    from oracle import franka as ofr
+    code = _franka_osc_loop_statements()
+    out = {}
+    n = 256
+    fi = syn.franka_inputs(n, seed=21)
+    g = torch.Generator().manual_seed(22)
+    rb = fi.rb_states.clone()
+    # hand quaternions stored un-normalised (the loop renormalises them, franka_osc.py:231)
+    rb[fi.hand_idxs, 3:7] *= (0.5 + torch.rand(n, 1, generator=g))
+    init_pos = torch.randn(n, 3, generator=g) * 0.3
+    orn_unit = torch.randn(n, 4, generator=g)
+    orn_unit = orn_unit / orn_unit.norm(dim=1, keepdim=True)
+    # the script's own randomisation (:206-207): rand_like divided by the norm of the WHOLE tensor
+    orn_script = torch.rand(n, 4, generator=g)
+    orn_script = orn_script / torch.norm(orn_script)
+    kp = 5
+    kv = 2 * math.sqrt(kp)                                       # examples/franka_osc.py:191-192
+    itr = 37
+    # stored inputs: the used jacobian slot (N,6,9), the mass matrix, dof velocities, the hand rigid-body rows
+    out.update(j_eef9=fi.jacobian[:, syn.FRANKA_JACOBIAN_SLOT].numpy(), mass_matrix=fi.mass_matrix.numpy(),
+               dof_vel=fi.dof_vel.squeeze(-1).numpy(), hand_rows=rb[fi.hand_idxs].numpy(), init_pos=init_pos.numpy(),
+               orn_unit=orn_unit.numpy(), orn_script=orn_script.numpy(), kp=np.float64(kp), kv=np.float64(kv),
+               itr=np.int64(itr), seed=np.int64(21))
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        for case, pos_control, orn in (("pos", True, orn_unit), ("orn", False, orn_script)):
+            ns = {"torch": torch, "math": math, "np": np, "quat_mul": ofr.quat_mul, "quat_conjugate": ofr.quat_conjugate}
+            rl.extract_functions("examples/franka_osc.py", ["orientation_error"], ns)
+            ns.update(args=types.SimpleNamespace(pos_control=pos_control, orn_control=not pos_control),
+                      rb_states=rb.to(dt), hand_idxs=fi.hand_idxs.tolist(), itr=itr, kp=kp, kv=kv,
+                      init_pos=init_pos.to(dt), pos_des=init_pos.to(dt).clone(), orn_des=orn.to(dt).clone(),
+                      j_eef=fi.jacobian.to(dt)[:, syn.FRANKA_JACOBIAN_SLOT, :],        # (N,6,9), :180-181
+                      mm=fi.mass_matrix.to(dt), dof_vel=fi.dof_vel.to(dt))
+            exec(code, ns)
+            out[f"{case}_{tag}_pos_des"] = ns["pos_des"].numpy()
+            out[f"{case}_{tag}_dpose"] = ns["dpose"].numpy()
+            out[f"{case}_{tag}_u"] = ns["u"].numpy()
+    # explicit-argument control_ik and the scalar orientation_error of the nut-bolt script (:27-38)
+    fj = syn.franka_inputs(n, seed=23)
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        ns = {"torch": torch, "math": math, "np": np, "device": "cpu", "quat_mul": ofr.quat_mul,
+              "quat_conjugate": ofr.quat_conjugate}
+        rl.extract_functions("examples/franka_nut_bolt_ik_osc.py", ["control_ik", "orientation_error"], ns)
+        out[f"nutbolt_ik_{tag}"] = ns["control_ik"](fj.dpose.to(dt), 0.05, fj.j_eef.to(dt), n).numpy()
+        out[f"nutbolt_orn_err_{tag}"] = torch.stack(
+            [ns["orientation_error"](orn_unit[i].to(dt), rb[fi.hand_idxs[i], 3:7].to(dt)) for i in range(16)]).numpy()
+    out.update(nutbolt_j_eef=fj.j_eef.numpy(), nutbolt_dpose=fj.dpose.numpy(), nutbolt_damping=np.float64(0.05))
+    np.savez_compressed(os.path.join(HERE, "franka_full.npz"), **out)
+    rel = np.abs(out["pos_f32_u"] - out["pos_f64_u"]).max() / np.abs(out["pos_f64_u"]).max()
+    print("franka_full: u", out["pos_f32_u"].shape, "fp32-vs-fp64 max rel", rel)
+
+
 if __name__ == "__main__":
     if not rl.available():
         sys.exit("reference checkout not found at " + rl.REFERENCE_ROOT)
@@ -313,3 +385,4 @@ if __name__ == "__main__":
     gen_franka()
     gen_pd_fragments()
     gen_franka_task()
+    gen_franka_full()

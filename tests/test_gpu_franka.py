@@ -224,3 +224,94 @@ def test_franka_staging_plans(layout):
     osc32 = ctl.control_osc(dpose).cpu()
     ctl.bind(precision=0)
     assert np.median(_rel(osc32, ref)) <= 1e-5
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) rank 2, pinned to reference-executed fixtures
+def _embed_full(g, n, pad_rows=3):
+    """The fixture's slot / hand rows placed back into gym-shaped tensors: jacobian (N,10,6,9) with the (N,6,9) slot at
+    FRANKA_JACOBIAN_SLOT, rb_states (13 N + pad, 13) with the hand rows at 13 i + 10, dof_state (9 N, 2)."""
+    jac = torch.zeros(n, 10, 6, 9)
+    jac[:, syn.FRANKA_JACOBIAN_SLOT] = torch.from_numpy(g["j_eef9"])
+    rb = torch.randn(n * 13 + pad_rows, 13, generator=torch.Generator().manual_seed(1))
+    idx = torch.arange(n) * 13 + syn.FRANKA_HAND_BODY
+    rb[idx] = torch.from_numpy(g["hand_rows"])
+    dof = torch.zeros(n * 9, 2)
+    dof[:, 1] = torch.from_numpy(g["dof_vel"]).reshape(-1)
+    return jac.to(DEV), rb.to(DEV), idx.to(DEV), dof.to(DEV)
+
+
+def test_franka_osc_loop_law_vs_reference_fixture(franka_full):
+    """b200ctl_franka_osc_step / b200ctl_osc_full against examples/franka_osc.py:221-241 executed in place
+    (tests/golden/franka_full.npz): dpose within 2 ulp of the reference's fp32 run, u within 1e-4 of its fp64 run."""
+    import test_isaacgym_b200.franka_osc as fosc
+    from test_oracle_franka_pd import franka_full_case
+    g = franka_full
+    n = g["mass_matrix"].shape[0]
+    jac, rb, idx, dof = _embed_full(g, n)
+    j9 = jac[:, syn.FRANKA_JACOBIAN_SLOT, :]                       # (N,6,9) view, strides (540,9,1)
+    mm = torch.from_numpy(g["mass_matrix"]).to(DEV)
+    dof_vel = dof[:, 1].view(n, 9, 1)                              # stride-2 view like franka_osc.py:198
+    cond = ofr.conditioning(torch.from_numpy(g["j_eef9"]), torch.from_numpy(g["mass_matrix"])).numpy()
+    rb_before = rb.clone()
+    for case in ("pos", "orn"):
+        a = franka_full_case(g, case, torch.float32)
+        init_pos = torch.from_numpy(g["init_pos"]).to(DEV)
+        pos_des = init_pos.clone()
+        if case == "pos":
+            fosc.update_pos_des(pos_des, init_pos, int(g["itr"]))
+            assert np.array_equal(pos_des.cpu().numpy(), g["pos_f32_pos_des"])
+        dpose = torch.zeros(n, 6, device=DEV)
+        u = fosc.osc_step(rb, idx.tolist(), pos_des, a["orn_des"].to(DEV), j9, mm, dof_vel, a["kp"], a["kv"],
+                          pos_control=a["pos_control"], dpose_out=dpose)
+        ref_dp = g[f"{case}_f32_dpose"]
+        got_dp = dpose.cpu().numpy()
+        assert np.array_equal(got_dp[:, :3], ref_dp[:, :3])                 # kp (pos_des - pos_cur): same two roundings
+        assert np.abs(got_dp[:, 3:].astype(np.float64) - ref_dp[:, 3:]).max() <= 2.4e-7    # 2 ulp of the unit-scale terms
+        assert (got_dp == ref_dp).mean() > 0.9
+        r = _rel(u.cpu().squeeze(-1), g[f"{case}_f64_u"].squeeze(-1))
+        ref32 = _rel(g[f"{case}_f32_u"].squeeze(-1), g[f"{case}_f64_u"].squeeze(-1))
+        print(f"franka_osc {case}: kernel rel err max {r.max():.2e} gated {r[cond <= 1e4].max():.2e} | reference fp32 max {ref32.max():.2e}")
+        assert r[cond <= 1e4].max() <= 1e-4
+        # without a dpose tensor: same torques; the solve alone on the reference's own dpose agrees too
+        assert torch.equal(fosc.osc_step(rb, idx, pos_des, a["orn_des"].to(DEV), j9, mm, dof_vel, a["kp"], a["kv"],
+                                         pos_control=a["pos_control"]), u)
+        u2 = fosc.control_osc(torch.from_numpy(ref_dp).to(DEV), j9, mm, dof_vel, a["kp"], a["kv"])
+        assert _rel(u2.cpu().squeeze(-1), g[f"{case}_f64_u"].squeeze(-1))[cond <= 1e4].max() <= 1e-4
+    assert torch.equal(rb, rb_before)                              # the script normalises a gathered COPY (:222,:231)
+
+
+def test_nutbolt_control_ik_vs_reference_fixture(franka_full):
+    """control_ik(dpose, damping, j_eef, num_envs) of examples/franka_nut_bolt_ik_osc.py:33-38 executed in place."""
+    g = franka_full
+    j = torch.from_numpy(g["nutbolt_j_eef"]).to(DEV)
+    dp = torch.from_numpy(g["nutbolt_dpose"]).to(DEV)
+    u = ctl.control_ik(dp, float(g["nutbolt_damping"]), j, j.shape[0])
+    cond = ofr.conditioning(torch.from_numpy(g["nutbolt_j_eef"]), None, float(g["nutbolt_damping"])).numpy()
+    r = _rel(u.cpu(), g["nutbolt_ik_f64"])
+    print(f"nut-bolt IK: kernel rel err max {r.max():.2e} | reference fp32 max {_rel(g['nutbolt_ik_f32'], g['nutbolt_ik_f64']).max():.2e}")
+    assert r[cond <= 1e4].max() <= 1e-4
+    oe = ctl.orientation_error(torch.from_numpy(g["orn_unit"][:16]).to(DEV), torch.from_numpy(g["hand_rows"][:16, 3:7]).to(DEV))
+    assert np.abs(oe.cpu().numpy() - g["nutbolt_orn_err_f32"]).max() <= 1e-6
+
+
+def test_out_of_range_gather_index_gives_nan_not_a_fault():
+    """device-side index lists cannot be validated on the host; a bad row is never dereferenced."""
+    n = 200
+    fi = syn.franka_inputs(n, seed=9)
+    d = _bind(fi)
+    idx = d.hand_idxs.clone()
+    idx[5], idx[77] = -3, d.rb_states.shape[0] + 100
+    ctl.bind_hand(d.rb_states, idx)
+    st = _lib.stats_buffer(torch.device(DEV))
+    u = ctl.control_osc(d.dpose, stats=st)
+    torch.cuda.synchronize()
+    bad = torch.isnan(u).any(dim=1).cpu()
+    assert bad[5] and bad[77] and int(bad.sum()) == 2
+    assert int(st[_lib_stat("N_NONFINITE")].item()) == 2
+    g = ctl.gather_rows(d.rb_states, idx, 7, 6).cpu()
+    assert torch.isnan(g[5]).all() and torch.isnan(g[77]).all() and torch.equal(g[6], fi.rb_states[fi.hand_idxs[6], 7:])
+    ctl._hand_index = None
+
+
+def _lib_stat(name):
+    return {"N_ENV": 0, "SUM_ABS": 1, "SUM_SQ": 2, "N_SAT": 3, "N_NONFINITE": 4}[name]   # include/b200ctl.h:84-88

@@ -217,3 +217,60 @@ def test_pd_vector_path_for_any_dof_count(d, flags):
         assert torch.allclose(s[1:3], ref[1:3], rtol=1e-6)
     host = pd_torque(pi.dof_state, pi.q_target, pi.kp, pi.kd, None, pi.tau_max, pi.q_lo, pi.q_hi, flags)
     assert torch.equal(host, opd.pd_torque(pi.dof_state, pi.q_target, pi.kp, pi.kd, None, pi.tau_max, pi.q_lo, pi.q_hi, flags))
+
+
+def test_pd_in_place_and_alias_rules():
+    """ADVICE r1: tau_out == q_target (or qd_target) exactly is the supported in-place form (plain-load kernel);
+    a shifted / partial overlap, or an output inside dof_state, returns E_ALIAS instead of racing."""
+    n, d = 4096, 12
+    pi = syn.pd_inputs(n, d, seed=31, qd_target_std=1.0)
+    c = lambda t: t.to(DEV)
+    ref = opd.pd_torque(pi.dof_state, pi.q_target, pi.kp, pi.kd, pi.qd_target, pi.tau_max, pi.q_lo, pi.q_hi, WRAP_ANGLE)
+    state, kp, kd, tm = c(pi.dof_state), c(pi.kp), c(pi.kd), c(pi.tau_max)
+    tgt = c(pi.q_target)
+    out = pd_torque(state, tgt, kp, kd, c(pi.qd_target), tm, flags=WRAP_ANGLE, out=tgt)          # tau_out IS q_target
+    assert out.data_ptr() == tgt.data_ptr() and torch.equal(tgt.cpu(), ref)
+    qd = c(pi.qd_target)
+    pd_torque(state, c(pi.q_target), kp, kd, qd, tm, flags=WRAP_ANGLE, out=qd)                   # tau_out IS qd_target
+    assert torch.equal(qd.cpu(), ref)
+    buf = torch.zeros(n * d + 4, device=DEV)
+    buf[:n * d] = c(pi.q_target).reshape(-1)
+    with pytest.raises(_lib.B200CtlError, match="E_ALIAS"):
+        pd_torque(state, buf[:n * d].view(n, d), kp, kd, None, tm, out=buf[4:].view(n, d))       # shifted by one vector
+    with pytest.raises(_lib.B200CtlError, match="E_ALIAS"):
+        pd_torque(state, c(pi.q_target), kp, kd, None, tm, out=state.view(-1)[:n * d].view(n, d))
+
+
+def test_pd_many_dofs_does_not_need_a_shared_memory_opt_in():
+    """D above 2048 (20 D bytes of staged parameters would pass 48 KB) takes the strided kernel."""
+    for d in (2048, 3000, 4096):
+        pi = syn.pd_inputs(4, d, seed=d)
+        tau, ref32, _, _ = _run(pi, WRAP_ANGLE | CLAMP_TARGET, qd=True)
+        assert torch.equal(tau, ref32)
+
+
+def test_stats_and_aux_buffers_are_validated():
+    """stats / aux cross the ABI as raw pointers -- wrong device, dtype or length must raise, not fault."""
+    import ctypes
+    from test_isaacgym_b200.servo_step import ServoStep
+    pi = syn.pd_inputs(64, 12, seed=2)
+    c = lambda t: t.to(DEV)
+    args = (c(pi.dof_state), c(pi.q_target), c(pi.kp), c(pi.kd))
+    for bad, kind in ((torch.zeros(8, dtype=torch.float64), "E_DEVICE"), (torch.zeros(8, device=DEV), "E_DTYPE"),
+                      (torch.zeros(4, dtype=torch.float64, device=DEV), "E_SHAPE")):
+        with pytest.raises(_lib.B200CtlError, match=kind):
+            pd_torque(*args, stats=bad)
+        with pytest.raises(_lib.B200CtlError, match=kind):
+            ServoStep(1600, 900).bind(syn.servo_root_state(8, seed=0).to(DEV), stats=bad)
+    with pytest.raises(_lib.B200CtlError, match="E_SHAPE"):
+        ServoStep(1600, 900)(syn.servo_root_state(8, seed=0).to(DEV), aux=torch.zeros(8, 4, dtype=torch.float64, device=DEV))
+    # the library's own check of the raw pointer (a non-torch host has only this one): pinned host memory is refused
+    host = torch.zeros(8, dtype=torch.float64).pin_memory()
+    a = [_lib.dl(t) for t in args] + [_lib.dl(torch.empty(64, 12, device=DEV))]
+    rc = _lib.lib().b200ctl_pd_torque(a[0][0], a[1][0], None, a[2][0], a[3][0], None, None, None, 0, a[4][0],
+                                      ctypes.c_void_p(host.data_ptr()), _lib.stream_ptr(torch.device(DEV)))
+    assert rc == -2 and b"stats" in _lib.lib().b200ctl_last_error()
+    rc = _lib.lib().b200ctl_pd_torque(a[0][0], a[1][0], None, a[2][0], a[3][0], None, None, None, 0, a[4][0],
+                                      ctypes.c_void_p(_lib.stats_buffer(torch.device(DEV)).data_ptr() + 4), _lib.stream_ptr(torch.device(DEV)))
+    assert rc == -5
+    torch.cuda.synchronize()

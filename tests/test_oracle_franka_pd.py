@@ -112,3 +112,49 @@ def test_task_step_oracle_matches_reference_loop_body():
         assert np.array_equal(grip.numpy(), g[c + "_pos_action"][:, 7:9])
     # every predicate of the loop fires for a sizeable fraction of the synthetic envs
     assert 0.1 < g["ik_above_box"].mean() < 0.9 and 0.05 < g["ik_gripped"].mean() < 0.9
+
+
+# ------------------------------------------------------------------ franka_osc.py / nut-bolt control_ik
+def franka_full_case(g, case, dt):
+    """Inputs of one `franka_full.npz` case as torch tensors of dtype `dt` (rb_states holds the hand rows only)."""
+    t = lambda k: torch.from_numpy(g[k]).to(dt)
+    n = g["mass_matrix"].shape[0]
+    orn = t("orn_unit") if case == "pos" else t("orn_script")
+    pos_des = ofr.franka_osc_pos_des(t("init_pos"), int(g["itr"])) if case == "pos" else t("init_pos")
+    return dict(n=n, rb=t("hand_rows"), idx=torch.arange(n), pos_des=pos_des, orn_des=orn, j=t("j_eef9"),
+                mm=t("mass_matrix"), qd=t("dof_vel").unsqueeze(-1), kp=float(g["kp"]), kv=float(g["kv"]),
+                pos_control=(case == "pos"))
+
+
+def test_franka_osc_oracle_matches_reference_loop_body(franka_full):
+    """oracle.franka.franka_osc_step == the statements of examples/franka_osc.py:221-241 executed in place."""
+    g = franka_full
+    for case in ("pos", "orn"):
+        a = franka_full_case(g, case, torch.float64)
+        assert np.allclose(a["pos_des"].numpy(), g[f"{case}_f64_pos_des"], rtol=0, atol=1e-15)
+        dpose, u = ofr.franka_osc_step(a["rb"], a["idx"], a["pos_des"], a["orn_des"], a["j"], a["mm"], a["qd"], a["kp"], a["kv"],
+                                       a["pos_control"])
+        assert np.abs(dpose.numpy() - g[f"{case}_f64_dpose"]).max() < 1e-14
+        scale = np.abs(g[f"{case}_f64_u"]).max()
+        assert np.abs(u.numpy() - g[f"{case}_f64_u"]).max() < 1e-10 * scale
+        a = franka_full_case(g, case, torch.float32)
+        dpose, u = ofr.franka_osc_step(a["rb"], a["idx"], a["pos_des"], a["orn_des"], a["j"], a["mm"], a["qd"], a["kp"], a["kv"],
+                                       a["pos_control"])
+        assert np.array_equal(dpose.numpy(), g[f"{case}_f32_dpose"])          # same torch ops, same order
+        assert np.allclose(u.numpy(), g[f"{case}_f32_u"], rtol=1e-4, atol=1e-4 * np.abs(g[f"{case}_f32_u"]).max())
+        # the solve alone (control_osc_full) on the reference's dpose
+        u2 = ofr.control_osc_full(torch.from_numpy(g[f"{case}_f64_dpose"]), *(franka_full_case(g, case, torch.float64)[k] for k in ("j", "mm", "qd")),
+                                  a["kp"], a["kv"])
+        assert np.abs(u2.numpy() - g[f"{case}_f64_u"]).max() < 1e-10 * scale
+
+
+def test_nutbolt_control_ik_oracle_matches_reference(franka_full):
+    """examples/franka_nut_bolt_ik_osc.py:33-38 (explicit arguments) and its scalar orientation_error (:27-30)."""
+    g = franka_full
+    j, dp = torch.from_numpy(g["nutbolt_j_eef"]), torch.from_numpy(g["nutbolt_dpose"])
+    ik64 = ofr.control_ik(dp.double(), j.double(), float(g["nutbolt_damping"]))
+    assert np.abs(ik64.numpy() - g["nutbolt_ik_f64"]).max() < 1e-12
+    ik32 = ofr.control_ik(dp, j, float(g["nutbolt_damping"]))
+    assert np.array_equal(ik32.numpy(), g["nutbolt_ik_f32"])
+    oe = ofr.orientation_error(torch.from_numpy(g["orn_unit"][:16]).double(), torch.from_numpy(g["hand_rows"][:16, 3:7]).double())
+    assert np.abs(oe.numpy() - g["nutbolt_orn_err_f64"]).max() < 1e-15

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from test_isaacgym_b200 import _lib, rollout, synthetic as syn
+from test_isaacgym_b200 import _lib, rollout, testing, synthetic as syn
 
 
 # ------------------------------------------------------------------------------------------ CPU
@@ -68,7 +68,7 @@ def test_franka_backend_issues_the_reference_calls(fake_isaacgym):
 
 
 def test_rollouts_refuse_cpu_tensors():
-    b = rollout.KinematicServoBackend(syn.servo_root_state(8, seed=0))
+    b = testing.KinematicServoBackend(syn.servo_root_state(8, seed=0))
     with pytest.raises(_lib.B200CtlError):
         rollout.ServoRollout(b, 1600, 900)
 
@@ -77,7 +77,7 @@ def test_kinematic_backend_integrates_in_place():
     s = syn.servo_root_state(4, seed=1)
     s[:, :, 7:10] = torch.tensor([1.0, -2.0, 0.5])
     p0 = s[:, :, :3].clone()
-    b = rollout.KinematicServoBackend(s, dt=0.5)
+    b = testing.KinematicServoBackend(s, dt=0.5)
     b.simulate()
     assert torch.allclose(s[:, :, :3], p0 + 0.5 * torch.tensor([1.0, -2.0, 0.5])) and b.root_state.data_ptr() == s.data_ptr()
 
@@ -103,7 +103,7 @@ def test_servo_closed_loop_follows_the_reference_loop():
     s0 = syn.servo_root_state(n, seed=5)
     want, pix_ref = _oracle_rollout(s0, steps, dt, w, h)
 
-    b = rollout.KinematicServoBackend(s0.to(DEV), dt)
+    b = testing.KinematicServoBackend(s0.to(DEV), dt)
     r = rollout.ServoRollout(b, w, h)
     pix = []
     for _ in range(steps):
@@ -128,8 +128,8 @@ def test_servo_closed_loop_follows_the_reference_loop():
 def test_servo_graph_replay_equals_eager(precision):
     n, steps = 4096 + 37, 25
     s0 = syn.servo_root_state(n, seed=6)
-    a = rollout.ServoRollout(rollout.KinematicServoBackend(s0.to(DEV)), 1600, 900, precision=precision)
-    g = rollout.ServoRollout(rollout.KinematicServoBackend(s0.to(DEV)), 1600, 900, precision=precision)
+    a = rollout.ServoRollout(testing.KinematicServoBackend(s0.to(DEV)), 1600, 900, precision=precision)
+    g = rollout.ServoRollout(testing.KinematicServoBackend(s0.to(DEV)), 1600, 900, precision=precision)
     n0 = _lib.launch_count()
     a.run(steps, graph=False)
     assert _lib.launch_count() - n0 == steps                      # one b200ctl kernel per sim step
@@ -150,13 +150,13 @@ def test_franka_pick_rollout_equals_stepwise_calls(controller):
     ti, fi = syn.franka_task_inputs(n, seed=8), syn.franka_inputs(n, seed=9)
     outs = []
     for graph in (False, True):
-        b = rollout.ReplayFrankaBackend(ti, fi, DEV)
+        b = testing.ReplayFrankaBackend(ti, fi, DEV)
         r = rollout.FrankaPickRollout(b, controller)
         r.run(steps, graph=graph)
         outs.append((b.pos_action.clone(), b.effort_action.clone(), b.hand_restart.clone(), b.dof_state.clone()))
     assert all(torch.equal(x, y) for x, y in zip(*outs))
 
-    b = rollout.ReplayFrankaBackend(ti, fi, DEV)
+    b = testing.ReplayFrankaBackend(ti, fi, DEV)
     ctl.bind(j_eef=b.j_eef, mm=b.mm, dof_pos=b.dof_pos, dof_vel=b.dof_vel, default_dof_pos_tensor=b.default_dof_pos,
              num_envs=n, precision=0)
     ctl.bind_hand(b.rb_states, b.hand_idxs)
