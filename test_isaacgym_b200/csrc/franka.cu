@@ -45,6 +45,25 @@ constexpr float kPiF = 3.14159265358979323846f;
 constexpr float kTwoPiF = 6.28318530717958647692f;
 constexpr int kTileEnvs = 64;
 constexpr int kMaxSeg = 6;
+#ifndef B200_OSC_L2PF
+#define B200_OSC_L2PF 0       // A/B knob: 1 = the persistent OSC kernel L2-prefetches its next-but-one tile
+#endif
+#ifndef B200_OSC_DEBUG
+#define B200_OSC_DEBUG 0      // A/B only (wrong results): 1 = skip the factorisation chain, 2 = skip the staging copies and waits
+#endif
+#ifdef B200_OSC_TRACE          // A/B only: per-CTA phase timestamps (globaltimer, ns) of the first tile of osc_kernel
+__device__ unsigned long long g_osc_trace[8][4096];
+__device__ __forceinline__ void osc_trace(int k) {
+  if (threadIdx.x == 0 && blockIdx.x < 4096) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_osc_trace[k][blockIdx.x] = t;
+  }
+}
+#define OSC_TRACE(k) osc_trace(k)
+#else
+#define OSC_TRACE(k)
+#endif
 #ifndef B200_OSC_F64_MAXREG
 #define B200_OSC_F64_MAXREG 255   // register cap of the fp64-chain OSC kernel (A/B knob, profiles/): 200 = 5 tiles per SM
 #endif
@@ -146,10 +165,23 @@ __device__ __forceinline__ void chol_solve2(const T (&L)[N][N], const T (&rdiag)
   }
 }
 
+// General floor-mod by 2 pi (python / torch `%`): out of line -- the routine is ~40 instructions and a loop, it was
+// inlined seven times per env (a third of the instructions between "tile landed" and "operands in registers"), and joint
+// angles never take it.
+__device__ __noinline__ float floor_mod_two_pi(float s) {
+  float m = fmodf(s, kTwoPiF);
+  if (m < 0.0f) m = __fadd_rn(m, kTwoPiF);
+  return m;
+}
 __device__ __forceinline__ float wrap_pi(float e) {
   // ((e + pi) % (2 pi)) - pi with python floor-mod semantics (franka_cube_ik_osc.py:75)
-  float m = fmodf(__fadd_rn(e, kPiF), kTwoPiF);
-  if (m < 0.0f) m = __fadd_rn(m, kTwoPiF);
+  const float s = __fadd_rn(e, kPiF);
+  float m;
+  // fmodf is exact; for s in [0, 4 pi) so are these two forms (s itself, or s - 2 pi by Sterbenz' lemma: y <= s <= 2 y),
+  // i.e. bit-identical to the general routine
+  if (s >= 0.0f && s < kTwoPiF) m = s;
+  else if (s >= kTwoPiF && s < 2.0f * kTwoPiF) m = __fsub_rn(s, kTwoPiF);
+  else m = floor_mod_two_pi(s);
   return __fsub_rn(m, kPiF);
 }
 
@@ -179,9 +211,22 @@ struct StagePlan {
   int tmap_region;        // bulk plan: destination offset (floats) and bytes of the mode-4 tensor-map copy (0 = none)
   unsigned tmap_bytes;
   int bulk_ok;            // 0: every tile uses the canonical LDGSTS plan
+  int bulk_all;           // 1: in the bulk plan EVERY operand is bulk-staged (no column-owner LDGSTS walk): a tile is then
+                          //    readable once its mbarrier phase completes, and the only cp.async copies in flight are the
+                          //    ones a thread issued for ITS OWN env (the index-gathered extras), which it may wait for later
   int smem_floats;        // dynamic shared memory, in floats (max of both plans)
 };
 struct SAddr { int off, es, rs, cs; };   // resolved smem addressing of one operand for this CTA
+// The same with the row / column strides known at compile time: an operand staged in its Isaac Gym layout (jacobian rows
+// of 9 floats, 9 x 9 mass matrix, interleaved dof state).  Every element is then `LDS [base + immediate]` instead of
+// two integer multiply-adds and a load -- 150 of the 1,000 instructions between "tile landed" and "operands in registers".
+template <int RS, int CS>
+struct SAddrC {
+  int off, es;
+  static constexpr int rs = RS, cs = CS;
+  __device__ __forceinline__ SAddrC() {}
+  __device__ __forceinline__ explicit SAddrC(const SAddr& a) : off(a.off), es(a.es) {}
+};
 
 __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -195,18 +240,44 @@ __device__ __forceinline__ void tensor2d_g2s(void* smem_dst, const CUtensorMap* 
                ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
+// L2 prefetch of a tile the CTA will stage LATER (no shared memory needed): the persistent kernel's one tile buffer
+// cannot take the next tile's copies before this tile has been gathered out of it, so without the prefetch DRAM idles
+// for this CTA during every gather; with it the later TMA copy is an L2 hit.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tensor2d_prefetch_l2(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+
+// Shared-memory addressing of the operands is fixed PER LAUNCH (not per tile): an operand that is bulk-staged keeps
+// its bulk layout (global strides) in every tile -- the ragged last tile, which no bulk copy may fetch, is written by the
+// LDGSTS walk to the same addresses -- and an operand that cannot be bulk-staged lives in the dense per-env rows.
+template <int NSEG>
+__device__ __forceinline__ void stage_addr(const StagePlan& P, SAddr (&addr)[NSEG]) {
+#pragma unroll
+  for (int i = 0; i < NSEG; ++i) {
+    const StageSeg& s = P.seg[i];
+    if (P.bulk_ok && s.mode != 0) addr[i] = SAddr{s.b_off, s.b_es, s.b_rs, s.b_cs};
+    else if (P.bulk_ok) addr[i] = SAddr{s.l_off, P.bulk_ts, s.cols, 1};
+    else addr[i] = SAddr{s.c_off, P.canon_ts, s.cols, 1};
+  }
+}
+__device__ __forceinline__ int stage_extras_off(const StagePlan& P) { return P.bulk_ok ? P.x_off_b : P.x_off_c; }
+__device__ __forceinline__ int stage_extras_ts(const StagePlan& P) { return P.bulk_ok ? P.bulk_ts : P.canon_ts; }
+
 // Column-owner LDGSTS walk: thread t owns entries t, t+64, ... of the list of scalars (J[r][c], M[r][c], q[c] ...)
-// that are NOT bulk-staged, resolves (pointer, env stride, tile offset) once, then bumps a pointer per env.
+// that this tile does not receive by bulk copy (`bulk`: only the operands that are never bulk-staged; otherwise all of
+// them), resolves (pointer, env stride, destination, destination stride) once, then bumps two pointers per env.
 template <int NSEG>
 __device__ __forceinline__ void stage_ldgsts(const StagePlan& P, int64_t env0, int nenv, bool bulk, float* tile) {
-  const int ts = bulk ? P.bulk_ts : P.canon_ts;
   int total = 0;
 #pragma unroll
   for (int i = 0; i < NSEG; ++i) total += (bulk && P.seg[i].mode != 0) ? 0 : P.seg[i].rows * P.seg[i].cols;
   for (int id = threadIdx.x; id < total; id += blockDim.x) {
     const float* g = nullptr;
     int64_t step = 0;
-    int toff = 0, k = id;
+    int toff = 0, dstep = 0, k = id;
 #pragma unroll
     for (int i = 0; i < NSEG; ++i) {
       const StageSeg& s = P.seg[i];
@@ -215,7 +286,8 @@ __device__ __forceinline__ void stage_ldgsts(const StagePlan& P, int64_t env0, i
         const int r = k / s.cols, c = k - r * s.cols;
         g = s.base + env0 * s.s0 + r * s.s1 + c * s.s2;
         step = s.s0;
-        toff = (bulk ? s.l_off : s.c_off) + k;
+        if (P.bulk_ok && s.mode != 0) { toff = s.b_off + r * s.b_rs + c * s.b_cs; dstep = s.b_es; }
+        else { toff = (P.bulk_ok ? s.l_off : s.c_off) + k; dstep = P.bulk_ok ? P.bulk_ts : P.canon_ts; }
       }
       k -= cnt;
     }
@@ -223,7 +295,7 @@ __device__ __forceinline__ void stage_ldgsts(const StagePlan& P, int64_t env0, i
 #pragma unroll 4
     for (int e = 0; e < nenv; ++e) {
       cp_async_f32(dst, g);
-      dst += ts;
+      dst += dstep;
       g += step;
     }
   }
@@ -234,19 +306,19 @@ __device__ __forceinline__ void stage_ldgsts(const StagePlan& P, int64_t env0, i
 // in order, and the first use of the index stalls it for a full memory latency):
 //   gather_row   loads this thread's source row number (the load only, nothing consumes it yet),
 //   gather_copy  issues the C 4-byte copies of that row.
-__device__ __forceinline__ int64_t gather_row(const TView& index, int has_index, int64_t env0, int nenv, int64_t nrows) {
+__device__ __forceinline__ int64_t gather_row(const TView& index, int has_index, int64_t env0, int nenv) {
   if ((int)threadIdx.x >= nenv) return 0;
   const int64_t env = env0 + threadIdx.x;
-  const int64_t row = has_index ? __ldg(reinterpret_cast<const int64_t*>(index.p) + env * index.s[0]) : env;
-  // device-side index lists are not visible to the host-side validation: a row outside the source tensor is never
-  // dereferenced -- the env's gathered operand becomes NaN, so do its outputs, and N_NONFINITE counts it
-  return (row >= 0 && row < nrows) ? row : -1;
+  return has_index ? __ldg(reinterpret_cast<const int64_t*>(index.p) + env * index.s[0]) : env;   // NOT consumed here
 }
 template <int C>
 __device__ __forceinline__ void gather_copy(const TView& v, int64_t row, int nenv, float* dst_row0, int ts) {
   if ((int)threadIdx.x < nenv) {
     float* d = dst_row0 + threadIdx.x * ts;
-    if (row < 0) {
+    // device-side index lists are not visible to the host-side validation: a row outside the source tensor is never
+    // dereferenced -- the env's gathered operand becomes NaN, so do its outputs, and N_NONFINITE counts it.  (The
+    // check sits here, at the first real use of the index, so the load stays in flight across the TMA issue.)
+    if (row < 0 || row >= v.n[0]) {
 #pragma unroll
       for (int c = 0; c < C; ++c) d[c] = __int_as_float(0x7fc00000);
       return;
@@ -264,12 +336,33 @@ __device__ __forceinline__ int tile_count(int64_t n) { return (int)((n + kTileEn
 // Staging is split in three so a persistent CTA can refill its tile buffer while it computes:
 //   stage_begin  once per CTA (mbarrier init),
 //   stage_issue  starts every copy of tile t (bulk TMA on the mbarrier + the per-thread LDGSTS walk),
-//   stage_wait   resolves the smem addressing of tile t, waits for its copies and ends with a __syncthreads().
+//   stage_wait   waits for the copies of tile t and ends with a __syncthreads()
+//   (stage_addr resolves the operands' shared-memory addressing, once per launch).
 // The buffer may be re-issued as soon as every thread has copied what it needs into registers and passed a
 // __syncthreads(); mbarrier phases alternate, `phase` is the caller's parity bit.
-__device__ __forceinline__ void stage_begin(const StagePlan& P, uint64_t* bar) {
+// Kernel parameters live in constant bank 0 and are fetched on first use, one 64-byte line at a time: the staging plan
+// alone spans ten lines, and a warp that issues in order paid for each miss AFTER the dependency wait (0.7 us between
+// the wait and the first TMA copy at 16,384 envs, profiles/experiments/osc_trace.py).  The time before the wait is idle
+// (the previous kernel is still running), so every line is touched there.
+__device__ __forceinline__ int warm_view(const TView& v) { return (int)(uintptr_t)v.p ^ (int)v.s[1] ^ v.dtype; }
+template <typename... Views>
+__device__ __forceinline__ void stage_begin(const StagePlan& P, const CUtensorMap* tmap, uint64_t* bar, const Views&... views) {
+  __shared__ int s_warm;
+  if (threadIdx.x == 0) {
+    int w = P.nseg ^ P.smem_floats ^ P.bulk_all;
+#pragma unroll
+    for (int i = 0; i < kMaxSeg; ++i) w ^= (int)(uintptr_t)P.seg[i].base ^ P.seg[i].rows ^ P.seg[i].b_off ^ P.seg[i].c_off;
+    const int vw[] = {0, warm_view(views)...};
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(vw) / sizeof(int)); ++i) w ^= vw[i];
+    s_warm = w;
+  }
   if (P.bulk_ok) {
-    if (threadIdx.x == 0) mbar_init(bar, blockDim.x);
+    if (threadIdx.x == 0) {
+      mbar_init(bar, blockDim.x);
+      // the tensor map is a kernel parameter too: its descriptor goes into the TMA unit's cache ahead of the wait
+      if (P.tmap_bytes) asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+    }
     __syncthreads();
   }
 }
@@ -279,6 +372,7 @@ __device__ __forceinline__ void stage_issue(const StagePlan& P, const CUtensorMa
   const int64_t env0 = (int64_t)t * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
   const bool bulk = tile_is_bulk(P, t, ntiles);
+  if (B200_OSC_DEBUG == 2) return;
   if (bulk) {
     unsigned my_bytes = threadIdx.x == 0 ? P.tmap_bytes : 0u;
 #pragma unroll
@@ -299,19 +393,23 @@ __device__ __forceinline__ void stage_issue(const StagePlan& P, const CUtensorMa
   }
   stage_ldgsts<NSEG>(P, env0, nenv, bulk, tile);
 }
+// Thread 0: L2 prefetch of the bulk-staged operands of tile t (a full, non-last tile), see bulk_prefetch_l2.
 template <int NSEG>
-__device__ __forceinline__ void stage_wait(const StagePlan& P, int t, int ntiles, uint64_t* bar, unsigned& phase,
-                                           SAddr (&addr)[NSEG]) {
-  const bool bulk = tile_is_bulk(P, t, ntiles);
+__device__ __forceinline__ void stage_prefetch(const StagePlan& P, const CUtensorMap* tmap, int t, int ntiles) {
+  if (threadIdx.x != 0 || t >= ntiles || !tile_is_bulk(P, t, ntiles)) return;
+  const int64_t env0 = (int64_t)t * kTileEnvs;
+  if (P.tmap_bytes) tensor2d_prefetch_l2(tmap, 0, (int)env0);
 #pragma unroll
   for (int i = 0; i < NSEG; ++i) {
     const StageSeg& s = P.seg[i];
-    if (bulk && s.mode != 0) addr[i] = SAddr{s.b_off, s.b_es, s.b_rs, s.b_cs};
-    else if (bulk) addr[i] = SAddr{s.l_off, P.bulk_ts, s.cols, 1};
-    else addr[i] = SAddr{s.c_off, P.canon_ts, s.cols, 1};
+    if (s.mode == 1) bulk_prefetch_l2(reinterpret_cast<const char*>(s.base + env0 * s.s0) - s.delta, s.bytes);
   }
+}
+template <int NSEG>
+__device__ __forceinline__ void stage_wait(const StagePlan& P, int t, int ntiles, uint64_t* bar, unsigned& phase) {
+  const bool bulk = tile_is_bulk(P, t, ntiles);
   cp_async_wait_all();
-  if (bulk) { mbar_wait(bar, phase); phase ^= 1u; }
+  if (bulk && B200_OSC_DEBUG != 2) { mbar_wait(bar, phase); phase ^= 1u; }
   __syncthreads();
 }
 
@@ -321,8 +419,9 @@ __device__ __forceinline__ void stage_all(const StagePlan& P, const CUtensorMap*
                                           uint64_t* bar, SAddr (&addr)[NSEG]) {
   unsigned phase = 0;
   const int64_t n = env0 + nenv;      // only the last tile is ragged, so this clamps exactly like the true n
+  stage_addr<NSEG>(P, addr);
   stage_issue<NSEG>(P, tmap, blockIdx.x, gridDim.x, n, tile, bar);
-  stage_wait<NSEG>(P, blockIdx.x, gridDim.x, bar, phase, addr);
+  stage_wait<NSEG>(P, blockIdx.x, gridDim.x, bar, phase);
 }
 
 #define SM(a, e, r, c) tile[(a).off + (e) * (a).es + (r) * (a).rs + (c) * (a).cs]
@@ -406,7 +505,7 @@ __global__ void __launch_bounds__(kTileEnvs)
 ik_dls_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float lambda2, int has_pos, TView out, int64_t n) {
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
-  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  stage_begin(P, &tmap, &bar, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
@@ -439,9 +538,9 @@ struct OscRegs {
   T Mu0[7];       // M u0 with M as given (:77)
   T w[6];         // kp dpose - kd v_hand - J u0
 };
-template <typename T, typename TaskSpaceTarget>
-__device__ __forceinline__ void osc_gather(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQ,
-                                           const SAddr& aQD, int e, TaskSpaceTarget&& target, const float* q_default,
+template <typename T, typename AJ, typename AM, typename AQ, typename AQD, typename TaskSpaceTarget>
+__device__ __forceinline__ void osc_gather(const float* tile, const AJ& aJ, const AM& aM, const AQ& aQ,
+                                           const AQD& aQD, int e, TaskSpaceTarget&& target, const float* q_default,
                                            float kp_null, float kd_null, OscRegs<T>& R) {
   constexpr int D = 7;
 #pragma unroll
@@ -490,9 +589,9 @@ __device__ __forceinline__ void osc_solve(OscRegs<T>& R, float (&u_out)[7]) {
     u_out[c] = (float)u;
   }
 }
-template <typename T, typename TaskSpaceTarget>
-__device__ __forceinline__ void osc_compute(const float* tile, const SAddr& aJ, const SAddr& aM, const SAddr& aQ,
-                                            const SAddr& aQD, int e, TaskSpaceTarget&& target,
+template <typename T, typename AJ, typename AM, typename AQ, typename AQD, typename TaskSpaceTarget>
+__device__ __forceinline__ void osc_compute(const float* tile, const AJ& aJ, const AM& aM, const AQ& aQ,
+                                            const AQD& aQD, int e, TaskSpaceTarget&& target,
                                             const float* q_default, float kp_null, float kd_null, float (&u_out)[7]) {
   OscRegs<T> R;
   osc_gather<T>(tile, aJ, aM, aQ, aQD, e, target, q_default, kp_null, kd_null, R);
@@ -501,8 +600,18 @@ __device__ __forceinline__ void osc_compute(const float* tile, const SAddr& aJ, 
 
 // ------------------------------------------------------------------ a10: control_osc
 // segments: 0 = J (6x7), 1 = M (7x7), 2 = dof_pos (1x7), 3 = dof_vel (1x7), 4 = dpose (1x6);
-// the index-gathered hand velocity (1x6) goes to the extras slot of the active plan.
-template <typename T>
+// the index-gathered hand velocity (1x6) goes to the extras slot of the plan.
+// GYM: the operands are staged in their Isaac Gym strides (host-checked): compile-time row / column strides.
+template <bool GYM> struct OscLayout {
+  using J = SAddr; using M = SAddr; using Q = SAddr; using QD = SAddr; using DP = SAddr;
+};
+template <> struct OscLayout<true> {
+  using J = SAddrC<9, 1>; using M = SAddrC<9, 1>; using Q = SAddrC<0, 2>; using QD = SAddrC<0, 2>; using DP = SAddrC<0, 1>;
+};
+// keeps a value computed ahead of the dependency wait from being sunk below it by the compiler
+__device__ __forceinline__ void pin(int& v) { asm volatile("" : "+r"(v)); }
+
+template <typename T, bool GYM>
 // Tried and measured slower: register caps for 5 tiles/SM (168 regs: -13 %, 200 regs: -6 %, both
 // spill); splitting one env over two warps that share Lambda^-1 through shared memory (redundant Cholesky work +
 // a CTA barrier: -70 %).
@@ -510,23 +619,41 @@ __global__ void __launch_bounds__(kTileEnvs) __maxnreg__(sizeof(T) == 8 ? B200_O
 osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel, TView hand_index, int has_index, TView q_default,
            float kp, float kd, float kp_null, float kd_null, TView out, int64_t n, double* __restrict__ stats) {
   constexpr int D = 7;
+  using Lay = OscLayout<GYM>;
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
-  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  OSC_TRACE(0);
+  stage_begin(P, &tmap, &bar, hand_vel, hand_index, q_default, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  // everything that depends on the launch parameters only is resolved while the previous kernel is still running
+  SAddr a[5];
+  stage_addr<5>(P, a);
+  typename Lay::J aJ(a[0]);
+  typename Lay::M aM(a[1]);
+  typename Lay::Q aQ(a[2]);
+  typename Lay::QD aQD(a[3]);
+  typename Lay::DP aDp(a[4]);
+  const int x_ts = stage_extras_ts(P);
+  int hv_off = stage_extras_off(P) + (int)threadIdx.x * x_ts;
+  int ntiles = (int)((n + kTileEnvs - 1) / kTileEnvs);
+  pin(aJ.off); pin(aJ.es); pin(aM.off); pin(aM.es); pin(aQ.off); pin(aQD.off); pin(aDp.off); pin(hv_off); pin(ntiles);
   pdl_prologue();
+  OSC_TRACE(1);
   // persistent CTA: tiles blockIdx.x, + gridDim.x, ...; the tile buffer is refilled while the previous tile's
   // factorisation runs out of registers
-  const int ntiles = (int)((n + kTileEnvs - 1) / kTileEnvs);
   auto tile_envs = [&](int t) { const int64_t left = n - (int64_t)t * kTileEnvs; return (int)(left < kTileEnvs ? left : kTileEnvs); };
-  // the hand-velocity row number of tile t is loaded one tile ahead of its use (row_of), so the gather copies -- the
-  // longest latency of the staging, issued first -- do not wait for the index (profiles/: 6.6 % of the stall samples
-  // of the fp64 chain sat on that first use).  Issuing the first tile's TMA copies ahead of its gather instead
-  // measured the same.
-  auto row_of = [&](int t) { return gather_row(hand_index, has_index, (int64_t)t * kTileEnvs, tile_envs(t), hand_vel.n[0]); };
+  // the hand-velocity row number of tile t is loaded one tile ahead of its use (row_of), and for the CTA's first tile
+  // it stays in flight across the TMA issue: gather_copy is its first consumer
+  auto row_of = [&](int t) { return gather_row(hand_index, has_index, (int64_t)t * kTileEnvs, tile_envs(t)); };
   auto issue = [&](int t, int64_t row) {
-    const bool bulk = tile_is_bulk(P, t, ntiles);
-    gather_copy<6>(hand_vel, row, tile_envs(t), tile + (bulk ? P.x_off_b : P.x_off_c), bulk ? P.bulk_ts : P.canon_ts);
+#ifdef B200_OSC_TRACE
+    if (t == (int)blockIdx.x) OSC_TRACE(6);
+#endif
     stage_issue<5>(P, &tmap, t, ntiles, n, tile, &bar);
+    if (t == (int)blockIdx.x) OSC_TRACE(7);
+    gather_copy<6>(hand_vel, row, tile_envs(t), tile + stage_extras_off(P), x_ts);
+#if B200_OSC_L2PF
+    stage_prefetch<5>(P, &tmap, t + (int)gridDim.x, ntiles);      // the tile after this one: in L2 when its turn comes
+#endif
   };
   unsigned phase = 0;
   // default joint positions (:74-76): one global read per CTA instead of seven per env.  Loaded into a register here
@@ -537,6 +664,7 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   int t = blockIdx.x;
   int64_t row = t < ntiles ? row_of(t) : 0;
   if (t < ntiles) issue(t, row);
+  OSC_TRACE(2);
   if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;      // published by the barrier that ends stage_wait
   // statistics live in shared memory between tiles: four fp64 accumulators are eight registers this kernel does not
   // have (the fp64 chain sits at the 255-register limit)
@@ -547,27 +675,31 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   for (; t < ntiles; t += gridDim.x) {
     const int64_t env0 = (int64_t)t * kTileEnvs;
     const int nenv = tile_envs(t);
-    const bool bulk = tile_is_bulk(P, t, ntiles);
     const int t_next = t + (int)gridDim.x;
     if (t_next < ntiles) row = row_of(t_next);     // in flight across the wait and the gather
-    SAddr a[5];
-    stage_wait<5>(P, t, ntiles, &bar, phase, a);
+    stage_wait<5>(P, t, ntiles, &bar, phase);
+    if (t == (int)blockIdx.x) OSC_TRACE(3);
     const bool live = (int)threadIdx.x < nenv;
     const int e = threadIdx.x;
     OscRegs<T> R;
     if (live) {
-      const float* hv = tile + (bulk ? P.x_off_b : P.x_off_c) + e * (bulk ? P.bulk_ts : P.canon_ts);
-      const SAddr aDp = a[4];
-      osc_gather<T>(tile, a[0], a[1], a[2], a[3], e, [&](float (&w)[6]) {
+      const float* hv = tile + hv_off;
+      osc_gather<T>(tile, aJ, aM, aQ, aQD, e, [&](float (&w)[6]) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) w[r] = __fsub_rn(__fmul_rn(kp, SM(aDp, e, 0, r)), __fmul_rn(kd, hv[r]));
       }, s_qdef, kp_null, kd_null, R);
     }
     __syncthreads();                      // every thread has its operands in registers: the buffer is free
+    if (t == (int)blockIdx.x) OSC_TRACE(4);
     if (t_next < ntiles) issue(t_next, row);
     if (live) {
       float u[D];
+#if B200_OSC_DEBUG == 1
+#pragma unroll
+      for (int c = 0; c < D; ++c) u[c] = (float)(R.Mu0[c] + R.w[c % 6] + R.L[c][c / 2] + (T)R.J[c % 6][c]);
+#else
       osc_solve<T>(R, u);
+#endif
       float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + (env0 + e) * out.s[0];
       bool finite = true;
       double sum_abs = 0.0, sum_sq = 0.0;
@@ -585,6 +717,7 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
       s_cnt[0][e] += 1u;
       s_cnt[1][e] += finite ? 0u : 1u;
     }
+    if (t == (int)blockIdx.x) OSC_TRACE(5);
   }
   if (stats) {
     double acc[2] = {s_acc[0][threadIdx.x], s_acc[1][threadIdx.x]};
@@ -607,25 +740,25 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   constexpr int D = 7;
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
-  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  stage_begin(P, &tmap, &bar, rb, box_index, hand_index, q_default, dpose_out, grip, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   pdl_prologue();
   const int ntiles = tile_count(n);
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? ((n - env0) > 0 ? (n - env0) : 0) : kTileEnvs);
-  const bool bulk = tile_is_bulk(P, blockIdx.x, ntiles);
-  const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
-  float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
+  const int x_ts = stage_extras_ts(P);
+  float* x0 = tile + stage_extras_off(P);
   // index loads first, then the TMA / LDGSTS issue, then the copies that need the indices (see gather_row)
-  const int64_t box_row = gather_row(box_index, 1, env0, nenv, rb.n[0]), hand_row = gather_row(hand_index, 1, env0, nenv, rb.n[0]);
+  const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
   __shared__ float s_qdef[8];
   const float qdef_mine = threadIdx.x < 7 ? ldf(q_default, threadIdx.x * q_default.s[0]) : 0.f;
   SAddr a[6];
+  stage_addr<6>(P, a);
   unsigned phase = 0;
   stage_issue<6>(P, &tmap, blockIdx.x, ntiles, n, tile, &bar);
   gather_copy<7>(rb, box_row, nenv, x0, x_ts);              // box pos + quat          (:348-349)
   gather_copy<13>(rb, hand_row, nenv, x0 + 7, x_ts);        // hand pos + quat + vel   (:351-353)
   if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;     // stored after the issue, see osc_kernel
-  stage_wait<6>(P, blockIdx.x, ntiles, &bar, phase, a);
+  stage_wait<6>(P, blockIdx.x, ntiles, &bar, phase);
 
   double acc[2] = {0, 0};        // sum |u|, sum u^2
   unsigned cnt[2] = {0, 0};      // envs, envs with a non-finite torque
@@ -689,20 +822,20 @@ pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, 
   constexpr int D = 7;
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
-  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  stage_begin(P, &tmap, &bar, rb, box_index, hand_index, dpose_out, grip, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  const bool bulk = tile_is_bulk(P, blockIdx.x, gridDim.x);
-  const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
-  float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
-  const int64_t box_row = gather_row(box_index, 1, env0, nenv, rb.n[0]), hand_row = gather_row(hand_index, 1, env0, nenv, rb.n[0]);
+  const int x_ts = stage_extras_ts(P);
+  float* x0 = tile + stage_extras_off(P);
+  const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
   SAddr a[4];
+  stage_addr<4>(P, a);
   unsigned phase = 0;
   stage_issue<4>(P, &tmap, blockIdx.x, gridDim.x, n, tile, &bar);
   gather_copy<7>(rb, box_row, nenv, x0, x_ts);
   gather_copy<7>(rb, hand_row, nenv, x0 + 7, x_ts);
-  stage_wait<4>(P, blockIdx.x, gridDim.x, &bar, phase, a);
+  stage_wait<4>(P, blockIdx.x, gridDim.x, &bar, phase);
   if (threadIdx.x >= nenv) return;
   const int e = threadIdx.x;
   const int64_t env = env0 + e;
@@ -773,7 +906,7 @@ __global__ void __launch_bounds__(kTileEnvs)
 osc_full_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float kp, float kv, TView out, int64_t n) {
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
-  stage_begin(P, &bar);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  stage_begin(P, &tmap, &bar, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
@@ -799,20 +932,20 @@ franka_osc_step_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TV
                        int pos_control, TView dpose_out, int has_dpose, TView out, int64_t n) {
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
-  stage_begin(P, &bar);
+  stage_begin(P, &tmap, &bar, rb, hand_index, dpose_out, out);
   pdl_prologue();
   const int ntiles = tile_count(n);
   const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
   const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
-  const bool bulk = tile_is_bulk(P, blockIdx.x, ntiles);
-  const int x_ts = bulk ? P.bulk_ts : P.canon_ts;
-  float* x0 = tile + (bulk ? P.x_off_b : P.x_off_c);
-  const int64_t hand_row = gather_row(hand_index, 1, env0, nenv, rb.n[0]);
+  const int x_ts = stage_extras_ts(P);
+  float* x0 = tile + stage_extras_off(P);
+  const int64_t hand_row = gather_row(hand_index, 1, env0, nenv);
   SAddr a[5];
+  stage_addr<5>(P, a);
   unsigned phase = 0;
   stage_issue<5>(P, &tmap, blockIdx.x, ntiles, n, tile, &bar);
   gather_copy<7>(rb, hand_row, nenv, x0, x_ts);
-  stage_wait<5>(P, blockIdx.x, ntiles, &bar, phase, a);
+  stage_wait<5>(P, blockIdx.x, ntiles, &bar, phase);
   if (threadIdx.x >= nenv) return;
   const int e = threadIdx.x;
   const int64_t env = env0 + e;
@@ -1019,11 +1152,13 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
       if (s.mode == 0) { s.l_off = rows0 + row; row += s.rows * s.cols; }
     }
     P.x_off_b = rows0 + row;
+    P.bulk_all = row == 0 ? 1 : 0;
     P.bulk_ts = (row + extras) | 1;
     const int bulk_floats = rows0 + kTileEnvs * P.bulk_ts;
     if (bulk_floats * 4 > 160 * 1024) {
       // an exotic layout whose dense blocks do not fit comfortably in shared memory: LDGSTS plan for every tile
       P.bulk_ok = 0;
+      P.bulk_all = 0;
       P.tmap_bytes = 0;
       for (int i = 0; i < nseg; ++i) P.seg[i].mode = 0;
     } else if (bulk_floats > P.smem_floats) {
@@ -1076,6 +1211,12 @@ static int persistent_grid(K kernel, int smem, int ntiles, int* grid) {
 }  // namespace b200ctl
 
 using namespace b200ctl;
+
+#ifdef B200_OSC_TRACE
+extern "C" __attribute__((visibility("default"))) int b200ctl_debug_osc_trace(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_osc_trace, sizeof(unsigned long long) * 8 * 4096);
+}
+#endif
 
 extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, double lambda,
                               const DLTensor* dof_pos, int32_t precision, DLTensor* out, b200ctl_stream_t stream) {
@@ -1149,17 +1290,21 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
   const int smem = P.smem_floats * 4;
   int grid = 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (precision == 0) {
-    B200_TRY(set_smem(osc_kernel<double>, smem));
-    B200_TRY(persistent_grid(osc_kernel<double>, smem, tiles(n), &grid));
-    launch_pdl(osc_kernel<double>, grid, kTileEnvs, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, (float)kd,
-               (float)kp_null, (float)kd_null, o, n, stats);
-  } else {
-    B200_TRY(set_smem(osc_kernel<float>, smem));
-    B200_TRY(persistent_grid(osc_kernel<float>, smem, tiles(n), &grid));
-    launch_pdl(osc_kernel<float>, grid, kTileEnvs, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, (float)kd,
-               (float)kp_null, (float)kd_null, o, n, stats);
-  }
+  // compile-time strides when every operand is staged in its Isaac Gym layout (the reference's views)
+  const bool gym = P.bulk_ok && P.seg[0].mode != 0 && P.seg[0].b_rs == 9 && P.seg[0].b_cs == 1 &&
+                   P.seg[1].mode != 0 && P.seg[1].b_rs == 9 && P.seg[1].b_cs == 1 &&
+                   P.seg[2].mode != 0 && P.seg[2].b_cs == 2 && P.seg[3].mode != 0 && P.seg[3].b_cs == 2 &&
+                   P.seg[4].mode != 0 && P.seg[4].b_cs == 1 && !getenv("B200CTL_NO_GYM_LAYOUT");
+#define LAUNCH_OSC(T, G)                                                                                     \
+  do {                                                                                                       \
+    B200_TRY(set_smem(osc_kernel<T, G>, smem));                                                              \
+    B200_TRY(persistent_grid(osc_kernel<T, G>, smem, tiles(n), &grid));                                      \
+    launch_pdl(osc_kernel<T, G>, grid, kTileEnvs, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, (float)kd, \
+               (float)kp_null, (float)kd_null, o, n, stats);                                                 \
+  } while (0)
+  if (precision == 0) { if (gym) LAUNCH_OSC(double, true); else LAUNCH_OSC(double, false); }
+  else                { if (gym) LAUNCH_OSC(float, true); else LAUNCH_OSC(float, false); }
+#undef LAUNCH_OSC
   return post_launch("osc_kernel");
 }
 

@@ -37,22 +37,16 @@ struct ServoConst {
 // the one-thread form (same bits).  It halves the serial chain of a tile: the small-N step is one wave of CTAs whose
 // time IS that chain (65,536 envs), while at 1M envs the step is issue bound and the form does not matter.
 #ifndef B200_SERVO_STATS_NBUF
-#define B200_SERVO_STATS_NBUF 1      // A/B knob: 2 = double-buffered tiles in the persistent (statistics) form
+#define B200_SERVO_STATS_NBUF 2      // tile buffers of the persistent (statistics) form: 2 = the next tile's bulk load runs under this tile's arithmetic
 #endif
 #ifndef B200_SERVO_PERSIST_ALL
 #define B200_SERVO_PERSIST_ALL 0     // A/B knob: 1 = the persistent grid (and its tile buffers) without statistics too
-#endif
-#ifndef B200_SERVO_STATS_F32ERR
-#define B200_SERVO_STATS_F32ERR 0    // A/B knob: 1 = the statistics' pixel-error norm is formed in fp32 from the fp64 pixel move
-#endif
-#ifndef B200_SERVO_STATS_SMEM
-#define B200_SERVO_STATS_SMEM 0      // A/B knob: 1 = the per-thread statistics accumulators live in shared memory between tiles
 #endif
 template <int PREC, bool STATS, int TILE, bool SPLIT>
 __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64_t num_envs, const ServoConst& k,
                                                 double* __restrict__ aux, double* __restrict__ stats, int vec_ok) {
   constexpr int NT = SPLIT ? 2 * TILE : TILE;      // threads per CTA
-  // Tile buffers of a persistent CTA.  NBUF == 2 (A/B knob B200_SERVO_STATS_NBUF, not the default: unmeasured) lets the
+  // Tile buffers of a persistent CTA.  NBUF == 2 (default; B200_SERVO_STATS_NBUF=1 is the single-buffer form) lets the
   // bulk load of the CTA's NEXT tile run under the arithmetic of the current one -- the CTAs of a persistent grid move
   // in step, so with one buffer the SM alternates between a load phase and an arithmetic phase.
   constexpr int NBUF = ((STATS || B200_SERVO_PERSIST_ALL) && !SPLIT) ? B200_SERVO_STATS_NBUF : 1;
@@ -73,15 +67,6 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   unsigned phases = 0;               // bit b: phase parity of bars[b]
   double acc_d[2] = {0, 0};          // sum |pixel error|, sum error^2
   unsigned acc_u[3] = {0, 0, 0};     // envs, envs with the target behind the camera, non-finite attitudes
-  // B200_SERVO_STATS_SMEM: the accumulators cross the tile loop in shared memory instead of seven registers the
-  // reference-precision kernel does not have (64-register cap for 16 resident tiles per SM: 52 bytes spilled)
-  constexpr bool ACC_SMEM = STATS && B200_SERVO_STATS_SMEM && PREC == 0;
-  __shared__ double s_accd[ACC_SMEM ? 2 : 1][ACC_SMEM ? NT : 1];
-  __shared__ unsigned s_accu[ACC_SMEM ? 3 : 1][ACC_SMEM ? NT : 1];
-  if (ACC_SMEM) {
-    s_accd[0][threadIdx.x] = 0.0; s_accd[1][threadIdx.x] = 0.0;
-    s_accu[0][threadIdx.x] = 0u; s_accu[1][threadIdx.x] = 0u; s_accu[2][threadIdx.x] = 0u;
-  }
   auto full_tile = [&](int t) { return vec_ok && (num_envs - (int64_t)t * TILE) >= TILE; };
   auto fetch = [&](int t, int b) {   // thread 0: one bulk copy of tile t into buffer b
     mbar_arrive_expect_tx(&bars[b], kBytes);
@@ -192,10 +177,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
         constexpr double kPi = 3.141592653589793238462643383279502884;
         rolld = ang[0] * 180.0 / kPi; pitchd = ang[1] * 180.0 / kPi; yawd = ang[2] * 180.0 / kPi;   // :196
       }
-      if (STATS) {
-        if (B200_SERVO_STATS_F32ERR) { const float ex = (float)mvx, ey = (float)mvy; err = (double)sqrtf(fmaf(ex, ex, ey * ey)); }
-        else err = sqrt(mvx * mvx + mvy * mvy);
-      }
+      if (STATS) err = sqrt(mvx * mvx + mvy * mvy);
     } else {
       float R[9];
       quat_to_mat<float>(qx, qy, qz, qw, R);
@@ -224,25 +206,14 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       double* a = aux + (env0 + e) * 5;
       a[0] = pu; a[1] = pv; a[2] = rolld; a[3] = pitchd; a[4] = yawd;
     }
-#ifdef B200_SERVO_STATS_DEBUG
-    if (B200_SERVO_STATS_DEBUG == 2) { acc_d[0] = 1.0; acc_d[1] = 1.0; acc_u[0] = 1u; acc_u[1] = 1u; acc_u[2] = 1u; } else
-#endif
     if (STATS) {
       const bool finite = isfinite(oq[0]) && isfinite(oq[1]) && isfinite(oq[2]) && isfinite(oq[3]);
       if (!isfinite(err)) err = 0.0;
-      if (ACC_SMEM) {
-        s_accd[0][threadIdx.x] += err;
-        s_accd[1][threadIdx.x] = fma(err, err, s_accd[1][threadIdx.x]);
-        s_accu[0][threadIdx.x] += 1u;
-        s_accu[1][threadIdx.x] += behind ? 1u : 0u;
-        s_accu[2][threadIdx.x] += finite ? 0u : 1u;
-      } else {
-        acc_d[0] += err;
-        acc_d[1] = fma(err, err, acc_d[1]);
-        acc_u[0] += 1u;
-        acc_u[1] += behind ? 1u : 0u;
-        acc_u[2] += finite ? 0u : 1u;
-      }
+      acc_d[0] += err;
+      acc_d[1] = fma(err, err, acc_d[1]);
+      acc_u[0] += 1u;
+      acc_u[1] += behind ? 1u : 0u;
+      acc_u[2] += finite ? 0u : 1u;
     }
     }   // attitude
   }
@@ -268,14 +239,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   }
   }   // tile loop
   if (NBUF == 2 && threadIdx.x == 0) bulk_wait_read();   // shared memory outlives the last write-back's read
-#ifdef B200_SERVO_STATS_DEBUG      // A/B only: 1 = accumulate but never commit, 2 = commit constants without accumulating
-  if (B200_SERVO_STATS_DEBUG == 1) { if (acc_d[0] == 12345.678) stats[7] = acc_d[1] + acc_u[0] + acc_u[1] + acc_u[2]; return; }
-#endif
   if (STATS) {
-    if (ACC_SMEM) {
-      acc_d[0] = s_accd[0][threadIdx.x]; acc_d[1] = s_accd[1][threadIdx.x];
-      acc_u[0] = s_accu[0][threadIdx.x]; acc_u[1] = s_accu[1][threadIdx.x]; acc_u[2] = s_accu[2][threadIdx.x];
-    }
     const int slots[5] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_SAT,
                           B200CTL_STAT_N_NONFINITE};
     block_stats_commit<2, 3>(acc_d, acc_u, stats, slots);
