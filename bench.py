@@ -10,7 +10,9 @@ PER GPU (BASELINE.json configs[3] at one shard per GPU; it fits one GPU, and it 
 north-star target is quoted on).  One "step" = one evaluation of the law over the whole batch:
 one kernel launch with the fused statistics epilogue.  Envs shard as contiguous slices, one
 process per GPU, no data-path collective ("scaling": "weak"); at N > 1 the float64[8] statistics
-vector is all-reduced over NCCL every --stats-every steps on a side stream.
+vector is all-reduced over NCCL every --stats-every steps: in order on the control stream, or with
+--stats-overlap on a side stream next to the control kernels (one CTA slot reserved for NCCL's
+128-thread CTA).  N > 1 lines also carry `strong`: 1,048,576 envs IN TOTAL split over the N GPUs.
 
 Printed keys beyond the base contract:
   roofline      dominant kernel vs measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes
@@ -40,8 +42,9 @@ ENVS_PER_GPU = 1_048_576
 NUM_DOFS = 12
 PD_BYTES_PER_ENV = NUM_DOFS * 16          # 8 B state + 4 B target + 4 B output per DOF
 SERVO_BYTES_PER_ENV = 96
-IK_BYTES_PER_ENV, IK_FLOPS = 248, 480
-OSC_BYTES_PER_ENV, OSC_FLOPS = 496, 1850
+IK_BYTES_PER_ENV, IK_FLOPS, IK_FLOPS_LITERAL = 248, 480, 1530        # canonical (Cholesky route) / literal
+OSC_BYTES_PER_ENV, OSC_FLOPS, OSC_FLOPS_LITERAL = 496, 1850, 5270     # (the reference's LU inversions + dense bmm)
+L2_BYTES = 126 << 20
 FALLBACK_HBM_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md fallback
 # measured DRAM traffic per env (ncu --set full, read + write), by family-entry prefix
 DRAM_BYTES_PER_ENV = {
@@ -63,6 +66,15 @@ def hbm_peak():
 
 def workload_name():
     return f"pd_torque: {ENVS_PER_GPU} envs x {NUM_DOFS} DOF per GPU (BASELINE configs[3], one env slice per GPU)"
+
+
+def make_config(world, envs_per_gpu, stats_every=None, stats_mode=None, sets=4):
+    """`config` of the JSON line -- the SAME keys and values for the repo arm and the reference arm, so the two lines
+    describe one workload (the driver compares them)."""
+    return {"workload": workload_name(), "envs_per_gpu": envs_per_gpu, "num_dofs": NUM_DOFS, "global_envs": envs_per_gpu * world,
+            "parallelism": f"env-slices x{world}", "stats_allreduce_every": stats_every if world > 1 else None,
+            "stats_allreduce": stats_mode if world > 1 else None,
+            "l2_policy": f"inputs > L2: {sets} rotating buffer sets of 201 MB (151 MB in + 50 MB out each)"}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -173,13 +185,13 @@ class PdWorkload:
 
 
 # ------------------------------------------------------------------------------------------ families (rank 0, N=1)
-def graph_time(calls, device, reps, warm=3, runs=3, warm_ms=30.0, stat="min"):
+def graph_time(calls, device, reps, warm=3, runs=5, warm_ms=30.0, stat="min"):
     """Capture `calls` (bound C-ABI calls, one kernel each) into one CUDA graph (`StepGraph`) and time `reps`
     replays with CUDA events on the replaying stream, `runs` times.  Returns ms per kernel launch: the best run
-    (`stat="min"`) or the median.  The graph removes the host launch cost, which at 64K envs is larger than the
-    kernels themselves.  Replays run for `warm_ms` before the first timed run: these entries follow seconds of host-side
-    input generation, and an idle GPU needs tens of milliseconds to come back to its boost clock (a single timed run
-    after three warm replays read 5-8 % high on the latency-bound kernels)."""
+    (`stat="min"`), the median (`"median"`) or both (`"both"` -> (best, median)).  The graph removes the host launch
+    cost, which at 64K envs is larger than the kernels themselves.  Replays run for `warm_ms` before the first timed
+    run: these entries follow seconds of host-side input generation, and an idle GPU needs tens of milliseconds to come
+    back to its boost clock (a single timed run after three warm replays read 5-8 % high on the latency-bound kernels)."""
     from test_isaacgym_b200.graph import StepGraph
     g = StepGraph(calls, device)
     stream = torch.cuda.current_stream(device)
@@ -201,7 +213,29 @@ def graph_time(calls, device, reps, warm=3, runs=3, warm_ms=30.0, stat="min"):
         stream.synchronize()
         times.append(start.elapsed_time(end) / (reps * len(calls)))
     times.sort()
-    return times[0] if stat == "min" else times[len(times) // 2]
+    best, med = times[0], times[len(times) // 2]
+    return (best, med) if stat == "both" else (best if stat == "min" else med)
+
+
+def sets_for(touched_bytes_per_set, lo=3, hi=64):
+    """Rotating buffer sets needed for the bytes a launch actually TOUCHES (not the bytes allocated: the O kernels read
+    15 MB of a 47 MB set at 16,384 envs) to exceed twice the 126 MB L2 between two uses of the same set."""
+    return int(max(lo, min(hi, -(-2 * L2_BYTES // max(1, touched_bytes_per_set)))))
+
+
+def _lib_stats(device):
+    from test_isaacgym_b200 import _lib
+    return _lib.stats_buffer(device)
+
+
+def measure_fma_peaks(device):
+    """FMA-pipe peaks measured by the library's own micro-benchmark in this process (MEASURED_PEAKS.json has none)."""
+    from test_isaacgym_b200 import _lib
+    f32b, f32m = _lib.measure_fma_peak("f32", device, 7)
+    f64b, f64m = _lib.measure_fma_peak("f64", device, 7)
+    return {"fp32_tflops": f32b, "fp32_tflops_median": f32m, "fp64_tflops": f64b, "fp64_tflops_median": f64m,
+            "how": "b200ctl_measure_fma_peak: 16 dependent-FMA chains per thread, full occupancy, 7 launches of ~5 ms, CUDA events; "
+                   "nominal 148 SM x 128 (64) lanes x 2 x 1.965 GHz = 74.4 (37.2) TFLOP/s"}
 
 
 def family_numbers(device, peak_gbs):
@@ -211,16 +245,25 @@ def family_numbers(device, peak_gbs):
     from test_isaacgym_b200.pd_control import PDController
     from test_isaacgym_b200.servo_step import ServoStep, PRECISION_FAST
     import test_isaacgym_b200.franka_cube_ik_osc as ctl
-    out = {"_timing_note": "each entry: CUDA-graph replays of bound calls over rotating buffer sets larger than L2, "
-                           "30 ms of warm replays, best of 3 timed runs of `reps` replays"}
+    out = {"_timing_note": "each entry: CUDA-graph replays of bound calls over rotating buffer sets whose TOUCHED bytes exceed "
+                           "twice the 126 MB L2, 30 ms of warm replays, 5 timed runs of `reps` replays: us_per_step = best, "
+                           "us_per_step_median = median"}
 
-    def record(name, n, bytes_per_env, calls, reps, flops=None):
-        ms = graph_time(calls, device, reps)
+    fma = out["_fma_peak"] = measure_fma_peaks(device)
+
+    def record(name, n, bytes_per_env, calls, reps, flops=None, flops_literal=None, fp64_chain=False):
+        ms, ms_med = graph_time(calls, device, reps, stat="both")
         rate = n / (ms * 1e-3)
-        e = {"envs": n, "us_per_step": round(ms * 1e3, 3), "env_steps_per_s": rate,
+        e = {"envs": n, "us_per_step": round(ms * 1e3, 3), "us_per_step_median": round(ms_med * 1e3, 3), "env_steps_per_s": rate,
              "hbm_frac": rate * bytes_per_env / (peak_gbs * 1e9), "buffer_sets": len(calls)}
         if flops:
+            # FP32-pipe utilisation the metric asks for, against the MEASURED FMA peak: canonical = the flops of the
+            # factorisation route this kernel takes, literal = the reference's own operation count (LU inversions, bmm)
             e["tflops_canonical"] = rate * flops / 1e12
+            e["fp32_frac_canonical"] = rate * flops / 1e12 / fma["fp32_tflops"]
+            e["fp32_frac_literal"] = rate * flops_literal / 1e12 / fma["fp32_tflops"]
+            if fp64_chain:      # the default precision runs the chain on the fp64 pipe: that is the pipe it occupies
+                e["fp64_pipe_frac"] = rate * flops / 1e12 / fma["fp64_tflops"]
         # DRAM bytes per env actually moved (ncu dram__bytes_read + write at the throughput size, profiles/): the gym
         # layouts (13-float rows, a 6x7 slot of a 10x6x9 jacobian, a 7x7 corner of a 9x9 matrix) are fetched at
         # 64-byte granularity, so this exceeds the algorithmic bytes without any re-read
@@ -229,6 +272,7 @@ def family_numbers(device, peak_gbs):
                 e["dram_bytes_per_env_ncu"] = b
                 e["dram_frac"] = rate * b / (peak_gbs * 1e9)
                 e["dram_bytes_source"] = src
+                e["touched_mb_per_set"] = round(n * b / 1e6, 1)
         out[name] = e
 
     # P at C2 (65,536 x 12 = 12.6 MB per set): 24 rotating sets (302 MB)
@@ -263,7 +307,20 @@ def family_numbers(device, peak_gbs):
     tg = [pi.q_target.to(device).clone() for _ in range(sets)]
     ou = [torch.empty(n, NUM_DOFS, device=device) for _ in range(sets)]
     record("pd_1048576x12_nostats", n, PD_BYTES_PER_ENV, [c4.bind(st[k], tg[k], ou[k]) for k in range(sets)], reps=20)
-    del st, tg, ou
+    # the fully featured instantiation (north_star: "fused clamp/limit/gain logic in one pass"): floor-mod angle wrap +
+    # target clamp into the joint limits + a velocity-target tensor + torque saturation, 240 B/env; with and without
+    # the statistics epilogue
+    cf = PDController(NUM_DOFS, pi.kp, pi.kd, tau_max=pi.tau_max, q_lo=pi.q_lo, q_hi=pi.q_hi, wrap_angle=True,
+                      clamp_target=True, device=device)
+    qd = [syn.pd_inputs(n, NUM_DOFS, seed=2, qd_target_std=1.0).qd_target.to(device) for _ in range(sets)]
+    full_bytes = PD_BYTES_PER_ENV + 4 * NUM_DOFS
+    record("pd_1048576x12_fullflags", n, full_bytes, [cf.bind(st[k], tg[k], ou[k], qd_target=qd[k]) for k in range(sets)], reps=20)
+    fs = _lib_stats(device)
+    record("pd_1048576x12_fullflags_stats", n, full_bytes,
+           [cf.bind(st[k], tg[k], ou[k], qd_target=qd[k], stats=fs) for k in range(sets)], reps=20)
+    for k_ in ("pd_1048576x12_fullflags", "pd_1048576x12_fullflags_stats"):
+        out[k_]["kernel"] = "pd_torque_vec4_kernel<WRAP=1,CLAMP_TGT=1,HAS_QD=1,HAS_TMAX=1>"
+    del st, tg, ou, qd
 
     # P on the Franka's own DOF count (D = 9: a 128-bit vector straddles two envs, per-element DOF indices)
     n, sets, d9 = 1_048_576, 4, 9
@@ -288,32 +345,51 @@ def family_numbers(device, peak_gbs):
             record(f"servo_step_{tag}_{n}_stats", n, SERVO_BYTES_PER_ENV, [step.bind(b, stats=sbuf) for b in bufs], reps=reps)
         del bufs, base
 
-    # O at C3 (16,384 envs: 47 MB of gym tensors per set) and at 262,144 envs (750 MB per set)
-    for n, sets, reps in ((16_384, 4, 20), (262_144, 2, 20)):
+    # O at C3 (16,384 envs: 47 MB of gym tensors per set, of which a launch touches 15.7 MB (OSC) / 7.5 MB (IK)) and at
+    # 262,144 envs (750 MB per set).  The number of rotating sets follows the TOUCHED bytes (IK's, the smaller): round 1
+    # rotated 4 sets at C3 -- 188 MB allocated but only 61 MB touched per cycle, i.e. L2-resident.
+    def to_dev(obj):
+        return obj.__class__(**{k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in obj.__dict__.items()})
+
+    def dev_clone(obj):
+        return obj.__class__(**{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in obj.__dict__.items()})
+
+    for n, reps in ((16_384, 10), (262_144, 20)):
+        sets = sets_for(n * DRAM_BYTES_PER_ENV["ik_"][0], lo=3, hi=40)
         fi = syn.franka_inputs(n, seed=3)
+        base = to_dev(fi)
+        keep = [base] + [dev_clone(base) for _ in range(sets - 1)]
+        outs = [torch.zeros(n, 9, device=device) for _ in range(sets)]
         for prec, ptag in ((0, "fp64chain"), (1, "fp32")):
-            osc_calls, ik_calls, keep = [], [], []
-            for _ in range(sets):
-                d = fi.__class__(**{k: (v.to(device).clone() if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
-                o = torch.zeros(n, 9, device=device)
+            osc_calls, ik_calls = [], []
+            for d, o in zip(keep, outs):
                 ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=d.dof_pos, dof_vel=d.dof_vel,
                          default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=prec)
                 ctl.bind_hand(d.rb_states, d.hand_idxs)
                 osc_calls.append(ctl.bind_control_osc(d.dpose, o[:, :7]))
                 ik_calls.append(ctl.bind_control_ik(d.dpose, o[:, :7], dof_pos=d.dof_pos))
-                keep.append((d, o))
-            record(f"osc_{ptag}_{n}", n, OSC_BYTES_PER_ENV, osc_calls, reps, flops=OSC_FLOPS)
-            record(f"ik_{ptag}_{n}", n, IK_BYTES_PER_ENV, ik_calls, reps, flops=IK_FLOPS)
-            del osc_calls, ik_calls, keep
+            record(f"osc_{ptag}_{n}", n, OSC_BYTES_PER_ENV, osc_calls, reps, flops=OSC_FLOPS, flops_literal=OSC_FLOPS_LITERAL,
+                   fp64_chain=prec == 0)
+            record(f"ik_{ptag}_{n}", n, IK_BYTES_PER_ENV, ik_calls, reps, flops=IK_FLOPS, flops_literal=IK_FLOPS_LITERAL,
+                   fp64_chain=prec == 0)
+            if prec == 1:
+                for k_ in (f"osc_{ptag}_{n}", f"ik_{ptag}_{n}"):
+                    out[k_]["tolerance_note"] = ("all-fp32 chain: meets the 1e-4 bar only on well-conditioned envs (tests/test_gpu_franka.py: "
+                                                 "bound stated and asserted there); the fp64-chain entries are the parity-bar numbers")
+            del osc_calls, ik_calls
+        del keep, outs, base
         ctl.bind(precision=0)
+        torch.cuda.empty_cache()
 
     # the whole pick step of examples/franka_cube_ik_osc.py:348-410 at C3: goal logic + OSC as two kernels
-    n, sets = 16_384, 4
+    n = 16_384
+    sets = sets_for(n * DRAM_BYTES_PER_ENV["franka_task"][0], lo=4, hi=40)
     ti, fi = syn.franka_task_inputs(n, seed=4), syn.franka_inputs(n, seed=5)
+    t0_, d0_ = to_dev(ti), to_dev(fi)
     task_calls, step_calls, keep = [], [], []
-    for _ in range(sets):
-        t = ti.__class__(**{k: (v.to(device).clone() if isinstance(v, torch.Tensor) else v) for k, v in ti.__dict__.items()})
-        d = fi.__class__(**{k: (v.to(device).clone() if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+    for k_ in range(sets):
+        t = t0_ if k_ == 0 else dev_clone(t0_)
+        d = d0_ if k_ == 0 else dev_clone(d0_)
         dpose = torch.zeros(n, 6, 1, device=device)
         pos_action, effort = torch.zeros(n, 9, device=device), torch.zeros(n, 9, device=device)
         task = ctl.TaskStep(t.rb_states, t.box_idxs, t.hand_idxs, t.dof_pos, t.init_pos, t.init_rot, t.hand_restart, "osc")
@@ -325,8 +401,8 @@ def family_numbers(device, peak_gbs):
         task_calls.append(tc)
         step_calls += [tc, oc]
         keep.append((t, d, dpose, pos_action, effort, task))
-    record(f"franka_task_{n}", n, 150, task_calls, 20)
-    ms_pair = graph_time(step_calls, device, 20) * 2      # per (task + osc) pair
+    record(f"franka_task_{n}", n, 150, task_calls, 10)
+    ms_pair = graph_time(step_calls, device, 10) * 2      # per (task + osc) pair
     out[f"franka_pick_step_{n}"] = {"envs": n, "us_per_step": round(ms_pair * 1e3, 3), "env_steps_per_s": n / (ms_pair * 1e-3),
                                     "kernels_per_step": 2, "note": "franka_task + osc (fp64 chain), CUDA-graph replay"}
     fused = []
@@ -334,16 +410,31 @@ def family_numbers(device, peak_gbs):
         ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=t.dof_pos, dof_vel=t.dof_state[:, 1].view(n, 9, 1),
                  default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=0)
         fused.append(ctl.bind_pick_osc(task, effort[:, :7], pos_action[:, 7:9]))
-    ms_fused = graph_time(fused, device, 20)
+    ms_fused = graph_time(fused, device, 10)
     out[f"franka_pick_step_fused_{n}"] = {"envs": n, "us_per_step": round(ms_fused * 1e3, 3), "env_steps_per_s": n / (ms_fused * 1e-3),
                                           "kernels_per_step": 1, "note": "b200ctl_franka_pick_osc (fp64 chain), CUDA-graph replay"}
     fused_ik = []
     for (t, d, dpose, pos_action, effort, task) in keep:
         ctl.bind(j_eef=d.j_eef, num_envs=n, precision=0)
         fused_ik.append(ctl.bind_pick_ik(task, pos_action[:, :7], pos_action[:, 7:9]))
-    ms_ik = graph_time(fused_ik, device, 20)
+    ms_ik = graph_time(fused_ik, device, 10)
     out[f"franka_pick_ik_step_fused_{n}"] = {"envs": n, "us_per_step": round(ms_ik * 1e3, 3), "env_steps_per_s": n / (ms_ik * 1e-3),
                                              "kernels_per_step": 1, "note": "b200ctl_franka_pick_ik (default controller, fp64 chain), CUDA-graph replay"}
+    # the loop law of examples/franka_osc.py:221-241 (all 9 DOFs) as one launch: hand-pose gather, quaternion
+    # renormalisation, orientation error, dpose, OSC solve.  Algorithmic bytes: J 216 + M 324 + qd 36 + hand pose 28 +
+    # pos_des 12 + orn_des 16 + u 36 = 668 B/env
+    import test_isaacgym_b200.franka_osc as fosc
+    osc9 = []
+    for (t, d, dpose, pos_action, effort, task) in keep:
+        pos_des = torch.zeros(n, 3, device=device)
+        orn_des = torch.zeros(n, 4, device=device)
+        orn_des[:, 3] = 1.0
+        u9 = torch.zeros(n, 9, 1, device=device)
+        osc9.append(fosc.bind_osc_step(t.rb_states, t.hand_idxs, pos_des, orn_des, d.jacobian[:, syn.FRANKA_JACOBIAN_SLOT],
+                                       d.mass_matrix, t.dof_state[:, 1].view(n, 9, 1), u9))
+        osc9[-1].keep = (osc9[-1].keep, pos_des, orn_des, u9)
+    record(f"franka_osc_step_{n}", n, 668, osc9, 10)
+    out[f"franka_osc_step_{n}"]["note"] = "b200ctl_franka_osc_step, 9 DOF, fp64 chain (examples/franka_osc.py:221-241 in one launch)"
     return out
 
 
@@ -410,6 +501,15 @@ def cpu_family_baselines(families):
                              f"osc/ik) on {torch.get_num_threads()} host threads, median of 3-10 steps at the same size")
 
 
+def stats_mode_name(args):
+    where = "on a side stream next to the following step" if args.stats_overlap else "in order on the control stream"
+    if args.stats_collective == "peer":
+        return "b200ctl peer-memory all-reduce kernel (NVLink), " + where
+    if args.stats_collective == "peer-lagged":
+        return "b200ctl peer-memory all-reduce kernel (NVLink), one window lagged (never waits for a peer), " + where
+    return "NCCL, " + ("side stream, one CTA slot reserved" if args.stats_overlap else "in order on the control stream")
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -435,8 +535,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * (n / sample), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(), "sample_envs_per_step": sample},
+            "config": make_config(world, ENVS_PER_GPU, max(1, args.stats_every), stats_mode_name(args)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample_envs_per_step": sample,
                              "sample": f"{args.steps} steps x {sample} envs x {NUM_DOFS} DOF (oracle/pd.py, torch-CPU fp32, "
                                        f"{torch.get_num_threads()} threads); the reference has no single function for this law"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -446,6 +547,97 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def strong_scaling(device, rank, world, reducer, stats_every, overlap, steps, weak_ms_per_step):
+    """BASELINE configs[3] as written: 1,048,576 envs IN TOTAL split as contiguous env slices over the N GPUs (strong
+    scaling).  One CUDA graph holds one statistics window (`stats_every` PD steps over rotating buffer sets), the window's
+    all-reduce follows it (in order, or on the side stream); device time by CUDA events, max over ranks.  Efficiency is
+    against the single-GPU time of the same 1,048,576 envs measured in this run (the weak-scaling step of this rank)."""
+    import torch.distributed as dist
+    from test_isaacgym_b200 import _lib
+    from test_isaacgym_b200.graph import StepGraph
+    from test_isaacgym_b200.sharding import env_slice
+    lo, hi = env_slice(ENVS_PER_GPU, rank, world)
+    n = hi - lo
+    sets = sets_for(n * PD_BYTES_PER_ENV, lo=4, hi=48)
+    wl = PdWorkload(device, n, seed=2000 + rank, sets=sets)
+    bufs = [_lib.stats_buffer(device), _lib.stats_buffer(device)]
+    graphs = []
+    for b in bufs:
+        calls = [wl.ctl.bind(wl.state[i % sets], wl.tgt[i % sets], wl.out[i % sets], stats=b) for i in range(stats_every)]
+        graphs.append(StepGraph(calls, device, restore=[b]))
+    events = [None, None]
+
+    from test_isaacgym_b200.sharding import PeerStatsReducer
+    fused_zero = isinstance(reducer, PeerStatsReducer)
+
+    def window(w):
+        k = w & 1
+        if events[k] is not None:
+            torch.cuda.current_stream(device).wait_event(events[k])
+            events[k] = None
+        if not fused_zero:
+            bufs[k].zero_()
+        graphs[k]()
+        if fused_zero:
+            reducer.all_reduce(bufs[k], zero_after=bufs[k ^ 1])
+        elif reducer is not None:
+            events[k] = reducer.all_reduce(bufs[k], overlap=overlap)
+
+    windows = max(4, -(-steps // stats_every))
+    for w in range(4):
+        window(w)
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for w in range(windows):
+        window(w)
+    end.record()
+    torch.cuda.synchronize(device)
+    if reducer is not None:
+        reducer.wait()
+    ms = torch.tensor([start.elapsed_time(end)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    us = ms.item() * 1e3 / (windows * stats_every)
+    ideal_us = weak_ms_per_step * 1e3 / world
+    floor_us = 1.55 + n * PD_BYTES_PER_ENV / 6539.2e3        # one launch + the slice's bytes at the measured copy bandwidth
+    return {"global_envs": ENVS_PER_GPU, "envs_per_gpu": n, "us_per_step": us, "env_steps_per_s": ENVS_PER_GPU / (us * 1e-6),
+            "n1_us_per_step": weak_ms_per_step * 1e3, "efficiency_vs_n1": ideal_us / us, "stats_allreduce_every": stats_every,
+            "buffer_sets": sets, "steps": windows * stats_every,
+            "limiter": (f"{n} envs per GPU are {n * PD_BYTES_PER_ENV / 1e6:.1f} MB per step: {floor_us:.1f} us = one launch (1.55 us) + the "
+                        f"bytes at HBM speed; the step no longer hides the launch floor, and the statistics all-reduce "
+                        f"(~25-30 us of NCCL latency per window of {stats_every} steps) adds its share")}
+
+
+def host_link_ceiling(device, hs, ht, hout, world):
+    """What the host link gives every rank when ALL ranks copy at once: the e2e step's 151 MB up and 50 MB down as plain
+    async copies on two streams (no kernel), barrier-aligned, CUDA events.  The e2e figure cannot exceed this."""
+    import torch.distributed as dist
+    up, down = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    ds, dt_ = torch.empty_like(hs, device=device), torch.empty_like(ht, device=device)
+    do = torch.empty(hout.shape, dtype=hout.dtype, device=device)
+    best = 1e9
+    for it in range(4):
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(up):
+            ds.copy_(hs, non_blocking=True)
+            dt_.copy_(ht, non_blocking=True)
+        with torch.cuda.stream(down):
+            hout.copy_(do, non_blocking=True)
+        torch.cuda.synchronize(device)
+        if it:
+            best = min(best, time.perf_counter() - t0)
+    t = torch.tensor([best], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
 def run_b200(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
@@ -454,23 +646,27 @@ def run_b200(args):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     import torch.distributed as dist
-    if world > 1:
-        # NCCL on a HIGH-PRIORITY stream: the control kernels are persistent grids chained by programmatic dependent
-        # launch, so a normal-priority collective kernel is starved of an SM slot until the control stream itself
-        # blocks on the window's event -- and then waits for the peer to reach the same point (measured at N=2:
-        # 47.8 us/step instead of 32.6)
-        from test_isaacgym_b200.sharding import nccl_options
-        dist.init_process_group("nccl", device_id=device, pg_options=nccl_options())
     from test_isaacgym_b200 import _lib
-    from test_isaacgym_b200.sharding import StatsReducer, StatsWindow, env_slice
+    from test_isaacgym_b200.sharding import StatsReducer, StatsWindow, env_slice, nccl_options, configure_nccl_for_control_loops
+    if world > 1:
+        # NCCL sized to sit NEXT to the persistent control grids: one channel, 128-thread CTAs (= one CTA slot of the PD
+        # kernel), on a high-priority stream; with --stats-overlap every persistent grid leaves that slot free
+        configure_nccl_for_control_loops()
+        dist.init_process_group("nccl", device_id=device, pg_options=nccl_options())
     from test_isaacgym_b200.pd_control import pd_torque
 
     peak, peak_src = hbm_peak()
     total_envs = ENVS_PER_GPU * world
     lo, hi = env_slice(total_envs, rank, world)
     wl = PdWorkload(device, hi - lo, seed=1000 + rank)
-    reducer = StatsReducer("torch", device) if world > 1 else None
+    from test_isaacgym_b200.sharding import PeerStatsReducer
+    if world > 1 and args.stats_collective != "nccl":
+        reducer = PeerStatsReducer(device, lagged=args.stats_collective == "peer-lagged")
+    else:
+        reducer = StatsReducer("torch", device) if world > 1 else None
     stats_every = max(1, args.stats_every)
+    if world > 1 and args.stats_overlap and args.stats_collective == "nccl":
+        _lib.reserve_cta_slots(device, args.reserve_slots)
     wl.bind(StatsWindow(device, reducer, stats_every, overlap=args.stats_overlap))
     step = wl.step
 
@@ -487,7 +683,7 @@ def run_b200(args):
                 dist.all_reduce(go, op=dist.ReduceOp.MIN)
             if int(go.item()) == 0:
                 break
-            for _ in range(200):
+            for _ in range(208):          # a multiple of the statistics window: every rank ends on a window boundary
                 wl.step(it)
                 it += 1
             torch.cuda.synchronize(device)
@@ -529,31 +725,68 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_checksum = float(hout[::4097].double().abs().sum())
+        link_s = host_link_ceiling(device, hs, ht, hout, world)
 
-    ms_per_step = ms_total / args.steps
+        ms_per_step = ms_total / args.steps
+        per_step_stats = None
+        if world > 1 and not args.no_strong:
+            # north_star: "all-reduce the per-step episode statistics".  The headline exchanges every `stats_every`
+            # steps; this is the same loop exchanging EVERY step: the lagged peer-memory form on the side stream (the
+            # vector of step s is globally summed while step s + 1 runs and readable one step later)
+            lag = PeerStatsReducer(device, lagged=True)
+            wl.bind(StatsWindow(device, lag, 1, overlap=True))
+            for i in range(64):
+                wl.step(i)
+            torch.cuda.synchronize(device)
+            dist.barrier()
+            s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s1.record()
+            for i in range(args.steps):
+                wl.step(i)
+            e1.record()
+            torch.cuda.synchronize(device)
+            wl.window.finish()
+            t1 = torch.tensor([s1.elapsed_time(e1)], device=device, dtype=torch.float64)
+            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+            us1 = t1.item() * 1e3 / args.steps
+            per_step_stats = {"stats_allreduce_every": 1, "us_per_step": us1, "env_steps_per_s": total_envs / (us1 * 1e-6),
+                              "vs_headline": (ms_per_step * 1e3) / us1, "timeouts": lag.timeouts(),
+                              "collective": "b200ctl peer-memory all-reduce kernel, lagged by one step, on a side stream next to the following step"}
+        strong = None
+        if world > 1 and not args.no_strong:
+            _lib.reserve_cta_slots(device, args.reserve_slots if (args.stats_overlap and args.stats_collective == "nccl") else 0)
+            strong = strong_scaling(device, rank, world, reducer, stats_every, args.stats_overlap, args.steps, ms_per_step)
+
     value = total_envs * args.steps / (ms_total * 1e-3)
     per_gpu_rate = (hi - lo) / (ms_per_step * 1e-3)
     achieved = per_gpu_rate * PD_BYTES_PER_ENV / 1e9
     e2e_value = total_envs * e2e_steps / e2e_s.item()
+    step_bytes = (hs.numel() + ht.numel() + hout.numel()) * 4
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "envs_per_gpu": hi - lo, "num_dofs": NUM_DOFS, "global_envs": total_envs,
-                   "parallelism": f"env-slices x{world}", "stats_allreduce_every": stats_every if world > 1 else None,
-                   "stats_allreduce": ("side stream" if args.stats_overlap else "in order on the control stream") if world > 1 else None,
-                   "l2_policy": f"inputs > L2: {wl.sets} rotating buffer sets of 201 MB (151 MB in + 50 MB out each)"},
+        "config": make_config(world, hi - lo, stats_every, stats_mode_name(args), wl.sets),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "pd_torque_vec4_kernel", "bytes_per_launch": (hi - lo) * PD_BYTES_PER_ENV,
                      "peak_source": peak_src, "of": "measured" if peak_src.startswith("measured") else "fallback"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (hs.numel() + ht.numel()) * 4 * world,
                 "d2h_bytes_per_step": hout.numel() * 4 * world, "steps": e2e_steps,
                 "api": "test_isaacgym_b200.pd_control.pd_torque(host tensors) -> b200ctl_pd_torque_host",
-                "checksum": e2e_checksum},
+                "checksum": e2e_checksum,
+                "host_link_ceiling": {"env_steps_per_s": total_envs / link_s, "ms_per_step": link_s * 1e3,
+                                      "gb_per_s_per_rank": step_bytes / link_s / 1e9, "gb_per_s_all_ranks": step_bytes * world / link_s / 1e9,
+                                      "how": "the step's host-to-device and device-to-host bytes as plain async copies on two streams "
+                                             "from the same pinned buffers, no kernel, all ranks at once (barrier-aligned), slowest rank"},
+                "frac_of_host_link_ceiling": link_s / (e2e_s.item() / e2e_steps)},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
+    if strong is not None:
+        line["strong"] = strong
+    if per_step_stats is not None:
+        line["per_step_stats"] = per_step_stats
     traffic_file = os.path.join(ROOT, "profiles", "pd_traffic.json")
     if os.path.isfile(traffic_file):
         try:
@@ -610,12 +843,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--stats-every", type=int, default=16, help="all-reduce the statistics vector every k steps (N > 1)")
-    ap.add_argument("--stats-overlap", action="store_true", help="all-reduce on a side stream instead of in order (N > 1)")
+    ap.add_argument("--stats-overlap", action="store_true", help="all-reduce on a side stream (the default for the peer-memory collective)")
+    ap.add_argument("--stats-in-order", action="store_true", help="all-reduce in order on the control stream (the default for NCCL)")
+    ap.add_argument("--reserve-slots", type=int, default=1, help="CTA slots every persistent grid leaves free with --stats-overlap")
+    ap.add_argument("--stats-collective", default="peer", choices=["peer", "peer-lagged", "nccl"],
+                    help="N > 1: the library's own all-reduce over NVLink peer memory (default), its lagged form, or NCCL")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (N > 1)")
     ap.add_argument("--sustain-s", type=float, default=1.0, help="seconds of pre-load before the timed region (clock sampling)")
     ap.add_argument("--no-families", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # NCCL's 640-thread CTA cannot sit next to the persistent control grids (it needs an empty SM): in order unless asked;
+    # the library's own 64-thread all-reduce kernel can: side stream unless asked otherwise
+    args.stats_overlap = args.stats_overlap or (args.stats_collective != "nccl" and not args.stats_in_order)
     return run_reference(args) if args.impl == "reference" else run_b200(args)
 
 

@@ -272,6 +272,21 @@ B200CTL_API int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* do
 B200CTL_API int b200ctl_gather_rows(const DLTensor* src, const DLTensor* index, int32_t col0, int32_t ncols,
                         DLTensor* dst, b200ctl_stream_t stream);
 
+/* Persistent grids (the statistics-carrying control kernels) fill every CTA slot of the device; a kernel of ANOTHER
+ * stream that must run next to them -- the statistics all-reduce on its side stream -- then finds no slot until a
+ * control CTA retires, and takes one from the NEXT step's grid, which spills into a second wave.  `slots` CTA slots
+ * (in units of the launching kernel's own CTA) are left free by every persistent grid launched on `device` from now
+ * on; 0 restores the default.  Process-wide per device; affects grid sizes only, never results. */
+B200CTL_API int b200ctl_reserve_cta_slots(int32_t device, int32_t slots);
+
+/* =========================== measurement: FMA-pipe peak ====================
+ * The metric reports family O as a fraction of the FP32 (and FP64) CUDA-core pipe; MEASURED_PEAKS.json has no such
+ * figure, so the library measures it: a dependent-FMA micro-benchmark (16 chains per thread, full occupancy) timed
+ * with CUDA events, `launches` launches of ~5 ms after three warm-ups.  dtype 0 = fp32, 1 = fp64.  Synchronous
+ * (it allocates, times and frees); not a control-path entry point.  tflops_best / tflops_median: 2 flop per FMA. */
+B200CTL_API int b200ctl_measure_fma_peak(int32_t dtype, int32_t device, int32_t launches, double* tflops_best,
+                             double* tflops_median);
+
 /* =========================== multi-GPU: statistics all-reduce ==============
  * ncclAllReduce(sum, double) of `n` stats entries in place.  `comm` is an
  * ncclComm_t; NCCL is resolved at run time from the already-loaded libnccl
@@ -282,6 +297,33 @@ B200CTL_API int b200ctl_nccl_unique_id(void* id_out_128_bytes);
 B200CTL_API int b200ctl_nccl_comm_init(void** comm_out, int32_t world_size, const void* id_128_bytes, int32_t rank);
 B200CTL_API int b200ctl_nccl_comm_destroy(void* comm);
 B200CTL_API int b200ctl_stats_allreduce(void* comm, double* stats, int32_t n, b200ctl_stream_t stream);
+
+/* The library's OWN all-reduce of the statistics vector over NVLink peer memory (csrc/peer.cu): one 64-thread kernel
+ * per window, enqueued in order on the control stream.  Every rank owns a mailbox in its device memory and maps the
+ * peers' mailboxes through CUDA IPC (one process per GPU, one NVSwitch box):
+ *   b200ctl_peer_mailbox_create   allocate + zero this rank's mailbox, return its 64-byte IPC handle (exchange the
+ *                                 handles with any host-side all-gather)
+ *   b200ctl_peer_mailbox_open     map a peer's mailbox from its handle (peer access enabled lazily)
+ *   b200ctl_stats_allreduce_peer  stats[0..count) <- sum over ranks, in place.  `mailboxes` is a HOST array of `world`
+ *                                 device pointers (entry `rank` = the rank's own mailbox).  `window` must increase by one
+ *                                 per call and be the same on every rank.  lagged = 0: the sum of THIS window (waits for
+ *                                 every peer's row: one NVLink round trip); lagged = 1: the sum of the PREVIOUS window
+ *                                 (rows that arrived a window ago: never waits for a peer; window 0 yields zeros).
+ *                                 All ranks add the rows in rank order: bit-identical sums everywhere.
+ *                                 zero_after (optional, device double[8], != stats): cleared by the same kernel -- the
+ *                                 accumulator of the next window -- so the step loop needs no separate fill launch.
+ *                                 out (optional, device double[8]): out-of-place form -- the sum goes to `out` and the
+ *                                 source `stats` is CLEARED by the same kernel (it is complete: recycle it), so the call
+ *                                 can run on a side stream next to the following step with two alternating accumulators.
+ *   A peer that never publishes cannot hang the GPU: after `timeout_s` (<= 0: 2 s) the kernel writes NaN into the sum
+ *   and counts the event (b200ctl_peer_mailbox_timeouts). */
+B200CTL_API int b200ctl_peer_mailbox_create(int32_t device, void** mailbox_out, void* ipc_handle_out_64_bytes);
+B200CTL_API int b200ctl_peer_mailbox_open(int32_t device, const void* ipc_handle_64_bytes, void** peer_out);
+B200CTL_API int b200ctl_peer_mailbox_close(int32_t device, void* mailbox, int32_t is_peer);
+B200CTL_API int b200ctl_peer_mailbox_timeouts(int32_t device, const void* mailbox, uint64_t* count_out);
+B200CTL_API int b200ctl_stats_allreduce_peer(void* const* mailboxes, int32_t rank, int32_t world, uint64_t window,
+                                 int32_t lagged, double* stats, int32_t count, double* zero_after,
+                                 double* out, double timeout_s, int32_t device, b200ctl_stream_t stream);
 
 #ifdef __cplusplus
 }

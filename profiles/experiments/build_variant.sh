@@ -9,7 +9,7 @@ SRC=$ROOT/test_isaacgym_b200/csrc
 OUT=$ROOT/profiles/experiments/variants
 mkdir -p "$OUT" "$SRC/build_$NAME"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -cudart static --expt-relaxed-constexpr"
-for f in runtime pd_torque servo franka franka_task; do
+for f in runtime pd_torque servo franka franka_task peaks peer; do
   nvcc $FLAGS $EXTRA -c "$SRC/$f.cu" -o "$SRC/build_$NAME/$f.o" &
 done
 wait

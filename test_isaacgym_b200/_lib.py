@@ -91,10 +91,18 @@ _SIGNATURES = {
                                         c_int32, _DL, _DL, _DL, c_void_p, c_void_p]),
     "b200ctl_franka_pick_ik": (c_int, [_DL] * 8 + [POINTER(FrankaTaskParams), c_double, c_int32, _DL, _DL, _DL, c_void_p]),
     "b200ctl_gather_rows": (c_int, [_DL, _DL, c_int32, c_int32, _DL, c_void_p]),
+    "b200ctl_reserve_cta_slots": (c_int, [c_int32, c_int32]),
+    "b200ctl_measure_fma_peak": (c_int, [c_int32, c_int32, c_int32, POINTER(c_double), POINTER(c_double)]),
     "b200ctl_nccl_unique_id": (c_int, [c_void_p]),
     "b200ctl_nccl_comm_init": (c_int, [POINTER(c_void_p), c_int32, c_void_p, c_int32]),
     "b200ctl_nccl_comm_destroy": (c_int, [c_void_p]),
     "b200ctl_stats_allreduce": (c_int, [c_void_p, c_void_p, c_int32, c_void_p]),
+    "b200ctl_peer_mailbox_create": (c_int, [c_int32, POINTER(c_void_p), c_void_p]),
+    "b200ctl_peer_mailbox_open": (c_int, [c_int32, c_void_p, POINTER(c_void_p)]),
+    "b200ctl_peer_mailbox_close": (c_int, [c_int32, c_void_p, c_int32]),
+    "b200ctl_peer_mailbox_timeouts": (c_int, [c_int32, c_void_p, POINTER(c_uint64)]),
+    "b200ctl_stats_allreduce_peer": (c_int, [POINTER(c_void_p), c_int32, c_int32, c_uint64, c_int32, c_void_p, c_int32,
+                                             c_void_p, c_void_p, c_double, c_int32, c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -173,6 +181,18 @@ def dl(t):
         if _DL_CACHE_MAX:
             _DL_CACHE[key] = p
     return p.ref, (p, t)
+
+
+def reserve_cta_slots(device: torch.device, slots: int) -> None:
+    """Leave ``slots`` CTA slots free in every persistent control grid on ``device`` (room for a co-resident collective)."""
+    check(lib().b200ctl_reserve_cta_slots(device.index or 0, int(slots)))
+
+
+def measure_fma_peak(dtype: str, device: torch.device, launches: int = 7) -> tuple[float, float]:
+    """(best, median) TFLOP/s of the dependent-FMA micro-benchmark on ``device`` (``dtype`` "f32" | "f64")."""
+    best, med = c_double(), c_double()
+    check(lib().b200ctl_measure_fma_peak({"f32": 0, "f64": 1}[dtype], device.index or 0, launches, ctypes.byref(best), ctypes.byref(med)))
+    return best.value, med.value
 
 
 def stream_ptr(device: torch.device) -> c_void_p:

@@ -73,6 +73,13 @@ inline bool is_compact(const TView& v) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count(int dev);
+// CTA slots a persistent grid leaves free on `dev` (b200ctl_reserve_cta_slots): room for a co-resident kernel of another
+// stream -- the statistics all-reduce -- so that it does not push one CTA of a one-wave grid into a second wave.
+int reserved_slots(int dev);
+inline int usable_slots(int dev, int per_sm) {
+  const int all = sm_count(dev) * (per_sm > 0 ? per_sm : 1), r = reserved_slots(dev);
+  return r < all ? all - r : 1;
+}
 
 // Raw device pointers of the ABI (`stats`, `aux`: float64 accumulators that carry no DLTensor descriptor) are checked
 // against the driver's own record before a kernel may atomicAdd / store through them: device (or managed) memory of

@@ -1199,11 +1199,10 @@ static int set_smem(K kernel, int bytes) {
 // there are fewer tiles than slots.
 template <typename K>
 static int persistent_grid(K kernel, int smem, int ntiles, int* grid) {
-  int dev = 0, sms = 0, occ = 0;
+  int dev = 0, occ = 0;
   B200_CUDA(cudaGetDevice(&dev));
-  B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTileEnvs, smem));
-  const int slots = sms * (occ > 0 ? occ : 1);
+  const int slots = usable_slots(dev, occ);
   *grid = ntiles < slots ? ntiles : slots;
   return 0;
 }

@@ -312,7 +312,7 @@ template <typename K>
 static int pd_grid(K kernel, size_t smem, int dev, int64_t work_items, int block, int waves) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-  const int64_t full = (int64_t)sm_count(dev) * per_sm * waves;
+  const int64_t full = waves == 1 ? (int64_t)usable_slots(dev, per_sm) : (int64_t)sm_count(dev) * per_sm * waves;
   const int64_t need = (work_items + block - 1) / block;
   return (int)(need < full ? (need > 0 ? need : 1) : full);
 }

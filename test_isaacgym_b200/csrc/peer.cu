@@ -1,0 +1,170 @@
+// Statistics all-reduce over NVLink peer memory: the library's own collective for the one exchange step of the path.
+//
+// Every rank (one process per GPU of one NVSwitch box) owns a MAILBOX in its device memory and maps every peer's
+// mailbox through CUDA IPC.  One tiny kernel per window, launched IN ORDER on the control stream (programmatic dependent
+// launch like every other kernel of the library: no stream hop, no second process-group stream):
+//   1. publish   lane j of the CTA stores entry j of this rank's partial statistics vector into slot [window % 4][rank]
+//                of EVERY rank's mailbox (plain stores over NVLink, then a system-scope release store of the stamp);
+//   2. consume   it waits (acquire loads, with a deadline) until all `world` stamps of the window it consumes have
+//                arrived in ITS OWN mailbox and sums the rows in rank order -- the same order on every rank, so all
+//                ranks hold bit-identical sums.
+// `lagged` = 0 consumes the window it just published (a classic all-reduce: one NVLink round trip on the critical
+// path); `lagged` = 1 consumes the PREVIOUS window, whose rows arrived a whole window ago -- the collective then never
+// waits for a peer and its cost is the launch alone, which is what a per-step statistics exchange needs.
+// A ring of four slots per rank: a rank can publish window w + 1 only after it consumed w - 1 (lagged) from everyone,
+// i.e. after every peer published w - 1 and therefore finished reading w - 2 or older; slots w + 1 and w - 3 coincide.
+// NCCL's all-reduce of the same 64 bytes costs ~34 us per call on the control stream of this box (two stream hops and a
+// 640-thread kernel that needs an empty SM); this one costs ~3 us.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace b200ctl {
+
+constexpr int kRing = 4;
+constexpr int kMaxWorld = 16;
+struct __align__(128) MailSlot {
+  double v[B200CTL_STATS_LEN];
+  unsigned long long stamp;        // window + 1 once v[] is complete (0 = never written)
+  unsigned long long pad[7];
+};
+struct Mailbox {
+  MailSlot slot[kRing][kMaxWorld];
+  unsigned long long timeouts;     // consume deadlines missed (the sum then holds NaN): a peer died or never published
+};
+struct PeerTable { Mailbox* box[kMaxWorld]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(64)
+stats_allreduce_peer_kernel(PeerTable peers, int rank, int world, unsigned long long window, int lagged, int count,
+                            double* stats, double* __restrict__ zero_after, double* out, int clear_source,
+                            long long deadline_ns) {
+  pdl_prologue();
+  const int t = threadIdx.x;
+  // the accumulator of the NEXT window is cleared here, so that the step loop needs no separate fill kernel (an
+  // ordinary launch that would break the chain of programmatically dependent launches)
+  if (zero_after && t < B200CTL_STATS_LEN) zero_after[t] = 0.0;
+  const int ring = (int)(window % kRing);
+  // ---- publish this rank's partial sums of `window` to every rank (its own mailbox included)
+  if (t < count) {
+    const double v = stats[t];
+    // out-of-place form: the source accumulator is complete (its kernels finished), so it can be recycled right here
+    // -- the step loop then alternates two accumulators while this kernel runs NEXT to the following step
+    if (clear_source) stats[t] = 0.0;
+    for (int p = 0; p < world; ++p) peers.box[p]->slot[ring][rank].v[t] = v;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (t < world) st_release_sys(&peers.box[t]->slot[ring][rank].stamp, window + 1);
+  // ---- consume
+  if (lagged && window == 0) {      // nothing older to consume yet: the reduced vector of "window -1" is zero
+    if (t < count) out[t] = 0.0;
+    return;
+  }
+  const unsigned long long cw = lagged ? window - 1 : window;
+  const int cring = (int)(cw % kRing);
+  Mailbox* mine = peers.box[rank];
+  __shared__ int s_ok;
+  if (t == 0) s_ok = 1;
+  __syncthreads();
+  if (t < world) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(&mine->slot[cring][t].stamp) != cw + 1) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if ((long long)(now - t0) > deadline_ns) {      // never hang the GPU on a dead peer
+        s_ok = 0;
+        atomicAdd(&mine->timeouts, 1ull);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (t < count) {
+    double s = 0.0;
+    for (int p = 0; p < world; ++p) s += *reinterpret_cast<volatile double*>(&mine->slot[cring][p].v[t]);
+    out[t] = s_ok ? s : __longlong_as_double(0x7ff8000000000000ll);
+  }
+}
+
+}  // namespace b200ctl
+
+using namespace b200ctl;
+
+extern "C" int b200ctl_peer_mailbox_create(int32_t device, void** mailbox_out, void* ipc_handle_out_64_bytes) {
+  if (!mailbox_out || !ipc_handle_out_64_bytes) B200_FAIL(B200CTL_E_NULL, "output pointer is NULL");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DeviceGuard g;
+  B200_TRY(g.enter(device));
+  void* p = nullptr;
+  B200_CUDA(cudaMalloc(&p, sizeof(Mailbox)));
+  B200_CUDA(cudaMemset(p, 0, sizeof(Mailbox)));
+  B200_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  B200_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(ipc_handle_out_64_bytes, &h, sizeof(h));
+  *mailbox_out = p;
+  return 0;
+}
+
+extern "C" int b200ctl_peer_mailbox_open(int32_t device, const void* ipc_handle_64_bytes, void** peer_out) {
+  if (!ipc_handle_64_bytes || !peer_out) B200_FAIL(B200CTL_E_NULL, "handle / output pointer is NULL");
+  DeviceGuard g;
+  B200_TRY(g.enter(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle_64_bytes, sizeof(h));
+  B200_CUDA(cudaIpcOpenMemHandle(peer_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int b200ctl_peer_mailbox_close(int32_t device, void* mailbox, int32_t is_peer) {
+  if (!mailbox) return 0;
+  DeviceGuard g;
+  B200_TRY(g.enter(device));
+  if (is_peer) B200_CUDA(cudaIpcCloseMemHandle(mailbox));
+  else B200_CUDA(cudaFree(mailbox));
+  return 0;
+}
+
+extern "C" int b200ctl_peer_mailbox_timeouts(int32_t device, const void* mailbox, uint64_t* count_out) {
+  if (!mailbox || !count_out) B200_FAIL(B200CTL_E_NULL, "mailbox / output pointer is NULL");
+  DeviceGuard g;
+  B200_TRY(g.enter(device));
+  B200_CUDA(cudaMemcpy(count_out, &static_cast<const Mailbox*>(mailbox)->timeouts, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int b200ctl_stats_allreduce_peer(void* const* mailboxes, int32_t rank, int32_t world, uint64_t window,
+                                            int32_t lagged, double* stats, int32_t count, double* zero_after,
+                                            double* out, double timeout_s, int32_t device, b200ctl_stream_t stream) {
+  if (!mailboxes || !stats) B200_FAIL(B200CTL_E_NULL, "mailboxes / stats is NULL");
+  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world) B200_FAIL(B200CTL_E_VALUE, "bad rank %d / world %d (max %d)", rank, world, kMaxWorld);
+  if (count < 1 || count > B200CTL_STATS_LEN) B200_FAIL(B200CTL_E_VALUE, "count must be in [1, %d]", B200CTL_STATS_LEN);
+  B200_TRY(check_f64_device_ptr(stats, "stats", device));
+  B200_TRY(check_f64_device_ptr(zero_after, "zero_after", device));
+  B200_TRY(check_f64_device_ptr(out, "out", device));
+  if (zero_after == stats || (zero_after && zero_after == out)) B200_FAIL(B200CTL_E_ALIAS, "zero_after must not be the vector being reduced / written");
+  const int clear_source = out != nullptr && out != stats;
+  if (!out) out = stats;
+  PeerTable T{};
+  for (int p = 0; p < world; ++p) {
+    if (!mailboxes[p]) B200_FAIL(B200CTL_E_NULL, "mailbox of rank %d is NULL", p);
+    T.box[p] = static_cast<Mailbox*>(mailboxes[p]);
+  }
+  DeviceGuard g;
+  B200_TRY(g.enter(device));
+  const long long deadline_ns = (long long)((timeout_s > 0 ? timeout_s : 2.0) * 1e9);
+  launch_pdl(stats_allreduce_peer_kernel, 1, 64, 0, (cudaStream_t)stream, T, (int)rank, (int)world,
+             (unsigned long long)window, lagged ? 1 : 0, (int)count, stats, zero_after, out, clear_source, deadline_ns);
+  return post_launch("stats_allreduce_peer_kernel");
+}

@@ -69,6 +69,9 @@ int sm_count(int dev) {
   return cache[dev];
 }
 
+static std::atomic<int> g_reserved[64];
+int reserved_slots(int dev) { return (dev >= 0 && dev < 64) ? g_reserved[dev].load(std::memory_order_relaxed) : 0; }
+
 int check_f64_device_ptr(const void* p, const char* name, int dev) {
   if (!p) return 0;
   if (reinterpret_cast<uintptr_t>(p) & 7u) B200_FAIL(B200CTL_E_LAYOUT, "%s: pointer is not 8-byte aligned (float64 expected)", name);
@@ -115,6 +118,13 @@ using namespace b200ctl;
 extern "C" int b200ctl_version(void) { return B200CTL_VERSION; }
 extern "C" const char* b200ctl_last_error(void) { return t_error; }
 extern "C" uint64_t b200ctl_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" int b200ctl_reserve_cta_slots(int32_t device, int32_t slots) {
+  if (device < 0 || device >= 64) B200_FAIL(B200CTL_E_DEVICE, "device %d out of range", device);
+  if (slots < 0 || slots > 4096) B200_FAIL(B200CTL_E_VALUE, "slots must be in [0, 4096]");
+  g_reserved[device].store(slots, std::memory_order_relaxed);
+  return 0;
+}
 
 extern "C" int b200ctl_gather_rows(const DLTensor* src, const DLTensor* index, int32_t col0, int32_t ncols,
                                    DLTensor* dst, b200ctl_stream_t stream) {

@@ -607,14 +607,14 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
   };
   int occ = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick(false), tile, 0));
-  int slots = sm_count(dev) * (occ > 0 ? occ : 1);
+  int slots = usable_slots(dev, occ);
   // (measured, us per step at 16,384 / 65,536 envs: reference precision 3.08 -> 2.39 / 5.66 -> 5.36, fast 2.31 -> 2.05 /
   // 4.74 -> 4.70; forced at 1M envs 36.2 -> 44.6; the fast statistics variant with its 128-env tiles loses: 5.55 -> 6.06)
   const bool split = ntiles <= slots && !(stats && params->precision == 1);
   Kern kern = pick(split);
   if (split) {
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 2 * tile, 0));
-    slots = sm_count(dev) * (occ > 0 ? occ : 1);
+    slots = usable_slots(dev, occ);
   }
   // Persistent grid of FOUR waves of resident CTAs (A/B knob, profiles/r01_ab_servo_stats_waves.txt): one wave pays for
   // its static tile stride at the tail, many waves pay in commits on the one L2 line of the vector -- per 1M envs,

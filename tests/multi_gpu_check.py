@@ -6,7 +6,9 @@
 (a) slice equivalence: the concatenation of the per-rank outputs equals the single-GPU output bit for bit;
 (b) the statistics vector all-reduced over NCCL -- through torch.distributed AND through the C-ABI
     ``b200ctl_stats_allreduce`` on an ``ncclComm_t`` created by ``b200ctl_nccl_comm_init`` -- equals the
-    single-GPU statistics (counts exactly, sums to 1e-12)."""
+    single-GPU statistics (counts exactly, sums to 1e-12);
+(c) the library's own peer-memory all-reduce (``b200ctl_stats_allreduce_peer``): same, bit-identical on all ranks,
+    37 windows through the four-slot ring, and the lagged form."""
 import os
 import sys
 
@@ -47,9 +49,32 @@ def main():
         assert st[0].item() == n and st[3].item() == st_full[3].item() and st[4].item() == st_full[4].item(), backend
         assert torch.allclose(st[1:3], st_full[1:3], rtol=1e-12), backend
         red.close()
+    # (c) the library's own all-reduce over NVLink peer memory: exact counts, sums to 1e-12, BIT-IDENTICAL on all ranks;
+    #     many windows back to back (ring of four slots), then the lagged form (window w yields the sum of w - 1)
+    from test_isaacgym_b200.sharding import PeerStatsReducer
+    red = PeerStatsReducer(dev)
+    for w in range(37):
+        st = st_local.clone() * (w + 1)
+        red.all_reduce(st)
+        torch.cuda.synchronize(dev)
+        assert st[0].item() == n * (w + 1), ("peer", w, st)
+        assert torch.allclose(st[1:3], st_full[1:3] * (w + 1), rtol=1e-12), ("peer", w)
+        ref = st.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(ref, st), "ranks disagree on the bits of the reduced vector"
+    assert red.timeouts() == 0
+    red.close()
+    lag = PeerStatsReducer(dev, lagged=True)
+    for w in range(23):
+        st = st_local.clone() * (w + 1)
+        lag.all_reduce(st)
+        torch.cuda.synchronize(dev)
+        assert st[0].item() == n * w, ("peer-lagged", w, st)          # the previous window's sum (zeros at w = 0)
+    assert lag.timeouts() == 0
+    lag.close()
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU check OK on {world} GPUs: slices bit-exact, stats all-reduce (torch + C-ABI NCCL) exact")
+        print(f"multi-GPU check OK on {world} GPUs: slices bit-exact, stats all-reduce (torch NCCL, C-ABI NCCL, b200ctl peer-memory kernel incl. lagged form) exact")
     dist.destroy_process_group()
 
 

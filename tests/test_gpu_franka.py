@@ -94,14 +94,18 @@ def test_osc_persistent_many_tiles_per_cta():
                           f(fi.default_dof_pos), KP, KD, KP_NULL, KD_NULL)
     cond = ofr.conditioning(fi.j_eef, fi.mm).numpy()
     outs = {}
-    for prec, tol in ((0, 1e-4), (1, 2e-2)):
+    for prec in (0, 1):
         ctl.bind(precision=prec)
         st = _lib.stats_buffer(torch.device(DEV))
         osc = ctl.control_osc(d.dpose, stats=st)
         outs[prec] = osc
         r = _rel(osc.cpu(), ref)
         print(f"precision {prec}: rel err median {np.median(r):.2e} gated max {r[cond <= 1e4].max():.2e}")
-        assert r[cond <= 1e4].max() <= tol
+        if prec == 0:
+            assert r[cond <= 1e4].max() <= 1e-4
+        else:
+            # the all-fp32 chain's stated bound (test_fp32_chain_error_bound): north_star's 1e-4 up to cond 1e3 only
+            assert (r <= 2e-7 * cond).all() and r[cond <= 1e3].max() <= 1e-4
         st = st.cpu()
         assert st[0] == n and st[4] == 0
         assert abs(st[1].item() - osc.abs().double().sum().item()) <= 1e-9 * st[1].item()
@@ -115,6 +119,45 @@ def test_osc_persistent_many_tiles_per_cta():
         small = ctl.control_osc(d.dpose[lo:lo + m])
         assert torch.equal(small, outs[prec][lo:lo + m])
     ctl.bind(precision=0)
+
+
+def test_fp32_chain_error_bound():
+    """`precision=1` (all-fp32 factorisation chain) is NOT the parity path: an fp32 chain cannot hold north_star's 1e-4
+    up to cond 1e4.  Its stated bound, measured in profiles/experiments/fp32_chain_error.py (32,768 envs of set R:
+    err / cond <= 9.3e-8) and asserted here with a factor of two of margin:
+
+        ||u - u_ref64|| / ||u_ref64||  <=  2e-7 * cond(J M^-1 J^T)        (IK: cond(J J^T + lambda^2 I))
+
+    i.e. it meets the 1e-4 bar on envs with cond <= 1e3 (also asserted), and it is never worse than the reference's own
+    fp32 evaluation in err / cond terms.  The fp64-chain default is what every parity number in DESIGN.md refers to."""
+    n = 16_384
+    fi = syn.franka_inputs(n, seed=1)
+    d = _bind(fi)
+    ctl.bind_hand(d.rb_states, d.hand_idxs)
+    f = lambda t: t.double()
+    ref = ofr.control_osc(f(fi.dpose), f(fi.j_eef), f(fi.mm), f(fi.dof_pos), f(fi.dof_vel), f(fi.hand_vel),
+                          f(fi.default_dof_pos), KP, KD, KP_NULL, KD_NULL)
+    ref32 = ofr.control_osc(fi.dpose, fi.j_eef, fi.mm, fi.dof_pos, fi.dof_vel, fi.hand_vel, fi.default_dof_pos,
+                            KP, KD, KP_NULL, KD_NULL)
+    ref_ik = ofr.control_ik(f(fi.dpose), f(fi.j_eef), DAMPING)
+    cond = ofr.conditioning(fi.j_eef, fi.mm).numpy()
+    cond_ik = ofr.conditioning(fi.j_eef, None, DAMPING).numpy()
+    ctl.bind(precision=1)
+    try:
+        r = _rel(ctl.control_osc(d.dpose).cpu(), ref)
+        ri = _rel(ctl.control_ik(d.dpose).cpu(), ref_ik)
+    finally:
+        ctl.bind(precision=0)
+    rr = _rel(ref32, ref)
+    for lo, hi in ((1, 1e2), (1e2, 1e3), (1e3, 1e4), (1e4, 1e12)):
+        m = (cond >= lo) & (cond < hi)
+        print(f"fp32 chain, cond in [{lo:.0e},{hi:.0e}): {m.sum():6d} envs, rel err median {np.median(r[m]):.2e} max {r[m].max():.2e}"
+              f" | reference fp32 max {rr[m].max():.2e}")
+    print(f"err / cond: kernel max {np.max(r / cond):.2e}, reference fp32 max {np.max(rr / cond):.2e}")
+    assert (r <= 2e-7 * cond).all()
+    assert r[cond <= 1e3].max() <= 1e-4
+    assert (ri <= 2e-7 * cond_ik).all() and ri[cond_ik <= 1e3].max() <= 1e-4
+    assert np.max(r / cond) <= 2 * np.max(rr / cond)
 
 
 def test_franka_gather_scatter_bit_exact():
