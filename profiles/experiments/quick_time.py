@@ -43,12 +43,13 @@ def main():
     elif a.family in ("osc", "ik"):
         import test_isaacgym_b200.franka_cube_ik_osc as ctl
         for n in [int(x) for x in (a.sizes or "16384,262144").split(",")]:
-            sets = 4 if n <= 32768 else 2
+            sets = bench.sets_for(n * (958 if a.family == "osc" else 460), lo=2, hi=40)      # touched bytes > 2 x L2
             fi = syn.franka_inputs(n, seed=3)
+            base = fi.__class__(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
             for prec, ptag in ((0, "fp64"), (1, "fp32")):
                 calls, keep = [], []
                 for _ in range(sets):
-                    d = fi.__class__(**{k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+                    d = base.__class__(**{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in base.__dict__.items()})
                     o = torch.zeros(n, 9, device=dev)
                     ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=d.dof_pos, dof_vel=d.dof_vel,
                              default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=prec)
@@ -74,9 +75,11 @@ def main():
         for n in [int(x) for x in (a.sizes or "16384").split(",")]:
             ti, fi = syn.franka_task_inputs(n, seed=4), syn.franka_inputs(n, seed=5)
             osc, ik, keep = [], [], []
-            for _ in range(4 if n <= 32768 else 2):
-                t = ti.__class__(**{k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in ti.__dict__.items()})
-                d = fi.__class__(**{k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+            tb = ti.__class__(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in ti.__dict__.items()})
+            db = fi.__class__(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+            for _ in range(bench.sets_for(n * 438, lo=2, hi=40)):
+                t = tb.__class__(**{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in tb.__dict__.items()})
+                d = db.__class__(**{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in db.__dict__.items()})
                 pos_action, effort = torch.zeros(n, 9, device=dev), torch.zeros(n, 9, device=dev)
                 task = ctl.TaskStep(t.rb_states, t.box_idxs, t.hand_idxs, t.dof_pos, t.init_pos, t.init_rot, t.hand_restart, "osc")
                 ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=t.dof_pos, dof_vel=t.dof_state[:, 1].view(n, 9, 1),

@@ -43,7 +43,10 @@ namespace b200ctl {
 
 constexpr float kPiF = 3.14159265358979323846f;
 constexpr float kTwoPiF = 6.28318530717958647692f;
-constexpr int kTileEnvs = 64;
+constexpr int kTileEnvs = 64;        // envs per tile = threads per CTA ...
+constexpr int kMaxTileEnvs = 128;    // ... or 128 when the whole batch is then ONE tile per SM (pick_tile): device code
+                                     // takes the tile size from blockDim.x
+#define TILE_ENVS ((int)blockDim.x)
 constexpr int kMaxSeg = 6;
 #ifndef B200_OSC_L2PF
 #define B200_OSC_L2PF 0       // A/B knob: 1 = the persistent OSC kernel L2-prefetches its next-but-one tile
@@ -52,7 +55,7 @@ constexpr int kMaxSeg = 6;
 #define B200_OSC_DEBUG 0      // A/B only (wrong results): 1 = skip the factorisation chain, 2 = skip the staging copies and waits
 #endif
 #ifdef B200_OSC_TRACE          // A/B only: per-CTA phase timestamps (globaltimer, ns) of the first tile of osc_kernel
-__device__ unsigned long long g_osc_trace[8][4096];
+__device__ unsigned long long g_osc_trace[10][4096];
 __device__ __forceinline__ void osc_trace(int k) {
   if (threadIdx.x == 0 && blockIdx.x < 4096) {
     unsigned long long t;
@@ -331,7 +334,7 @@ __device__ __forceinline__ void gather_copy(const TView& v, int64_t row, int nen
 
 // The last tile always takes the LDGSTS plan: bulk copies fetch whole aligned blocks past the operand.
 __device__ __forceinline__ bool tile_is_bulk(const StagePlan& P, int t, int ntiles) { return P.bulk_ok && (t + 1 < ntiles); }
-__device__ __forceinline__ int tile_count(int64_t n) { return (int)((n + kTileEnvs - 1) / kTileEnvs); }
+__device__ __forceinline__ int tile_count(int64_t n) { return (int)((n + TILE_ENVS - 1) / TILE_ENVS); }
 
 // Staging is split in three so a persistent CTA can refill its tile buffer while it computes:
 //   stage_begin  once per CTA (mbarrier init),
@@ -340,6 +343,18 @@ __device__ __forceinline__ int tile_count(int64_t n) { return (int)((n + kTileEn
 //   (stage_addr resolves the operands' shared-memory addressing, once per launch).
 // The buffer may be re-issued as soon as every thread has copied what it needs into registers and passed a
 // __syncthreads(); mbarrier phases alternate, `phase` is the caller's parity bit.
+// Thread 0: L2 prefetch of the bulk-staged operands of tile t (a full, non-last tile), see bulk_prefetch_l2.
+template <int NSEG>
+__device__ __forceinline__ void stage_prefetch(const StagePlan& P, const CUtensorMap* tmap, int t, int ntiles) {
+  if (threadIdx.x != 0 || t >= ntiles || !tile_is_bulk(P, t, ntiles)) return;
+  const int64_t env0 = (int64_t)t * TILE_ENVS;
+  if (P.tmap_bytes) tensor2d_prefetch_l2(tmap, 0, (int)env0);
+#pragma unroll
+  for (int i = 0; i < NSEG; ++i) {
+    const StageSeg& s = P.seg[i];
+    if (s.mode == 1) bulk_prefetch_l2(reinterpret_cast<const char*>(s.base + env0 * s.s0) - s.delta, s.bytes);
+  }
+}
 // Kernel parameters live in constant bank 0 and are fetched on first use, one 64-byte line at a time: the staging plan
 // alone spans ten lines, and a warp that issues in order paid for each miss AFTER the dependency wait (0.7 us between
 // the wait and the first TMA copy at 16,384 envs, profiles/experiments/osc_trace.py).  The time before the wait is idle
@@ -366,11 +381,41 @@ __device__ __forceinline__ void stage_begin(const StagePlan& P, const CUtensorMa
     __syncthreads();
   }
 }
+
+// L2 prefetch of the CTA's FIRST tile, issued AHEAD of the dependency wait.  A prefetch consumes nothing -- L2 is the
+// coherence point, so lines the previous kernel is still writing are simply updated in place -- but it starts this
+// step's DRAM reads while the previous kernel is draining: after the wait the TMA copies, the index load and the
+// index-dependent row gather (two DEPENDENT misses, the longest chain of the staging) are L2 hits.
+// `speculative row`: the index is read before the wait only to compute a prefetch address (range-checked); the real
+// gather re-reads it after the wait.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int NSEG>
+__device__ __forceinline__ void stage_prefetch_first(const StagePlan& P, const CUtensorMap* tmap, int64_t n) {
+#ifdef B200_NO_PREWAIT_PF
+  return;
+#endif
+  const int ntiles = tile_count(n);
+  if ((int)blockIdx.x >= ntiles) return;
+  stage_prefetch<NSEG>(P, tmap, blockIdx.x, ntiles);
+}
+__device__ __forceinline__ void gather_prefetch(const TView& index, int has_index, const TView& rows, int64_t n) {
+#ifdef B200_NO_PREWAIT_PF
+  return;
+#endif
+  const int64_t env = (int64_t)blockIdx.x * TILE_ENVS + threadIdx.x;
+  if ((int)threadIdx.x >= TILE_ENVS || env >= n) return;
+  int64_t row = env;
+  if (has_index) {
+    const int64_t* ip = reinterpret_cast<const int64_t*>(index.p) + env * index.s[0];
+    asm volatile("ld.global.relaxed.gpu.u64 %0, [%1];" : "=l"(row) : "l"(ip));      // may be stale: a hint only
+  }
+  if (row >= 0 && row < rows.n[0]) prefetch_l2(reinterpret_cast<const float*>(rows.p) + row * rows.s[0]);
+}
 template <int NSEG>
 __device__ __forceinline__ void stage_issue(const StagePlan& P, const CUtensorMap* tmap, int t, int ntiles, int64_t n,
                                             float* tile, uint64_t* bar) {
-  const int64_t env0 = (int64_t)t * kTileEnvs;
-  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  const int64_t env0 = (int64_t)t * TILE_ENVS;
+  const int nenv = (int)((n - env0) < TILE_ENVS ? (n - env0) : TILE_ENVS);
   const bool bulk = tile_is_bulk(P, t, ntiles);
   if (B200_OSC_DEBUG == 2) return;
   if (bulk) {
@@ -393,23 +438,17 @@ __device__ __forceinline__ void stage_issue(const StagePlan& P, const CUtensorMa
   }
   stage_ldgsts<NSEG>(P, env0, nenv, bulk, tile);
 }
-// Thread 0: L2 prefetch of the bulk-staged operands of tile t (a full, non-last tile), see bulk_prefetch_l2.
-template <int NSEG>
-__device__ __forceinline__ void stage_prefetch(const StagePlan& P, const CUtensorMap* tmap, int t, int ntiles) {
-  if (threadIdx.x != 0 || t >= ntiles || !tile_is_bulk(P, t, ntiles)) return;
-  const int64_t env0 = (int64_t)t * kTileEnvs;
-  if (P.tmap_bytes) tensor2d_prefetch_l2(tmap, 0, (int)env0);
-#pragma unroll
-  for (int i = 0; i < NSEG; ++i) {
-    const StageSeg& s = P.seg[i];
-    if (s.mode == 1) bulk_prefetch_l2(reinterpret_cast<const char*>(s.base + env0 * s.s0) - s.delta, s.bytes);
-  }
-}
 template <int NSEG>
 __device__ __forceinline__ void stage_wait(const StagePlan& P, int t, int ntiles, uint64_t* bar, unsigned& phase) {
   const bool bulk = tile_is_bulk(P, t, ntiles);
   cp_async_wait_all();
+#ifdef B200_OSC_TRACE
+  if (t == (int)blockIdx.x) osc_trace(6);
+#endif
   if (bulk && B200_OSC_DEBUG != 2) { mbar_wait(bar, phase); phase ^= 1u; }
+#ifdef B200_OSC_TRACE
+  if (t == (int)blockIdx.x) osc_trace(8);
+#endif
   __syncthreads();
 }
 
@@ -501,14 +540,15 @@ __device__ __forceinline__ void ik_compute(const float* tile, const SAddr& aJ, i
 // ------------------------------------------------------------------ a9: control_ik
 // segments: 0 = J (6 x D), 1 = dpose (1 x 6), 2 = dof_pos (1 x D, optional)
 template <typename T, int D>
-__global__ void __launch_bounds__(kTileEnvs)
+__global__ void __launch_bounds__(kMaxTileEnvs)
 ik_dls_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float lambda2, int has_pos, TView out, int64_t n) {
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   stage_begin(P, &tmap, &bar, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  stage_prefetch_first<3>(P, &tmap, n);
   pdl_prologue();
-  const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
-  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  const int64_t env0 = (int64_t)blockIdx.x * TILE_ENVS;
+  const int nenv = (int)((n - env0) < TILE_ENVS ? (n - env0) : TILE_ENVS);
   SAddr a[3];
   stage_all<3>(P, &tmap, env0, nenv, tile, &bar, a);
   if (threadIdx.x >= nenv) return;
@@ -615,7 +655,7 @@ template <typename T, bool GYM>
 // Tried and measured slower: register caps for 5 tiles/SM (168 regs: -13 %, 200 regs: -6 %, both
 // spill); splitting one env over two warps that share Lambda^-1 through shared memory (redundant Cholesky work +
 // a CTA barrier: -70 %).
-__global__ void __launch_bounds__(kTileEnvs) __maxnreg__(sizeof(T) == 8 ? B200_OSC_F64_MAXREG : 255)
+__global__ void __launch_bounds__(kMaxTileEnvs) __maxnreg__(sizeof(T) == 8 ? B200_OSC_F64_MAXREG : 255)
 osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel, TView hand_index, int has_index, TView q_default,
            float kp, float kd, float kp_null, float kd_null, TView out, int64_t n, double* __restrict__ stats) {
   constexpr int D = 7;
@@ -623,7 +663,12 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   OSC_TRACE(0);
+#ifdef B200_OSC_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 4096) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_osc_trace[9][blockIdx.x] = sm; }
+#endif
   stage_begin(P, &tmap, &bar, hand_vel, hand_index, q_default, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  stage_prefetch_first<5>(P, &tmap, n);
+  gather_prefetch(hand_index, has_index, hand_vel, n);
   // everything that depends on the launch parameters only is resolved while the previous kernel is still running
   SAddr a[5];
   stage_addr<5>(P, a);
@@ -634,20 +679,17 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   typename Lay::DP aDp(a[4]);
   const int x_ts = stage_extras_ts(P);
   int hv_off = stage_extras_off(P) + (int)threadIdx.x * x_ts;
-  int ntiles = (int)((n + kTileEnvs - 1) / kTileEnvs);
+  int ntiles = (int)((n + TILE_ENVS - 1) / TILE_ENVS);
   pin(aJ.off); pin(aJ.es); pin(aM.off); pin(aM.es); pin(aQ.off); pin(aQD.off); pin(aDp.off); pin(hv_off); pin(ntiles);
   pdl_prologue();
   OSC_TRACE(1);
   // persistent CTA: tiles blockIdx.x, + gridDim.x, ...; the tile buffer is refilled while the previous tile's
   // factorisation runs out of registers
-  auto tile_envs = [&](int t) { const int64_t left = n - (int64_t)t * kTileEnvs; return (int)(left < kTileEnvs ? left : kTileEnvs); };
+  auto tile_envs = [&](int t) { const int64_t left = n - (int64_t)t * TILE_ENVS; return (int)(left < TILE_ENVS ? left : TILE_ENVS); };
   // the hand-velocity row number of tile t is loaded one tile ahead of its use (row_of), and for the CTA's first tile
   // it stays in flight across the TMA issue: gather_copy is its first consumer
-  auto row_of = [&](int t) { return gather_row(hand_index, has_index, (int64_t)t * kTileEnvs, tile_envs(t)); };
+  auto row_of = [&](int t) { return gather_row(hand_index, has_index, (int64_t)t * TILE_ENVS, tile_envs(t)); };
   auto issue = [&](int t, int64_t row) {
-#ifdef B200_OSC_TRACE
-    if (t == (int)blockIdx.x) OSC_TRACE(6);
-#endif
     stage_issue<5>(P, &tmap, t, ntiles, n, tile, &bar);
     if (t == (int)blockIdx.x) OSC_TRACE(7);
     gather_copy<6>(hand_vel, row, tile_envs(t), tile + stage_extras_off(P), x_ts);
@@ -668,12 +710,12 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;      // published by the barrier that ends stage_wait
   // statistics live in shared memory between tiles: four fp64 accumulators are eight registers this kernel does not
   // have (the fp64 chain sits at the 255-register limit)
-  __shared__ double s_acc[2][kTileEnvs];        // sum |u|, sum u^2
-  __shared__ unsigned s_cnt[2][kTileEnvs];      // envs, envs with a non-finite torque
+  __shared__ double s_acc[2][kMaxTileEnvs];        // sum |u|, sum u^2
+  __shared__ unsigned s_cnt[2][kMaxTileEnvs];      // envs, envs with a non-finite torque
 #pragma unroll
   for (int k = 0; k < 2; ++k) { s_acc[k][threadIdx.x] = 0.0; s_cnt[k][threadIdx.x] = 0u; }
   for (; t < ntiles; t += gridDim.x) {
-    const int64_t env0 = (int64_t)t * kTileEnvs;
+    const int64_t env0 = (int64_t)t * TILE_ENVS;
     const int nenv = tile_envs(t);
     const int t_next = t + (int)gridDim.x;
     if (t_next < ntiles) row = row_of(t_next);     // in flight across the wait and the gather
@@ -733,7 +775,7 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
 // segments: 0 = J (6x7), 1 = M (7x7), 2 = dof_pos (1x9: the fingers feed gripper_sep), 3 = dof_vel (1x7),
 // 4 = init_pos (1x3), 5 = init_rot (1x4); extras: box row (7) + hand row (13: pose and velocity) gathered by index.
 template <typename T>
-__global__ void __launch_bounds__(kTileEnvs)
+__global__ void __launch_bounds__(kMaxTileEnvs)
 pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, TView box_index, TView hand_index, uint8_t* __restrict__ hand_restart,
                 int64_t hr_stride, TaskConst tk, TView q_default, float kp, float kd, float kp_null, float kd_null,
                 TView dpose_out, int has_dpose, TView grip, TView out, int64_t n, double* __restrict__ stats) {
@@ -741,10 +783,13 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   stage_begin(P, &tmap, &bar, rb, box_index, hand_index, q_default, dpose_out, grip, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  stage_prefetch_first<6>(P, &tmap, n);
+  gather_prefetch(box_index, 1, rb, n);
+  gather_prefetch(hand_index, 1, rb, n);
   pdl_prologue();
   const int ntiles = tile_count(n);
-  const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
-  const int nenv = (int)((n - env0) < kTileEnvs ? ((n - env0) > 0 ? (n - env0) : 0) : kTileEnvs);
+  const int64_t env0 = (int64_t)blockIdx.x * TILE_ENVS;
+  const int nenv = (int)((n - env0) < TILE_ENVS ? ((n - env0) > 0 ? (n - env0) : 0) : TILE_ENVS);
   const int x_ts = stage_extras_ts(P);
   float* x0 = tile + stage_extras_off(P);
   // index loads first, then the TMA / LDGSTS issue, then the copies that need the indices (see gather_row)
@@ -816,16 +861,19 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
 // pos_action[:, :7] = dof_pos[:, :7] + control_ik(dpose), pos_action[:, 7:9] = grip_acts in one launch.
 // segments: 0 = J (6x7), 1 = dof_pos (1x9), 2 = init_pos (1x3), 3 = init_rot (1x4); extras: box row (7) + hand row (7).
 template <typename T>
-__global__ void __launch_bounds__(kTileEnvs)
+__global__ void __launch_bounds__(kMaxTileEnvs)
 pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, TView box_index, TView hand_index, uint8_t* __restrict__ hand_restart,
                int64_t hr_stride, TaskConst tk, float lambda2, TView dpose_out, int has_dpose, TView grip, TView out, int64_t n) {
   constexpr int D = 7;
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   stage_begin(P, &tmap, &bar, rb, box_index, hand_index, dpose_out, grip, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  stage_prefetch_first<4>(P, &tmap, n);
+  gather_prefetch(box_index, 1, rb, n);
+  gather_prefetch(hand_index, 1, rb, n);
   pdl_prologue();
-  const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
-  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  const int64_t env0 = (int64_t)blockIdx.x * TILE_ENVS;
+  const int nenv = (int)((n - env0) < TILE_ENVS ? (n - env0) : TILE_ENVS);
   const int x_ts = stage_extras_ts(P);
   float* x0 = tile + stage_extras_off(P);
   const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
@@ -902,14 +950,15 @@ __device__ __forceinline__ void osc_full_solve(const float* tile, const SAddr& a
 
 // segments: 0 = J (6xD), 1 = M (DxD), 2 = dof_vel (1xD), 3 = dpose (1x6)
 template <typename T, int D>
-__global__ void __launch_bounds__(kTileEnvs)
+__global__ void __launch_bounds__(kMaxTileEnvs)
 osc_full_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float kp, float kv, TView out, int64_t n) {
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   stage_begin(P, &tmap, &bar, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
+  stage_prefetch_first<4>(P, &tmap, n);
   pdl_prologue();
-  const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
-  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  const int64_t env0 = (int64_t)blockIdx.x * TILE_ENVS;
+  const int nenv = (int)((n - env0) < TILE_ENVS ? (n - env0) : TILE_ENVS);
   SAddr a[4];
   stage_all<4>(P, &tmap, env0, nenv, tile, &bar, a);
   if (threadIdx.x >= nenv) return;
@@ -927,16 +976,18 @@ osc_full_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, float kp,
 // reference's operand order up to dpose, which never leaves registers unless a tensor is given.
 // segments: 0 = J (6xD), 1 = M (DxD), 2 = dof_vel (1xD), 3 = pos_des (1x3), 4 = orn_des (1x4); extras: hand row (7).
 template <typename T, int D>
-__global__ void __launch_bounds__(kTileEnvs)
+__global__ void __launch_bounds__(kMaxTileEnvs)
 franka_osc_step_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, TView hand_index, float kp, float kv,
                        int pos_control, TView dpose_out, int has_dpose, TView out, int64_t n) {
   extern __shared__ __align__(128) float tile[];
   __shared__ __align__(8) uint64_t bar;
   stage_begin(P, &tmap, &bar, rb, hand_index, dpose_out, out);
+  stage_prefetch_first<5>(P, &tmap, n);
+  gather_prefetch(hand_index, 1, rb, n);
   pdl_prologue();
   const int ntiles = tile_count(n);
-  const int64_t env0 = (int64_t)blockIdx.x * kTileEnvs;
-  const int nenv = (int)((n - env0) < kTileEnvs ? (n - env0) : kTileEnvs);
+  const int64_t env0 = (int64_t)blockIdx.x * TILE_ENVS;
+  const int nenv = (int)((n - env0) < TILE_ENVS ? (n - env0) : TILE_ENVS);
   const int x_ts = stage_extras_ts(P);
   float* x0 = tile + stage_extras_off(P);
   const int64_t hand_row = gather_row(hand_index, 1, env0, nenv);
@@ -1017,7 +1068,20 @@ static int vec_rows(const DLTensor* t, const char* name, int64_t n, int64_t min_
   return 0;
 }
 
-static inline int tiles(int64_t n) { return (int)((n + kTileEnvs - 1) / kTileEnvs); }
+static inline int tiles(int64_t n, int tile) { return (int)((n + tile - 1) / tile); }
+
+// Tile size of a launch: 64 envs (two warps; four tiles resident per SM at the throughput sizes).  The device code takes
+// the tile size from blockDim.x, so B200CTL_TILE_ENVS=128 can select 128-env tiles for experiments.  Measured and
+// rejected as a dispatch for 16,384 envs (one 128-env tile per SM instead of 108 SMs with two 64-env tiles and 40 with
+// one): osc 7.81 -> 8.96 us, pick_osc 8.57 -> 10.18 us, ik 4.02 -> 4.61 us (profiles/r02_osc_trace.txt).
+static int pick_tile(int64_t n, int dev) {
+  (void)n; (void)dev;
+  static const int forced = [] { const char* e = getenv("B200CTL_TILE_ENVS"); return e ? atoi(e) : 0; }();
+  return forced == kMaxTileEnvs ? kMaxTileEnvs : kTileEnvs;
+}
+  const int sms = sm_count(dev);
+  return (tiles(n, kTileEnvs) > sms && tiles(n, kMaxTileEnvs) <= sms) ? kMaxTileEnvs : kTileEnvs;
+}
 
 static int check_precision(int precision) {
   if (precision != 0 && precision != 1) B200_FAIL(B200CTL_E_VALUE, "precision must be 0 (fp64 factorisation) or 1 (all fp32)");
@@ -1043,9 +1107,9 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // Tensor map of a sparse per-env slot: rows = envs at pitch `env_stride` floats, `valid` floats per row starting at
-// the 16-byte aligned address `base`; box = kTileEnvs rows x (4 * odd) floats so per-thread row reads stay 4-way
+// the 16-byte aligned address `base`; box = `tile` rows x (4 * odd) floats so per-thread row reads stay 4-way
 // bank-conflicted at worst (as in the per-env plan).  Fills seg->b_es / seg->bytes.  Returns false if unavailable.
-static bool encode_slot_map(CUtensorMap* map, const void* base, int valid, int64_t env_stride, int64_t n, StageSeg* seg) {
+static bool encode_slot_map(CUtensorMap* map, const void* base, int valid, int64_t env_stride, int64_t n, int tile, StageSeg* seg) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc || n > 0x7fffffff || valid <= 0 || valid > 252) return false;
   int box = (valid + 3) & ~3;
@@ -1053,14 +1117,14 @@ static bool encode_slot_map(CUtensorMap* map, const void* base, int valid, int64
   if (box > 256) return false;
   const cuuint64_t gdim[2] = {(cuuint64_t)valid, (cuuint64_t)n};
   const cuuint64_t gstride[1] = {(cuuint64_t)env_stride * 4};
-  const cuuint32_t bdim[2] = {(cuuint32_t)box, (cuuint32_t)kTileEnvs};
+  const cuuint32_t bdim[2] = {(cuuint32_t)box, (cuuint32_t)tile};
   const cuuint32_t estride[2] = {1, 1};
   if (enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, bdim, estride,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
   seg->b_es = box;
-  seg->bytes = (unsigned)(kTileEnvs * box * 4);
+  seg->bytes = (unsigned)(tile * box * 4);
   return true;
 }
 
@@ -1068,7 +1132,7 @@ static bool encode_slot_map(CUtensorMap* map, const void* base, int valid, int64
 // passed with rows = 1 and use (s0, -, s1).  `extras` floats per env are reserved in either plan's dense row
 // for operands staged outside the plan (the gathered hand velocity).
 struct SegSpec { const TView* v; int rows, cols; };
-static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n, CUtensorMap* tmap) {
+static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n, int tile, CUtensorMap* tmap) {
   StagePlan P{};
   memset(tmap, 0, sizeof(*tmap));
   bool tmap_used = false;
@@ -1089,12 +1153,12 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
   }
   P.x_off_c = canon;
   P.canon_ts = (canon + extras) | 1;                       // odd row stride: conflict-free per-thread row reads
-  const int canon_floats = kTileEnvs * P.canon_ts;
+  const int canon_floats = tile * P.canon_ts;
 
   // ---- bulk plan: bulk regions first, then one dense row per env for the LDGSTS operands + extras
   int region = 0;
   bool any_bulk = false;
-  for (int i = 0; i < nseg && n > kTileEnvs; ++i) {
+  for (int i = 0; i < nseg && n > tile; ++i) {
     StageSeg& s = P.seg[i];
     if (s.rows * s.cols == 0 || s.s0 <= 0 || s.s1 < 0 || s.s2 <= 0) continue;
     const int64_t window = (int64_t)(s.rows - 1) * s.s1 + (int64_t)(s.cols - 1) * s.s2 + 1;   // floats spanned per env
@@ -1120,14 +1184,14 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
     if (s.s0 <= 2 * window && s.s0 <= 256) {
       // dense enough: one bulk copy brings the whole 64-env block
       s.mode = 1;
-      s.bytes = (unsigned)((s.delta + kTileEnvs * s.s0 * 4 + 15) & ~(int64_t)15);
+      s.bytes = (unsigned)((s.delta + tile * s.s0 * 4 + 15) & ~(int64_t)15);
       s.region = region;
       s.b_off = region + s.delta / 4;
       s.b_es = (int)s.s0; s.b_rs = (int)s.s1; s.b_cs = (int)s.s2;
       region += (int)(s.bytes / 4);
       any_bulk = true;
     } else if ((s.s0 * 4) % 16 == 0 && window <= 128 && !tmap_used &&
-               encode_slot_map(tmap, reinterpret_cast<const char*>(s.base) - s.delta, s.delta / 4 + (int)window, s.s0, n, &s)) {
+               encode_slot_map(tmap, reinterpret_cast<const char*>(s.base) - s.delta, s.delta / 4 + (int)window, s.s0, n, tile, &s)) {
       // sparse slot of a wide row, as a 2-D tensor (element in slot, env) with the env stride as row pitch: ONE
       // tensor-map copy per tile.  Elements past the window and rows past N are zero-filled, never read.
       tmap_used = true;
@@ -1136,7 +1200,7 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
       s.region = region;
       s.b_off = region + s.delta / 4;
       s.b_rs = (int)s.s1; s.b_cs = (int)s.s2;     // b_es / bytes set by encode_slot_map (box row = 4 * odd floats)
-      region += kTileEnvs * s.b_es;
+      region += tile * s.b_es;
       P.tmap_region = s.region;
       P.tmap_bytes = s.bytes;
       any_bulk = true;
@@ -1154,7 +1218,7 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
     P.x_off_b = rows0 + row;
     P.bulk_all = row == 0 ? 1 : 0;
     P.bulk_ts = (row + extras) | 1;
-    const int bulk_floats = rows0 + kTileEnvs * P.bulk_ts;
+    const int bulk_floats = rows0 + tile * P.bulk_ts;
     if (bulk_floats * 4 > 160 * 1024) {
       // an exotic layout whose dense blocks do not fit comfortably in shared memory: LDGSTS plan for every tile
       P.bulk_ok = 0;
@@ -1198,10 +1262,10 @@ static int set_smem(K kernel, int bytes) {
 // Grid of a persistent tile kernel: every CTA slot of the device (occupancy x SM count), or one CTA per tile when
 // there are fewer tiles than slots.
 template <typename K>
-static int persistent_grid(K kernel, int smem, int ntiles, int* grid) {
+static int persistent_grid(K kernel, int smem, int ntiles, int tile, int* grid) {
   int dev = 0, occ = 0;
   B200_CUDA(cudaGetDevice(&dev));
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTileEnvs, smem));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, tile, smem));
   const int slots = usable_slots(dev, occ);
   *grid = ntiles < slots ? ntiles : slots;
   return 0;
@@ -1213,7 +1277,7 @@ using namespace b200ctl;
 
 #ifdef B200_OSC_TRACE
 extern "C" __attribute__((visibility("default"))) int b200ctl_debug_osc_trace(unsigned long long* host_out) {
-  return (int)cudaMemcpyFromSymbol(host_out, g_osc_trace, sizeof(unsigned long long) * 8 * 4096);
+  return (int)cudaMemcpyFromSymbol(host_out, g_osc_trace, sizeof(unsigned long long) * 10 * 4096);
 }
 #endif
 
@@ -1235,7 +1299,8 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
   B200_TRY(g.enter(dev));
   const SegSpec spec[3] = {{&j, 6, (int)D}, {&dp, 1, 6}, {&q, 1, has_pos ? (int)D : 0}};
   CUtensorMap tmap;
-  const StagePlan P = make_plan(spec, 3, 0, n, &tmap);
+  const int tile = pick_tile(n, dev);
+  const StagePlan P = make_plan(spec, 3, 0, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
   // lambda^2 is formed in fp32 like torch.eye(6) * damping**2 (:57)
   const float l2 = (float)(lambda * lambda);
@@ -1243,7 +1308,7 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
 #define LAUNCH_IK(T, DD)                                                          \
   do {                                                                            \
     B200_TRY(set_smem(ik_dls_kernel<T, DD>, smem));                               \
-    launch_pdl(ik_dls_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, tmap, l2, has_pos, o, n); \
+    launch_pdl(ik_dls_kernel<T, DD>, tiles(n, tile), tile, smem, s, P, tmap, l2, has_pos, o, n); \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_IK(double, 7); else LAUNCH_IK(float, 7); }
   else        { if (precision == 0) LAUNCH_IK(double, 9); else LAUNCH_IK(float, 9); }
@@ -1285,7 +1350,8 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
   B200_TRY(g.enter(dev));
   const SegSpec spec[5] = {{&j, 6, 7}, {&m, 7, 7}, {&q, 1, 7}, {&qd, 1, 7}, {&dp, 1, 6}};
   CUtensorMap tmap;
-  const StagePlan P = make_plan(spec, 5, 6, n, &tmap);
+  const int tile = pick_tile(n, dev);
+  const StagePlan P = make_plan(spec, 5, 6, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
   int grid = 0;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1297,8 +1363,8 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
 #define LAUNCH_OSC(T, G)                                                                                     \
   do {                                                                                                       \
     B200_TRY(set_smem(osc_kernel<T, G>, smem));                                                              \
-    B200_TRY(persistent_grid(osc_kernel<T, G>, smem, tiles(n), &grid));                                      \
-    launch_pdl(osc_kernel<T, G>, grid, kTileEnvs, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, (float)kd, \
+    B200_TRY(persistent_grid(osc_kernel<T, G>, smem, tiles(n, tile), tile, &grid));                                      \
+    launch_pdl(osc_kernel<T, G>, grid, tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, (float)kd, \
                (float)kp_null, (float)kd_null, o, n, stats);                                                 \
   } while (0)
   if (precision == 0) { if (gym) LAUNCH_OSC(double, true); else LAUNCH_OSC(double, false); }
@@ -1325,14 +1391,15 @@ extern "C" int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const
   B200_TRY(g.enter(dev));
   const SegSpec spec[4] = {{&j, 6, (int)D}, {&m, (int)D, (int)D}, {&qd, 1, (int)D}, {&dp, 1, 6}};
   CUtensorMap tmap;
-  const StagePlan P = make_plan(spec, 4, 0, n, &tmap);
+  const int tile = pick_tile(n, dev);
+  const StagePlan P = make_plan(spec, 4, 0, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
   cudaStream_t s = (cudaStream_t)stream;
   const float fkp = (float)kp, fkv = (float)kv;
 #define LAUNCH_FULL(T, DD)                                                       \
   do {                                                                           \
     B200_TRY(set_smem(osc_full_kernel<T, DD>, smem));                            \
-    launch_pdl(osc_full_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, tmap, fkp, fkv, o, n); \
+    launch_pdl(osc_full_kernel<T, DD>, tiles(n, tile), tile, smem, s, P, tmap, fkp, fkv, o, n); \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_FULL(double, 7); else LAUNCH_FULL(float, 7); }
   else        { if (precision == 0) LAUNCH_FULL(double, 9); else LAUNCH_FULL(float, 9); }
@@ -1370,14 +1437,15 @@ extern "C" int b200ctl_franka_osc_step(const DLTensor* j_eef, const DLTensor* mm
   B200_TRY(g.enter(dev));
   const SegSpec spec[5] = {{&j, 6, (int)D}, {&m, (int)D, (int)D}, {&qd, 1, (int)D}, {&pd, 1, 3}, {&od, 1, 4}};
   CUtensorMap tmap;
-  const StagePlan P = make_plan(spec, 5, 7, n, &tmap);
+  const int tile = pick_tile(n, dev);
+  const StagePlan P = make_plan(spec, 5, 7, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
   cudaStream_t s = (cudaStream_t)stream;
   const float fkp = (float)kp, fkv = (float)kv;
 #define LAUNCH_STEP(T, DD)                                                              \
   do {                                                                                  \
     B200_TRY(set_smem(franka_osc_step_kernel<T, DD>, smem));                            \
-    launch_pdl(franka_osc_step_kernel<T, DD>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, hi, fkp, fkv, pos_control ? 1 : 0, \
+    launch_pdl(franka_osc_step_kernel<T, DD>, tiles(n, tile), tile, smem, s, P, tmap, rb, hi, fkp, fkv, pos_control ? 1 : 0, \
                dp, has_dpose, o, n);                                                    \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_STEP(double, 7); else LAUNCH_STEP(float, 7); }
@@ -1429,18 +1497,19 @@ extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm
   B200_TRY(g.enter(dev));
   const SegSpec spec[6] = {{&j, 6, 7}, {&m, 7, 7}, {&q, 1, 9}, {&qd, 1, 7}, {&ip, 1, 3}, {&iq, 1, 4}};
   CUtensorMap tmap;
-  const StagePlan P = make_plan(spec, 6, 20, n, &tmap);
+  const int tile = pick_tile(n, dev);
+  const StagePlan P = make_plan(spec, 6, 20, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
   const TaskConst tk = make_task_const(*task);
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
   if (precision == 0) {
     B200_TRY(set_smem(pick_osc_kernel<double>, smem));
-    launch_pdl(pick_osc_kernel<double>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
+    launch_pdl(pick_osc_kernel<double>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
                (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
   } else {
     B200_TRY(set_smem(pick_osc_kernel<float>, smem));
-    launch_pdl(pick_osc_kernel<float>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
+    launch_pdl(pick_osc_kernel<float>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
                (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
   }
   return post_launch("pick_osc_kernel");
@@ -1481,7 +1550,8 @@ extern "C" int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* dof
   B200_TRY(g.enter(dev));
   const SegSpec spec[4] = {{&j, 6, 7}, {&q, 1, 9}, {&ip, 1, 3}, {&iq, 1, 4}};
   CUtensorMap tmap;
-  const StagePlan P = make_plan(spec, 4, 14, n, &tmap);
+  const int tile = pick_tile(n, dev);
+  const StagePlan P = make_plan(spec, 4, 14, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
   const TaskConst tk = make_task_const(*task);
   const float l2 = (float)(lambda * lambda);
@@ -1489,10 +1559,10 @@ extern "C" int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* dof
   uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
   if (precision == 0) {
     B200_TRY(set_smem(pick_ik_kernel<double>, smem));
-    launch_pdl(pick_ik_kernel<double>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+    launch_pdl(pick_ik_kernel<double>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
   } else {
     B200_TRY(set_smem(pick_ik_kernel<float>, smem));
-    launch_pdl(pick_ik_kernel<float>, tiles(n), kTileEnvs, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+    launch_pdl(pick_ik_kernel<float>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
   }
   return post_launch("pick_ik_kernel");
 }
