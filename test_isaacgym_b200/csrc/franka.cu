@@ -1079,9 +1079,6 @@ static int pick_tile(int64_t n, int dev) {
   static const int forced = [] { const char* e = getenv("B200CTL_TILE_ENVS"); return e ? atoi(e) : 0; }();
   return forced == kMaxTileEnvs ? kMaxTileEnvs : kTileEnvs;
 }
-  const int sms = sm_count(dev);
-  return (tiles(n, kTileEnvs) > sms && tiles(n, kMaxTileEnvs) <= sms) ? kMaxTileEnvs : kTileEnvs;
-}
 
 static int check_precision(int precision) {
   if (precision != 0 && precision != 1) B200_FAIL(B200CTL_E_VALUE, "precision must be 0 (fp64 factorisation) or 1 (all fp32)");
