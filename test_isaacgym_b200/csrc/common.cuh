@@ -124,6 +124,15 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// L2 prefetches issued AHEAD of the dependency wait (the CTAs of a programmatically dependent launch are resident
+// while the previous kernel drains): a prefetch consumes nothing, and L2 is the coherence point -- a line the previous
+// kernel still writes is updated in place -- so this is always safe; it starts the step's first DRAM reads early, which
+// is most of what a 16K-64K-env launch waits for.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg{};

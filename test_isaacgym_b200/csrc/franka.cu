@@ -246,9 +246,6 @@ __device__ __forceinline__ void tensor2d_g2s(void* smem_dst, const CUtensorMap* 
 // L2 prefetch of a tile the CTA will stage LATER (no shared memory needed): the persistent kernel's one tile buffer
 // cannot take the next tile's copies before this tile has been gathered out of it, so without the prefetch DRAM idles
 // for this CTA during every gather; with it the later TMA copy is an L2 hit.
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void tensor2d_prefetch_l2(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
@@ -388,7 +385,6 @@ __device__ __forceinline__ void stage_begin(const StagePlan& P, const CUtensorMa
 // index-dependent row gather (two DEPENDENT misses, the longest chain of the staging) are L2 hits.
 // `speculative row`: the index is read before the wait only to compute a prefetch address (range-checked); the real
 // gather re-reads it after the wait.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int NSEG>
 __device__ __forceinline__ void stage_prefetch_first(const StagePlan& P, const CUtensorMap* tmap, int64_t n) {
 #ifdef B200_NO_PREWAIT_PF

@@ -17,10 +17,24 @@ namespace b200ctl {
 __global__ void __launch_bounds__(128)
 franka_task_kernel(TView rb, TView box_index, TView hand_index, TView dof_pos, TView init_pos, TView init_rot,
                    uint8_t* __restrict__ hand_restart, int64_t hr_stride, TaskConst k, TView dpose, TView grip, int64_t n) {
-  pdl_prologue();
   const int64_t env = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (env >= n) return;
   const float* rbp = reinterpret_cast<const float*>(rb.p);
+#ifndef B200_NO_PREWAIT_PF
+  if (env < n) {
+    // index -> row is two DEPENDENT misses: ahead of the dependency wait the indices are read as hints only (they are
+    // re-read below) and the rows they name are requested into L2 (common.cuh: prefetch_l2)
+    int64_t b0, h0;
+    asm volatile("ld.global.relaxed.gpu.u64 %0, [%1];" : "=l"(b0) : "l"(reinterpret_cast<const int64_t*>(box_index.p) + env * box_index.s[0]));
+    asm volatile("ld.global.relaxed.gpu.u64 %0, [%1];" : "=l"(h0) : "l"(reinterpret_cast<const int64_t*>(hand_index.p) + env * hand_index.s[0]));
+    if (b0 >= 0 && b0 < rb.n[0]) prefetch_l2(rbp + b0 * rb.s[0]);
+    if (h0 >= 0 && h0 < rb.n[0]) prefetch_l2(rbp + h0 * rb.s[0]);
+    prefetch_l2(reinterpret_cast<const float*>(dof_pos.p) + env * dof_pos.s[0] + 7 * dof_pos.s[1]);
+    prefetch_l2(reinterpret_cast<const float*>(init_pos.p) + env * init_pos.s[0]);
+    prefetch_l2(reinterpret_cast<const float*>(init_rot.p) + env * init_rot.s[0]);
+  }
+#endif
+  pdl_prologue();
+  if (env >= n) return;
   const int64_t brow = reinterpret_cast<const int64_t*>(box_index.p)[env * box_index.s[0]];
   const int64_t hrow = reinterpret_cast<const int64_t*>(hand_index.p)[env * hand_index.s[0]];
   float box[7], hand[7];

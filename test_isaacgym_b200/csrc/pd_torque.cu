@@ -170,12 +170,22 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
                       const float4* __restrict__ qd_tgt, PdParams pp, int num_dofs, int64_t nvec, int64_t num_envs,
                       float4* __restrict__ tau_out, double* __restrict__ stats) {
   extern __shared__ __align__(16) float s_par[];   // [5][D]: kp, kd, tmax, lo, hi
-  pdl_prologue();
   // 32-bit vector indices (the host routes nvec >= 2^31 to the strided kernel): one IMAD.WIDE per address instead of a
   // 64-bit multiply-add chain
   typedef B200_PD_INDEX_T idx_t;
   const idx_t stride = (idx_t)(gridDim.x * blockDim.x);
   const idx_t v0 = (idx_t)(blockIdx.x * blockDim.x + threadIdx.x);
+#ifndef B200_NO_PREWAIT_PF
+  // the first iteration's lines, requested while the previous kernel drains (common.cuh: prefetch_l2).  Small launches
+  // only (65,536 envs x 12: 3.67 -> 2.99 us): at 1M envs most CTAs start after the wait, where the prefetch is just a
+  // second request for the line the load right behind it asks for (30.8 -> 32.1 us)
+  if (v0 < nvec && nvec <= (int64_t)1 << 19) {
+    prefetch_l2(state + 2 * v0);
+    prefetch_l2(q_tgt + v0);
+    if (HAS_QD) prefetch_l2(qd_tgt + v0);
+  }
+#endif
+  pdl_prologue();
   // The loop is rotated: the streaming loads of an iteration are issued at the end of the previous one, and those of
   // the first iteration HERE, ahead of the per-DOF parameter staging -- otherwise every CTA spends one L2 round trip
   // (parameter load -> shared store -> barrier) before its first byte of dof_state is requested, which is 8 % of a
