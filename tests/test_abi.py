@@ -51,6 +51,21 @@ def test_no_cpu_fallback():
         cclvf2(torch.zeros(4, 3), torch.zeros(4, 3), 50, 30)
 
 
+def test_argument_checks_that_need_no_gpu():
+    L = _lib.lib()
+    import ctypes as C
+    best, med = C.c_double(), C.c_double()
+    assert L.b200ctl_measure_fma_peak(2, 0, 3, C.byref(best), C.byref(med)) == -6          # E_VALUE: dtype
+    assert L.b200ctl_reserve_cta_slots(99, 1) == -2 and L.b200ctl_reserve_cta_slots(0, -1) == -6
+    assert L.b200ctl_reserve_cta_slots(0, 0) == 0
+    boxes = (C.c_void_p * 2)()
+    assert L.b200ctl_stats_allreduce_peer(boxes, 2, 2, 0, 0, None, 8, None, None, 2.0, 0, None) == -1   # NULL stats
+    assert L.b200ctl_peer_mailbox_create(0, None, None) == -1
+    with pytest.raises(_lib.B200CtlError, match="E_DEVICE"):
+        _lib.stats_arg(torch.zeros(8, dtype=torch.float64), None)
+    assert _lib.stats_arg(None, None) is None
+
+
 def test_cpu_tensor_rejected_at_the_abi():
     t = torch.zeros(4, 3)
     with pytest.raises(_lib.B200CtlError):

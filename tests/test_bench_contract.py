@@ -26,6 +26,20 @@ def test_reference_arm_json_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
     assert "workload" in line["config"] and "model" not in line["config"]
+    # the two arms describe ONE workload: the reference arm's config is built by the same function as the repo arm's
+    import bench
+    assert line["config"] == bench.make_config(1, bench.ENVS_PER_GPU, 16, "x")
+    assert set(line["config"]) == {"workload", "envs_per_gpu", "num_dofs", "global_envs", "parallelism",
+                                   "stats_allreduce_every", "stats_allreduce", "l2_policy"}
+
+
+def test_rotation_follows_touched_bytes():
+    """Buffer rotation is sized by the bytes a launch TOUCHES: twice the 126 MB L2 between two uses of a set."""
+    import bench
+    assert bench.sets_for(16_384 * 958) == 17            # OSC at C3: 15.7 MB touched of a 47 MB set
+    assert bench.sets_for(16_384 * 460, hi=40) == 36     # IK at C3
+    assert bench.sets_for(1_048_576 * 192) == 3          # PD headline: inputs alone exceed L2
+    assert bench.sets_for(1, hi=40) == 40 and bench.sets_for(10 ** 12) == 3
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():
