@@ -238,20 +238,31 @@ __device__ __forceinline__ void block_stats_commit(double (&d)[ND], unsigned (&u
     for (int k = 0; k < NI; ++k) s_u[k][warp] = u[k];
   }
   __syncthreads();
-  if (warp != 0 || lane >= ND + NI) return;
+  if (warp != 0) return;
+  // cross-warp stage as a second butterfly over the per-warp partials (lane w holds warp w's): straight-line code.
+  // The commit runs once per CTA at the cold tail of a kernel whose loop body fills the instruction cache -- a
+  // persistent servo grid of four waves pays it four times per CTA slot (profiles/r02_ab_servo_stats.txt) -- so its
+  // SIZE counts: the first version looped over the warps (unrolled sixteen-fold by the compiler: ~250 instructions).
   const int nwarp = (blockDim.x + 31) >> 5;
-  double v = 0.0;
-  if (lane < ND) {
-    for (int w = 0; w < nwarp; ++w) v += s_d[lane][w];
-  } else {
-    unsigned c = 0;
-    for (int w = 0; w < nwarp; ++w) c += s_u[lane - ND][w];
-    v = (double)c;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) d[k] = lane < nwarp ? s_d[k][lane] : 0.0;
+#pragma unroll
+  for (int k = 0; k < NI; ++k) u[k] = lane < nwarp ? s_u[k][lane] : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < ND; ++k) d[k] += __shfl_xor_sync(0xffffffffu, d[k], o);
   }
+#pragma unroll
+  for (int k = 0; k < NI; ++k) u[k] = __reduce_add_sync(0xffffffffu, u[k]);
+  // every lane holds the CTA totals; lane j owns entry j: ONE predicated RED instruction per CTA
+  double v = 0.0;
   int slot = 0;
 #pragma unroll
-  for (int j = 0; j < ND + NI; ++j) slot = (lane == j) ? slots[j] : slot;
-  if (v != 0.0) atomicAdd(stats + slot, v);
+  for (int j = 0; j < ND; ++j) { v = (lane == j) ? d[j] : v; slot = (lane == j) ? slots[j] : slot; }
+#pragma unroll
+  for (int j = 0; j < NI; ++j) { v = (lane == ND + j) ? (double)u[j] : v; slot = (lane == ND + j) ? slots[ND + j] : slot; }
+  if (lane < ND + NI && v != 0.0) atomicAdd(stats + slot, v);
 }
 
 #endif  // __CUDACC__

@@ -42,6 +42,19 @@ struct ServoConst {
 #ifndef B200_SERVO_PERSIST_ALL
 #define B200_SERVO_PERSIST_ALL 0     // A/B knob: 1 = the persistent grid (and its tile buffers) without statistics too
 #endif
+#ifdef B200_SERVO_TRACE       // A/B only: per-CTA timestamps (globaltimer ns): 0 entry, 1 after wait, 2 tile loop done, 3 committed
+__device__ unsigned long long g_servo_trace[4][16384];
+__device__ __forceinline__ void servo_trace(int k) {
+  if (threadIdx.x == 0 && blockIdx.x < 16384) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_servo_trace[k][blockIdx.x] = t;
+  }
+}
+#define SERVO_TRACE(k) servo_trace(k)
+#else
+#define SERVO_TRACE(k)
+#endif
 template <int PREC, bool STATS, int TILE, bool SPLIT>
 __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64_t num_envs, const ServoConst& k,
                                                 double* __restrict__ aux, double* __restrict__ stats, int vec_ok) {
@@ -52,6 +65,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   constexpr int NBUF = ((STATS || B200_SERVO_PERSIST_ALL) && !SPLIT) ? B200_SERVO_STATS_NBUF : 1;
   __shared__ __align__(128) float tiles[NBUF][TILE * kEnvRow];
   __shared__ __align__(8) uint64_t bars[NBUF];
+  SERVO_TRACE(0);
   if (threadIdx.x == 0) {                       // touches no global memory: done ahead of the dependency wait
 #pragma unroll
     for (int b = 0; b < NBUF; ++b) mbar_init(&bars[b], 1);
@@ -63,6 +77,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
 #endif
   }
   pdl_prologue();
+  SERVO_TRACE(1);
   __syncthreads();                              // the initialised barrier is visible to every waiter
   // Tiles blockIdx.x, + gridDim.x, ... through ONE tile buffer.  The host launches one CTA per tile without
   // statistics and a persistent grid with them: the statistics are accumulated in registers across tiles and
@@ -244,12 +259,14 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
     __syncthreads();              // every row is out before the next tile's loads overwrite the buffer
   }
   }   // tile loop
-  if (NBUF == 2 && threadIdx.x == 0) bulk_wait_read();   // shared memory outlives the last write-back's read
+  SERVO_TRACE(2);
   if (STATS) {
     const int slots[5] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_SAT,
                           B200CTL_STAT_N_NONFINITE};
-    block_stats_commit<2, 3>(acc_d, acc_u, stats, slots);
+    block_stats_commit<2, 3>(acc_d, acc_u, stats, slots);      // (uses its own shared arrays, not the tile buffers)
   }
+  if (NBUF == 2 && threadIdx.x == 0) bulk_wait_read();   // shared memory outlives the last write-back's read
+  SERVO_TRACE(3);
 }
 
 // Entry kernels per (precision, statistics) so each gets its own register budget: the fp64-stage kernel is latency
@@ -418,6 +435,12 @@ static inline int grid1d(int64_t n, int block) { return (int)((n + block - 1) / 
 }  // namespace b200ctl
 
 using namespace b200ctl;
+
+#ifdef B200_SERVO_TRACE
+extern "C" __attribute__((visibility("default"))) int b200ctl_debug_servo_trace(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_servo_trace, sizeof(unsigned long long) * 4 * 16384);
+}
+#endif
 
 extern "C" int b200ctl_cclvf(const DLTensor* pos, const DLTensor* tgt, double speed, double radius,
                              DLTensor* vel_out, b200ctl_stream_t stream) {
@@ -622,15 +645,18 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 2 * tile, 0));
     slots = usable_slots(dev, occ);
   }
-  // Persistent grid of FOUR waves of resident CTAs (A/B knob, profiles/r01_ab_servo_stats_waves.txt): one wave pays for
-  // its static tile stride at the tail, many waves pay in commits on the one L2 line of the vector -- per 1M envs,
-  // 1 / 2 / 4 / 8 waves / one CTA per tile: reference precision 43.8 / 42.4 / 41.0 / 44.8 / 45.1 us, fast 41.1 / 37.7 /
-  // 35.5 / 35.6 / 35.6 us.
-#ifndef B200_SERVO_STATS_WAVES
-#define B200_SERVO_STATS_WAVES 4
+  // Persistent grid of a few waves of resident CTAs when statistics are requested: one wave pays for its static tile
+  // stride at the tail, many waves pay one commit per CTA.  Per 1M envs, reference precision (64-env tiles, fp64 stages)
+  // 2 / 4 / 8 / 16 waves: 39.8 / 39.0 / 42.5 / 42.5 us -> FOUR; fp32 mode (128-env tiles) 37.2 / 35.4 / 35.0 / 34.9 us
+  // -> SIXTEEN, i.e. one CTA per tile, where its statistics are free (34.9 us without them)
+  // (profiles/r02_ab_servo_stats.txt; A/B knob B200_SERVO_STATS_WAVES).
+#ifdef B200_SERVO_STATS_WAVES
+  const int waves = B200_SERVO_STATS_WAVES;
+#else
+  const int waves = params->precision == 1 ? 16 : 4;
 #endif
   const bool persist = stats != nullptr || B200_SERVO_PERSIST_ALL;
-  const int grid = (persist && ntiles > slots * B200_SERVO_STATS_WAVES) ? slots * B200_SERVO_STATS_WAVES : ntiles;
+  const int grid = (persist && ntiles > slots * waves) ? slots * waves : ntiles;
   const int vec_ok = aligned16(st) ? 1 : 0;
   launch_pdl(kern, grid, split ? 2 * tile : tile, 0, (cudaStream_t)stream, st, n, k, aux_out, stats, vec_ok);
   return post_launch("servo_step_kernel");
