@@ -21,6 +21,8 @@
 // contraction): bit-identical to the torch expression of the reference.
 #include "common.cuh"
 
+#include <string.h>
+
 #include <mutex>
 
 namespace b200ctl {
@@ -484,6 +486,8 @@ struct HostPipe {
   float* d_qd[kSlots] = {};
   float* d_out[kSlots] = {};
   float* d_par = nullptr;                  // 5 * 4096 floats
+  float h_par[5][4096];                    // what d_par holds (host shadow): unchanged gain / limit vectors are not re-sent
+  int h_par_len[5] = {-1, -1, -1, -1, -1};
   double* d_stats = nullptr;
   cudaStream_t up = nullptr, run = nullptr, down = nullptr;
   cudaEvent_t uploaded[kSlots] = {}, computed[kSlots] = {}, drained[kSlots] = {};
@@ -550,13 +554,17 @@ extern "C" int b200ctl_pd_torque_host(const float* dof_state, const float* q_tar
   if (chunk_envs > num_envs) chunk_envs = num_envs;
   B200_TRY(pipe_prepare(P, device, (size_t)chunk_envs * D));
 
-  // per-DOF parameters
-  B200_CUDA(cudaMemcpyAsync(P.d_par, kp, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
-  B200_CUDA(cudaMemcpyAsync(P.d_par + 4096, kd, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
-  if (tau_max) B200_CUDA(cudaMemcpyAsync(P.d_par + 2 * 4096, tau_max, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
-  if (clamp) {
-    B200_CUDA(cudaMemcpyAsync(P.d_par + 3 * 4096, q_lo, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
-    B200_CUDA(cudaMemcpyAsync(P.d_par + 4 * 4096, q_hi, D * sizeof(float), cudaMemcpyHostToDevice, P.up));
+  // per-DOF parameters.  The callers' vectors are small pageable arrays: each upload is a staged, host-blocking copy
+  // (~15 us) ahead of the first chunk's transfer, so vectors whose bytes did not change since the last call stay put
+  {
+    const float* src[5] = {kp, kd, tau_max, clamp ? q_lo : nullptr, clamp ? q_hi : nullptr};
+    for (int i = 0; i < 5; ++i) {
+      if (!src[i]) continue;
+      if (P.h_par_len[i] == D && memcmp(P.h_par[i], src[i], D * sizeof(float)) == 0) continue;
+      memcpy(P.h_par[i], src[i], D * sizeof(float));
+      P.h_par_len[i] = D;
+      B200_CUDA(cudaMemcpyAsync(P.d_par + i * 4096, P.h_par[i], D * sizeof(float), cudaMemcpyHostToDevice, P.up));
+    }
   }
   if (stats_out) B200_CUDA(cudaMemsetAsync(P.d_stats, 0, B200CTL_STATS_LEN * sizeof(double), P.run));
 
@@ -572,6 +580,8 @@ extern "C" int b200ctl_pd_torque_host(const float* dof_state, const float* q_tar
   int64_t done = 0;
   for (int64_t c = 0; done < num_envs; ++c) {
     const int slot = (int)(c % HostPipe::kSlots);
+    // (a tapering tail -- half, then quarter chunks, to shorten what is left to download after the last upload -- and
+    // 0.25 / 0.5 / 2 / 4 M-element chunks were measured: 3.00 ms per 1M-env step either way at 1 M elements, worse elsewhere)
     const int64_t n = (num_envs - done) < chunk_envs ? (num_envs - done) : chunk_envs;
     const size_t elems = (size_t)n * D, off = (size_t)done * D;
     // the slot is free once its previous result has been downloaded

@@ -25,6 +25,9 @@ CLAMP_TARGET = _lib.PD_CLAMP_TARGET
 def _vec(x, num_dofs: int, device, name: str):
     if x is None:
         return None
+    if isinstance(x, torch.Tensor) and x.dtype == torch.float32 and x.shape == (num_dofs,) and x.device == device \
+            and x.is_contiguous():
+        return x                      # already what the ABI takes: the per-call cost of the host path is mostly these
     if not isinstance(x, torch.Tensor):
         x = torch.as_tensor(x, dtype=torch.float32)
     if x.dim() == 0:
