@@ -10,9 +10,12 @@ PER GPU (BASELINE.json configs[3] at one shard per GPU; it fits one GPU, and it 
 north-star target is quoted on).  One "step" = one evaluation of the law over the whole batch:
 one kernel launch with the fused statistics epilogue.  Envs shard as contiguous slices, one
 process per GPU, no data-path collective ("scaling": "weak"); at N > 1 the float64[8] statistics
-vector is all-reduced over NCCL every --stats-every steps: in order on the control stream, or with
---stats-overlap on a side stream next to the control kernels (one CTA slot reserved for NCCL's
-128-thread CTA).  N > 1 lines also carry `strong`: 1,048,576 envs IN TOTAL split over the N GPUs.
+vector is exchanged EVERY step inside the PD kernel itself (--stats-collective fused, the default:
+one publisher CTA per launch stores the previous step's vector into every rank's mailbox over
+NVLink peer memory and sums the rows of the step before).  Other forms: the library's stand-alone
+all-reduce kernel (peer / peer-lagged, every --stats-every steps) or NCCL (nccl).  N > 1 lines
+also carry `strong` (1,048,576 envs IN TOTAL split over the N GPUs) and `per_step_stats` (the same
+loop under the other exchange forms).
 
 Printed keys beyond the base contract:
   roofline      dominant kernel vs measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes
@@ -502,6 +505,9 @@ def cpu_family_baselines(families):
 
 
 def stats_mode_name(args):
+    if args.stats_collective == "fused":
+        return ("EVERY step, inside the PD kernel (b200ctl_pd_torque_published): a publisher CTA stores the previous step's vector "
+                "into every rank's mailbox over NVLink and sums the rows of the step before")
     where = "on a side stream next to the following step" if args.stats_overlap else "in order on the control stream"
     if args.stats_collective == "peer":
         return "b200ctl peer-memory all-reduce kernel (NVLink), " + where
@@ -535,7 +541,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * (n / sample), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": make_config(world, ENVS_PER_GPU, max(1, args.stats_every), stats_mode_name(args)),
+            "config": make_config(world, ENVS_PER_GPU, 1 if args.stats_collective == "fused" else max(1, args.stats_every), stats_mode_name(args)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample_envs_per_step": sample,
                              "sample": f"{args.steps} steps x {sample} envs x {NUM_DOFS} DOF (oracle/pd.py, torch-CPU fp32, "
@@ -547,7 +553,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def strong_scaling(device, rank, world, reducer, stats_every, overlap, steps, weak_ms_per_step):
+def strong_scaling(device, rank, world, reducer, stats_every, overlap, steps, weak_ms_per_step, fused_pub=None):
     """BASELINE configs[3] as written: 1,048,576 envs IN TOTAL split as contiguous env slices over the N GPUs (strong
     scaling).  One CUDA graph holds one statistics window (`stats_every` PD steps over rotating buffer sets), the window's
     all-reduce follows it (in order, or on the side stream); device time by CUDA events, max over ranks.  Efficiency is
@@ -562,15 +568,26 @@ def strong_scaling(device, rank, world, reducer, stats_every, overlap, steps, we
     wl = PdWorkload(device, n, seed=2000 + rank, sets=sets)
     bufs = [_lib.stats_buffer(device), _lib.stats_buffer(device)]
     graphs = []
-    for b in bufs:
-        calls = [wl.ctl.bind(wl.state[i % sets], wl.tgt[i % sets], wl.out[i % sets], stats=b) for i in range(stats_every)]
-        graphs.append(StepGraph(calls, device, restore=[b]))
-    events = [None, None]
-
     from test_isaacgym_b200.sharding import PeerStatsReducer
+    in_kernel = fused_pub is not None
+    if in_kernel:
+        # statistics exchanged every step inside the PD kernel (publisher CTA): one graph of an even number of steps
+        stats_every = stats_every + (stats_every & 1)
+        red = _lib.stats_buffer(device)
+        calls = [wl.ctl.bind(wl.state[i % sets], wl.tgt[i % sets], wl.out[i % sets], stats=bufs[i & 1], stats_prev=bufs[(i & 1) ^ 1],
+                             publish=fused_pub, reduced=red) for i in range(stats_every)]
+        graphs = [StepGraph(calls, device, warmup=0)] * 2
+    else:
+        for b in bufs:
+            calls = [wl.ctl.bind(wl.state[i % sets], wl.tgt[i % sets], wl.out[i % sets], stats=b) for i in range(stats_every)]
+            graphs.append(StepGraph(calls, device, restore=[b]))
+    events = [None, None]
     fused_zero = isinstance(reducer, PeerStatsReducer)
 
     def window(w):
+        if in_kernel:
+            graphs[0]()
+            return
         k = w & 1
         if events[k] is not None:
             torch.cuda.current_stream(device).wait_event(events[k])
@@ -604,11 +621,11 @@ def strong_scaling(device, rank, world, reducer, stats_every, overlap, steps, we
     ideal_us = weak_ms_per_step * 1e3 / world
     floor_us = 1.55 + n * PD_BYTES_PER_ENV / 6539.2e3        # one launch + the slice's bytes at the measured copy bandwidth
     return {"global_envs": ENVS_PER_GPU, "envs_per_gpu": n, "us_per_step": us, "env_steps_per_s": ENVS_PER_GPU / (us * 1e-6),
-            "n1_us_per_step": weak_ms_per_step * 1e3, "efficiency_vs_n1": ideal_us / us, "stats_allreduce_every": stats_every,
+            "n1_us_per_step": weak_ms_per_step * 1e3, "efficiency_vs_n1": ideal_us / us,
+            "stats_allreduce_every": 1 if in_kernel else stats_every,
             "buffer_sets": sets, "steps": windows * stats_every,
             "limiter": (f"{n} envs per GPU are {n * PD_BYTES_PER_ENV / 1e6:.1f} MB per step: {floor_us:.1f} us = one launch (1.55 us) + the "
-                        f"bytes at HBM speed; the step no longer hides the launch floor, and the statistics all-reduce "
-                        f"(~25-30 us of NCCL latency per window of {stats_every} steps) adds its share")}
+                        f"bytes at HBM speed; the step no longer hides the launch floor (which is per launch, not per byte)")}
 
 
 def host_link_ceiling(device, hs, ht, hout, world):
@@ -660,15 +677,28 @@ def run_b200(args):
     lo, hi = env_slice(total_envs, rank, world)
     wl = PdWorkload(device, hi - lo, seed=1000 + rank)
     from test_isaacgym_b200.sharding import PeerStatsReducer
+    in_kernel = world > 1 and args.stats_collective == "fused"
     if world > 1 and args.stats_collective != "nccl":
         reducer = PeerStatsReducer(device, lagged=args.stats_collective == "peer-lagged")
     else:
         reducer = StatsReducer("torch", device) if world > 1 else None
-    stats_every = max(1, args.stats_every)
+    stats_every = 1 if in_kernel else max(1, args.stats_every)
     if world > 1 and args.stats_overlap and args.stats_collective == "nccl":
         _lib.reserve_cta_slots(device, args.reserve_slots)
-    wl.bind(StatsWindow(device, reducer, stats_every, overlap=args.stats_overlap))
+    wl.bind(StatsWindow(device, reducer, max(1, args.stats_every), overlap=args.stats_overlap))
     step = wl.step
+    fused_pub = None
+    if in_kernel:
+        # the headline at N > 1: north_star's "all-reduce the per-step episode statistics" taken literally -- EVERY step,
+        # inside the control kernel: one extra CTA of each launch (the publisher) clears the previous step's accumulator,
+        # stores its vector into every rank's mailbox over NVLink and sums the rows of the step before, while the other
+        # CTAs stream the law (compute + collective in one launch; nothing at the tail of the kernel)
+        fused_pub = PeerStatsReducer(device, lagged=True)
+        acc2, reduced2 = [_lib.stats_buffer(device), _lib.stats_buffer(device)], _lib.stats_buffer(device)
+        assert wl.sets % 2 == 0          # consecutive steps alternate the two accumulators
+        fused = [wl.ctl.bind(wl.state[k], wl.tgt[k], wl.out[k], stats=acc2[k & 1], stats_prev=acc2[(k & 1) ^ 1],
+                             publish=fused_pub, reduced=reduced2) for k in range(wl.sets)]
+        step = lambda i=0: fused[i % wl.sets]()      # noqa: E731
 
     with ClockSampler(local_rank) as clocks:
         # sustained warm-up so the clock samples describe the loaded state of this very kernel
@@ -684,7 +714,7 @@ def run_b200(args):
             if int(go.item()) == 0:
                 break
             for _ in range(208):          # a multiple of the statistics window: every rank ends on a window boundary
-                wl.step(it)
+                step(it)
                 it += 1
             torch.cuda.synchronize(device)
         for i in range(args.warmup):
@@ -702,6 +732,9 @@ def run_b200(args):
         torch.cuda.synchronize(device)
         launches = _lib.launch_count() - launches0
         wl.window.finish()
+        stats_check = None
+        if in_kernel:      # the exchanged vector of a full step: every rank must read the global env count
+            stats_check = {"reduced_n_env": float(reduced2[0].item()), "expected": float(total_envs), "timeouts": fused_pub.timeouts()}
         if world > 1:
             dist.barrier()
         ms = torch.tensor([start.elapsed_time(end)], device=device, dtype=torch.float64)
@@ -730,32 +763,46 @@ def run_b200(args):
         ms_per_step = ms_total / args.steps
         per_step_stats = None
         if world > 1 and not args.no_strong:
-            # north_star: "all-reduce the per-step episode statistics".  The headline exchanges every `stats_every`
-            # steps; this is the same loop exchanging EVERY step: the lagged peer-memory form on the side stream (the
-            # vector of step s is globally summed while step s + 1 runs and readable one step later)
-            lag = PeerStatsReducer(device, lagged=True)
-            wl.bind(StatsWindow(device, lag, 1, overlap=True))
-            for i in range(64):
-                wl.step(i)
-            torch.cuda.synchronize(device)
-            dist.barrier()
-            s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s1.record()
-            for i in range(args.steps):
-                wl.step(i)
-            e1.record()
-            torch.cuda.synchronize(device)
-            wl.window.finish()
-            t1 = torch.tensor([s1.elapsed_time(e1)], device=device, dtype=torch.float64)
-            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
-            us1 = t1.item() * 1e3 / args.steps
-            per_step_stats = {"stats_allreduce_every": 1, "us_per_step": us1, "env_steps_per_s": total_envs / (us1 * 1e-6),
-                              "vs_headline": (ms_per_step * 1e3) / us1, "timeouts": lag.timeouts(),
-                              "collective": "b200ctl peer-memory all-reduce kernel, lagged by one step, on a side stream next to the following step"}
+            # the other forms of the exchange on the same loop, for comparison with the headline's
+            def timed_loop(step_fn):
+                for i in range(64):
+                    step_fn(i)
+                torch.cuda.synchronize(device)
+                dist.barrier()
+                s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s1.record()
+                for i in range(args.steps):
+                    step_fn(i)
+                e1.record()
+                torch.cuda.synchronize(device)
+                t1 = torch.tensor([s1.elapsed_time(e1)], device=device, dtype=torch.float64)
+                dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+                return t1.item() * 1e3 / args.steps
+
+            forms = {}
+            for name, every, lagged in (("peer_kernel_side_stream_every_16", 16, False), ("peer_kernel_side_stream_lagged_every_1", 1, True)):
+                red_ = PeerStatsReducer(device, lagged=lagged)
+                wl.bind(StatsWindow(device, red_, every, overlap=True))
+                forms[name] = timed_loop(wl.step)
+                wl.window.finish()
+            if not in_kernel:
+                pub_ = PeerStatsReducer(device, lagged=True)
+                acc1, reduced1 = [_lib.stats_buffer(device), _lib.stats_buffer(device)], _lib.stats_buffer(device)
+                fz = [wl.ctl.bind(wl.state[k], wl.tgt[k], wl.out[k], stats=acc1[k & 1], stats_prev=acc1[(k & 1) ^ 1], publish=pub_,
+                                  reduced=reduced1) for k in range(wl.sets)]
+                forms["in_kernel_publisher_cta_every_1"] = timed_loop(lambda i: fz[i % wl.sets]())
+            else:
+                forms["in_kernel_publisher_cta_every_1"] = ms_per_step * 1e3
+            per_step_stats = {"us_per_step_by_exchange_form": forms,
+                              "note": "same PD loop, 1,048,576 envs per GPU; in_kernel_publisher_cta = b200ctl_pd_torque_published "
+                                      "(statistics of step s published from one extra CTA of kernel s + 1 over NVLink, global sum readable "
+                                      "two steps later); peer_kernel = the stand-alone b200ctl all-reduce kernel; NCCL in order measured "
+                                      "33 us (every 16) / 67 us (every step) at N=2, profiles/r02_ab_stats_allreduce_n2.txt"}
         strong = None
         if world > 1 and not args.no_strong:
             _lib.reserve_cta_slots(device, args.reserve_slots if (args.stats_overlap and args.stats_collective == "nccl") else 0)
-            strong = strong_scaling(device, rank, world, reducer, stats_every, args.stats_overlap, args.steps, ms_per_step)
+            strong = strong_scaling(device, rank, world, reducer, max(1, args.stats_every), args.stats_overlap, args.steps, ms_per_step,
+                                    fused_pub=PeerStatsReducer(device, lagged=True) if in_kernel else None)
 
     value = total_envs * args.steps / (ms_total * 1e-3)
     per_gpu_rate = (hi - lo) / (ms_per_step * 1e-3)
@@ -787,6 +834,8 @@ def run_b200(args):
         line["strong"] = strong
     if per_step_stats is not None:
         line["per_step_stats"] = per_step_stats
+    if stats_check is not None:
+        line["stats_check"] = stats_check
     traffic_file = os.path.join(ROOT, "profiles", "pd_traffic.json")
     if os.path.isfile(traffic_file):
         try:
@@ -846,8 +895,9 @@ def main():
     ap.add_argument("--stats-overlap", action="store_true", help="all-reduce on a side stream (the default for the peer-memory collective)")
     ap.add_argument("--stats-in-order", action="store_true", help="all-reduce in order on the control stream (the default for NCCL)")
     ap.add_argument("--reserve-slots", type=int, default=1, help="CTA slots every persistent grid leaves free with --stats-overlap")
-    ap.add_argument("--stats-collective", default="peer", choices=["peer", "peer-lagged", "nccl"],
-                    help="N > 1: the library's own all-reduce over NVLink peer memory (default), its lagged form, or NCCL")
+    ap.add_argument("--stats-collective", default="fused", choices=["fused", "peer", "peer-lagged", "nccl"],
+                    help="N > 1: statistics exchanged every step inside the PD kernel (default), the library's stand-alone "
+                         "all-reduce kernel over NVLink peer memory every --stats-every steps, its lagged form, or NCCL")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (N > 1)")
     ap.add_argument("--sustain-s", type=float, default=1.0, help="seconds of pre-load before the timed region (clock sampling)")
     ap.add_argument("--no-families", action="store_true")

@@ -317,6 +317,20 @@ B200CTL_API int b200ctl_stats_allreduce(void* comm, double* stats, int32_t n, b2
  *                                 can run on a side stream next to the following step with two alternating accumulators.
  *   A peer that never publishes cannot hang the GPU: after `timeout_s` (<= 0: 2 s) the kernel writes NaN into the sum
  *   and counts the event (b200ctl_peer_mailbox_timeouts). */
+/* The PD law with its statistics exchange riding in the control kernel itself (compute and collective in one launch,
+ * per step): same arguments as b200ctl_pd_torque (stats required; vector path only: compact, 16-byte aligned tensors),
+ * plus the OTHER accumulator and the mailbox table.  The caller alternates two accumulators: `stats` receives this step's
+ * partial sums; `stats_prev` holds the previous step's, complete since that kernel ended.  One extra CTA of the grid -- the
+ * publisher, which takes no elements -- reads stats_prev, CLEARS it, stores the vector into every rank's mailbox over
+ * NVLink and writes to reduced_out (device double[8]) the global sum of the step before (rows that arrived a step ago: it
+ * never waits for a peer; zeros until two steps have run), while the other CTAs stream the law.  Every rank must make the
+ * same sequence of calls on mailboxes used for nothing else (the window counter lives in the mailbox, so CUDA-graph
+ * replays stay in step). */
+B200CTL_API int b200ctl_pd_torque_published(const DLTensor* dof_state, const DLTensor* q_target, const DLTensor* qd_target,
+                                const DLTensor* kp, const DLTensor* kd, const DLTensor* tau_max,
+                                const DLTensor* q_lo, const DLTensor* q_hi, int flags, DLTensor* tau_out,
+                                double* stats, double* stats_prev, void* const* mailboxes, int32_t rank, int32_t world,
+                                double* reduced_out, double timeout_s, b200ctl_stream_t stream);
 B200CTL_API int b200ctl_peer_mailbox_create(int32_t device, void** mailbox_out, void* ipc_handle_out_64_bytes);
 B200CTL_API int b200ctl_peer_mailbox_open(int32_t device, const void* ipc_handle_64_bytes, void** peer_out);
 B200CTL_API int b200ctl_peer_mailbox_close(int32_t device, void* mailbox, int32_t is_peer);

@@ -71,6 +71,8 @@ _SIGNATURES = {
     "b200ctl_last_error": (c_char_p, []),
     "b200ctl_launch_count": (c_uint64, []),
     "b200ctl_pd_torque": (c_int, [_DL, _DL, _DL, _DL, _DL, _DL, _DL, _DL, c_int, _DL, c_void_p, c_void_p]),
+    "b200ctl_pd_torque_published": (c_int, [_DL, _DL, _DL, _DL, _DL, _DL, _DL, _DL, c_int, _DL, c_void_p, c_void_p,
+                                            POINTER(c_void_p), c_int32, c_int32, c_void_p, c_double, c_void_p]),
     "b200ctl_pd_torque_host": (c_int, [c_void_p] * 8 + [c_int, c_int64, c_int32, c_void_p, c_void_p, c_int32]),
     "b200ctl_cclvf": (c_int, [_DL, _DL, c_double, c_double, _DL, c_void_p]),
     "b200ctl_world2pixel": (c_int, [_DL, _DL, _DL, c_double, c_double, c_double, c_double, _DL, c_void_p]),

@@ -19,7 +19,7 @@
 // statistics epilogue (one RED instruction per CTA), four without.
 // Arithmetic is fp32 with explicit round-to-nearest intrinsics (no FMA
 // contraction): bit-identical to the torch expression of the reference.
-#include "common.cuh"
+#include "peer.cuh"
 
 #include <string.h>
 
@@ -144,6 +144,37 @@ __device__ __forceinline__ void pd_commit_stats(const PdAcc& a, double* stats, i
   if (lane < 5 && val != 0.0) atomicAdd(stats + slot, val);
 }
 
+// ---------------------------------------------------------------- statistics published from the control kernel itself
+// north_star: "all-reduce the per-step episode statistics".  Exchanged EVERY step, a separate all-reduce kernel costs one
+// more dependent launch per step (37.4 vs 32.8 us per 1M-env step on 8 GPUs), and publishing from the control kernel's
+// LAST CTA (ticket + fences + the NVLink stores at the very end of the kernel, where nothing overlaps them) measured
+// worse still (38.5 us).  So the exchange rides at the FRONT of the next step instead: the grid gets one extra CTA that
+// does no element work -- the publisher.  The statistics of step s are complete when kernel s + 1 starts (kernel
+// boundary: no ticket, no fence), so the publisher of kernel s + 1 reads step s's accumulator, clears it, stores the vector
+// into every rank's mailbox over NVLink and sums the rows of step s - 1 (which arrived a step ago: it never waits for a
+// peer) into `reduced`, all while the other CTAs of kernel s + 1 stream their elements.  The caller alternates two
+// accumulators (`stats` = this step's, `stats_prev` = the previous step's); the window counter lives in the mailbox.
+struct PdPublish {
+  PeerTable peers;
+  int rank, world;            // world == 0: not published
+  double* prev;               // the previous step's accumulator: published and cleared by this launch
+  double* reduced;            // device double[8]: the global sum of the step before that
+  long long deadline_ns;
+};
+__device__ __forceinline__ void pd_publisher_cta(const PdPublish& pub) {
+  Mailbox* mine = pub.peers.box[pub.rank];
+  const int t = threadIdx.x;
+  double v = 0.0;
+  if (t < B200CTL_STATS_LEN) {
+    v = __ldcg(pub.prev + t);
+    pub.prev[t] = 0.0;
+  }
+  const unsigned long long window = mine->step;
+  __syncthreads();
+  if (t == 0) mine->step = window + 1;
+  peer_publish_consume(pub.peers, pub.rank, pub.world, window, /*lagged=*/1, B200CTL_STATS_LEN, v, pub.reduced, pub.deadline_ns);
+}
+
 // ---------------------------------------------------------------- fast path
 // Compact tensors, 16-byte aligned bases, D % 4 == 0.  `nvec` = N*D/4.
 // CTA shape: 256 threads; 6 resident CTAs per SM (40 registers) without statistics.  The statistics variant keeps
@@ -170,12 +201,19 @@ template <bool WRAP, bool CLAMP_TGT, bool HAS_QD, bool HAS_TMAX, bool STATS, boo
 __global__ void __launch_bounds__(pd_block(STATS), pd_ctas(STATS))
 pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict__ q_tgt,
                       const float4* __restrict__ qd_tgt, PdParams pp, int num_dofs, int64_t nvec, int64_t num_envs,
-                      float4* __restrict__ tau_out, double* __restrict__ stats) {
+                      float4* __restrict__ tau_out, double* stats, PdPublish pub) {
   extern __shared__ __align__(16) float s_par[];   // [5][D]: kp, kd, tmax, lo, hi
   // 32-bit vector indices (the host routes nvec >= 2^31 to the strided kernel): one IMAD.WIDE per address instead of a
   // 64-bit multiply-add chain
   typedef B200_PD_INDEX_T idx_t;
-  const idx_t stride = (idx_t)(gridDim.x * blockDim.x);
+  // with published statistics the LAST CTA of the grid is the publisher (pd_publisher_cta) and takes no elements
+  const unsigned nwork = (STATS && pub.world > 0) ? gridDim.x - 1 : gridDim.x;
+  if (STATS && pub.world > 0 && blockIdx.x == nwork) {
+    pdl_prologue();
+    pd_publisher_cta(pub);
+    return;
+  }
+  const idx_t stride = (idx_t)(nwork * blockDim.x);
   const idx_t v0 = (idx_t)(blockIdx.x * blockDim.x + threadIdx.x);
 #ifndef B200_NO_PREWAIT_PF
   // the first iteration's lines, requested while the previous kernel drains (common.cuh: prefetch_l2).  Small launches
@@ -316,6 +354,7 @@ struct PdLaunch {
   double* stats;
   int dev;
   cudaStream_t stream;
+  PdPublish pub;
 };
 
 // Grid = (resident CTAs per SM for THIS instantiation) x (SM count), never more than the work:
@@ -339,9 +378,13 @@ static void pd_launch_one(const PdLaunch& L) {
     // One wave of CTAs with statistics (one commit per CTA: 2 / 4 waves cost +0.7 / +1.4 us per 1M envs); four
     // without -- same speed, and a co-resident kernel of another stream then costs its share of the SM slots instead
     // of pushing a straggler wave behind a one-wave grid.
-    const int grid = pd_grid(kern, smem, L.dev, L.num_envs * L.num_dofs / 4, block, STATS ? 1 : 4);
+    int grid = pd_grid(kern, smem, L.dev, L.num_envs * L.num_dofs / 4, block, STATS ? 1 : 4);
+    if (STATS && L.pub.world > 0) {      // one slot of the persistent grid goes to the publisher CTA
+      const int slots = usable_slots(L.dev, pd_ctas(true));
+      grid = (grid >= slots && grid > 1 ? slots - 1 : grid) + 1;
+    }
     launch_pdl(kern, grid, block, smem, L.stream, L.state4, L.tgt4, L.qd4, L.pp, L.num_dofs,
-               L.num_envs * L.num_dofs / 4, L.num_envs, L.out4, L.stats);
+               L.num_envs * L.num_dofs / 4, L.num_envs, L.out4, L.stats, L.pub);
   } else {
     auto kern = pd_torque_strided_kernel<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX, STATS>;
     const int grid = pd_grid(kern, 0, L.dev, L.num_envs * L.num_dofs, 256, STATS ? 1 : 4);
@@ -402,10 +445,10 @@ static int pd_vector_param(const DLTensor* t, const char* name, int num_dofs, in
 
 using namespace b200ctl;
 
-extern "C" int b200ctl_pd_torque(const DLTensor* dof_state, const DLTensor* q_target, const DLTensor* qd_target,
-                                 const DLTensor* kp, const DLTensor* kd, const DLTensor* tau_max,
-                                 const DLTensor* q_lo, const DLTensor* q_hi, int flags,
-                                 DLTensor* tau_out, double* stats, b200ctl_stream_t stream) {
+static int pd_torque_impl(const DLTensor* dof_state, const DLTensor* q_target, const DLTensor* qd_target,
+                          const DLTensor* kp, const DLTensor* kd, const DLTensor* tau_max,
+                          const DLTensor* q_lo, const DLTensor* q_hi, int flags,
+                          DLTensor* tau_out, double* stats, const PdPublish* pub, b200ctl_stream_t stream) {
   int dev = -1;
   PdLaunch L{};
   B200_TRY(view_of(q_target, "q_target", M_F32, 2, 2, &dev, &L.tgt));
@@ -466,10 +509,45 @@ extern "C" int b200ctl_pd_torque(const DLTensor* dof_state, const DLTensor* q_ta
   L.out4 = reinterpret_cast<float4*>(const_cast<void*>(L.out.p));
   L.dev = dev;
 
+  if (pub) {
+    if (!stats) B200_FAIL(B200CTL_E_NULL, "published statistics need a stats vector");
+    if (!L.vec4) B200_FAIL(B200CTL_E_LAYOUT, "published statistics need the vector path (compact, 16-byte aligned tensors, N * D % 4 == 0)");
+    B200_TRY(check_f64_device_ptr(pub->reduced, "reduced_out", dev));
+    B200_TRY(check_f64_device_ptr(pub->prev, "stats_prev", dev));
+    if (pub->prev == stats) B200_FAIL(B200CTL_E_ALIAS, "stats_prev must be the OTHER accumulator (the caller alternates two)");
+    L.pub = *pub;
+  }
   DeviceGuard g;
   B200_TRY(g.enter(dev));
   pd_launch(L, wrap, clamp, has_qd, tmax, stats != nullptr);
   return post_launch(L.vec4 ? "pd_torque_vec4_kernel" : "pd_torque_strided_kernel");
+}
+
+extern "C" int b200ctl_pd_torque(const DLTensor* dof_state, const DLTensor* q_target, const DLTensor* qd_target,
+                                 const DLTensor* kp, const DLTensor* kd, const DLTensor* tau_max,
+                                 const DLTensor* q_lo, const DLTensor* q_hi, int flags,
+                                 DLTensor* tau_out, double* stats, b200ctl_stream_t stream) {
+  return pd_torque_impl(dof_state, q_target, qd_target, kp, kd, tau_max, q_lo, q_hi, flags, tau_out, stats, nullptr, stream);
+}
+
+extern "C" int b200ctl_pd_torque_published(const DLTensor* dof_state, const DLTensor* q_target, const DLTensor* qd_target,
+                                           const DLTensor* kp, const DLTensor* kd, const DLTensor* tau_max,
+                                           const DLTensor* q_lo, const DLTensor* q_hi, int flags, DLTensor* tau_out,
+                                           double* stats, double* stats_prev, void* const* mailboxes, int32_t rank,
+                                           int32_t world, double* reduced_out, double timeout_s, b200ctl_stream_t stream) {
+  if (!mailboxes || !reduced_out || !stats_prev) B200_FAIL(B200CTL_E_NULL, "mailboxes / stats_prev / reduced_out is NULL");
+  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world) B200_FAIL(B200CTL_E_VALUE, "bad rank %d / world %d (max %d)", rank, world, kMaxWorld);
+  PdPublish pub{};
+  for (int p = 0; p < world; ++p) {
+    if (!mailboxes[p]) B200_FAIL(B200CTL_E_NULL, "mailbox of rank %d is NULL", p);
+    pub.peers.box[p] = static_cast<Mailbox*>(mailboxes[p]);
+  }
+  pub.rank = rank;
+  pub.world = world;
+  pub.reduced = reduced_out;
+  pub.prev = stats_prev;
+  pub.deadline_ns = (long long)((timeout_s > 0 ? timeout_s : 2.0) * 1e9);
+  return pd_torque_impl(dof_state, q_target, qd_target, kp, kd, tau_max, q_lo, q_hi, flags, tau_out, stats, &pub, stream);
 }
 
 // ---------------------------------------------------------------- host-buffer pipeline

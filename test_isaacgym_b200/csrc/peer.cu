@@ -15,33 +15,11 @@
 // i.e. after every peer published w - 1 and therefore finished reading w - 2 or older; slots w + 1 and w - 3 coincide.
 // NCCL's all-reduce of the same 64 bytes costs ~34 us per call on the control stream of this box (two stream hops and a
 // 640-thread kernel that needs an empty SM); this one costs ~3 us.
-#include "common.cuh"
+#include "peer.cuh"
 
 #include <string.h>
 
 namespace b200ctl {
-
-constexpr int kRing = 4;
-constexpr int kMaxWorld = 16;
-struct __align__(128) MailSlot {
-  double v[B200CTL_STATS_LEN];
-  unsigned long long stamp;        // window + 1 once v[] is complete (0 = never written)
-  unsigned long long pad[7];
-};
-struct Mailbox {
-  MailSlot slot[kRing][kMaxWorld];
-  unsigned long long timeouts;     // consume deadlines missed (the sum then holds NaN): a peer died or never published
-};
-struct PeerTable { Mailbox* box[kMaxWorld]; };
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 
 __global__ void __launch_bounds__(64)
 stats_allreduce_peer_kernel(PeerTable peers, int rank, int world, unsigned long long window, int lagged, int count,
@@ -52,49 +30,14 @@ stats_allreduce_peer_kernel(PeerTable peers, int rank, int world, unsigned long 
   // the accumulator of the NEXT window is cleared here, so that the step loop needs no separate fill kernel (an
   // ordinary launch that would break the chain of programmatically dependent launches)
   if (zero_after && t < B200CTL_STATS_LEN) zero_after[t] = 0.0;
-  const int ring = (int)(window % kRing);
-  // ---- publish this rank's partial sums of `window` to every rank (its own mailbox included)
+  double v = 0.0;
   if (t < count) {
-    const double v = stats[t];
+    v = stats[t];
     // out-of-place form: the source accumulator is complete (its kernels finished), so it can be recycled right here
     // -- the step loop then alternates two accumulators while this kernel runs NEXT to the following step
     if (clear_source) stats[t] = 0.0;
-    for (int p = 0; p < world; ++p) peers.box[p]->slot[ring][rank].v[t] = v;
-    __threadfence_system();
   }
-  __syncthreads();
-  if (t < world) st_release_sys(&peers.box[t]->slot[ring][rank].stamp, window + 1);
-  // ---- consume
-  if (lagged && window == 0) {      // nothing older to consume yet: the reduced vector of "window -1" is zero
-    if (t < count) out[t] = 0.0;
-    return;
-  }
-  const unsigned long long cw = lagged ? window - 1 : window;
-  const int cring = (int)(cw % kRing);
-  Mailbox* mine = peers.box[rank];
-  __shared__ int s_ok;
-  if (t == 0) s_ok = 1;
-  __syncthreads();
-  if (t < world) {
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (ld_acquire_sys(&mine->slot[cring][t].stamp) != cw + 1) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if ((long long)(now - t0) > deadline_ns) {      // never hang the GPU on a dead peer
-        s_ok = 0;
-        atomicAdd(&mine->timeouts, 1ull);
-        break;
-      }
-      __nanosleep(64);
-    }
-  }
-  __syncthreads();
-  if (t < count) {
-    double s = 0.0;
-    for (int p = 0; p < world; ++p) s += *reinterpret_cast<volatile double*>(&mine->slot[cring][p].v[t]);
-    out[t] = s_ok ? s : __longlong_as_double(0x7ff8000000000000ll);
-  }
+  peer_publish_consume(peers, rank, world, window, lagged, count, v, out, deadline_ns);
 }
 
 }  // namespace b200ctl

@@ -126,11 +126,26 @@ class PDController:
             raise ValueError("clamp_target needs q_lo and q_hi")
 
     def bind(self, dof_state: torch.Tensor, q_target: torch.Tensor, out: torch.Tensor, qd_target=None,
-             stats: torch.Tensor | None = None) -> "_lib.BoundCall":
+             stats: torch.Tensor | None = None, publish=None, reduced: torch.Tensor | None = None,
+             stats_prev: torch.Tensor | None = None) -> "_lib.BoundCall":
         """Marshal the call once for tensors that persist across steps (the gym-wrapped tensors do);
-        the returned object is a zero-argument callable costing one foreign call per step."""
+        the returned object is a zero-argument callable costing one foreign call per step.
+
+        ``publish`` (a ``sharding.PeerStatsReducer``) + ``stats_prev`` + ``reduced`` (device float64[8] each): the
+        statistics are exchanged EVERY step inside the control kernel (``b200ctl_pd_torque_published``).  Alternate two
+        accumulators between consecutive steps (bind one call per parity): ``stats`` takes this step's sums, ``stats_prev``
+        (the previous step's) is published to all ranks over NVLink and cleared by one extra CTA of this launch, and
+        ``reduced`` receives the global sum of the step before."""
         a = [_lib.dl(t) for t in (dof_state, q_target, qd_target, self.kp, self.kd, self.tau_max, self.q_lo,
                                   self.q_hi, out)]
+        if publish is not None:
+            if stats is None or reduced is None or stats_prev is None:
+                raise ValueError("publish needs stats=, stats_prev= and reduced=")
+            args = [a[0][0], a[1][0], a[2][0], a[3][0], a[4][0], a[5][0], a[6][0], a[7][0], int(self.flags), a[8][0],
+                    _lib.stats_arg(stats, dof_state.device), _lib.stats_arg(stats_prev, dof_state.device), publish._boxes,
+                    publish.rank, publish.world, _lib.stats_arg(reduced, dof_state.device), publish.timeout_s, None]
+            return _lib.BoundCall(_lib.lib().b200ctl_pd_torque_published, args, 17, dof_state.device,
+                                  (a, stats, stats_prev, reduced, publish), out)
         args = [a[0][0], a[1][0], a[2][0], a[3][0], a[4][0], a[5][0], a[6][0], a[7][0], int(self.flags), a[8][0],
                 _lib.stats_arg(stats, dof_state.device), None]
         return _lib.BoundCall(_lib.lib().b200ctl_pd_torque, args, 11, dof_state.device, (a, stats), out)

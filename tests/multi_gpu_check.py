@@ -72,9 +72,39 @@ def main():
         assert st[0].item() == n * w, ("peer-lagged", w, st)          # the previous window's sum (zeros at w = 0)
     assert lag.timeouts() == 0
     lag.close()
+    # (d) statistics exchanged inside the PD kernel (b200ctl_pd_torque_published, publisher CTA): two alternating
+    #     accumulators; after step s, `reduced` holds the global sum of step s - 2; also through a CUDA graph (the window
+    #     counter lives in the mailbox, so replays stay in step)
+    from test_isaacgym_b200.graph import StepGraph
+    pub = PeerStatsReducer(dev, lagged=True)
+    acc, reduced = [_lib.stats_buffer(dev), _lib.stats_buffer(dev)], _lib.stats_buffer(dev)
+    st_in, tg_in = slice_rows(full.dof_state, d, lo, hi).to(dev), full.q_target[lo:hi].to(dev)
+    n_loc = hi - lo                                # D = 12: N * D % 4 == 0, the vector path the published form needs
+    out_p = torch.empty(n_loc, d, device=dev)
+    calls = [ctl.bind(st_in, tg_in, out_p, stats=acc[k], stats_prev=acc[k ^ 1], publish=pub, reduced=reduced) for k in (0, 1)]
+    n_glob = torch.tensor([n_loc], device=dev, dtype=torch.float64)
+    dist.all_reduce(n_glob)
+    for s_ in range(9):
+        calls[s_ & 1]()
+        torch.cuda.synchronize(dev)
+        assert acc[s_ & 1][0].item() == n_loc, "this step's accumulator holds this step"
+        assert acc[(s_ & 1) ^ 1].abs().sum().item() == 0.0, "the publisher CTA must clear the previous step's accumulator"
+        # step s publishes step s - 1 and yields the global sum of step s - 2
+        assert reduced[0].item() == (0 if s_ < 2 else n_glob.item()), ("published", s_, reduced)
+    assert torch.equal(out_p, whole[lo:hi])
+    g = StepGraph([calls[1], calls[0]], dev, warmup=0)          # step 9 is odd: the alternation continues inside the graph
+    for _ in range(5):
+        g()
+    torch.cuda.synchronize(dev)
+    assert reduced[0].item() == n_glob.item() and pub.timeouts() == 0
+    assert torch.allclose(reduced[1:3], st_full[1:3], rtol=1e-12) and reduced[3].item() == st_full[3].item()
+    ref = reduced.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(ref, reduced), "ranks disagree on the published sum"
+    pub.close()
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU check OK on {world} GPUs: slices bit-exact, stats all-reduce (torch NCCL, C-ABI NCCL, b200ctl peer-memory kernel incl. lagged form) exact")
+        print(f"multi-GPU check OK on {world} GPUs: slices bit-exact, stats all-reduce (torch NCCL, C-ABI NCCL, b200ctl peer-memory kernel incl. lagged form, statistics published by the PD kernel) exact")
     dist.destroy_process_group()
 
 
