@@ -187,6 +187,63 @@ class PdWorkload:
         self.window.step_done()
 
 
+class StepLoop:
+    """The headline loop.  `sets` consecutive PD steps (one per rotating buffer set) are captured ONCE as a CUDA graph
+    (`StepGraph`, the way the rollout harness issues its control steps) and replayed; steps that do not fill a whole
+    block are issued as single bound calls.  The statistics window logic (buffer swap, all-reduce every k steps) stays
+    outside the graph on the same stream.  Measured on one B200 (profiles/r02_k20_probe.txt): a 20-step timed region
+    reads 33.9-34.1 us/step issued call by call (the first launch after the synchronize arrives ~10 us late), 33.4 at
+    400 steps, and 33.0-33.3 as graph replays (kernel-to-kernel edges inside a graph are tighter than stream launches)."""
+
+    def __init__(self, device, wl, fused=None, use_graph=True):
+        from test_isaacgym_b200.graph import StepGraph
+        self.wl, self.fused, self.sets = wl, fused, wl.sets
+        self.pos = 0            # steps issued so far; pos % sets is the buffer set of the next step
+        self.replays = 0
+        for _ in range(self.sets):      # every entry point has run once before capture (module load)
+            self._single()
+        # one graph per rotation offset r (steps over sets r, r+1, ... mod sets), so that a timed region can start anywhere
+        self.graphs = None
+        rot = [[(r + j) % self.sets for j in range(self.sets)] for r in range(self.sets)]
+        if use_graph and fused is not None:        # accumulator parity = set parity (sets is even): any rotation alternates
+            self.graphs = [[StepGraph([fused[k] for k in ks], device, warmup=0)] for ks in rot]
+        elif use_graph and (wl.window.reducer is None or wl.window.every >= self.sets):
+            self.graphs = [[StepGraph([wl.calls[k][b] for k in ks], device, warmup=0) for b in (0, 1)] for ks in rot]
+
+    def _single(self):
+        if self.fused is not None:
+            self.fused[self.pos % self.sets]()
+        else:
+            self.wl.step(self.pos)
+        self.pos += 1
+
+    def _block_fits(self):
+        """A replayed block must not straddle a statistics exchange (the all-reduce is issued between two steps).  With no
+        reducer (N = 1) nothing is exchanged: the local accumulator swap simply happens after the block."""
+        if self.fused is not None or self.wl.window.reducer is None:
+            return True
+        w = self.wl.window
+        return w.every - (w._steps % w.every) >= self.sets
+
+    def run(self, k):
+        done = 0
+        while done < k:
+            if self.graphs is not None and k - done >= self.sets and self._block_fits():
+                r = self.pos % self.sets
+                if self.fused is not None:
+                    self.graphs[r][0]()
+                else:
+                    self.graphs[r][self.wl.window.cur]()
+                    for _ in range(self.sets):
+                        self.wl.window.step_done()
+                self.replays += 1
+                self.pos += self.sets
+                done += self.sets
+            else:
+                self._single()
+                done += 1
+
+
 # ------------------------------------------------------------------------------------------ families (rank 0, N=1)
 def graph_time(calls, device, reps, warm=3, runs=5, warm_ms=30.0, stat="min"):
     """Capture `calls` (bound C-ABI calls, one kernel each) into one CUDA graph (`StepGraph`) and time `reps`
@@ -686,8 +743,7 @@ def run_b200(args):
     if world > 1 and args.stats_overlap and args.stats_collective == "nccl":
         _lib.reserve_cta_slots(device, args.reserve_slots)
     wl.bind(StatsWindow(device, reducer, max(1, args.stats_every), overlap=args.stats_overlap))
-    step = wl.step
-    fused_pub = None
+    fused_pub, fused = None, None
     if in_kernel:
         # the headline at N > 1: north_star's "all-reduce the per-step episode statistics" taken literally -- EVERY step,
         # inside the control kernel: one extra CTA of each launch (the publisher) clears the previous step's accumulator,
@@ -698,7 +754,7 @@ def run_b200(args):
         assert wl.sets % 2 == 0          # consecutive steps alternate the two accumulators
         fused = [wl.ctl.bind(wl.state[k], wl.tgt[k], wl.out[k], stats=acc2[k & 1], stats_prev=acc2[(k & 1) ^ 1],
                              publish=fused_pub, reduced=reduced2) for k in range(wl.sets)]
-        step = lambda i=0: fused[i % wl.sets]()      # noqa: E731
+    loop = StepLoop(device, wl, fused=fused if in_kernel else None, use_graph=not args.no_graph)
 
     with ClockSampler(local_rank) as clocks:
         # sustained warm-up so the clock samples describe the loaded state of this very kernel
@@ -706,31 +762,27 @@ def run_b200(args):
         # whose clocks disagree on when the warm-up ends would enqueue different numbers of collectives and deadlock;
         # the continue / stop decision is therefore itself reduced over the ranks)
         t_end = time.perf_counter() + args.sustain_s
-        it = 0
         while True:
             go = torch.tensor([1 if time.perf_counter() < t_end else 0], device=device, dtype=torch.int32)
             if world > 1:
                 dist.all_reduce(go, op=dist.ReduceOp.MIN)
             if int(go.item()) == 0:
                 break
-            for _ in range(208):          # a multiple of the statistics window: every rank ends on a window boundary
-                step(it)
-                it += 1
+            loop.run(208)                 # a multiple of the statistics window: every rank ends on a window boundary
             torch.cuda.synchronize(device)
-        for i in range(args.warmup):
-            step(i)
+        loop.run(args.warmup)
         torch.cuda.synchronize(device)
         if world > 1:
             dist.barrier()
-        launches0 = _lib.launch_count()
+        launches0, replays0 = _lib.launch_count(), loop.replays
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(device)
         start.record()
-        for i in range(args.steps):
-            step(i)
+        loop.run(args.steps)
         end.record()
         torch.cuda.synchronize(device)
-        launches = _lib.launch_count() - launches0
+        # kernels launched inside the timed region: C-ABI calls issued one by one + the kernels of the replayed graphs
+        launches = _lib.launch_count() - launches0 + (loop.replays - replays0) * wl.sets
         wl.window.finish()
         stats_check = None
         if in_kernel:      # the exchanged vector of a full step: every rank must read the global env count
@@ -763,16 +815,14 @@ def run_b200(args):
         ms_per_step = ms_total / args.steps
         per_step_stats = None
         if world > 1 and not args.no_strong:
-            # the other forms of the exchange on the same loop, for comparison with the headline's
-            def timed_loop(step_fn):
-                for i in range(64):
-                    step_fn(i)
+            # the other forms of the exchange on the same loop (same 4-step graph replays), for comparison with the headline's
+            def timed_loop(lp):
+                lp.run(64)
                 torch.cuda.synchronize(device)
                 dist.barrier()
                 s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s1.record()
-                for i in range(args.steps):
-                    step_fn(i)
+                lp.run(args.steps)
                 e1.record()
                 torch.cuda.synchronize(device)
                 t1 = torch.tensor([s1.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -783,16 +833,15 @@ def run_b200(args):
             for name, every, lagged in (("peer_kernel_side_stream_every_16", 16, False), ("peer_kernel_side_stream_lagged_every_1", 1, True)):
                 red_ = PeerStatsReducer(device, lagged=lagged)
                 wl.bind(StatsWindow(device, red_, every, overlap=True))
-                forms[name] = timed_loop(wl.step)
+                forms[name] = timed_loop(StepLoop(device, wl, use_graph=not args.no_graph))
                 wl.window.finish()
-            if not in_kernel:
-                pub_ = PeerStatsReducer(device, lagged=True)
-                acc1, reduced1 = [_lib.stats_buffer(device), _lib.stats_buffer(device)], _lib.stats_buffer(device)
-                fz = [wl.ctl.bind(wl.state[k], wl.tgt[k], wl.out[k], stats=acc1[k & 1], stats_prev=acc1[(k & 1) ^ 1], publish=pub_,
-                                  reduced=reduced1) for k in range(wl.sets)]
-                forms["in_kernel_publisher_cta_every_1"] = timed_loop(lambda i: fz[i % wl.sets]())
-            else:
-                forms["in_kernel_publisher_cta_every_1"] = ms_per_step * 1e3
+            pub_ = PeerStatsReducer(device, lagged=True)      # measured again here, next to the others (the headline ran minutes earlier)
+            acc1, reduced1 = [_lib.stats_buffer(device), _lib.stats_buffer(device)], _lib.stats_buffer(device)
+            fz = [wl.ctl.bind(wl.state[k], wl.tgt[k], wl.out[k], stats=acc1[k & 1], stats_prev=acc1[(k & 1) ^ 1], publish=pub_,
+                              reduced=reduced1) for k in range(wl.sets)]
+            forms["in_kernel_publisher_cta_every_1"] = timed_loop(StepLoop(device, wl, fused=fz, use_graph=not args.no_graph))
+            wl.bind(StatsWindow(device, None, 16))
+            forms["no_exchange"] = timed_loop(StepLoop(device, wl, use_graph=not args.no_graph))
             per_step_stats = {"us_per_step_by_exchange_form": forms,
                               "note": "same PD loop, 1,048,576 envs per GPU; in_kernel_publisher_cta = b200ctl_pd_torque_published "
                                       "(statistics of step s published from one extra CTA of kernel s + 1 over NVLink, global sum readable "
@@ -828,6 +877,9 @@ def run_b200(args):
                                              "from the same pinned buffers, no kernel, all ranks at once (barrier-aligned), slowest rank"},
                 "frac_of_host_link_ceiling": link_s / (e2e_s.item() / e2e_steps)},
         "gpu_launches": int(launches),
+        "step_issue": ("single bound calls (--no-graph)" if loop.graphs is None else
+                       f"CUDA graphs of {wl.sets} consecutive steps (one per buffer set), replayed: {loop.replays - replays0} replays + "
+                       f"{int(launches) - (loop.replays - replays0) * wl.sets} single launches in the timed region"),
         "clocks": clocks.summary(),
     }
     if strong is not None:
@@ -845,7 +897,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_families:
         # give the headline's 1.6 GB of buffers back first: the family entries are then laid out in device memory as
         # in a process of their own (with the buffers alive the 262,144-env OSC entry read 53.9 us instead of 50.9)
-        del step, wl, hs, ht, hout, h
+        del loop, wl, hs, ht, hout, h
         torch.cuda.empty_cache()
         line["families"] = family_numbers(device, peak)
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -900,6 +952,7 @@ def main():
                          "all-reduce kernel over NVLink peer memory every --stats-every steps, its lagged form, or NCCL")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (N > 1)")
     ap.add_argument("--sustain-s", type=float, default=1.0, help="seconds of pre-load before the timed region (clock sampling)")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step as a single bound call instead of replaying 4-step CUDA graphs")
     ap.add_argument("--no-families", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

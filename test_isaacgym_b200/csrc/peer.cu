@@ -3,11 +3,12 @@
 // Every rank (one process per GPU of one NVSwitch box) owns a MAILBOX in its device memory and maps every peer's
 // mailbox through CUDA IPC.  One tiny kernel per window, launched IN ORDER on the control stream (programmatic dependent
 // launch like every other kernel of the library: no stream hop, no second process-group stream):
-//   1. publish   lane j of the CTA stores entry j of this rank's partial statistics vector into slot [window % 4][rank]
-//                of EVERY rank's mailbox (plain stores over NVLink, then a system-scope release store of the stamp);
-//   2. consume   it waits (acquire loads, with a deadline) until all `world` stamps of the window it consumes have
-//                arrived in ITS OWN mailbox and sums the rows in rank order -- the same order on every rank, so all
-//                ranks hold bit-identical sums.
+//   1. publish   the rank's partial statistics vector goes into row [window % 4][rank] of EVERY rank's mailbox as sixteen
+//                self-validating 64-bit words (32 bits of payload + the 32-bit window tag, peer.cuh): relaxed stores over
+//                NVLink, no fence, no separate flag;
+//   2. consume   it polls (with a deadline) the `world` rows of the window it consumes in ITS OWN mailbox until every
+//                word carries that window's tag, and sums the rows in rank order -- the same order on every rank, so
+//                all ranks hold bit-identical sums.
 // `lagged` = 0 consumes the window it just published (a classic all-reduce: one NVLink round trip on the critical
 // path); `lagged` = 1 consumes the PREVIOUS window, whose rows arrived a whole window ago -- the collective then never
 // waits for a peer and its cost is the launch alone, which is what a per-step statistics exchange needs.
