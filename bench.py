@@ -15,7 +15,11 @@ one publisher CTA per launch stores the previous step's vector into every rank's
 NVLink peer memory and sums the rows of the step before).  Other forms: the library's stand-alone
 all-reduce kernel (peer / peer-lagged, every --stats-every steps) or NCCL (nccl).  N > 1 lines
 also carry `strong` (1,048,576 envs IN TOTAL split over the N GPUs) and `per_step_stats` (the same
-loop under the other exchange forms).
+loop under the other exchange forms, measured side by side in this process).  The loop is issued the
+way the rollout harness issues control steps: 4 consecutive steps (one per rotating buffer set)
+captured once as a CUDA graph and replayed (`step_issue`; --no-graph issues single bound calls).
+If the peer mailboxes cannot be mapped (no peer access) every rank falls back to NCCL in order and
+the line says so (`stats_collective_note`).
 
 Printed keys beyond the base contract:
   roofline      dominant kernel vs measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes
@@ -734,11 +738,17 @@ def run_b200(args):
     lo, hi = env_slice(total_envs, rank, world)
     wl = PdWorkload(device, hi - lo, seed=1000 + rank)
     from test_isaacgym_b200.sharding import PeerStatsReducer
-    in_kernel = world > 1 and args.stats_collective == "fused"
+    collective_note = None
+    reducer = None
     if world > 1 and args.stats_collective != "nccl":
-        reducer = PeerStatsReducer(device, lagged=args.stats_collective == "peer-lagged")
-    else:
-        reducer = StatsReducer("torch", device) if world > 1 else None
+        try:
+            reducer = PeerStatsReducer(device, lagged=args.stats_collective == "peer-lagged")
+        except _lib.B200CtlError as e:      # raised on every rank together: no peer access on this box -> NCCL, in order
+            collective_note = f"--stats-collective {args.stats_collective} unavailable ({e}); fell back to NCCL in order"
+            args.stats_collective, args.stats_overlap = "nccl", False
+    if world > 1 and reducer is None:
+        reducer = StatsReducer("torch", device)
+    in_kernel = world > 1 and args.stats_collective == "fused"
     stats_every = 1 if in_kernel else max(1, args.stats_every)
     if world > 1 and args.stats_overlap and args.stats_collective == "nccl":
         _lib.reserve_cta_slots(device, args.reserve_slots)
@@ -814,7 +824,7 @@ def run_b200(args):
 
         ms_per_step = ms_total / args.steps
         per_step_stats = None
-        if world > 1 and not args.no_strong:
+        if world > 1 and not args.no_strong and collective_note is None:
             # the other forms of the exchange on the same loop (same 4-step graph replays), for comparison with the headline's
             def timed_loop(lp):
                 lp.run(64)
@@ -888,6 +898,8 @@ def run_b200(args):
         line["per_step_stats"] = per_step_stats
     if stats_check is not None:
         line["stats_check"] = stats_check
+    if collective_note is not None:
+        line["stats_collective_note"] = collective_note
     traffic_file = os.path.join(ROOT, "profiles", "pd_traffic.json")
     if os.path.isfile(traffic_file):
         try:

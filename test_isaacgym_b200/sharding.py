@@ -2,10 +2,16 @@
 
 Environments are independent: GPU ``g`` of ``G`` owns envs
 ``[g*N/G, (g+1)*N/G)`` and the control step moves no bytes between GPUs.  The
-only collective is a sum all-reduce of the ``float64[8]`` statistics vector the
-kernels accumulate, every k steps (``StatsWindow``): in order on the control stream by
-default, or on a side stream next to the control kernels (``overlap=True`` together with
-``configure_nccl_for_control_loops`` and one reserved CTA slot).
+only exchange is a sum all-reduce of the ``float64[8]`` statistics vector the
+kernels accumulate.  Three carriers, fastest first:
+
+* inside the control kernel itself, every step (``PDController.bind(..., publish=PeerStatsReducer(...))`` ->
+  ``b200ctl_pd_torque_published``): one extra CTA of each launch publishes the previous step's vector over NVLink
+  peer memory and sums the rows of the step before;
+* the library's stand-alone peer-memory kernel (``PeerStatsReducer.all_reduce``) every k steps (``StatsWindow``),
+  in order on the control stream or on a side stream next to the control kernels (``overlap=True``);
+* NCCL (``StatsReducer``), in order on the control stream (its 640-thread CTA does not fit next to persistent grids;
+  ``configure_nccl_for_control_loops`` + one reserved CTA slot is the side-stream form, measured slower).
 """
 from __future__ import annotations
 
@@ -175,15 +181,26 @@ class PeerStatsReducer:
         else:
             handles = [bytes(mine.tolist())]
         self._boxes = (ctypes.c_void_p * self.world)()
+        failure = None
         for r in range(self.world):
             if r == self.rank:
                 self._boxes[r] = self._mine.value
             else:
                 peer = ctypes.c_void_p()
-                _lib.check(L.b200ctl_peer_mailbox_open(device.index or 0, handles[r], ctypes.byref(peer)))
+                try:
+                    _lib.check(L.b200ctl_peer_mailbox_open(device.index or 0, handles[r], ctypes.byref(peer)))
+                except _lib.B200CtlError as e:      # no peer access to rank r (no NVLink / IPC closed in this container)
+                    failure = failure or e
                 self._boxes[r] = peer.value
         if self.world > 1:
-            dist.barrier()          # every mailbox is mapped everywhere before the first publish
+            # every mailbox is mapped everywhere before the first publish; the same collective carries the verdict, so
+            # that a rank that could not map a peer does not leave the others waiting: all ranks raise together
+            ok = torch.tensor([0 if failure else 1], dtype=torch.int32, device=device if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                raise _lib.B200CtlError(-2, f"peer mailboxes could not be mapped on every rank ({failure or 'another rank failed'})")
+        elif failure:
+            raise failure
 
     def all_reduce(self, stats: torch.Tensor, overlap: bool = False, zero_after: torch.Tensor | None = None,
                    out: torch.Tensor | None = None):
