@@ -1073,7 +1073,7 @@ static inline int tiles(int64_t n, int tile) { return (int)((n + tile - 1) / til
 static int pick_tile(int64_t n, int dev) {
   (void)n; (void)dev;
   static const int forced = [] { const char* e = getenv("B200CTL_TILE_ENVS"); return e ? atoi(e) : 0; }();
-  return forced == kMaxTileEnvs ? kMaxTileEnvs : kTileEnvs;
+  return (forced == kMaxTileEnvs || forced == 32) ? forced : kTileEnvs;
 }
 
 static int check_precision(int precision) {
