@@ -86,7 +86,11 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   const int ntiles = (int)((num_envs + TILE - 1) / TILE);
   constexpr unsigned kBytes = TILE * kEnvRow * sizeof(float);
   unsigned phases = 0;               // bit b: phase parity of bars[b]
-  double acc_d[2] = {0, 0};          // sum |pixel error|, sum error^2
+  // sum |pixel error|, sum error^2: per-THREAD partial sums in fp32 (a thread adds one value per tile it walks, a handful
+  // in all; the cross-thread reduction of the commit is fp64), and the norm itself is an fp32 square root of the fp64 sum
+  // of squares -- the reference-precision kernel is issue bound on its fp64 stages, and libdevice's fp64 sqrt plus the
+  // fp64 accumulation cost 2.9 us per 1M envs for a diagnostic that is exchanged as an 8-entry vector
+  float acc_f[2] = {0.f, 0.f};
   unsigned acc_u[3] = {0, 0, 0};     // envs, envs with the target behind the camera, non-finite attitudes
   auto full_tile = [&](int t) { return vec_ok && (num_envs - (int64_t)t * TILE) >= TILE; };
   auto fetch = [&](int t, int b) {   // thread 0: one bulk copy of tile t into buffer b
@@ -174,7 +178,8 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
     if (do_attitude) {
     const float qx = row[3], qy = row[4], qz = row[5], qw = row[6];
     float oq[4];
-    double pu, pv, rolld = 0, pitchd = 0, yawd = 0, err = 0;   // err = |order_pixel_move| (test10:432), statistics only
+    double pu, pv, rolld = 0, pitchd = 0, yawd = 0;
+    float err2 = 0.f;                                          // |order_pixel_move|^2 (test10:432), statistics only
     bool behind;
     if (PREC == 0) {
       double R[9];
@@ -198,7 +203,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
         constexpr double kPi = 3.141592653589793238462643383279502884;
         rolld = ang[0] * 180.0 / kPi; pitchd = ang[1] * 180.0 / kPi; yawd = ang[2] * 180.0 / kPi;   // :196
       }
-      if (STATS) err = sqrt(mvx * mvx + mvy * mvy);
+      if (STATS) err2 = (float)fma(mvx, mvx, mvy * mvy);
     } else {
       float R[9];
       quat_to_mat<float>(qx, qy, qz, qw, R);
@@ -217,7 +222,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       oq[0] = q[0]; oq[1] = q[1]; oq[2] = q[2]; oq[3] = q[3];
       if (aux) { rolld = ang[0] * 57.29577951308232f; pitchd = ang[1] * 57.29577951308232f; yawd = ang[2] * 57.29577951308232f; }
       const float ex = (float)(k.width * 0.5) - fu, ey = (float)(k.height * 0.5) - fv;
-      if (STATS) err = sqrtf(ex * ex + ey * ey);
+      if (STATS) err2 = fmaf(ex, ex, ey * ey);
     }
 
     // ---- scatter into the staged row (test10:451)
@@ -228,10 +233,11 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       a[0] = pu; a[1] = pv; a[2] = rolld; a[3] = pitchd; a[4] = yawd;
     }
     if (STATS) {
-      const bool finite = isfinite(oq[0]) && isfinite(oq[1]) && isfinite(oq[2]) && isfinite(oq[3]);
-      if (!isfinite(err)) err = 0.0;
-      acc_d[0] += err;
-      acc_d[1] = fma(err, err, acc_d[1]);
+      // a unit quaternion's components cannot overflow their sum: the sum is finite iff all four are
+      const bool finite = isfinite((oq[0] + oq[1]) + (oq[2] + oq[3]));
+      if (!isfinite(err2)) err2 = 0.f;
+      acc_f[0] += sqrtf(err2);
+      acc_f[1] += err2;
       acc_u[0] += 1u;
       acc_u[1] += behind ? 1u : 0u;
       acc_u[2] += finite ? 0u : 1u;
@@ -263,6 +269,7 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   if (STATS) {
     const int slots[5] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_SAT,
                           B200CTL_STAT_N_NONFINITE};
+    double acc_d[2] = {(double)acc_f[0], (double)acc_f[1]};
     block_stats_commit<2, 3>(acc_d, acc_u, stats, slots);      // (uses its own shared arrays, not the tile buffers)
   }
   if (NBUF == 2 && threadIdx.x == 0) bulk_wait_read();   // shared memory outlives the last write-back's read
