@@ -75,47 +75,64 @@ template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 
-template <typename T> __device__ __forceinline__ T rsqrt_t(T d);
-template <> __device__ __forceinline__ float rsqrt_t<float>(float d) {
-  const float r = rsqrtf(d);
-  return r * fmaf(-0.5f * d * r, r, 1.5f);   // one Newton step: full fp32 accuracy
-}
-// fp64 reciprocal square root of the Cholesky pivots.  Thirteen of them sit on the serial critical path of every env
-// (7 + 6 pivots), so their LATENCY counts, not their throughput: libdevice's rsqrt (special-case code, ~1 ulp) ->
-// MUFU.RSQ64H seed + two Newton steps (2 ulp, profiles/experiments/rsqrt_ulp.cu) took the fp64-chain OSC from
-// 55.5 to 51.0 us per 262,144 envs and from 7.20 to 6.69 us at 16,384.  Pivots of an SPD matrix are positive normal
-// numbers; a non-positive pivot (not SPD) gives NaN either way.
+// Reciprocal square root of a Cholesky pivot.  fp32: MUFU seed + one Newton step (full fp32 accuracy).
+// fp64: thirteen pivots sit on the serial critical path of every env (7 + 6), so their LATENCY counts, not their
+// throughput: libdevice's rsqrt (special-case code, ~1 ulp) -> MUFU.RSQ64H seed + two Newton steps (2 ulp,
+// profiles/experiments/rsqrt_ulp.cu) took the fp64-chain OSC from 55.5 to 51.0 us per 262,144 envs and from 7.20 to
+// 6.69 us at 16,384.  Pivots of an SPD matrix are positive normal numbers; a non-positive pivot (not SPD) gives NaN
+// either way.  V selects the refinement: 0 libdevice, 1 seed + two Newton steps (eight dependent operations), 2 seed + ONE
+// cubic step (four dependent operations, three more instructions), 3 seed + one Newton step (2^-43).  A launch of one wave
+// of tiles is a single latency chain and takes the short dependency chain (osc 16,384 envs 7.58 -> 7.01 us, 4,096 envs
+// 6.11 -> 5.86 us); a persistent multi-wave launch is bound by instruction issue next to its loads and keeps form 1
+// (262,144 envs: 49.3 us against 50.3 with form 2) -- profiles/r02_osc_trace.txt, session 3.
 #ifndef B200_OSC_RSQRT
-#define B200_OSC_RSQRT 1      // A/B knob (profiles/): 0 libdevice, 1 seed + two Newton steps, 2 seed + one cubic step
+#define B200_OSC_RSQRT 1      // default form of every kernel that does not choose (A/B knob, profiles/)
 #endif
-template <> __device__ __forceinline__ double rsqrt_t<double>(double d) {
-#if B200_OSC_RSQRT == 0
-  return ::rsqrt(d);
-#else
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-#if B200_OSC_RSQRT == 1
-  const double h = 0.5 * d;
-  y = fma(y, fma(-h, y * y, 0.5), y);
-  y = fma(y, fma(-h, y * y, 0.5), y);
-  return y;
-#else
-  const double e = fma(-(d * y), y, 1.0);           // e = 1 - d y^2;  1/sqrt(1 - e) = 1 + e/2 + 3 e^2 / 8 + O(e^3)
-  return fma(y * e, fma(e, 0.375, 0.5), y);
+#ifndef B200_OSC_SHORT
+#define B200_OSC_SHORT 2      // form taken by one-wave launches (A/B knob)
 #endif
-#endif
+constexpr int kRsqrtShortChain = B200_OSC_SHORT;
+template <typename T, int V = B200_OSC_RSQRT>
+__device__ __forceinline__ T rsqrt_t(T d) {
+  if constexpr (sizeof(T) == 4) {
+    const float r = rsqrtf(d);
+    return r * fmaf(-0.5f * d * r, r, 1.5f);
+  } else if constexpr (V == 0) {
+    return ::rsqrt(d);
+  } else {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    if constexpr (V == 1) {
+      const double h = 0.5 * d;
+      y = fma(y, fma(-h, y * y, 0.5), y);
+      y = fma(y, fma(-h, y * y, 0.5), y);
+      return y;
+    } else if constexpr (V == 3) {
+      const double h = 0.5 * d;
+      return fma(y, fma(-h, y * y, 0.5), y);
+    } else if constexpr (V == 4) {                      // Newton step arranged for depth: e off y^2, half of y on the side
+      const double e = fma(-d, y * y, 1.0);
+      return fma(0.5 * y, e, y);
+    } else if constexpr (V == 5) {                      // cubic step, e off y^2 (one dependent operation fewer than form 2)
+      const double e = fma(-d, y * y, 1.0);
+      return fma(y * e, fma(e, 0.375, 0.5), y);
+    } else {
+      const double e = fma(-(d * y), y, 1.0);           // e = 1 - d y^2;  1/sqrt(1 - e) = 1 + e/2 + 3 e^2 / 8 + O(e^3)
+      return fma(y * e, fma(e, 0.375, 0.5), y);
+    }
+  }
 }
 
 // In-place Cholesky of the lower triangle of an SPD matrix held in registers; returns the
 // reciprocal diagonal so the substitutions multiply instead of divide.
-template <typename T, int N>
+template <typename T, int N, int RSQ = B200_OSC_RSQRT>
 __device__ __forceinline__ void chol_inplace(T (&a)[N][N], T (&rdiag)[N]) {
 #pragma unroll
   for (int j = 0; j < N; ++j) {
     T d = a[j][j];
 #pragma unroll
     for (int k = 0; k < j; ++k) d = fma_t<T>(-a[j][k], a[j][k], d);
-    const T r = rsqrt_t<T>(d);
+    const T r = rsqrt_t<T, RSQ>(d);
     rdiag[j] = r;
     a[j][j] = d * r;
 #pragma unroll
@@ -467,10 +484,10 @@ __device__ __forceinline__ void stage_all(const StagePlan& P, const CUtensorMap*
 // Row k of Y is X[k][0..k] . J[:, 0..k]: the rows are independent of each other (six forward substitutions would be
 // a 7-step serial chain with all of Y -- 84 registers at fp64 -- live at once), and each row is folded into
 // Lambda^-1 += y y^T as soon as it exists, so Y is never stored.  Peak live set 178 registers at fp64 instead of 208.
-template <typename T, int D>
+template <typename T, int D, int RSQ = B200_OSC_RSQRT>
 __device__ __forceinline__ void task_space_factor(const float (&J)[6][D], T (&L)[D][D], T (&A)[6][6], T (&rda)[6]) {
   T rdm[D];
-  chol_inplace<T, D>(L, rdm);
+  chol_inplace<T, D, RSQ>(L, rdm);
   // X = L^-1 in place, column by column: X[j][j] = 1 / L[j][j], X[i][j] = -(sum_{k=j}^{i-1} L[i][k] X[k][j]) / L[i][i]
 #pragma unroll
   for (int j = 0; j < D; ++j) {
@@ -498,7 +515,7 @@ __device__ __forceinline__ void task_space_factor(const float (&J)[6][D], T (&L)
 #pragma unroll
       for (int c = 0; c <= r; ++c) A[r][c] = (k == 0) ? y[r] * y[c] : fma_t<T>(y[r], y[c], A[r][c]);
   }
-  chol_inplace<T, 6>(A, rda);
+  chol_inplace<T, 6, RSQ>(A, rda);
 }
 
 // DLS-IK step of env `e` (examples/franka_cube_ik_osc.py:53-59) from the staged jacobian; dp = dpose in registers.
@@ -611,11 +628,11 @@ __device__ __forceinline__ void osc_gather(const float* tile, const AJ& aJ, cons
     R.Mu0[c] = u;
   }
 }
-template <typename T>
+template <typename T, int RSQ = B200_OSC_RSQRT>
 __device__ __forceinline__ void osc_solve(OscRegs<T>& R, float (&u_out)[7]) {
   constexpr int D = 7;
   T A[6][6], rda[6];
-  task_space_factor<T, D>(R.J, R.L, A, rda);
+  task_space_factor<T, D, RSQ>(R.J, R.L, A, rda);
   chol_solve<T, 6>(A, rda, R.w);          // w <- Lambda (w - J u0)
 #pragma unroll
   for (int c = 0; c < D; ++c) {
@@ -647,7 +664,7 @@ template <> struct OscLayout<true> {
 // keeps a value computed ahead of the dependency wait from being sunk below it by the compiler
 __device__ __forceinline__ void pin(int& v) { asm volatile("" : "+r"(v)); }
 
-template <typename T, bool GYM>
+template <typename T, bool GYM, int RSQ>
 // Tried and measured slower: register caps for 5 tiles/SM (168 regs: -13 %, 200 regs: -6 %, both
 // spill); splitting one env over two warps that share Lambda^-1 through shared memory (redundant Cholesky work +
 // a CTA barrier: -70 %).
@@ -736,7 +753,7 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
 #pragma unroll
       for (int c = 0; c < D; ++c) u[c] = (float)(R.Mu0[c] + R.w[c % 6] + R.L[c][c / 2] + (T)R.J[c % 6][c]);
 #else
-      osc_solve<T>(R, u);
+      osc_solve<T, RSQ>(R, u);
 #endif
       float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + (env0 + e) * out.s[0];
       bool finite = true;
@@ -1255,12 +1272,13 @@ static int set_smem(K kernel, int bytes) {
 // Grid of a persistent tile kernel: every CTA slot of the device (occupancy x SM count), or one CTA per tile when
 // there are fewer tiles than slots.
 template <typename K>
-static int persistent_grid(K kernel, int smem, int ntiles, int tile, int* grid) {
+static int persistent_grid(K kernel, int smem, int ntiles, int tile, int* grid, int* slots_out = nullptr) {
   int dev = 0, occ = 0;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, tile, smem));
   const int slots = usable_slots(dev, occ);
   *grid = ntiles < slots ? ntiles : slots;
+  if (slots_out) *slots_out = slots;
   return 0;
 }
 
@@ -1353,12 +1371,23 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
                    P.seg[1].mode != 0 && P.seg[1].b_rs == 9 && P.seg[1].b_cs == 1 &&
                    P.seg[2].mode != 0 && P.seg[2].b_cs == 2 && P.seg[3].mode != 0 && P.seg[3].b_cs == 2 &&
                    P.seg[4].mode != 0 && P.seg[4].b_cs == 1 && !getenv("B200CTL_NO_GYM_LAYOUT");
+  // at most half a wave of tiles (two 64-env tiles per SM: every warp has a scheduler to itself and the launch is one
+  // latency chain) -> the short-chain pivot refinement.  Measured crossover: 16,384 envs 7.58 -> 6.95 us, 32,768 envs
+  // 9.74 -> 9.95 us (profiles/r02_osc_trace.txt)
+  int slots_of_grid = 0;
+  static const bool no_short_chain = getenv("B200CTL_NO_SHORT_CHAIN") != nullptr;      // A/B switch for profiles/
 #define LAUNCH_OSC(T, G)                                                                                     \
   do {                                                                                                       \
-    B200_TRY(set_smem(osc_kernel<T, G>, smem));                                                              \
-    B200_TRY(persistent_grid(osc_kernel<T, G>, smem, tiles(n, tile), tile, &grid));                                      \
-    launch_pdl(osc_kernel<T, G>, grid, tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, (float)kd, \
-               (float)kp_null, (float)kd_null, o, n, stats);                                                 \
+    B200_TRY(set_smem(osc_kernel<T, G, B200_OSC_RSQRT>, smem));                                              \
+    B200_TRY(persistent_grid(osc_kernel<T, G, B200_OSC_RSQRT>, smem, tiles(n, tile), tile, &grid, &slots_of_grid)); \
+    if (2 * tiles(n, tile) <= slots_of_grid && sizeof(T) == 8 && !no_short_chain) {                          \
+      B200_TRY(set_smem(osc_kernel<T, G, kRsqrtShortChain>, smem));                                          \
+      launch_pdl(osc_kernel<T, G, kRsqrtShortChain>, grid, tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
+                 (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                                    \
+    } else {                                                                                                 \
+      launch_pdl(osc_kernel<T, G, B200_OSC_RSQRT>, grid, tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
+                 (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                                    \
+    }                                                                                                        \
   } while (0)
   if (precision == 0) { if (gym) LAUNCH_OSC(double, true); else LAUNCH_OSC(double, false); }
   else                { if (gym) LAUNCH_OSC(float, true); else LAUNCH_OSC(float, false); }
