@@ -642,13 +642,13 @@ __device__ __forceinline__ void osc_solve(OscRegs<T>& R, float (&u_out)[7]) {
     u_out[c] = (float)u;
   }
 }
-template <typename T, typename AJ, typename AM, typename AQ, typename AQD, typename TaskSpaceTarget>
+template <typename T, int RSQ, typename AJ, typename AM, typename AQ, typename AQD, typename TaskSpaceTarget>
 __device__ __forceinline__ void osc_compute(const float* tile, const AJ& aJ, const AM& aM, const AQ& aQ,
                                             const AQD& aQD, int e, TaskSpaceTarget&& target,
                                             const float* q_default, float kp_null, float kd_null, float (&u_out)[7]) {
   OscRegs<T> R;
   osc_gather<T>(tile, aJ, aM, aQ, aQD, e, target, q_default, kp_null, kd_null, R);
-  osc_solve<T>(R, u_out);
+  osc_solve<T, RSQ>(R, u_out);
 }
 
 // ------------------------------------------------------------------ a10: control_osc
@@ -787,7 +787,7 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
 // that then solves the env's OSC system, so `dpose` never leaves registers and the step is ONE kernel.
 // segments: 0 = J (6x7), 1 = M (7x7), 2 = dof_pos (1x9: the fingers feed gripper_sep), 3 = dof_vel (1x7),
 // 4 = init_pos (1x3), 5 = init_rot (1x4); extras: box row (7) + hand row (13: pose and velocity) gathered by index.
-template <typename T>
+template <typename T, int RSQ>
 __global__ void __launch_bounds__(kMaxTileEnvs)
 pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, TView box_index, TView hand_index, uint8_t* __restrict__ hand_restart,
                 int64_t hr_stride, TaskConst tk, TView q_default, float kp, float kd, float kp_null, float kd_null,
@@ -826,7 +826,7 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
     const float* xr = x0 + e * x_ts;
     const SAddr aQ = a[2], aIp = a[4], aIq = a[5];
     float u[D];
-    osc_compute<T>(tile, a[0], a[1], a[2], a[3], e, [&](float (&w)[6]) {
+    osc_compute<T, RSQ>(tile, a[0], a[1], a[2], a[3], e, [&](float (&w)[6]) {
       float box[7], hand[7], ip[3], iq[4];
 #pragma unroll
       for (int c = 0; c < 7; ++c) { box[c] = xr[c]; hand[c] = xr[7 + c]; }
@@ -1091,6 +1091,14 @@ static int pick_tile(int64_t n, int dev) {
   (void)n; (void)dev;
   static const int forced = [] { const char* e = getenv("B200CTL_TILE_ENVS"); return e ? atoi(e) : 0; }();
   return (forced == kMaxTileEnvs || forced == 32) ? forced : kTileEnvs;
+}
+
+// Launches of at most two 64-env tiles per SM (every warp has a scheduler to itself: the launch is ONE latency chain) take the
+// short-chain refinement of the Cholesky pivots (rsqrt_t form 2).  Measured crossover for osc_kernel: 16,384 envs 7.58 -> 6.95 us,
+// 32,768 envs 9.74 -> 9.95 us (profiles/r02_osc_trace.txt).  One rule for b200ctl_osc and b200ctl_franka_pick_osc.
+static bool short_chain_launch(int64_t n, int tile, int dev) {
+  static const bool off = getenv("B200CTL_NO_SHORT_CHAIN") != nullptr;      // A/B switch for profiles/
+  return !off && tiles(n, tile) <= 2 * sm_count(dev);
 }
 
 static int check_precision(int precision) {
@@ -1371,16 +1379,11 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
                    P.seg[1].mode != 0 && P.seg[1].b_rs == 9 && P.seg[1].b_cs == 1 &&
                    P.seg[2].mode != 0 && P.seg[2].b_cs == 2 && P.seg[3].mode != 0 && P.seg[3].b_cs == 2 &&
                    P.seg[4].mode != 0 && P.seg[4].b_cs == 1 && !getenv("B200CTL_NO_GYM_LAYOUT");
-  // at most half a wave of tiles (two 64-env tiles per SM: every warp has a scheduler to itself and the launch is one
-  // latency chain) -> the short-chain pivot refinement.  Measured crossover: 16,384 envs 7.58 -> 6.95 us, 32,768 envs
-  // 9.74 -> 9.95 us (profiles/r02_osc_trace.txt)
-  int slots_of_grid = 0;
-  static const bool no_short_chain = getenv("B200CTL_NO_SHORT_CHAIN") != nullptr;      // A/B switch for profiles/
 #define LAUNCH_OSC(T, G)                                                                                     \
   do {                                                                                                       \
     B200_TRY(set_smem(osc_kernel<T, G, B200_OSC_RSQRT>, smem));                                              \
-    B200_TRY(persistent_grid(osc_kernel<T, G, B200_OSC_RSQRT>, smem, tiles(n, tile), tile, &grid, &slots_of_grid)); \
-    if (2 * tiles(n, tile) <= slots_of_grid && sizeof(T) == 8 && !no_short_chain) {                          \
+    B200_TRY(persistent_grid(osc_kernel<T, G, B200_OSC_RSQRT>, smem, tiles(n, tile), tile, &grid));          \
+    if (sizeof(T) == 8 && short_chain_launch(n, tile, dev)) {                                                \
       B200_TRY(set_smem(osc_kernel<T, G, kRsqrtShortChain>, smem));                                          \
       launch_pdl(osc_kernel<T, G, kRsqrtShortChain>, grid, tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
                  (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                                    \
@@ -1525,15 +1528,17 @@ extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm
   const TaskConst tk = make_task_const(*task);
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
-  if (precision == 0) {
-    B200_TRY(set_smem(pick_osc_kernel<double>, smem));
-    launch_pdl(pick_osc_kernel<double>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
-               (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
-  } else {
-    B200_TRY(set_smem(pick_osc_kernel<float>, smem));
-    launch_pdl(pick_osc_kernel<float>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, (float)kd,
-               (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
-  }
+  // the pivot refinement follows b200ctl_osc's rule, so the fused step stays bit-identical to task -> osc at every size
+#define LAUNCH_PICK(T, V)                                                                                              \
+  do {                                                                                                                 \
+    B200_TRY(set_smem(pick_osc_kernel<T, V>, smem));                                                                   \
+    launch_pdl(pick_osc_kernel<T, V>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, \
+               (float)kd, (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);                             \
+  } while (0)
+  if (precision != 0) LAUNCH_PICK(float, B200_OSC_RSQRT);
+  else if (short_chain_launch(n, tile, dev)) LAUNCH_PICK(double, kRsqrtShortChain);
+  else LAUNCH_PICK(double, B200_OSC_RSQRT);
+#undef LAUNCH_PICK
   return post_launch("pick_osc_kernel");
 }
 
