@@ -272,6 +272,11 @@ B200CTL_API int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* do
 B200CTL_API int b200ctl_gather_rows(const DLTensor* src, const DLTensor* index, int32_t col0, int32_t ncols,
                         DLTensor* dst, b200ctl_stream_t stream);
 
+/* Form of b200ctl_osc's fp64-chain launches: -1 (default) auto -- eight lanes per env for the smallest launches, four
+ * lanes for small ones, one thread per env (TMA-staged tiles) above; 0 never the lane form; 4 / 8 always.  The forms give
+ * bit-identical results (same operations in the same order); the choice only moves time.  Process-wide. */
+B200CTL_API int b200ctl_osc_set_lanes(int32_t lanes);
+
 /* Persistent grids (the statistics-carrying control kernels) fill every CTA slot of the device; a kernel of ANOTHER
  * stream that must run next to them -- the statistics all-reduce on its side stream -- then finds no slot until a
  * control CTA retires, and takes one from the NEXT step's grid, which spills into a second wave.  `slots` CTA slots

@@ -20,7 +20,12 @@ def main():
     ap.add_argument("--sizes", default="")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--lib", default="", help="time an A/B variant built by build_variant.sh instead of the in-tree library")
+    ap.add_argument("--lanes", type=int, default=-1, help="osc: b200ctl_osc_set_lanes (-1 auto, 0 tile kernel, 4 / 8 lanes per env)")
     a = ap.parse_args()
+    if a.lanes != -1:
+        from test_isaacgym_b200 import _lib as _l
+        _l.osc_set_lanes(a.lanes)
+        print("osc lanes:", a.lanes, flush=True)
     if a.lib:
         from test_isaacgym_b200 import _lib
         _lib.LIB_PATH = os.path.abspath(a.lib)

@@ -94,6 +94,7 @@ _SIGNATURES = {
     "b200ctl_franka_pick_ik": (c_int, [_DL] * 8 + [POINTER(FrankaTaskParams), c_double, c_int32, _DL, _DL, _DL, c_void_p]),
     "b200ctl_gather_rows": (c_int, [_DL, _DL, c_int32, c_int32, _DL, c_void_p]),
     "b200ctl_reserve_cta_slots": (c_int, [c_int32, c_int32]),
+    "b200ctl_osc_set_lanes": (c_int, [c_int32]),
     "b200ctl_measure_fma_peak": (c_int, [c_int32, c_int32, c_int32, POINTER(c_double), POINTER(c_double)]),
     "b200ctl_nccl_unique_id": (c_int, [c_void_p]),
     "b200ctl_nccl_comm_init": (c_int, [POINTER(c_void_p), c_int32, c_void_p, c_int32]),
@@ -183,6 +184,12 @@ def dl(t):
         if _DL_CACHE_MAX:
             _DL_CACHE[key] = p
     return p.ref, (p, t)
+
+
+def osc_set_lanes(lanes: int) -> None:
+    """Form of the fp64-chain ``control_osc`` launches: -1 auto (lanes per env for small launches), 0 one thread per env
+    always, 4 / 8 that many lanes per env always.  Same bits either way."""
+    check(lib().b200ctl_osc_set_lanes(int(lanes)))
 
 
 def reserve_cta_slots(device: torch.device, slots: int) -> None:

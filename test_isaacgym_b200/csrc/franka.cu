@@ -35,6 +35,7 @@
 // Roofline: HBM.  Algorithmic bytes per env: IK 248 B, OSC 496 B.
 #include "franka_task.cuh"
 
+#include <atomic>
 #include <mutex>
 
 #include <cuda.h>   // CUtensorMap + enums only: cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint
@@ -67,6 +68,12 @@ __device__ __forceinline__ void osc_trace(int k) {
 #else
 #define OSC_TRACE(k)
 #endif
+#ifndef B200_OSC_LANES8_ENVS_PER_SM
+#define B200_OSC_LANES8_ENVS_PER_SM 36     // auto rule of b200ctl_osc: eight lanes per env up to this many envs per SM (5,328) ...
+#endif
+#ifndef B200_OSC_LANES4_ENVS_PER_SM
+#define B200_OSC_LANES4_ENVS_PER_SM 0      // ... four lanes up to this many (0: never -- measured slower than eight lanes at every
+#endif                                     // size); above, one thread per env (tile kernel)
 #ifndef B200_OSC_F64_MAXREG
 #define B200_OSC_F64_MAXREG 255   // register cap of the fp64-chain OSC kernel (A/B knob, profiles/): 200 = 5 tiles per SM
 #endif
@@ -478,17 +485,12 @@ __device__ __forceinline__ void stage_all(const StagePlan& P, const CUtensorMap*
 
 #define SM(a, e, r, c) tile[(a).off + (e) * (a).es + (r) * (a).rs + (c) * (a).cs]
 
-// Lambda^-1 = J M^-1 J^T factored: on return A holds chol(Lambda^-1).  J is this thread's jacobian and L the lower
-// triangle of its mass matrix, both in registers (L is overwritten by the INVERSE of chol(M)).
-//   J M^-1 J^T = Y^T Y,  Y = X J^T,  X = chol(M)^-1  (lower triangular, formed in place: 56 FMAs for D = 7).
-// Row k of Y is X[k][0..k] . J[:, 0..k]: the rows are independent of each other (six forward substitutions would be
-// a 7-step serial chain with all of Y -- 84 registers at fp64 -- live at once), and each row is folded into
-// Lambda^-1 += y y^T as soon as it exists, so Y is never stored.  Peak live set 178 registers at fp64 instead of 208.
+// L (lower triangle of an SPD matrix, in registers) <- inverse of its Cholesky factor.
+// X = L^-1 in place, column by column: X[j][j] = 1 / L[j][j], X[i][j] = -(sum_{k=j}^{i-1} L[i][k] X[k][j]) / L[i][i]
 template <typename T, int D, int RSQ = B200_OSC_RSQRT>
-__device__ __forceinline__ void task_space_factor(const float (&J)[6][D], T (&L)[D][D], T (&A)[6][6], T (&rda)[6]) {
+__device__ __forceinline__ void chol_invert_inplace(T (&L)[D][D]) {
   T rdm[D];
   chol_inplace<T, D, RSQ>(L, rdm);
-  // X = L^-1 in place, column by column: X[j][j] = 1 / L[j][j], X[i][j] = -(sum_{k=j}^{i-1} L[i][k] X[k][j]) / L[i][i]
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     L[j][j] = rdm[j];
@@ -500,6 +502,17 @@ __device__ __forceinline__ void task_space_factor(const float (&J)[6][D], T (&L)
       L[i][j] = -s * rdm[i];
     }
   }
+}
+
+// Lambda^-1 = J M^-1 J^T factored: on return A holds chol(Lambda^-1).  J is this thread's jacobian and L the lower
+// triangle of its mass matrix, both in registers (L is overwritten by the INVERSE of chol(M)).
+//   J M^-1 J^T = Y^T Y,  Y = X J^T,  X = chol(M)^-1  (lower triangular, formed in place: 56 FMAs for D = 7).
+// Row k of Y is X[k][0..k] . J[:, 0..k]: the rows are independent of each other (six forward substitutions would be
+// a 7-step serial chain with all of Y -- 84 registers at fp64 -- live at once), and each row is folded into
+// Lambda^-1 += y y^T as soon as it exists, so Y is never stored.  Peak live set 178 registers at fp64 instead of 208.
+template <typename T, int D, int RSQ = B200_OSC_RSQRT>
+__device__ __forceinline__ void task_space_factor(const float (&J)[6][D], T (&L)[D][D], T (&A)[6][6], T (&rda)[6]) {
+  chol_invert_inplace<T, D, RSQ>(L);
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     T y[6];
@@ -777,6 +790,235 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   if (stats) {
     double acc[2] = {s_acc[0][threadIdx.x], s_acc[1][threadIdx.x]};
     unsigned cnt[2] = {s_cnt[0][threadIdx.x], s_cnt[1][threadIdx.x]};
+    const int slots[4] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_NONFINITE};
+    block_stats_commit<2, 2>(acc, cnt, stats, slots);
+  }
+}
+
+// ------------------------------------------------------------------ a10, small launches: LANES threads per environment
+// north_star's "one warp (or a warp group) per env" form, for the launches where it pays.  A launch of a few thousand envs
+// with one thread per env is the serial chain of ONE tile (profiles/r02_osc_trace.txt: 1.4 us launch gap, 0.7 us until the
+// last TMA instruction is issued, 0.5-1.3 us for the tile to land, 1.25 us to gather 117 operands out of shared memory, 0.9 us
+// of factorisation) on a device whose other schedulers idle.  Here LANES (8 or 4) adjacent lanes share an env:
+//   * no staging engine: lane g loads row g of M, row g and column g of J, joint g's state, task row g's target straight
+//     from global memory (coalesced: the lanes of an env read one contiguous row block), ~20 independent loads in flight
+//     per lane right behind the dependency wait, prefetched into L2 ahead of it;
+//   * each lane forms its OWN entries -- u0[g], (M u0)[g], w[g], column g of Y = X J^T, row g of Lambda^-1, u[g] -- and the
+//     lanes meet three times in shared memory (u0 + M, Y, Lambda^-1 + w: one __syncwarp each);
+//   * the two Cholesky factorisations, the triangular inverse and the 6x6 solve are a dependency chain that more lanes do not
+//     shorten; they run redundantly on every lane (the pipes are idle at these sizes) instead of through shuffles.
+// Every value is produced by the same operations in the same order as in osc_gather / osc_solve, so the result is
+// BIT-IDENTICAL to the one-thread-per-env kernel (tests/test_gpu_franka.py::test_osc_lanes_form_gives_the_same_bits) and the
+// fused pick step stays equal to task -> osc.  Operands are read through their strides: any view, no alignment rule.
+constexpr int kLaneThreads = 128;
+template <int LANES>
+struct LaneShared {
+  static constexpr int EPC = kLaneThreads / LANES;      // envs per CTA
+  float u0[EPC][8];
+  double M[EPC][7][8];      // row i: M[i][0..i] as fp64 (rows padded to 64 bytes: 128-bit accesses)
+  double Y[EPC][6][8];      // row r: column r of Y (7 entries)
+  double A[EPC][6][8];      // row r: Lambda^-1[r][0..5], w[r] at [6]
+};
+
+template <int LANES, int RSQ>
+__global__ void __launch_bounds__(kLaneThreads)
+osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_vel, TView hand_index, int has_index,
+                 TView q_default, float kp, float kd, float kp_null, float kd_null, TView out, int64_t n,
+                 double* __restrict__ stats) {
+  using T = double;
+  constexpr int D = 7;
+  constexpr int S = (D + LANES - 1) / LANES;      // rows / columns / joints per lane
+  constexpr int EPC = LaneShared<LANES>::EPC;
+  __shared__ __align__(16) LaneShared<LANES> sm;
+  const int g = threadIdx.x % LANES, el = threadIdx.x / LANES;
+  const int64_t env_raw = (int64_t)blockIdx.x * EPC + el;
+  const bool live = env_raw < n;
+  const int64_t env = live ? env_raw : n - 1;      // lanes of a missing env recompute the last one and store nothing
+  const float* jp = reinterpret_cast<const float*>(jv.p) + env * jv.s[0];
+  const float* mp = reinterpret_cast<const float*>(mv.p) + env * mv.s[0];
+  const float* qp = reinterpret_cast<const float*>(qv.p) + env * qv.s[0];
+  const float* qdp = reinterpret_cast<const float*>(qdv.p) + env * qdv.s[0];
+  const float* dpp = reinterpret_cast<const float*>(dpv.p) + env * dpv.s[0];
+  const int64_t* ip = reinterpret_cast<const int64_t*>(hand_index.p) + env * hand_index.s[0];
+  // ---- ahead of the dependency wait: this lane's rows into L2 (hints only, nothing is consumed)
+#ifndef B200_NO_PREWAIT_PF
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int i = g + s * LANES;
+    if (i < D) { prefetch_l2(mp + i * mv.s[1]); prefetch_l2(qp + i * qv.s[1]); }
+    if (i < 6) { prefetch_l2(jp + i * jv.s[1]); prefetch_l2(dpp + i * dpv.s[1]); }
+  }
+  if (g == 0) {
+    int64_t hint = env;
+    if (has_index) asm volatile("ld.global.relaxed.gpu.u64 %0, [%1];" : "=l"(hint) : "l"(ip));      // may be stale: a hint only
+    if (hint >= 0 && hint < hand_vel.n[0]) prefetch_l2(reinterpret_cast<const float*>(hand_vel.p) + hint * hand_vel.s[0]);
+  }
+#endif
+  pdl_prologue();
+
+  // ---- every load of the lane is issued before anything is consumed
+  const int64_t row = has_index ? __ldg(ip) : env;
+  float Mrow[S][D], Jrow[S][D], Jcol[S][6], q[S], qd[S], qdef[S], dp[S], hv[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int i = g + s * LANES;
+    const bool v7 = i < D, v6 = i < 6;
+#pragma unroll
+    for (int k = 0; k < D; ++k) Mrow[s][k] = v7 ? __ldg(mp + i * mv.s[1] + k * mv.s[2]) : 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) Jrow[s][k] = v6 ? __ldg(jp + i * jv.s[1] + k * jv.s[2]) : 0.f;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Jcol[s][r] = v7 ? __ldg(jp + r * jv.s[1] + i * jv.s[2]) : 0.f;
+    q[s] = v7 ? __ldg(qp + i * qv.s[1]) : 0.f;
+    qd[s] = v7 ? __ldg(qdp + i * qdv.s[1]) : 0.f;
+    qdef[s] = v7 ? ldf(q_default, i * q_default.s[0]) : 0.f;
+    dp[s] = v6 ? __ldg(dpp + i * dpv.s[1]) : 0.f;
+  }
+  // the index-gathered hand velocity: a row outside the source tensor is never dereferenced (NaN, counted as non-finite)
+  const bool row_ok = row >= 0 && row < hand_vel.n[0];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int i = g + s * LANES;
+    hv[s] = (i < 6 && row_ok) ? __ldg(reinterpret_cast<const float*>(hand_vel.p) + row * hand_vel.s[0] + i * hand_vel.s[1])
+                              : __int_as_float(0x7fc00000);
+  }
+
+  // ---- meeting 1: u0 (:74-76, fp32 in the reference's operand order) and the lower triangle of M as fp64
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int i = g + s * LANES;
+    if (i < D) {
+      sm.u0[el][i] = __fadd_rn(__fmul_rn(kd_null, -qd[s]), __fmul_rn(kp_null, wrap_pi(__fsub_rn(qdef[s], q[s]))));
+      double2* dst = reinterpret_cast<double2*>(sm.M[el][i]);
+#pragma unroll
+      for (int k = 0; k < 8; k += 2)
+        dst[k >> 1] = make_double2((double)Mrow[s][k], k + 1 < D ? (double)Mrow[s][k + 1 < D ? k + 1 : 0] : 0.0);
+    }
+  }
+  if (g == 0) sm.u0[el][7] = 0.f;
+  __syncwarp();
+  float u0[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(&sm.u0[el][0]), b = *reinterpret_cast<const float4*>(&sm.u0[el][4]);
+    u0[0] = a.x; u0[1] = a.y; u0[2] = a.z; u0[3] = a.w; u0[4] = b.x; u0[5] = b.y; u0[6] = b.z; u0[7] = b.w;
+  }
+  T L[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const double2* src = reinterpret_cast<const double2*>(sm.M[el][i]);
+#pragma unroll
+    for (int k = 0; k <= i; k += 2) {
+      const double2 v = src[k >> 1];
+      L[i][k] = v.x;
+      if (k + 1 <= i) L[i][k + 1] = v.y;
+    }
+  }
+  // this lane's entries of M u0 (:77) and of the task-space right-hand side kp dpose - kd v_hand - J u0 (:67-68)
+  T Mu0[S], w_mine[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    T u = (T)0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) u = fma_t<T>((T)Mrow[s][k], (T)u0[k], u);
+    Mu0[s] = u;
+    T t = (T)__fsub_rn(__fmul_rn(kp, dp[s]), __fmul_rn(kd, hv[s]));
+#pragma unroll
+    for (int c = 0; c < D; ++c) t = fma_t<T>(-(T)Jrow[s][c], (T)u0[c], t);
+    w_mine[s] = t;
+  }
+
+  // ---- X = chol(M)^-1 on every lane, then this lane's column(s) of Y = X J^T   (meeting 2)
+  chol_invert_inplace<T, D, RSQ>(L);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int r = g + s * LANES;
+    T y[8];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      T acc = (T)0;
+#pragma unroll
+      for (int jx = 0; jx <= k; ++jx) acc = fma_t<T>(L[k][jx], (T)Jrow[s][jx], acc);
+      y[k] = acc;
+    }
+    y[7] = 0.0;
+    if (r < 6) {
+      double2* dst = reinterpret_cast<double2*>(sm.Y[el][r]);
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) dst[k >> 1] = make_double2(y[k], y[k + 1]);
+    }
+  }
+  __syncwarp();
+  // ---- this lane's row(s) of Lambda^-1 = Y^T Y (lower part), next to its entry of w   (meeting 3)
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int r = g + s * LANES;
+    if (r < 6) {
+      T yr[8], a[8];
+      {
+        const double2* src = reinterpret_cast<const double2*>(sm.Y[el][r]);
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) { const double2 v = src[k >> 1]; yr[k] = v.x; yr[k + 1] = v.y; }
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double2* src = reinterpret_cast<const double2*>(sm.Y[el][c]);
+        T yc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) { const double2 v = src[k >> 1]; yc[k] = v.x; yc[k + 1] = v.y; }
+        T acc = yr[0] * yc[0];
+#pragma unroll
+        for (int k = 1; k < D; ++k) acc = fma_t<T>(yr[k], yc[k], acc);
+        a[c] = acc;
+      }
+      a[6] = w_mine[s];
+      a[7] = 0.0;
+      double2* dst = reinterpret_cast<double2*>(sm.A[el][r]);
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) dst[k >> 1] = make_double2(a[k], a[k + 1]);
+    }
+  }
+  __syncwarp();
+  T A[6][6], rda[6], w[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const double2* src = reinterpret_cast<const double2*>(sm.A[el][r]);
+#pragma unroll
+    for (int c = 0; c <= r; c += 2) {
+      const double2 v = src[c >> 1];
+      A[r][c] = v.x;
+      if (c + 1 <= r) A[r][c + 1] = v.y;
+    }
+    w[r] = src[3].x;
+  }
+  chol_inplace<T, 6, RSQ>(A, rda);
+  chol_solve<T, 6>(A, rda, w);          // w <- Lambda (w - J u0)
+
+  // ---- this lane's joint torque(s) (:76-79) and the statistics
+  double acc[2] = {0, 0};        // sum |u|, sum u^2
+  unsigned cnt[2] = {0, 0};      // envs, envs with a non-finite torque
+  bool finite = true;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int c = g + s * LANES;
+    T u = Mu0[s];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)Jcol[s][r], w[r], u);
+    const float uf = (float)u;
+    if (live && c < D) {
+      reinterpret_cast<float*>(const_cast<void*>(out.p))[env * out.s[0] + c * out.s[1]] = uf;
+      const bool f = isfinite(uf);
+      finite = finite && f;
+      const float v = f ? uf : 0.f;
+      acc[0] += fabsf(v);
+      acc[1] += (double)v * v;
+    }
+  }
+  if (stats) {
+    // an env is non-finite if any of its lanes saw a non-finite torque: one ballot, the env's first lane counts
+    const unsigned bad = __ballot_sync(0xffffffffu, !finite);
+    const int lane = threadIdx.x & 31;
+    const unsigned mine = (bad >> (lane - g)) & ((1u << LANES) - 1u);
+    if (g == 0 && live) { cnt[0] = 1u; cnt[1] = mine ? 1u : 0u; }
     const int slots[4] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_NONFINITE};
     block_stats_commit<2, 2>(acc, cnt, stats, slots);
   }
@@ -1101,6 +1343,24 @@ static bool short_chain_launch(int64_t n, int tile, int dev) {
   return !off && tiles(n, tile) <= 2 * sm_count(dev);
 }
 
+// Lanes per env of a b200ctl_osc launch (osc_lanes_kernel): 0 = the one-thread-per-env tile kernel.  Measured, us per launch
+// (cold data, graph replays; profiles/r02_osc_lanes.txt), tile kernel / 8 lanes / 4 lanes:
+//   256 envs 5.48 / 2.82 / 3.80    1,024 5.44 / 2.87 / 3.88    4,096 5.94 / 4.38 / 4.86    8,192 6.38 / 7.17 / 8.62
+//   16,384 6.98 / 11.2 / 13.1
+// Eight lanes halve a launch that leaves most schedulers idle and lose once every scheduler holds three warps of the lane
+// form (its two factorisations run redundantly on all eight lanes: ~4x the instruction issue of one thread per env); the
+// crossover is ~6,800 envs on 148 SMs.  b200ctl_osc_set_lanes overrides (-1 auto, 0 never, 4 / 8 always).  fp64 chain only.
+static std::atomic<int> g_osc_lanes{-1};
+static int osc_lanes_for(int64_t n, int precision, int dev) {
+  if (precision != 0) return 0;
+  const int mode = g_osc_lanes.load(std::memory_order_relaxed);
+  if (mode >= 0) return mode;
+  const int64_t sms = sm_count(dev);
+  if (n <= B200_OSC_LANES8_ENVS_PER_SM * sms) return 8;
+  if (n <= B200_OSC_LANES4_ENVS_PER_SM * sms) return 4;
+  return 0;
+}
+
 static int check_precision(int precision) {
   if (precision != 0 && precision != 1) B200_FAIL(B200CTL_E_VALUE, "precision must be 0 (fp64 factorisation) or 1 (all fp32)");
   return 0;
@@ -1335,6 +1595,12 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
   return post_launch("ik_dls_kernel");
 }
 
+extern "C" int b200ctl_osc_set_lanes(int32_t lanes) {
+  if (lanes != -1 && lanes != 0 && lanes != 4 && lanes != 8) B200_FAIL(B200CTL_E_VALUE, "lanes must be -1 (auto), 0, 4 or 8");
+  g_osc_lanes.store(lanes, std::memory_order_relaxed);
+  return 0;
+}
+
 extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTensor* dof_pos, const DLTensor* dof_vel,
                            const DLTensor* hand_vel, const DLTensor* hand_index, const DLTensor* dpose,
                            const DLTensor* q_default, double kp, double kd, double kp_null, double kd_null,
@@ -1367,6 +1633,21 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
+  if (const int lanes = osc_lanes_for(n, precision, dev)) {
+    // small launch: LANES threads per env straight from global memory (no staging plan, no tensor map); the pivot
+    // refinement follows the same rule as the tile kernel, so the two forms give the same bits at every size
+    const int epc = kLaneThreads / lanes;
+    const int grid = (int)((n + epc - 1) / epc);
+    const bool sc = short_chain_launch(n, kTileEnvs, dev);
+    cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH_LANES(LN, V)                                                                                              \
+    launch_pdl(osc_lanes_kernel<LN, V>, grid, kLaneThreads, 0, s, j, m, q, qd, dp, hv, hi, has_index, qdef, (float)kp,   \
+               (float)kd, (float)kp_null, (float)kd_null, o, n, stats)
+    if (lanes == 8) { if (sc) LAUNCH_LANES(8, kRsqrtShortChain); else LAUNCH_LANES(8, B200_OSC_RSQRT); }
+    else            { if (sc) LAUNCH_LANES(4, kRsqrtShortChain); else LAUNCH_LANES(4, B200_OSC_RSQRT); }
+#undef LAUNCH_LANES
+    return post_launch("osc_lanes_kernel");
+  }
   const SegSpec spec[5] = {{&j, 6, 7}, {&m, 7, 7}, {&q, 1, 7}, {&qd, 1, 7}, {&dp, 1, 6}};
   CUtensorMap tmap;
   const int tile = pick_tile(n, dev);

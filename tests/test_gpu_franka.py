@@ -259,7 +259,12 @@ def test_franka_staging_plans(layout):
              dof_pos=dofs[:, 0].view(n, 9, 1), dof_vel=dofs[:, 1].view(n, 9, 1),
              default_dof_pos_tensor=fi.default_dof_pos.to(DEV), num_envs=n, precision=0)
     ctl.bind_hand(rb, fi.hand_idxs.to(DEV))
-    osc = ctl.control_osc(dpose).cpu()
+    try:
+        _lib.osc_set_lanes(0)                   # the TMA-staged tile kernel: this test is about its staging plans
+        osc = ctl.control_osc(dpose).cpu()
+    finally:
+        _lib.osc_set_lanes(-1)
+    assert torch.equal(ctl.control_osc(dpose).cpu(), osc)      # auto: 1,000 envs take the lane form, same bits, any view
     ik = ctl.control_ik(dpose, dof_pos=None).cpu()
     assert _rel(osc, ref).max() <= 1e-4 and np.median(_rel(osc, ref)) <= 1e-6
     assert _rel(ik, ref_ik).max() <= 1e-5
@@ -354,6 +359,47 @@ def test_out_of_range_gather_index_gives_nan_not_a_fault():
     g = ctl.gather_rows(d.rb_states, idx, 7, 6).cpu()
     assert torch.isnan(g[5]).all() and torch.isnan(g[77]).all() and torch.equal(g[6], fi.rb_states[fi.hand_idxs[6], 7:])
     ctl._hand_index = None
+
+
+@pytest.mark.parametrize("n", [1, 7, 64, 593, 4096, 20_003])
+def test_osc_lanes_form_gives_the_same_bits(n):
+    """b200ctl_osc runs small fp64-chain launches with 8 or 4 lanes per env (osc_lanes_kernel: direct global loads, three
+    shared-memory meetings, redundant factorisations) and larger ones with one thread per env (TMA-staged tiles).  Every
+    value is produced by the same operations in the same order, so the forms must agree BIT FOR BIT -- full and ragged
+    sizes, index-gathered hand velocity incl. out-of-range rows, strided output, statistics."""
+    fi = syn.franka_inputs(n, seed=40 + n % 7)
+    d = _bind(fi)
+    idx = d.hand_idxs.clone()
+    if n > 64:
+        idx[5], idx[n - 2] = -1, d.rb_states.shape[0]
+    ctl.bind_hand(d.rb_states, idx)
+    outs, stats = {}, {}
+    try:
+        for lanes in (0, 4, 8, -1):
+            _lib.osc_set_lanes(lanes)
+            eff = torch.full((n, 9), 3.0, device=DEV)
+            st = _lib.stats_buffer(torch.device(DEV))
+            ctl.control_osc(d.dpose, out=eff[:, :7], stats=st)
+            assert (eff[:, 7:] == 3.0).all()
+            outs[lanes], stats[lanes] = eff[:, :7].clone(), st.cpu()
+    finally:
+        _lib.osc_set_lanes(-1)
+        ctl._hand_index = None
+    for lanes in (4, 8, -1):
+        a, b = outs[0], outs[lanes]
+        assert torch.equal(torch.isnan(a), torch.isnan(b))
+        assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), f"lanes={lanes} differs from the tile kernel"
+        assert stats[lanes][_lib_stat("N_ENV")] == n
+        assert stats[lanes][_lib_stat("N_NONFINITE")] == stats[0][_lib_stat("N_NONFINITE")] == (2 if n > 64 else 0)
+        for k in ("SUM_ABS", "SUM_SQ"):
+            assert abs(float(stats[lanes][_lib_stat(k)]) - float(stats[0][_lib_stat(k)])) <= 1e-12 * abs(float(stats[0][_lib_stat(k)]))
+    # and against the fp64 oracle (the tile kernel's gate)
+    f = lambda t: t.double()
+    hv = fi.rb_states[fi.hand_idxs, 7:]
+    ref = ofr.control_osc(f(fi.dpose), f(fi.j_eef), f(fi.mm), f(fi.dof_pos), f(fi.dof_vel), f(hv), f(fi.default_dof_pos),
+                          KP, KD, KP_NULL, KD_NULL)
+    ok = ~torch.isnan(outs[8]).any(dim=1).cpu().numpy() & (ofr.conditioning(fi.j_eef, fi.mm).numpy() <= 1e4)
+    assert _rel(outs[8].cpu(), ref)[ok].max() <= 1e-4
 
 
 def _lib_stat(name):
