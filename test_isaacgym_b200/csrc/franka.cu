@@ -819,12 +819,140 @@ struct LaneShared {
   double Y[EPC][6][8];      // row r: column r of Y (7 entries)
   double A[EPC][6][8];      // row r: Lambda^-1[r][0..5], w[r] at [6]
 };
+template <int LANES, int D>
+struct LaneSharedIk {
+  static constexpr int EPC = kLaneThreads / LANES;
+  double J[EPC][6][10];     // row r of J as fp64 (D <= 9 entries, rows padded to 80 bytes)
+  double A[EPC][6][8];      // row r: (J J^T + lambda^2 I)[r][0..5], dpose[r] at [6]
+};
 
-template <int LANES, int RSQ>
-__global__ void __launch_bounds__(kLaneThreads)
-osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_vel, TView hand_index, int has_index,
-                 TView q_default, float kp, float kd, float kp_null, float kd_null, TView out, int64_t n,
-                 double* __restrict__ stats) {
+__device__ __forceinline__ float pick6(const float* a, int i) {      // a[i], i in [0, 6), for register-resident a
+  float v = a[0];
+#pragma unroll
+  for (int k = 1; k < 6; ++k) v = (i == k) ? a[k] : v;
+  return v;
+}
+
+// Where the task-space input of a lane-form kernel comes from.
+//   LaneDposeTarget: the caller's dpose tensor (+ the index-gathered hand velocity for OSC)  -- b200ctl_osc / b200ctl_ik_dls
+//   LanePickTarget:  the pick loop's goal logic (franka_task.cuh), evaluated on every lane of the env from the gathered
+//                    box / hand rows; the env's first lane writes the latch, the gripper targets and dpose -- the fused steps
+// Interface: prefetch (hints ahead of the dependency wait), load (issue every load), resolve (arithmetic on the loaded
+// values), dpose(i) / hand_vel(i) for task row i, commit (side effects; called after the lanes have met at least once, so every
+// lane has read what the writer overwrites).
+template <int LANES, bool WITH_VEL>
+struct LaneDposeTarget {
+  static constexpr int S = (6 + LANES - 1) / LANES;
+  TView dpv, hand_vel, hand_index;
+  int has_index;
+  float dp[S], hv[S];
+  __device__ __forceinline__ void prefetch(int64_t env, int g) const {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int i = g + s * LANES;
+      if (i < 6) prefetch_l2(reinterpret_cast<const float*>(dpv.p) + env * dpv.s[0] + i * dpv.s[1]);
+    }
+    if (WITH_VEL && g == 0) {
+      int64_t hint = env;
+      if (has_index)      // may be stale: a hint only
+        asm volatile("ld.global.relaxed.gpu.u64 %0, [%1];" : "=l"(hint) : "l"(reinterpret_cast<const int64_t*>(hand_index.p) + env * hand_index.s[0]));
+      if (hint >= 0 && hint < hand_vel.n[0]) prefetch_l2(reinterpret_cast<const float*>(hand_vel.p) + hint * hand_vel.s[0]);
+    }
+  }
+  __device__ __forceinline__ void load(int64_t env, int g) {
+    int64_t row = env;
+    if (WITH_VEL && has_index) row = __ldg(reinterpret_cast<const int64_t*>(hand_index.p) + env * hand_index.s[0]);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int i = g + s * LANES;
+      dp[s] = i < 6 ? __ldg(reinterpret_cast<const float*>(dpv.p) + env * dpv.s[0] + i * dpv.s[1]) : 0.f;
+    }
+    if (WITH_VEL) {
+      // a row outside the source tensor is never dereferenced (NaN, counted as non-finite)
+      const bool row_ok = row >= 0 && row < hand_vel.n[0];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int i = g + s * LANES;
+        hv[s] = (i < 6 && row_ok) ? __ldg(reinterpret_cast<const float*>(hand_vel.p) + row * hand_vel.s[0] + i * hand_vel.s[1])
+                                  : __int_as_float(0x7fc00000);
+      }
+    }
+  }
+  __device__ __forceinline__ void resolve() {}
+  __device__ __forceinline__ float dpose(int s, int) const { return dp[s]; }
+  __device__ __forceinline__ float vel(int s, int) const { return hv[s]; }
+  __device__ __forceinline__ void commit(int64_t, bool) const {}
+};
+
+template <int LANES, bool WITH_VEL>
+struct LanePickTarget {
+  TView rb, box_index, hand_index, fingers, ipv, iqv, dpose_out, grip;      // fingers: dof_pos (N, >= 9)
+  uint8_t* hand_restart;
+  int64_t hr_stride;
+  TaskConst tk;
+  int has_dpose;
+  static constexpr int NH = WITH_VEL ? 13 : 7;
+  float box[7], hand[13], f7, f8, ip[3], iq[4];
+  bool restart_in;
+  TaskOut t;
+  __device__ __forceinline__ void prefetch(int64_t env, int g) const {
+    if (g < 2) {      // lane 0: box row, lane 1: hand row (index read as a hint only, see gather_prefetch)
+      const TView& ix = g == 0 ? box_index : hand_index;
+      int64_t hint;
+      asm volatile("ld.global.relaxed.gpu.u64 %0, [%1];" : "=l"(hint) : "l"(reinterpret_cast<const int64_t*>(ix.p) + env * ix.s[0]));
+      if (hint >= 0 && hint < rb.n[0]) prefetch_l2(reinterpret_cast<const float*>(rb.p) + hint * rb.s[0]);
+    } else if (g == 2) {
+      prefetch_l2(reinterpret_cast<const float*>(ipv.p) + env * ipv.s[0]);
+    } else if (g == 3) {
+      prefetch_l2(reinterpret_cast<const float*>(iqv.p) + env * iqv.s[0]);
+    }
+  }
+  __device__ __forceinline__ void load(int64_t env, int) {
+    const int64_t brow = __ldg(reinterpret_cast<const int64_t*>(box_index.p) + env * box_index.s[0]);
+    const int64_t hrow = __ldg(reinterpret_cast<const int64_t*>(hand_index.p) + env * hand_index.s[0]);
+    const float* fp = reinterpret_cast<const float*>(fingers.p) + env * fingers.s[0];
+    f7 = __ldg(fp + 7 * fingers.s[1]);
+    f8 = __ldg(fp + 8 * fingers.s[1]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ip[c] = __ldg(reinterpret_cast<const float*>(ipv.p) + env * ipv.s[0] + c * ipv.s[1]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) iq[c] = __ldg(reinterpret_cast<const float*>(iqv.p) + env * iqv.s[0] + c * iqv.s[1]);
+    restart_in = hand_restart[env * hr_stride] != 0;
+    const float nan = __int_as_float(0x7fc00000);      // device-side indices: a row outside rb_states is never dereferenced
+    const bool bok = brow >= 0 && brow < rb.n[0], hok = hrow >= 0 && hrow < rb.n[0];
+    const float* bp = reinterpret_cast<const float*>(rb.p) + brow * rb.s[0];
+    const float* hp = reinterpret_cast<const float*>(rb.p) + hrow * rb.s[0];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) box[c] = bok ? __ldg(bp + c * rb.s[1]) : nan;
+#pragma unroll
+    for (int c = 0; c < NH; ++c) hand[c] = hok ? __ldg(hp + c * rb.s[1]) : nan;
+  }
+  __device__ __forceinline__ void resolve() {
+    float h7[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) h7[c] = hand[c];
+    task_logic(box, h7, __fadd_rn(f7, f8), ip, iq, restart_in, tk, t);      // :348-391, :399-406
+  }
+  __device__ __forceinline__ float dpose(int, int i) const { return pick6(t.dpose, i); }
+  __device__ __forceinline__ float vel(int, int i) const { return pick6(hand + 7, i); }      // hand velocity, :353
+  __device__ __forceinline__ void commit(int64_t env, bool writer) const {
+    if (!writer) return;
+    hand_restart[env * hr_stride] = t.restart ? 1 : 0;
+    float* gr = reinterpret_cast<float*>(const_cast<void*>(grip.p)) + env * grip.s[0];
+    gr[0] = t.grip;
+    gr[grip.s[1]] = t.grip;
+    if (has_dpose) {
+      float* dpo = reinterpret_cast<float*>(const_cast<void*>(dpose_out.p)) + env * dpose_out.s[0];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) dpo[c * dpose_out.s[1]] = t.dpose[c];
+    }
+  }
+};
+
+template <int LANES, int RSQ, typename Target>
+__device__ __forceinline__ void osc_lanes_body(const TView& jv, const TView& mv, const TView& qv, const TView& qdv,
+                                               const TView& q_default, float kp, float kd, float kp_null, float kd_null,
+                                               const TView& out, int64_t n, double* __restrict__ stats, Target& tg) {
   using T = double;
   constexpr int D = 7;
   constexpr int S = (D + LANES - 1) / LANES;      // rows / columns / joints per lane
@@ -838,27 +966,21 @@ osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_
   const float* mp = reinterpret_cast<const float*>(mv.p) + env * mv.s[0];
   const float* qp = reinterpret_cast<const float*>(qv.p) + env * qv.s[0];
   const float* qdp = reinterpret_cast<const float*>(qdv.p) + env * qdv.s[0];
-  const float* dpp = reinterpret_cast<const float*>(dpv.p) + env * dpv.s[0];
-  const int64_t* ip = reinterpret_cast<const int64_t*>(hand_index.p) + env * hand_index.s[0];
   // ---- ahead of the dependency wait: this lane's rows into L2 (hints only, nothing is consumed)
 #ifndef B200_NO_PREWAIT_PF
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     const int i = g + s * LANES;
     if (i < D) { prefetch_l2(mp + i * mv.s[1]); prefetch_l2(qp + i * qv.s[1]); }
-    if (i < 6) { prefetch_l2(jp + i * jv.s[1]); prefetch_l2(dpp + i * dpv.s[1]); }
+    if (i < 6) prefetch_l2(jp + i * jv.s[1]);
   }
-  if (g == 0) {
-    int64_t hint = env;
-    if (has_index) asm volatile("ld.global.relaxed.gpu.u64 %0, [%1];" : "=l"(hint) : "l"(ip));      // may be stale: a hint only
-    if (hint >= 0 && hint < hand_vel.n[0]) prefetch_l2(reinterpret_cast<const float*>(hand_vel.p) + hint * hand_vel.s[0]);
-  }
+  tg.prefetch(env, g);
 #endif
   pdl_prologue();
 
   // ---- every load of the lane is issued before anything is consumed
-  const int64_t row = has_index ? __ldg(ip) : env;
-  float Mrow[S][D], Jrow[S][D], Jcol[S][6], q[S], qd[S], qdef[S], dp[S], hv[S];
+  tg.load(env, g);
+  float Mrow[S][D], Jrow[S][D], Jcol[S][6], q[S], qd[S], qdef[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     const int i = g + s * LANES;
@@ -872,16 +994,8 @@ osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_
     q[s] = v7 ? __ldg(qp + i * qv.s[1]) : 0.f;
     qd[s] = v7 ? __ldg(qdp + i * qdv.s[1]) : 0.f;
     qdef[s] = v7 ? ldf(q_default, i * q_default.s[0]) : 0.f;
-    dp[s] = v6 ? __ldg(dpp + i * dpv.s[1]) : 0.f;
   }
-  // the index-gathered hand velocity: a row outside the source tensor is never dereferenced (NaN, counted as non-finite)
-  const bool row_ok = row >= 0 && row < hand_vel.n[0];
-#pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const int i = g + s * LANES;
-    hv[s] = (i < 6 && row_ok) ? __ldg(reinterpret_cast<const float*>(hand_vel.p) + row * hand_vel.s[0] + i * hand_vel.s[1])
-                              : __int_as_float(0x7fc00000);
-  }
+  tg.resolve();
 
   // ---- meeting 1: u0 (:74-76, fp32 in the reference's operand order) and the lower triangle of M as fp64
 #pragma unroll
@@ -892,7 +1006,7 @@ osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_
       double2* dst = reinterpret_cast<double2*>(sm.M[el][i]);
 #pragma unroll
       for (int k = 0; k < 8; k += 2)
-        dst[k >> 1] = make_double2((double)Mrow[s][k], k + 1 < D ? (double)Mrow[s][k + 1 < D ? k + 1 : 0] : 0.0);
+        dst[k >> 1] = make_double2((double)Mrow[s][k < D ? k : 0], k + 1 < D ? (double)Mrow[s][k + 1 < D ? k + 1 : 0] : 0.0);
     }
   }
   if (g == 0) sm.u0[el][7] = 0.f;
@@ -917,11 +1031,12 @@ osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_
   T Mu0[S], w_mine[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) {
+    const int i = g + s * LANES;
     T u = (T)0;
 #pragma unroll
     for (int k = 0; k < D; ++k) u = fma_t<T>((T)Mrow[s][k], (T)u0[k], u);
     Mu0[s] = u;
-    T t = (T)__fsub_rn(__fmul_rn(kp, dp[s]), __fmul_rn(kd, hv[s]));
+    T t = (T)__fsub_rn(__fmul_rn(kp, tg.dpose(s, i)), __fmul_rn(kd, tg.vel(s, i)));
 #pragma unroll
     for (int c = 0; c < D; ++c) t = fma_t<T>(-(T)Jrow[s][c], (T)u0[c], t);
     w_mine[s] = t;
@@ -993,7 +1108,7 @@ osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_
   chol_inplace<T, 6, RSQ>(A, rda);
   chol_solve<T, 6>(A, rda, w);          // w <- Lambda (w - J u0)
 
-  // ---- this lane's joint torque(s) (:76-79) and the statistics
+  // ---- this lane's joint torque(s) (:76-79), the target's side effects, the statistics
   double acc[2] = {0, 0};        // sum |u|, sum u^2
   unsigned cnt[2] = {0, 0};      // envs, envs with a non-finite torque
   bool finite = true;
@@ -1013,6 +1128,7 @@ osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_
       acc[1] += (double)v * v;
     }
   }
+  tg.commit(env, live && g == 0);
   if (stats) {
     // an env is non-finite if any of its lanes saw a non-finite torque: one ballot, the env's first lane counts
     const unsigned bad = __ballot_sync(0xffffffffu, !finite);
@@ -1022,6 +1138,157 @@ osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_
     const int slots[4] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_NONFINITE};
     block_stats_commit<2, 2>(acc, cnt, stats, slots);
   }
+}
+
+// DLS-IK (:53-59) in the lane form: lane r forms row r of J J^T + lambda^2 I from the rows the lanes publish as fp64, the
+// 6x6 factorisation and solve run on every lane, lane c forms u[c] = (J^T y)[c].  Same operations and order as ik_compute.
+template <int LANES, int D, typename Target>
+__device__ __forceinline__ void ik_lanes_body(const TView& jv, const TView& posv, int has_pos, float lambda2, const TView& out,
+                                              int64_t n, Target& tg) {
+  using T = double;
+  constexpr int S = (D + LANES - 1) / LANES;      // columns per lane (D = 9 with eight lanes: two)
+  constexpr int SR = (6 + LANES - 1) / LANES;     // task rows per lane
+  constexpr int EPC = LaneSharedIk<LANES, D>::EPC;
+  __shared__ __align__(16) LaneSharedIk<LANES, D> sm;
+  const int g = threadIdx.x % LANES, el = threadIdx.x / LANES;
+  const int64_t env_raw = (int64_t)blockIdx.x * EPC + el;
+  const bool live = env_raw < n;
+  const int64_t env = live ? env_raw : n - 1;
+  const float* jp = reinterpret_cast<const float*>(jv.p) + env * jv.s[0];
+  const float* pp = reinterpret_cast<const float*>(posv.p) + env * posv.s[0];
+#ifndef B200_NO_PREWAIT_PF
+#pragma unroll
+  for (int s = 0; s < SR; ++s) {
+    const int r = g + s * LANES;
+    if (r < 6) prefetch_l2(jp + r * jv.s[1]);
+  }
+  if (has_pos && g == LANES - 1) prefetch_l2(pp);
+  tg.prefetch(env, g);
+#endif
+  pdl_prologue();
+  tg.load(env, g);
+  float Jrow[SR][D], Jcol[S][6], pos[S];
+#pragma unroll
+  for (int s = 0; s < SR; ++s) {
+    const int r = g + s * LANES;
+#pragma unroll
+    for (int k = 0; k < D; ++k) Jrow[s][k] = r < 6 ? __ldg(jp + r * jv.s[1] + k * jv.s[2]) : 0.f;
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int c = g + s * LANES;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Jcol[s][r] = c < D ? __ldg(jp + r * jv.s[1] + c * jv.s[2]) : 0.f;
+    pos[s] = (has_pos && c < D) ? __ldg(pp + c * posv.s[1]) : 0.f;
+  }
+  tg.resolve();
+  // ---- meeting 1: the rows of J as fp64
+#pragma unroll
+  for (int s = 0; s < SR; ++s) {
+    const int r = g + s * LANES;
+    if (r < 6) {
+      double2* dst = reinterpret_cast<double2*>(sm.J[el][r]);
+#pragma unroll
+      for (int k = 0; k < 10; k += 2)
+        dst[k >> 1] = make_double2(k < D ? (double)Jrow[s][k < D ? k : 0] : 0.0, k + 1 < D ? (double)Jrow[s][k + 1 < D ? k + 1 : 0] : 0.0);
+    }
+  }
+  __syncwarp();
+  // ---- this lane's row(s) of J J^T + lambda^2 I (:57-58), next to its dpose entry   (meeting 2)
+#pragma unroll
+  for (int s = 0; s < SR; ++s) {
+    const int r = g + s * LANES;
+    if (r < 6) {
+      T a[8];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double2* src = reinterpret_cast<const double2*>(sm.J[el][c]);
+        T acc = (r == c) ? (T)lambda2 : (T)0;
+#pragma unroll
+        for (int k = 0; k < D; k += 2) {
+          const double2 v = src[k >> 1];
+          acc = fma_t<T>((T)Jrow[s][k], v.x, acc);
+          if (k + 1 < D) acc = fma_t<T>((T)Jrow[s][k + 1 < D ? k + 1 : 0], v.y, acc);
+        }
+        a[c] = acc;
+      }
+      a[6] = (T)tg.dpose(s, r);
+      a[7] = 0.0;
+      double2* dst = reinterpret_cast<double2*>(sm.A[el][r]);
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) dst[k >> 1] = make_double2(a[k], a[k + 1]);
+    }
+  }
+  __syncwarp();
+  T A[6][6], rd[6], y[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const double2* src = reinterpret_cast<const double2*>(sm.A[el][r]);
+#pragma unroll
+    for (int c = 0; c <= r; c += 2) {
+      const double2 v = src[c >> 1];
+      A[r][c] = v.x;
+      if (c + 1 <= r) A[r][c + 1] = v.y;
+    }
+    y[r] = src[3].x;
+  }
+  chol_inplace<T, 6>(A, rd);
+  chol_solve<T, 6>(A, rd, y);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int c = g + s * LANES;
+    T u = (T)0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)Jcol[s][r], y[r], u);   // J^T y
+    float uf = (float)u;
+    if (has_pos) uf = __fadd_rn(pos[s], uf);                           // dof_pos[:, :7] + control_ik(dpose)  (:395)
+    if (live && c < D) reinterpret_cast<float*>(const_cast<void*>(out.p))[env * out.s[0] + c * out.s[1]] = uf;
+  }
+  tg.commit(env, live && g == 0);
+}
+
+template <int LANES, int RSQ>
+__global__ void __launch_bounds__(kLaneThreads)
+osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView dpv, TView hand_vel, TView hand_index, int has_index,
+                 TView q_default, float kp, float kd, float kp_null, float kd_null, TView out, int64_t n,
+                 double* __restrict__ stats) {
+  LaneDposeTarget<LANES, true> tg;
+  tg.dpv = dpv; tg.hand_vel = hand_vel; tg.hand_index = hand_index; tg.has_index = has_index;
+  osc_lanes_body<LANES, RSQ>(jv, mv, qv, qdv, q_default, kp, kd, kp_null, kd_null, out, n, stats, tg);
+}
+
+template <int LANES, int D>
+__global__ void __launch_bounds__(kLaneThreads)
+ik_lanes_kernel(TView jv, TView dpv, TView posv, int has_pos, float lambda2, TView out, int64_t n) {
+  LaneDposeTarget<LANES, false> tg;
+  tg.dpv = dpv; tg.has_index = 0;
+  ik_lanes_body<LANES, D>(jv, posv, has_pos, lambda2, out, n, tg);
+}
+
+// the fused pick steps (examples/franka_cube_ik_osc.py:348-410) in the lane form
+template <int LANES, int RSQ>
+__global__ void __launch_bounds__(kLaneThreads)
+pick_osc_lanes_kernel(TView jv, TView mv, TView qv, TView qdv, TView rb, TView box_index, TView hand_index, TView ipv, TView iqv,
+                      uint8_t* __restrict__ hand_restart, int64_t hr_stride, TaskConst tk, TView q_default, float kp, float kd,
+                      float kp_null, float kd_null, TView dpose_out, int has_dpose, TView grip, TView out, int64_t n,
+                      double* __restrict__ stats) {
+  LanePickTarget<LANES, true> tg;
+  tg.rb = rb; tg.box_index = box_index; tg.hand_index = hand_index; tg.fingers = qv; tg.ipv = ipv; tg.iqv = iqv;
+  tg.dpose_out = dpose_out; tg.grip = grip; tg.hand_restart = hand_restart; tg.hr_stride = hr_stride; tg.tk = tk;
+  tg.has_dpose = has_dpose;
+  osc_lanes_body<LANES, RSQ>(jv, mv, qv, qdv, q_default, kp, kd, kp_null, kd_null, out, n, stats, tg);
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kLaneThreads)
+pick_ik_lanes_kernel(TView jv, TView qv, TView rb, TView box_index, TView hand_index, TView ipv, TView iqv,
+                     uint8_t* __restrict__ hand_restart, int64_t hr_stride, TaskConst tk, float lambda2, TView dpose_out,
+                     int has_dpose, TView grip, TView out, int64_t n) {
+  LanePickTarget<LANES, false> tg;
+  tg.rb = rb; tg.box_index = box_index; tg.hand_index = hand_index; tg.fingers = qv; tg.ipv = ipv; tg.iqv = iqv;
+  tg.dpose_out = dpose_out; tg.grip = grip; tg.hand_restart = hand_restart; tg.hr_stride = hr_stride; tg.tk = tk;
+  tg.has_dpose = has_dpose;
+  ik_lanes_body<LANES, 7>(jv, qv, 1, lambda2, out, n, tg);
 }
 
 // ------------------------------------------------------------------ fused pick step: goal logic + OSC in one launch
@@ -1436,7 +1703,8 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
   // ---- bulk plan: bulk regions first, then one dense row per env for the LDGSTS operands + extras
   int region = 0;
   bool any_bulk = false;
-  for (int i = 0; i < nseg && n > tile; ++i) {
+  static const bool no_bulk = getenv("B200CTL_NO_BULK") != nullptr;      // A/B switch for profiles/: LDGSTS plan for every tile
+  for (int i = 0; i < nseg && n > tile && !no_bulk; ++i) {
     StageSeg& s = P.seg[i];
     if (s.rows * s.cols == 0 || s.s0 <= 0 || s.s1 < 0 || s.s2 <= 0) continue;
     const int64_t window = (int64_t)(s.rows - 1) * s.s1 + (int64_t)(s.cols - 1) * s.s2 + 1;   // floats spanned per env
@@ -1576,14 +1844,22 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
+  // lambda^2 is formed in fp32 like torch.eye(6) * damping**2 (:57)
+  const float l2 = (float)(lambda * lambda);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (const int lanes = osc_lanes_for(n, precision, dev)) {      // small launch: the lane form (same bits), see osc_lanes_kernel
+    const int grid = (int)((n + kLaneThreads / lanes - 1) / (kLaneThreads / lanes));
+    if (lanes == 8) { if (D == 7) launch_pdl(ik_lanes_kernel<8, 7>, grid, kLaneThreads, 0, s, j, dp, q, has_pos, l2, o, n);
+                      else        launch_pdl(ik_lanes_kernel<8, 9>, grid, kLaneThreads, 0, s, j, dp, q, has_pos, l2, o, n); }
+    else            { if (D == 7) launch_pdl(ik_lanes_kernel<4, 7>, grid, kLaneThreads, 0, s, j, dp, q, has_pos, l2, o, n);
+                      else        launch_pdl(ik_lanes_kernel<4, 9>, grid, kLaneThreads, 0, s, j, dp, q, has_pos, l2, o, n); }
+    return post_launch("ik_lanes_kernel");
+  }
   const SegSpec spec[3] = {{&j, 6, (int)D}, {&dp, 1, 6}, {&q, 1, has_pos ? (int)D : 0}};
   CUtensorMap tmap;
   const int tile = pick_tile(n, dev);
   const StagePlan P = make_plan(spec, 3, 0, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
-  // lambda^2 is formed in fp32 like torch.eye(6) * damping**2 (:57)
-  const float l2 = (float)(lambda * lambda);
-  cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH_IK(T, DD)                                                          \
   do {                                                                            \
     B200_TRY(set_smem(ik_dls_kernel<T, DD>, smem));                               \
@@ -1801,14 +2077,25 @@ extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
+  const TaskConst tk = make_task_const(*task);
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
+  if (const int lanes = osc_lanes_for(n, precision, dev)) {      // small launch: the lane form (same bits), see osc_lanes_kernel
+    const int grid = (int)((n + kLaneThreads / lanes - 1) / (kLaneThreads / lanes));
+    const bool sc = short_chain_launch(n, kTileEnvs, dev);
+#define LAUNCH_PICK_LANES(LN, V)                                                                                          \
+    launch_pdl(pick_osc_lanes_kernel<LN, V>, grid, kLaneThreads, 0, s, j, m, q, qd, rb, bi, hi, ip, iq, hrp, hr.s[0], tk, qdef, \
+               (float)kp, (float)kd, (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats)
+    if (lanes == 8) { if (sc) LAUNCH_PICK_LANES(8, kRsqrtShortChain); else LAUNCH_PICK_LANES(8, B200_OSC_RSQRT); }
+    else            { if (sc) LAUNCH_PICK_LANES(4, kRsqrtShortChain); else LAUNCH_PICK_LANES(4, B200_OSC_RSQRT); }
+#undef LAUNCH_PICK_LANES
+    return post_launch("pick_osc_lanes_kernel");
+  }
   const SegSpec spec[6] = {{&j, 6, 7}, {&m, 7, 7}, {&q, 1, 9}, {&qd, 1, 7}, {&ip, 1, 3}, {&iq, 1, 4}};
   CUtensorMap tmap;
   const int tile = pick_tile(n, dev);
   const StagePlan P = make_plan(spec, 6, 20, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
-  const TaskConst tk = make_task_const(*task);
-  cudaStream_t s = (cudaStream_t)stream;
-  uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
   // the pivot refinement follows b200ctl_osc's rule, so the fused step stays bit-identical to task -> osc at every size
 #define LAUNCH_PICK(T, V)                                                                                              \
   do {                                                                                                                 \
@@ -1856,15 +2143,21 @@ extern "C" int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* dof
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
+  const TaskConst tk = make_task_const(*task);
+  const float l2 = (float)(lambda * lambda);
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
+  if (const int lanes = osc_lanes_for(n, precision, dev)) {      // small launch: the lane form (same bits), see osc_lanes_kernel
+    const int grid = (int)((n + kLaneThreads / lanes - 1) / (kLaneThreads / lanes));
+    if (lanes == 8) launch_pdl(pick_ik_lanes_kernel<8>, grid, kLaneThreads, 0, s, j, q, rb, bi, hi, ip, iq, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+    else            launch_pdl(pick_ik_lanes_kernel<4>, grid, kLaneThreads, 0, s, j, q, rb, bi, hi, ip, iq, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+    return post_launch("pick_ik_lanes_kernel");
+  }
   const SegSpec spec[4] = {{&j, 6, 7}, {&q, 1, 9}, {&ip, 1, 3}, {&iq, 1, 4}};
   CUtensorMap tmap;
   const int tile = pick_tile(n, dev);
   const StagePlan P = make_plan(spec, 4, 14, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
-  const TaskConst tk = make_task_const(*task);
-  const float l2 = (float)(lambda * lambda);
-  cudaStream_t s = (cudaStream_t)stream;
-  uint8_t* hrp = reinterpret_cast<uint8_t*>(const_cast<void*>(hr.p));
   if (precision == 0) {
     B200_TRY(set_smem(pick_ik_kernel<double>, smem));
     launch_pdl(pick_ik_kernel<double>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);

@@ -191,3 +191,59 @@ def test_fused_pick_ik_equals_task_then_ik():
     cond = ofr.conditioning(fi.j_eef, None, 0.05).numpy()
     assert np.median(rel) <= 2e-6 and rel[cond <= 1e3].max() <= 5e-4      # same gate as test_full_pick_step_against_reference
     assert np.array_equal(pos.cpu().numpy()[:, 7:], ref[:, 7:]) and np.array_equal(r.cpu().numpy(), g["ik_hand_restart"])
+
+
+def _same(a, b):
+    return torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+
+
+@pytest.mark.parametrize("n", [5, 300, 2048, 9000])
+def test_lane_forms_of_ik_and_pick_steps_give_the_same_bits(n):
+    """Small fp64-chain launches of b200ctl_ik_dls / b200ctl_franka_pick_osc / b200ctl_franka_pick_ik run with eight (or four)
+    lanes per env, larger ones with one thread per env on TMA-staged tiles.  Same operations in the same order: every output
+    -- torques / position targets, gripper targets, dpose, the hand_restart latch, statistics counts -- must be bit-identical
+    whichever form runs, incl. out-of-range box / hand indices and the 9-DOF explicit-argument control_ik."""
+    from test_isaacgym_b200 import _lib
+    ti, fd = _dev(syn.franka_task_inputs(n, seed=61)), _dev(syn.franka_inputs(n, seed=62))
+    box_idx, hand_idx = ti.box_idxs.clone(), ti.hand_idxs.clone()
+    if n > 64:
+        box_idx[3], hand_idx[n - 5] = -7, ti.rb_states.shape[0] + 1
+    res = {}
+    try:
+        for lanes in (0, 4, 8, -1):
+            _lib.osc_set_lanes(lanes)
+            out = {}
+            ctl.bind(damping=0.05, kp=150., kd=2.0 * np.sqrt(150.), kp_null=10., kd_null=2.0 * np.sqrt(10.), j_eef=fd.j_eef,
+                     mm=fd.mm, dof_pos=ti.dof_pos, dof_vel=ti.dof_state[:, 1].view(n, 9, 1),
+                     default_dof_pos_tensor=fd.default_dof_pos, num_envs=n, precision=0)
+            ctl.bind_hand(ti.rb_states, hand_idx)
+            # control_ik, 7 DOF (+ dof_pos) and the explicit-argument 9-DOF twin
+            out["ik7"] = ctl.control_ik(fd.dpose, dof_pos=ti.dof_pos).clone()
+            out["ik9"] = ctl.control_ik(fd.dpose, 0.1, fd.jacobian[:, syn.FRANKA_JACOBIAN_SLOT], n).clone()
+            # fused pick steps
+            for tag in ("osc", "ik"):
+                r = ti.hand_restart.clone()
+                t = ctl.TaskStep(ti.rb_states, box_idx, hand_idx, ti.dof_pos, ti.init_pos, ti.init_rot, r, tag)
+                pos, eff = torch.zeros(n, 9, device=DEV), torch.full((n, 9), 3.0, device=DEV)
+                dpose = torch.zeros(n, 6, 1, device=DEV)
+                if tag == "osc":
+                    st = _lib_stats()
+                    ctl.bind_pick_osc(t, eff[:, :7], pos[:, 7:9], dpose=dpose, stats=st)()
+                    assert (eff[:, 7:] == 3.0).all()
+                    out["osc_counts"] = st.cpu()[[0, 4]].clone()
+                else:
+                    ctl.bind_pick_ik(t, pos[:, :7], pos[:, 7:9], dpose=dpose)()
+                out[tag] = (pos.clone(), eff.clone(), dpose.clone(), r.clone())
+            res[lanes] = out
+    finally:
+        _lib.osc_set_lanes(-1)
+        ctl._hand_index = None
+    for lanes in (4, 8, -1):
+        a, b = res[0], res[lanes]
+        assert _same(a["ik7"], b["ik7"]) and _same(a["ik9"], b["ik9"]), f"control_ik, lanes={lanes}"
+        assert torch.equal(a["osc_counts"], b["osc_counts"]) and a["osc_counts"][0] == n
+        for tag in ("osc", "ik"):
+            for x, y in zip(a[tag], b[tag]):
+                assert _same(x.float(), y.float()), f"pick_{tag}, lanes={lanes}"
+    if n > 64:
+        assert int(res[0]["osc_counts"][1]) >= 2      # the two envs with a bad index are counted, not dereferenced
