@@ -499,6 +499,40 @@ def family_numbers(device, peak_gbs):
         osc9[-1].keep = (osc9[-1].keep, pos_des, orn_des, u9)
     record(f"franka_osc_step_{n}", n, 668, osc9, 10)
     out[f"franka_osc_step_{n}"]["note"] = "b200ctl_franka_osc_step, 9 DOF, fp64 chain (examples/franka_osc.py:221-241 in one launch)"
+    del keep, task_calls, step_calls, fused, fused_ik, osc9
+    torch.cuda.empty_cache()
+
+    # Small launches -- the reference scripts' own default is 256 envs.  north_star's "one warp (or a warp group) per env" form:
+    # launches of at most 32 envs per SM run with EIGHT LANES per env (osc_lanes_kernel and its ik / pick twins: direct coalesced
+    # global loads, three shared-memory meetings, redundant factorisations; bit-identical to the tile kernels), timed here next
+    # to the one-thread-per-env tile kernel forced with b200ctl_osc_set_lanes(0)
+    small = {"_note": "us per launch, fp64 chain, CUDA-graph replays over 40 rotating sets (L2-resident at these sizes whatever "
+                      "the rotation); lanes8 = the form b200ctl picks by itself at this size, tile = one thread per env forced"}
+    for n in (256, 4096):
+        sets = 40
+        t0_, d0_ = to_dev(syn.franka_task_inputs(n, seed=4)), to_dev(syn.franka_inputs(n, seed=5))
+        keep = []
+        for k_ in range(sets):
+            t = t0_ if k_ == 0 else dev_clone(t0_)
+            d = d0_ if k_ == 0 else dev_clone(d0_)
+            keep.append((t, d, torch.zeros(n, 9, device=device), torch.zeros(n, 9, device=device),
+                         ctl.TaskStep(t.rb_states, t.box_idxs, t.hand_idxs, t.dof_pos, t.init_pos, t.init_rot, t.hand_restart, "osc")))
+        for form, mode in (("lanes8", -1), ("tile", 0)):
+            _lib.osc_set_lanes(mode)
+            calls = {"osc": [], "ik": [], "pick_osc": [], "pick_ik": []}
+            for (t, d, pos_action, effort, task) in keep:
+                ctl.bind(j_eef=d.j_eef, mm=d.mm, dof_pos=t.dof_pos, dof_vel=t.dof_state[:, 1].view(n, 9, 1),
+                         default_dof_pos_tensor=d.default_dof_pos, num_envs=n, precision=0)
+                ctl.bind_hand(t.rb_states, t.hand_idxs)
+                calls["osc"].append(ctl.bind_control_osc(d.dpose, effort[:, :7]))
+                calls["ik"].append(ctl.bind_control_ik(d.dpose, pos_action[:, :7], dof_pos=t.dof_pos))
+                calls["pick_osc"].append(ctl.bind_pick_osc(task, effort[:, :7], pos_action[:, 7:9]))
+                calls["pick_ik"].append(ctl.bind_pick_ik(task, pos_action[:, :7], pos_action[:, 7:9]))
+            for k_, cs in calls.items():
+                small.setdefault(f"{k_}_{n}", {})[f"{form}_us"] = round(graph_time(cs, device, 10) * 1e3, 3)
+        _lib.osc_set_lanes(-1)
+        del keep
+    out["small_launch_forms"] = small
     return out
 
 

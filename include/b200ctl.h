@@ -272,9 +272,12 @@ B200CTL_API int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* do
 B200CTL_API int b200ctl_gather_rows(const DLTensor* src, const DLTensor* index, int32_t col0, int32_t ncols,
                         DLTensor* dst, b200ctl_stream_t stream);
 
-/* Form of b200ctl_osc's fp64-chain launches: -1 (default) auto -- eight lanes per env for the smallest launches, four
- * lanes for small ones, one thread per env (TMA-staged tiles) above; 0 never the lane form; 4 / 8 always.  The forms give
- * bit-identical results (same operations in the same order); the choice only moves time.  Process-wide. */
+/* Form of the fp64-chain launches of b200ctl_osc, b200ctl_ik_dls, b200ctl_franka_pick_osc and b200ctl_franka_pick_ik:
+ * -1 (default) auto -- EIGHT LANES PER ENV (north_star's "one warp or a warp group per env": direct coalesced global loads,
+ * the lanes meet in shared memory, the factorisations run on every lane) for launches of at most 32 envs per SM, one thread
+ * per env on TMA-staged tiles above; 0 never the lane form; 4 / 8 that many lanes always.  The forms give bit-identical
+ * results (same operations in the same order); the choice only moves time (256 envs: osc 5.5 -> 2.8 us, ik 2.8 -> 1.6,
+ * pick_osc 6.6 -> 4.0, pick_ik 4.0 -> 2.8; at 16,384 envs the lane form would LOSE, 11.2 vs 7.0 us).  Process-wide. */
 B200CTL_API int b200ctl_osc_set_lanes(int32_t lanes);
 
 /* Persistent grids (the statistics-carrying control kernels) fill every CTA slot of the device; a kernel of ANOTHER

@@ -69,7 +69,7 @@ __device__ __forceinline__ void osc_trace(int k) {
 #define OSC_TRACE(k)
 #endif
 #ifndef B200_OSC_LANES8_ENVS_PER_SM
-#define B200_OSC_LANES8_ENVS_PER_SM 36     // auto rule of b200ctl_osc: eight lanes per env up to this many envs per SM (5,328) ...
+#define B200_OSC_LANES8_ENVS_PER_SM 32     // auto rule of the family-O entry points: eight lanes per env up to this many envs per SM (4,736) ...
 #endif
 #ifndef B200_OSC_LANES4_ENVS_PER_SM
 #define B200_OSC_LANES4_ENVS_PER_SM 0      // ... four lanes up to this many (0: never -- measured slower than eight lanes at every
@@ -1610,13 +1610,17 @@ static bool short_chain_launch(int64_t n, int tile, int dev) {
   return !off && tiles(n, tile) <= 2 * sm_count(dev);
 }
 
-// Lanes per env of a b200ctl_osc launch (osc_lanes_kernel): 0 = the one-thread-per-env tile kernel.  Measured, us per launch
-// (cold data, graph replays; profiles/r02_osc_lanes.txt), tile kernel / 8 lanes / 4 lanes:
-//   256 envs 5.48 / 2.82 / 3.80    1,024 5.44 / 2.87 / 3.88    4,096 5.94 / 4.38 / 4.86    8,192 6.38 / 7.17 / 8.62
-//   16,384 6.98 / 11.2 / 13.1
-// Eight lanes halve a launch that leaves most schedulers idle and lose once every scheduler holds three warps of the lane
-// form (its two factorisations run redundantly on all eight lanes: ~4x the instruction issue of one thread per env); the
-// crossover is ~6,800 envs on 148 SMs.  b200ctl_osc_set_lanes overrides (-1 auto, 0 never, 4 / 8 always).  fp64 chain only.
+// Lanes per env of a family-O launch (osc / ik / pick_osc / pick_ik lane kernels): 0 = the one-thread-per-env tile kernel.
+// Measured, us per launch (graph replays; profiles/r02_osc_lanes.txt), tile kernel / 8 lanes:
+//   osc       256 envs 5.48 / 2.82   4,096 5.94 / 4.38   5,920 5.48 / 5.46   8,192 6.38 / 7.17   16,384 6.98 / 11.2
+//   ik        256 envs 2.82 / 1.64   4,096 3.16 / 2.40   6,144 3.33 / 3.07   8,192 3.38 / 4.57   16,384 3.37 / 5.80
+//   pick_osc  256 envs 6.61 / 3.95   4,096 7.20 / 5.52   6,144 7.37 / 7.47   12,288 7.89 / 12.7
+//   pick_ik   256 envs 4.01 / 2.82   4,096 4.56 / 4.04   6,144 4.67 / 5.32   12,288 4.78 / 8.78
+// Eight lanes nearly halve a launch that leaves most schedulers idle and lose once every scheduler holds three or more warps
+// of the lane form (its factorisations run redundantly on all eight lanes: ~4x the instruction issue of one thread per env);
+// the crossovers lie between 5K and 7K envs on 148 SMs, the rule switches at 32 envs per SM (4,736).  Four lanes are slower
+// than eight at every size (two serial slots per lane).  b200ctl_osc_set_lanes overrides (-1 auto, 0 never, 4 / 8 always).
+// fp64 chain only.
 static std::atomic<int> g_osc_lanes{-1};
 static int osc_lanes_for(int64_t n, int precision, int dev) {
   if (precision != 0) return 0;
