@@ -272,7 +272,8 @@ B200CTL_API int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* do
 B200CTL_API int b200ctl_gather_rows(const DLTensor* src, const DLTensor* index, int32_t col0, int32_t ncols,
                         DLTensor* dst, b200ctl_stream_t stream);
 
-/* Form of the fp64-chain launches of b200ctl_osc, b200ctl_ik_dls, b200ctl_franka_pick_osc and b200ctl_franka_pick_ik:
+/* Form of the fp64-chain launches of b200ctl_osc, b200ctl_ik_dls, b200ctl_franka_pick_osc, b200ctl_franka_pick_ik,
+ * b200ctl_osc_full and b200ctl_franka_osc_step (the last two: eight lanes or none):
  * -1 (default) auto -- EIGHT LANES PER ENV (north_star's "one warp or a warp group per env": direct coalesced global loads,
  * the lanes meet in shared memory, the factorisations run on every lane) for launches of at most 32 envs per SM, one thread
  * per env on TMA-staged tiles above; 0 never the lane form; 4 / 8 that many lanes always.  The forms give bit-identical

@@ -96,6 +96,22 @@ def main():
             for tag, calls in (("pick_osc_fp64", osc), ("pick_ik_fp64", ik)):
                 ts = [bench.graph_time(calls, dev, a.reps) * 1e3 for _ in range(3)]
                 print(f"{tag} n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
+    elif a.family == "oscstep":
+        import test_isaacgym_b200.franka_osc as fosc
+        for n in [int(x) for x in (a.sizes or "256,16384").split(",")]:
+            fi = syn.franka_inputs(n, seed=5)
+            base = fi.__class__(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in fi.__dict__.items()})
+            calls, keep = [], []
+            for _ in range(bench.sets_for(n * 700, lo=2, hi=40)):
+                d = base.__class__(**{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in base.__dict__.items()})
+                pos_des, orn_des = torch.zeros(n, 3, device=dev), torch.zeros(n, 4, device=dev)
+                orn_des[:, 3] = 1.0
+                u9 = torch.zeros(n, 9, 1, device=dev)
+                calls.append(fosc.bind_osc_step(d.rb_states, d.hand_idxs, pos_des, orn_des, d.jacobian[:, syn.FRANKA_JACOBIAN_SLOT],
+                                                d.mass_matrix, d.dof_vel, u9))
+                keep.append((d, pos_des, orn_des, u9))
+            ts = [bench.graph_time(calls, dev, a.reps) * 1e3 for _ in range(3)]
+            print(f"franka_osc_step_fp64 n={n}: {min(ts):.2f} us (runs {', '.join('%.2f' % t for t in ts)})", flush=True)
     elif a.family == "pd":
         from test_isaacgym_b200.pd_control import PDController
         for n in [int(x) for x in (a.sizes or "65536,1048576").split(",")]:

@@ -1558,6 +1558,231 @@ franka_osc_step_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TV
 }
 #undef SM
 
+// ------------------------------------------------------------------ franka_osc.py:229-241 / :221-241, small launches
+// The all-DOF OSC law in the lane form (eight lanes per env; see osc_lanes_kernel): lane g owns rows g (, g + 8) of M, task
+// row g of J, output column(s) g (, g + 8).  Same operations in the same order as osc_full_solve: bit-identical.
+template <int D>
+struct LaneSharedFull {
+  static constexpr int EPC = kLaneThreads / 8;
+  double M[EPC][D][10];     // row i: M[i][0..i] as fp64 (D <= 9, rows padded to 80 bytes)
+  double Y[EPC][6][10];     // row r: column r of Y (D entries)
+  double A[EPC][6][8];      // row r: Lambda^-1[r][0..5], kp dpose[r] at [6]
+};
+
+// dpose of the franka_osc.py loop (:221-239) from the gathered hand pose, pos_des, orn_des -- evaluated on every lane
+struct LaneOscStepTarget {
+  TView rb, hand_index, pos_des, orn_des, dpose_out;
+  float kp;
+  int pos_control, has_dpose;
+  float hand[7], pd[3], od[4], dp[6];
+  __device__ __forceinline__ void prefetch(int64_t env, int g) const {
+    if (g == 0) {
+      int64_t hint;
+      asm volatile("ld.global.relaxed.gpu.u64 %0, [%1];" : "=l"(hint) : "l"(reinterpret_cast<const int64_t*>(hand_index.p) + env * hand_index.s[0]));
+      if (hint >= 0 && hint < rb.n[0]) prefetch_l2(reinterpret_cast<const float*>(rb.p) + hint * rb.s[0]);
+    } else if (g == 1) {
+      prefetch_l2(reinterpret_cast<const float*>(pos_des.p) + env * pos_des.s[0]);
+    } else if (g == 2) {
+      prefetch_l2(reinterpret_cast<const float*>(orn_des.p) + env * orn_des.s[0]);
+    }
+  }
+  __device__ __forceinline__ void load(int64_t env, int) {
+    const int64_t row = __ldg(reinterpret_cast<const int64_t*>(hand_index.p) + env * hand_index.s[0]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pd[c] = __ldg(reinterpret_cast<const float*>(pos_des.p) + env * pos_des.s[0] + c * pos_des.s[1]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) od[c] = __ldg(reinterpret_cast<const float*>(orn_des.p) + env * orn_des.s[0] + c * orn_des.s[1]);
+    const bool ok = row >= 0 && row < rb.n[0];      // a row outside rb_states is never dereferenced (NaN)
+    const float* hp = reinterpret_cast<const float*>(rb.p) + row * rb.s[0];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) hand[c] = ok ? __ldg(hp + c * rb.s[1]) : __int_as_float(0x7fc00000);
+  }
+  __device__ __forceinline__ void resolve() {
+    const float* xr = hand;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float pe = __fmul_rn(kp, __fsub_rn(pd[c], xr[c]));                  // :234
+      if (!pos_control) pe = __fmul_rn(pe, 0.0f);                         // :236-237
+      dp[c] = pe;
+    }
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(xr[3], xr[3]), __fmul_rn(xr[4], xr[4])), __fmul_rn(xr[5], xr[5])),
+                                           __fmul_rn(xr[6], xr[6])));      // :231
+    const float cx = __fdiv_rn(xr[3], nrm), cy = __fdiv_rn(xr[4], nrm), cz = __fdiv_rn(xr[5], nrm), cw = __fdiv_rn(xr[6], nrm);
+    const float ax = od[0], ay = od[1], az = od[2], aw = od[3];
+    const float bx = -cx, by = -cy, bz = -cz, bw = cw;                  // conj(current)
+    auto dot4 = [](float p0, float p1, float p2, float p3) { return __fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3); };
+    const float x = dot4(__fmul_rn(aw, bx), __fmul_rn(ax, bw), __fmul_rn(ay, bz), -__fmul_rn(az, by));
+    const float y = dot4(__fmul_rn(aw, by), -__fmul_rn(ax, bz), __fmul_rn(ay, bw), __fmul_rn(az, bx));
+    const float z = dot4(__fmul_rn(aw, bz), __fmul_rn(ax, by), -__fmul_rn(ay, bx), __fmul_rn(az, bw));
+    const float w = dot4(__fmul_rn(aw, bw), -__fmul_rn(ax, bx), -__fmul_rn(ay, by), -__fmul_rn(az, bz));
+    const float sg = (w > 0.f) ? 1.f : ((w < 0.f) ? -1.f : ((w == 0.f) ? 0.f : w));
+    dp[3] = x * sg; dp[4] = y * sg; dp[5] = z * sg;                      // :232
+  }
+  __device__ __forceinline__ float dpose(int, int i) const { return pick6(dp, i); }
+  __device__ __forceinline__ void commit(int64_t env, bool writer) const {
+    if (!writer || !has_dpose) return;
+    float* dpo = reinterpret_cast<float*>(const_cast<void*>(dpose_out.p)) + env * dpose_out.s[0];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) dpo[c * dpose_out.s[1]] = dp[c];
+  }
+};
+
+template <int D, typename Target>
+__device__ __forceinline__ void osc_full_lanes_body(const TView& jv, const TView& mv, const TView& qdv, float kp, float kv,
+                                                    const TView& out, int64_t n, Target& tg) {
+  using T = double;
+  constexpr int LANES = 8;
+  constexpr int S = (D + LANES - 1) / LANES;      // M rows / output columns per lane
+  constexpr int EPC = LaneSharedFull<D>::EPC;
+  __shared__ __align__(16) LaneSharedFull<D> sm;
+  const int g = threadIdx.x % LANES, el = threadIdx.x / LANES;
+  const int64_t env_raw = (int64_t)blockIdx.x * EPC + el;
+  const bool live = env_raw < n;
+  const int64_t env = live ? env_raw : n - 1;
+  const float* jp = reinterpret_cast<const float*>(jv.p) + env * jv.s[0];
+  const float* mp = reinterpret_cast<const float*>(mv.p) + env * mv.s[0];
+  const float* qdp = reinterpret_cast<const float*>(qdv.p) + env * qdv.s[0];
+#ifndef B200_NO_PREWAIT_PF
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int i = g + s * LANES;
+    if (i < D) prefetch_l2(mp + i * mv.s[1]);
+  }
+  if (g < 6) prefetch_l2(jp + g * jv.s[1]);
+  if (g == 7) prefetch_l2(qdp);
+  tg.prefetch(env, g);
+#endif
+  pdl_prologue();
+  tg.load(env, g);
+  float Mrow[S][D], Jrow[D], Jcol[S][6], qd[D];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int i = g + s * LANES;
+#pragma unroll
+    for (int k = 0; k < D; ++k) Mrow[s][k] = i < D ? __ldg(mp + i * mv.s[1] + k * mv.s[2]) : 0.f;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Jcol[s][r] = i < D ? __ldg(jp + r * jv.s[1] + i * jv.s[2]) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < D; ++k) Jrow[k] = g < 6 ? __ldg(jp + g * jv.s[1] + k * jv.s[2]) : 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) qd[k] = __ldg(qdp + k * qdv.s[1]);
+  tg.resolve();
+  // ---- meeting 1: the lower triangle of M as fp64
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int i = g + s * LANES;
+    if (i < D) {
+      double2* dst = reinterpret_cast<double2*>(sm.M[el][i]);
+#pragma unroll
+      for (int k = 0; k < 10; k += 2)
+        dst[k >> 1] = make_double2(k < D ? (double)Mrow[s][k < D ? k : 0] : 0.0, k + 1 < D ? (double)Mrow[s][k + 1 < D ? k + 1 : 0] : 0.0);
+    }
+  }
+  __syncwarp();
+  T L[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const double2* src = reinterpret_cast<const double2*>(sm.M[el][i]);
+#pragma unroll
+    for (int k = 0; k <= i; k += 2) {
+      const double2 v = src[k >> 1];
+      L[i][k] = v.x;
+      if (k + 1 <= i) L[i][k + 1] = v.y;
+    }
+  }
+  chol_invert_inplace<T, D>(L);
+  // ---- this lane's column of Y = X J^T   (meeting 2)
+  {
+    T y[10];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      T acc = (T)0;
+#pragma unroll
+      for (int jx = 0; jx <= k; ++jx) acc = fma_t<T>(L[k][jx], (T)Jrow[jx], acc);
+      y[k] = acc;
+    }
+#pragma unroll
+    for (int k = D; k < 10; ++k) y[k] = 0.0;
+    if (g < 6) {
+      double2* dst = reinterpret_cast<double2*>(sm.Y[el][g]);
+#pragma unroll
+      for (int k = 0; k < 10; k += 2) dst[k >> 1] = make_double2(y[k], y[k + 1]);
+    }
+  }
+  __syncwarp();
+  // ---- this lane's row of Lambda^-1 = Y^T Y, next to kp dpose[g]   (meeting 3)
+  if (g < 6) {
+    T yr[10], a[8];
+    {
+      const double2* src = reinterpret_cast<const double2*>(sm.Y[el][g]);
+#pragma unroll
+      for (int k = 0; k < 10; k += 2) { const double2 v = src[k >> 1]; yr[k] = v.x; yr[k + 1] = v.y; }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double2* src = reinterpret_cast<const double2*>(sm.Y[el][c]);
+      T yc[10];
+#pragma unroll
+      for (int k = 0; k < 10; k += 2) { const double2 v = src[k >> 1]; yc[k] = v.x; yc[k + 1] = v.y; }
+      T acc = yr[0] * yc[0];
+#pragma unroll
+      for (int k = 1; k < D; ++k) acc = fma_t<T>(yr[k], yc[k], acc);
+      a[c] = acc;
+    }
+    a[6] = (T)__fmul_rn(kp, tg.dpose(0, g));      // (kp * dpose) of :241, rounded in fp32 like the reference
+    a[7] = 0.0;
+    double2* dst = reinterpret_cast<double2*>(sm.A[el][g]);
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) dst[k >> 1] = make_double2(a[k], a[k + 1]);
+  }
+  __syncwarp();
+  T A[6][6], rda[6], w[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const double2* src = reinterpret_cast<const double2*>(sm.A[el][r]);
+#pragma unroll
+    for (int c = 0; c <= r; c += 2) {
+      const double2 v = src[c >> 1];
+      A[r][c] = v.x;
+      if (c + 1 <= r) A[r][c + 1] = v.y;
+    }
+    w[r] = src[3].x;
+  }
+  chol_inplace<T, 6>(A, rda);
+  chol_solve<T, 6>(A, rda, w);            // Lambda (kp dpose)
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int c = g + s * LANES;
+    T damp = (T)0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) damp = fma_t<T>((T)Mrow[s][k], (T)qd[k], damp);
+    T u = -(T)kv * damp;                  // - kv * M qd
+#pragma unroll
+    for (int r = 0; r < 6; ++r) u = fma_t<T>((T)Jcol[s][r], w[r], u);
+    if (live && c < D) reinterpret_cast<float*>(const_cast<void*>(out.p))[env * out.s[0] + c * out.s[1]] = (float)u;
+  }
+  tg.commit(env, live && g == 0);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kLaneThreads)
+osc_full_lanes_kernel(TView jv, TView mv, TView qdv, TView dpv, float kp, float kv, TView out, int64_t n) {
+  LaneDposeTarget<8, false> tg;
+  tg.dpv = dpv; tg.has_index = 0;
+  osc_full_lanes_body<D>(jv, mv, qdv, kp, kv, out, n, tg);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kLaneThreads)
+franka_osc_step_lanes_kernel(TView jv, TView mv, TView qdv, TView rb, TView hand_index, TView pos_des, TView orn_des, float kp,
+                             float kv, int pos_control, TView dpose_out, int has_dpose, TView out, int64_t n) {
+  LaneOscStepTarget tg;
+  tg.rb = rb; tg.hand_index = hand_index; tg.pos_des = pos_des; tg.orn_des = orn_des; tg.dpose_out = dpose_out;
+  tg.kp = kp; tg.pos_control = pos_control; tg.has_dpose = has_dpose;
+  osc_full_lanes_body<D>(jv, mv, qdv, kp, kv, out, n, tg);
+}
+
 // ------------------------------------------------------------------ a11: orientation_error
 __global__ void orientation_error_kernel(TView qd, TView qc, TView out, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1975,13 +2200,19 @@ extern "C" int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
+  cudaStream_t s = (cudaStream_t)stream;
+  const float fkp = (float)kp, fkv = (float)kv;
+  if (osc_lanes_for(n, precision, dev) == 8) {      // small launch: the lane form (same bits), see osc_full_lanes_body
+    const int grid = (int)((n + kLaneThreads / 8 - 1) / (kLaneThreads / 8));
+    if (D == 7) launch_pdl(osc_full_lanes_kernel<7>, grid, kLaneThreads, 0, s, j, m, qd, dp, fkp, fkv, o, n);
+    else        launch_pdl(osc_full_lanes_kernel<9>, grid, kLaneThreads, 0, s, j, m, qd, dp, fkp, fkv, o, n);
+    return post_launch("osc_full_lanes_kernel");
+  }
   const SegSpec spec[4] = {{&j, 6, (int)D}, {&m, (int)D, (int)D}, {&qd, 1, (int)D}, {&dp, 1, 6}};
   CUtensorMap tmap;
   const int tile = pick_tile(n, dev);
   const StagePlan P = make_plan(spec, 4, 0, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
-  cudaStream_t s = (cudaStream_t)stream;
-  const float fkp = (float)kp, fkv = (float)kv;
 #define LAUNCH_FULL(T, DD)                                                       \
   do {                                                                           \
     B200_TRY(set_smem(osc_full_kernel<T, DD>, smem));                            \
@@ -2021,13 +2252,21 @@ extern "C" int b200ctl_franka_osc_step(const DLTensor* j_eef, const DLTensor* mm
   if (n == 0) return 0;
   DeviceGuard g;
   B200_TRY(g.enter(dev));
+  cudaStream_t s = (cudaStream_t)stream;
+  const float fkp = (float)kp, fkv = (float)kv;
+  if (osc_lanes_for(n, precision, dev) == 8) {      // small launch: the lane form (same bits), see osc_full_lanes_body
+    const int grid = (int)((n + kLaneThreads / 8 - 1) / (kLaneThreads / 8));
+    if (D == 7) launch_pdl(franka_osc_step_lanes_kernel<7>, grid, kLaneThreads, 0, s, j, m, qd, rb, hi, pd, od, fkp, fkv,
+                           pos_control ? 1 : 0, dp, has_dpose, o, n);
+    else        launch_pdl(franka_osc_step_lanes_kernel<9>, grid, kLaneThreads, 0, s, j, m, qd, rb, hi, pd, od, fkp, fkv,
+                           pos_control ? 1 : 0, dp, has_dpose, o, n);
+    return post_launch("franka_osc_step_lanes_kernel");
+  }
   const SegSpec spec[5] = {{&j, 6, (int)D}, {&m, (int)D, (int)D}, {&qd, 1, (int)D}, {&pd, 1, 3}, {&od, 1, 4}};
   CUtensorMap tmap;
   const int tile = pick_tile(n, dev);
   const StagePlan P = make_plan(spec, 5, 7, n, tile, &tmap);
   const int smem = P.smem_floats * 4;
-  cudaStream_t s = (cudaStream_t)stream;
-  const float fkp = (float)kp, fkv = (float)kv;
 #define LAUNCH_STEP(T, DD)                                                              \
   do {                                                                                  \
     B200_TRY(set_smem(franka_osc_step_kernel<T, DD>, smem));                            \

@@ -402,5 +402,43 @@ def test_osc_lanes_form_gives_the_same_bits(n):
     assert _rel(outs[8].cpu(), ref)[ok].max() <= 1e-4
 
 
+@pytest.mark.parametrize("n", [3, 260, 3000, 9001])
+def test_all_dof_osc_lane_form_gives_the_same_bits(n):
+    """franka_osc.py's law (b200ctl_osc_full, b200ctl_franka_osc_step; 9 and 7 DOF) in the eight-lanes-per-env form against
+    the tile kernels: torques and dpose bit for bit, incl. an out-of-range hand index and both pos_control settings."""
+    import test_isaacgym_b200.franka_osc as fosc
+    fi = syn.franka_inputs(n, seed=70 + n % 5)
+    d = _bind(fi)
+    j9, m9 = d.jacobian[:, syn.FRANKA_JACOBIAN_SLOT], d.mass_matrix
+    j7, m7 = d.j_eef, d.mm
+    gen = torch.Generator().manual_seed(n)
+    pos_des = torch.randn(n, 3, generator=gen).to(DEV)
+    orn_des = torch.nn.functional.normalize(torch.randn(n, 4, generator=gen), dim=1).to(DEV)
+    idx = d.hand_idxs.clone()
+    if n > 64:
+        idx[11] = d.rb_states.shape[0] + 5
+    res = {}
+    try:
+        for lanes in (0, 8, -1):
+            _lib.osc_set_lanes(lanes)
+            out = []
+            dp = d.dpose.squeeze(-1)
+            out.append(ctl.control_osc_full(dp, j9, m9, d.dof_vel, KP, KD).clone())
+            out.append(ctl.control_osc_full(dp, j7, m7, d.dof_vel[:, :7], KP, KD).clone())
+            for pc in (True, False):
+                dpo = torch.zeros(n, 6, device=DEV)
+                out.append(fosc.osc_step(d.rb_states, idx, pos_des, orn_des, j9, m9, d.dof_vel, KP, KD, pos_control=pc,
+                                         dpose_out=dpo).clone())
+                out.append(dpo)
+            res[lanes] = out
+    finally:
+        _lib.osc_set_lanes(-1)
+    for lanes in (8, -1):
+        for a, b in zip(res[0], res[lanes]):
+            assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+    if n > 64:
+        assert torch.isnan(res[8][2][11]).all() and not torch.isnan(res[8][2][12]).any()
+
+
 def _lib_stat(name):
     return {"N_ENV": 0, "SUM_ABS": 1, "SUM_SQ": 2, "N_SAT": 3, "N_NONFINITE": 4}[name]   # include/b200ctl.h:84-88
