@@ -95,6 +95,9 @@ template <> __device__ __forceinline__ double fma_t<double>(double a, double b, 
 #ifndef B200_OSC_RSQRT
 #define B200_OSC_RSQRT 1      // default form of every kernel that does not choose (A/B knob, profiles/)
 #endif
+#ifndef B200_OSC_ONE
+#define B200_OSC_ONE true     // one-wave launches of osc_kernel: gather and factorisation without the barrier between them (A/B knob)
+#endif
 #ifndef B200_OSC_SHORT
 #define B200_OSC_SHORT 2      // form taken by one-wave launches (A/B knob)
 #endif
@@ -677,7 +680,9 @@ template <> struct OscLayout<true> {
 // keeps a value computed ahead of the dependency wait from being sunk below it by the compiler
 __device__ __forceinline__ void pin(int& v) { asm volatile("" : "+r"(v)); }
 
-template <typename T, bool GYM, int RSQ>
+template <typename T, bool GYM, int RSQ, bool ONE>
+// ONE: the host launched one CTA per tile (a one-wave launch): no refill of the tile buffer, so the gather and the factorisation
+// are one block of straight-line code that ptxas may interleave (no barrier between them).
 // Tried and measured slower: register caps for 5 tiles/SM (168 regs: -13 %, 200 regs: -6 %, both
 // spill); splitting one env over two warps that share Lambda^-1 through shared memory (redundant Cholesky work +
 // a CTA barrier: -70 %).
@@ -757,9 +762,11 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
         for (int r = 0; r < 6; ++r) w[r] = __fsub_rn(__fmul_rn(kp, SM(aDp, e, 0, r)), __fmul_rn(kd, hv[r]));
       }, s_qdef, kp_null, kd_null, R);
     }
-    __syncthreads();                      // every thread has its operands in registers: the buffer is free
-    if (t == (int)blockIdx.x) OSC_TRACE(4);
-    if (t_next < ntiles) issue(t_next, row);
+    if (!ONE) {
+      __syncthreads();                    // every thread has its operands in registers: the buffer is free
+      if (t == (int)blockIdx.x) OSC_TRACE(4);
+      if (t_next < ntiles) issue(t_next, row);
+    }
     if (live) {
       float u[D];
 #if B200_OSC_DEBUG == 1
@@ -2167,14 +2174,14 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
                    P.seg[4].mode != 0 && P.seg[4].b_cs == 1 && !getenv("B200CTL_NO_GYM_LAYOUT");
 #define LAUNCH_OSC(T, G)                                                                                     \
   do {                                                                                                       \
-    B200_TRY(set_smem(osc_kernel<T, G, B200_OSC_RSQRT>, smem));                                              \
-    B200_TRY(persistent_grid(osc_kernel<T, G, B200_OSC_RSQRT>, smem, tiles(n, tile), tile, &grid));          \
+    B200_TRY(set_smem(osc_kernel<T, G, B200_OSC_RSQRT, false>, smem));                                       \
+    B200_TRY(persistent_grid(osc_kernel<T, G, B200_OSC_RSQRT, false>, smem, tiles(n, tile), tile, &grid));   \
     if (sizeof(T) == 8 && short_chain_launch(n, tile, dev)) {                                                \
-      B200_TRY(set_smem(osc_kernel<T, G, kRsqrtShortChain>, smem));                                          \
-      launch_pdl(osc_kernel<T, G, kRsqrtShortChain>, grid, tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
+      B200_TRY(set_smem(osc_kernel<T, G, kRsqrtShortChain, B200_OSC_ONE>, smem));                            \
+      launch_pdl(osc_kernel<T, G, kRsqrtShortChain, B200_OSC_ONE>, tiles(n, tile), tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
                  (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                                    \
     } else {                                                                                                 \
-      launch_pdl(osc_kernel<T, G, B200_OSC_RSQRT>, grid, tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
+      launch_pdl(osc_kernel<T, G, B200_OSC_RSQRT, false>, grid, tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
                  (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                                    \
     }                                                                                                        \
   } while (0)
