@@ -134,10 +134,10 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned byte
 }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)block);
+  cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -146,6 +146,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+  return launch_pdl(kernel, grid, dim3((unsigned)block), smem, stream, args...);
 }
 
 // dtype-dispatched scalar load / store of a strided element (f32 or f64 storage).
@@ -223,7 +227,8 @@ __device__ __forceinline__ void block_stats_commit(double (&d)[ND], unsigned (&u
   static_assert(ND + NI <= 8, "statistics vector has 8 entries");
   __shared__ double s_d[ND][32];
   __shared__ unsigned s_u[NI][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;      // blocks are 1-D except the (env, role) blocks of osc_pair_kernel
+  const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -243,7 +248,7 @@ __device__ __forceinline__ void block_stats_commit(double (&d)[ND], unsigned (&u
   // The commit runs once per CTA at the cold tail of a kernel whose loop body fills the instruction cache -- a
   // persistent servo grid of four waves pays it four times per CTA slot (profiles/r02_ab_servo_stats.txt) -- so its
   // SIZE counts: the first version looped over the warps (unrolled sixteen-fold by the compiler: ~250 instructions).
-  const int nwarp = (blockDim.x + 31) >> 5;
+  const int nwarp = (blockDim.x * blockDim.y + 31) >> 5;
 #pragma unroll
   for (int k = 0; k < ND; ++k) d[k] = lane < nwarp ? s_d[k][lane] : 0.0;
 #pragma unroll

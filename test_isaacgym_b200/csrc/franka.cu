@@ -370,7 +370,7 @@ __device__ __forceinline__ int tile_count(int64_t n) { return (int)((n + TILE_EN
 // Thread 0: L2 prefetch of the bulk-staged operands of tile t (a full, non-last tile), see bulk_prefetch_l2.
 template <int NSEG>
 __device__ __forceinline__ void stage_prefetch(const StagePlan& P, const CUtensorMap* tmap, int t, int ntiles) {
-  if (threadIdx.x != 0 || t >= ntiles || !tile_is_bulk(P, t, ntiles)) return;
+  if (threadIdx.x != 0 || threadIdx.y != 0 || t >= ntiles || !tile_is_bulk(P, t, ntiles)) return;
   const int64_t env0 = (int64_t)t * TILE_ENVS;
   if (P.tmap_bytes) tensor2d_prefetch_l2(tmap, 0, (int)env0);
 #pragma unroll
@@ -387,7 +387,7 @@ __device__ __forceinline__ int warm_view(const TView& v) { return (int)(uintptr_
 template <typename... Views>
 __device__ __forceinline__ void stage_begin(const StagePlan& P, const CUtensorMap* tmap, uint64_t* bar, const Views&... views) {
   __shared__ int s_warm;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
     int w = P.nseg ^ P.smem_floats ^ P.bulk_all;
 #pragma unroll
     for (int i = 0; i < kMaxSeg; ++i) w ^= (int)(uintptr_t)P.seg[i].base ^ P.seg[i].rows ^ P.seg[i].b_off ^ P.seg[i].c_off;
@@ -397,7 +397,7 @@ __device__ __forceinline__ void stage_begin(const StagePlan& P, const CUtensorMa
     s_warm = w;
   }
   if (P.bulk_ok) {
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
       mbar_init(bar, blockDim.x);
       // the tensor map is a kernel parameter too: its descriptor goes into the TMA unit's cache ahead of the wait
       if (P.tmap_bytes) asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
@@ -797,6 +797,141 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   if (stats) {
     double acc[2] = {s_acc[0][threadIdx.x], s_acc[1][threadIdx.x]};
     unsigned cnt[2] = {s_cnt[0][threadIdx.x], s_cnt[1][threadIdx.x]};
+    const int slots[4] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_NONFINITE};
+    block_stats_commit<2, 2>(acc, cnt, stats, slots);
+  }
+}
+
+// ------------------------------------------------------------------ a10, one-wave launches: a thread PAIR per environment
+// Between the lane form (<= 32 envs per SM) and the persistent tile kernel (more than two tiles per SM) a launch is still one
+// latency chain per tile -- TMA landed -> 1.25 us gathering 117 operands out of shared memory -> factorisation -> store -- with
+// half of the SM's schedulers idle.  Here a 64-env tile gets (64, 2) threads: thread (e, 0) loads J and the lower triangle of
+// M and factors; thread (e, 1), on another warp, forms everything the factorisation does NOT need -- u0, M u0 and the
+// task-space right-hand side w (two thirds of the gather: 90 shared loads, ~100 conversions, 91 fp64 FMAs) -- and hands the
+// thirteen values over through shared memory; the solver meets them at ONE CTA barrier placed after the second Cholesky, when
+// the helper has long finished.  Same operations in the same order as osc_gather / osc_solve: bit-identical.
+template <typename T, typename AJ, typename AM, typename AQ, typename AQD, typename TaskSpaceTarget>
+__device__ __forceinline__ void osc_gather_rhs(const float* tile, const AJ& aJ, const AM& aM, const AQ& aQ, const AQD& aQD, int e,
+                                               TaskSpaceTarget&& target, const float* q_default, float kp_null, float kd_null,
+                                               T (&w)[6], T (&Mu0)[7]) {
+  constexpr int D = 7;
+  float u0[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c)
+    u0[c] = __fadd_rn(__fmul_rn(kd_null, -SM(aQD, e, 0, c)), __fmul_rn(kp_null, wrap_pi(__fsub_rn(q_default[c], SM(aQ, e, 0, c)))));
+  float wt[6];
+  target(wt);
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    T s = (T)wt[r];
+#pragma unroll
+    for (int c = 0; c < D; ++c) s = fma_t<T>(-(T)SM(aJ, e, r, c), (T)u0[c], s);
+    w[r] = s;
+  }
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    T u = (T)0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) u = fma_t<T>((T)SM(aM, e, c, k), (T)u0[k], u);
+    Mu0[c] = u;
+  }
+}
+
+template <typename T, bool GYM, int RSQ>
+__global__ void __launch_bounds__(2 * kTileEnvs)
+osc_pair_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel, TView hand_index, int has_index, TView q_default,
+                float kp, float kd, float kp_null, float kd_null, TView out, int64_t n, double* __restrict__ stats) {
+  constexpr int D = 7;
+  using Lay = OscLayout<GYM>;
+  extern __shared__ __align__(128) float tile[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(16) T s_rhs[kTileEnvs][14];      // per env: w[6], M u0 [7]
+  __shared__ float s_qdef[8];
+  const bool solver = threadIdx.y == 0;
+  stage_begin(P, &tmap, &bar, hand_vel, hand_index, q_default, out);
+  if (solver) {
+    stage_prefetch_first<5>(P, &tmap, n);
+    gather_prefetch(hand_index, has_index, hand_vel, n);
+  }
+  SAddr a[5];
+  stage_addr<5>(P, a);
+  typename Lay::J aJ(a[0]);
+  typename Lay::M aM(a[1]);
+  typename Lay::Q aQ(a[2]);
+  typename Lay::QD aQD(a[3]);
+  typename Lay::DP aDp(a[4]);
+  const int x_ts = stage_extras_ts(P);
+  int hv_off = stage_extras_off(P) + (int)threadIdx.x * x_ts;
+  int ntiles = (int)((n + TILE_ENVS - 1) / TILE_ENVS);
+  pin(aJ.off); pin(aJ.es); pin(aM.off); pin(aM.es); pin(aQ.off); pin(aQD.off); pin(aDp.off); pin(hv_off); pin(ntiles);
+  pdl_prologue();
+  const int t = blockIdx.x;      // one CTA per tile
+  const int64_t env0 = (int64_t)t * TILE_ENVS;
+  const int nenv = (int)((n - env0) < TILE_ENVS ? (n - env0) : TILE_ENVS);
+  unsigned phase = 0;
+  if (solver) {
+    const float qdef_mine = threadIdx.x < 7 ? ldf(q_default, threadIdx.x * q_default.s[0]) : 0.f;
+    const int64_t row = gather_row(hand_index, has_index, env0, nenv);
+    stage_issue<5>(P, &tmap, t, ntiles, n, tile, &bar);
+    gather_copy<6>(hand_vel, row, nenv, tile + stage_extras_off(P), x_ts);
+    if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;      // published by the barrier that ends stage_wait
+  }
+  stage_wait<5>(P, t, ntiles, &bar, phase);      // every thread: own cp.async copies (helpers: none), the TMA phase, a CTA barrier
+  const bool live = (int)threadIdx.x < nenv;
+  const int e = threadIdx.x;
+  T A[6][6], rda[6];
+  float J[6][D];
+  if (live && !solver) {
+    T w[6], Mu0[D];
+    const float* hv = tile + hv_off;
+    osc_gather_rhs<T>(tile, aJ, aM, aQ, aQD, e, [&](float (&wt)[6]) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) wt[r] = __fsub_rn(__fmul_rn(kp, SM(aDp, e, 0, r)), __fmul_rn(kd, hv[r]));
+    }, s_qdef, kp_null, kd_null, w, Mu0);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) s_rhs[e][r] = w[r];
+#pragma unroll
+    for (int c = 0; c < D; ++c) s_rhs[e][6 + c] = Mu0[c];
+  }
+  if (live && solver) {
+    T L[D][D];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) J[r][c] = SM(aJ, e, r, c);
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+      for (int k = 0; k <= c; ++k) L[c][k] = (T)SM(aM, e, c, k);
+    task_space_factor<T, D, RSQ>(J, L, A, rda);
+  }
+  __syncthreads();      // the helpers' thirteen values per env are in shared memory
+  double acc[2] = {0, 0};
+  unsigned cnt[2] = {0, 0};
+  if (live && solver) {
+    T w[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) w[r] = s_rhs[e][r];
+    chol_solve<T, 6>(A, rda, w);          // w <- Lambda (w - J u0)
+    float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + (env0 + e) * out.s[0];
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      T u = s_rhs[e][6 + c];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], w[r], u);          // + J^T Lambda (...)
+      const float uf = (float)u;
+      o[c * out.s[1]] = uf;
+      const bool f = isfinite(uf);
+      finite = finite && f;
+      const float v = f ? uf : 0.f;
+      acc[0] += fabsf(v);
+      acc[1] += (double)v * v;
+    }
+    cnt[0] = 1u;
+    cnt[1] = finite ? 0u : 1u;
+  }
+  if (stats) {
     const int slots[4] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_NONFINITE};
     block_stats_commit<2, 2>(acc, cnt, stats, slots);
   }
@@ -2172,11 +2307,17 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
                    P.seg[1].mode != 0 && P.seg[1].b_rs == 9 && P.seg[1].b_cs == 1 &&
                    P.seg[2].mode != 0 && P.seg[2].b_cs == 2 && P.seg[3].mode != 0 && P.seg[3].b_cs == 2 &&
                    P.seg[4].mode != 0 && P.seg[4].b_cs == 1 && !getenv("B200CTL_NO_GYM_LAYOUT");
+  // one-wave launches: a thread PAIR per env (osc_pair_kernel) unless B200CTL_NO_PAIR is set (A/B switch for profiles/)
+  static const bool use_pair = getenv("B200CTL_NO_PAIR") == nullptr;
 #define LAUNCH_OSC(T, G)                                                                                     \
   do {                                                                                                       \
     B200_TRY(set_smem(osc_kernel<T, G, B200_OSC_RSQRT, false>, smem));                                       \
     B200_TRY(persistent_grid(osc_kernel<T, G, B200_OSC_RSQRT, false>, smem, tiles(n, tile), tile, &grid));   \
-    if (sizeof(T) == 8 && short_chain_launch(n, tile, dev)) {                                                \
+    if (sizeof(T) == 8 && short_chain_launch(n, tile, dev) && use_pair && tile == kTileEnvs) {               \
+      B200_TRY(set_smem(osc_pair_kernel<T, G, kRsqrtShortChain>, smem));                                     \
+      launch_pdl(osc_pair_kernel<T, G, kRsqrtShortChain>, tiles(n, tile), dim3(kTileEnvs, 2), smem, s, P, tmap, hv, hi, has_index, qdef, \
+                 (float)kp, (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                         \
+    } else if (sizeof(T) == 8 && short_chain_launch(n, tile, dev)) {                                         \
       B200_TRY(set_smem(osc_kernel<T, G, kRsqrtShortChain, B200_OSC_ONE>, smem));                            \
       launch_pdl(osc_kernel<T, G, kRsqrtShortChain, B200_OSC_ONE>, tiles(n, tile), tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
                  (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                                    \
