@@ -1520,6 +1520,125 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   }
 }
 
+// The fused pick step in the thread-pair form (one-wave launches above the lane form's range; see osc_pair_kernel): the helper
+// thread runs the goal logic, writes its side effects and forms u0, M u0 and w from dpose while the solver thread factors.
+template <typename T, int RSQ>
+__global__ void __launch_bounds__(2 * kTileEnvs)
+pick_osc_pair_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, TView box_index, TView hand_index,
+                     uint8_t* __restrict__ hand_restart, int64_t hr_stride, TaskConst tk, TView q_default, float kp, float kd,
+                     float kp_null, float kd_null, TView dpose_out, int has_dpose, TView grip, TView out, int64_t n,
+                     double* __restrict__ stats) {
+  constexpr int D = 7;
+  extern __shared__ __align__(128) float tile[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(16) T s_rhs[kTileEnvs][14];      // per env: w[6], M u0 [7]
+  __shared__ float s_qdef[8];
+  const bool solver = threadIdx.y == 0;
+  stage_begin(P, &tmap, &bar, rb, box_index, hand_index, q_default, dpose_out, grip, out);
+  if (solver) {
+    stage_prefetch_first<6>(P, &tmap, n);
+    gather_prefetch(box_index, 1, rb, n);
+    gather_prefetch(hand_index, 1, rb, n);
+  }
+  pdl_prologue();
+  const int ntiles = tile_count(n);
+  const int64_t env0 = (int64_t)blockIdx.x * TILE_ENVS;
+  const int nenv = (int)((n - env0) < TILE_ENVS ? ((n - env0) > 0 ? (n - env0) : 0) : TILE_ENVS);
+  const int x_ts = stage_extras_ts(P);
+  float* x0 = tile + stage_extras_off(P);
+  SAddr a[6];
+  stage_addr<6>(P, a);
+  unsigned phase = 0;
+  if (solver) {
+    const int64_t box_row = gather_row(box_index, 1, env0, nenv), hand_row = gather_row(hand_index, 1, env0, nenv);
+    const float qdef_mine = threadIdx.x < 7 ? ldf(q_default, threadIdx.x * q_default.s[0]) : 0.f;
+    stage_issue<6>(P, &tmap, blockIdx.x, ntiles, n, tile, &bar);
+    gather_copy<7>(rb, box_row, nenv, x0, x_ts);              // box pos + quat          (:348-349)
+    gather_copy<13>(rb, hand_row, nenv, x0 + 7, x_ts);        // hand pos + quat + vel   (:351-353)
+    if (threadIdx.x < 7) s_qdef[threadIdx.x] = qdef_mine;
+  }
+  stage_wait<6>(P, blockIdx.x, ntiles, &bar, phase);
+  const bool live = (int)threadIdx.x < nenv;
+  const int e = threadIdx.x;
+  const int64_t env = env0 + e;
+  T A[6][6], rda[6];
+  float J[6][D];
+  if (live && !solver) {
+    const float* xr = x0 + e * x_ts;
+    const SAddr aQ = a[2], aIp = a[4], aIq = a[5];
+    T w[6], Mu0[D];
+    osc_gather_rhs<T>(tile, a[0], a[1], a[2], a[3], e, [&](float (&wt)[6]) {
+      float box[7], hand[7], ip[3], iq[4];
+#pragma unroll
+      for (int c = 0; c < 7; ++c) { box[c] = xr[c]; hand[c] = xr[7 + c]; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ip[c] = SM(aIp, e, 0, c);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) iq[c] = SM(aIq, e, 0, c);
+      const float sep = __fadd_rn(SM(aQ, e, 0, 7), SM(aQ, e, 0, 8));   // :364
+      TaskOut t;
+      task_logic(box, hand, sep, ip, iq, hand_restart[env * hr_stride] != 0, tk, t);
+      hand_restart[env * hr_stride] = t.restart ? 1 : 0;
+      float* gr = reinterpret_cast<float*>(const_cast<void*>(grip.p)) + env * grip.s[0];
+      gr[0] = t.grip;
+      gr[grip.s[1]] = t.grip;
+      if (has_dpose) {
+        float* dpo = reinterpret_cast<float*>(const_cast<void*>(dpose_out.p)) + env * dpose_out.s[0];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dpo[c * dpose_out.s[1]] = t.dpose[c];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) wt[r] = __fsub_rn(__fmul_rn(kp, t.dpose[r]), __fmul_rn(kd, xr[14 + r]));   // :67-68, hand vel :353
+    }, s_qdef, kp_null, kd_null, w, Mu0);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) s_rhs[e][r] = w[r];
+#pragma unroll
+    for (int c = 0; c < D; ++c) s_rhs[e][6 + c] = Mu0[c];
+  }
+  if (live && solver) {
+    T L[D][D];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) J[r][c] = SM(a[0], e, r, c);
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+      for (int k = 0; k <= c; ++k) L[c][k] = (T)SM(a[1], e, c, k);
+    task_space_factor<T, D, RSQ>(J, L, A, rda);
+  }
+  __syncthreads();
+  double acc[2] = {0, 0};
+  unsigned cnt[2] = {0, 0};
+  if (live && solver) {
+    T w[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) w[r] = s_rhs[e][r];
+    chol_solve<T, 6>(A, rda, w);
+    float* o = reinterpret_cast<float*>(const_cast<void*>(out.p)) + env * out.s[0];
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      T u = s_rhs[e][6 + c];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) u = fma_t<T>((T)J[r][c], w[r], u);
+      const float uf = (float)u;
+      o[c * out.s[1]] = uf;
+      const bool f = isfinite(uf);
+      finite = finite && f;
+      const float v = f ? uf : 0.f;
+      acc[0] += fabsf(v);
+      acc[1] += (double)v * v;
+    }
+    cnt[0] = 1u;
+    cnt[1] = finite ? 0u : 1u;
+  }
+  if (stats) {
+    const int slots[4] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_NONFINITE};
+    block_stats_commit<2, 2>(acc, cnt, stats, slots);
+  }
+}
+
 // ------------------------------------------------------------------ fused pick step, IK controller (the script's default)
 // examples/franka_cube_ik_osc.py:348-410 with --controller ik: goal logic, DLS-IK and
 // pos_action[:, :7] = dof_pos[:, :7] + control_ik(dpose), pos_action[:, 7:9] = grip_acts in one launch.
@@ -2494,7 +2613,13 @@ extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm
     launch_pdl(pick_osc_kernel<T, V>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, \
                (float)kd, (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);                             \
   } while (0)
+  static const bool use_pair = getenv("B200CTL_NO_PAIR") == nullptr;      // A/B switch for profiles/
   if (precision != 0) LAUNCH_PICK(float, B200_OSC_RSQRT);
+  else if (short_chain_launch(n, tile, dev) && use_pair && tile == kTileEnvs) {
+    B200_TRY(set_smem(pick_osc_pair_kernel<double, kRsqrtShortChain>, smem));
+    launch_pdl(pick_osc_pair_kernel<double, kRsqrtShortChain>, tiles(n, tile), dim3(kTileEnvs, 2), smem, s, P, tmap, rb, bi, hi, hrp,
+               hr.s[0], tk, qdef, (float)kp, (float)kd, (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
+  }
   else if (short_chain_launch(n, tile, dev)) LAUNCH_PICK(double, kRsqrtShortChain);
   else LAUNCH_PICK(double, B200_OSC_RSQRT);
 #undef LAUNCH_PICK
