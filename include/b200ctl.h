@@ -276,7 +276,9 @@ B200CTL_API int b200ctl_gather_rows(const DLTensor* src, const DLTensor* index, 
  * b200ctl_osc_full and b200ctl_franka_osc_step (the last two: eight lanes or none):
  * -1 (default) auto -- EIGHT LANES PER ENV (north_star's "one warp or a warp group per env": direct coalesced global loads,
  * the lanes meet in shared memory, the factorisations run on every lane) for launches of at most 32 envs per SM, one thread
- * per env on TMA-staged tiles above; 0 never the lane form; 4 / 8 that many lanes always.  The forms give bit-identical
+ * per env on TMA-staged tiles above (a thread PAIR per env -- solver + helper -- for b200ctl_osc / b200ctl_franka_pick_osc
+ * launches of at most two tiles per SM); 0 never the lane form; 1 one thread per env throughout (no lanes, no pairs);
+ * 4 / 8 that many lanes always.  The forms give bit-identical
  * results (same operations in the same order); the choice only moves time (256 envs: osc 5.5 -> 2.8 us, ik 2.8 -> 1.6,
  * pick_osc 6.6 -> 4.0, pick_ik 4.0 -> 2.8; at 16,384 envs the lane form would LOSE, 11.2 vs 7.0 us).  Process-wide. */
 B200CTL_API int b200ctl_osc_set_lanes(int32_t lanes);

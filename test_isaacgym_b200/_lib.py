@@ -187,8 +187,9 @@ def dl(t):
 
 
 def osc_set_lanes(lanes: int) -> None:
-    """Form of the fp64-chain ``control_osc`` launches: -1 auto (lanes per env for small launches), 0 one thread per env
-    always, 4 / 8 that many lanes per env always.  Same bits either way."""
+    """Form of the fp64-chain family-O launches: -1 auto (eight lanes per env for small launches, a thread pair per env for
+    one-wave ``control_osc`` / pick_osc launches, one thread per env above), 0 never the lane form, 1 one thread per env
+    throughout, 4 / 8 that many lanes per env always.  Same bits either way."""
     check(lib().b200ctl_osc_set_lanes(int(lanes)))
 
 

@@ -2111,11 +2111,19 @@ static std::atomic<int> g_osc_lanes{-1};
 static int osc_lanes_for(int64_t n, int precision, int dev) {
   if (precision != 0) return 0;
   const int mode = g_osc_lanes.load(std::memory_order_relaxed);
+  if (mode == 1) return 0;      // one thread per env, always (no lane form, no thread pairs: pair_form_allowed())
   if (mode >= 0) return mode;
   const int64_t sms = sm_count(dev);
   if (n <= B200_OSC_LANES8_ENVS_PER_SM * sms) return 8;
   if (n <= B200_OSC_LANES4_ENVS_PER_SM * sms) return 4;
   return 0;
+}
+
+// The thread-pair kernels (osc_pair_kernel, pick_osc_pair_kernel) take the one-wave launches the lane form leaves to the tile
+// kernels, unless b200ctl_osc_set_lanes(1) asks for one thread per env throughout.
+static bool pair_form_allowed() {
+  static const bool off = getenv("B200CTL_NO_PAIR") != nullptr;      // A/B switch for profiles/
+  return !off && g_osc_lanes.load(std::memory_order_relaxed) != 1;
 }
 
 static int check_precision(int precision) {
@@ -2362,7 +2370,8 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
 }
 
 extern "C" int b200ctl_osc_set_lanes(int32_t lanes) {
-  if (lanes != -1 && lanes != 0 && lanes != 4 && lanes != 8) B200_FAIL(B200CTL_E_VALUE, "lanes must be -1 (auto), 0, 4 or 8");
+  if (lanes != -1 && lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8)
+    B200_FAIL(B200CTL_E_VALUE, "lanes must be -1 (auto), 0, 1, 4 or 8");
   g_osc_lanes.store(lanes, std::memory_order_relaxed);
   return 0;
 }
@@ -2426,8 +2435,7 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
                    P.seg[1].mode != 0 && P.seg[1].b_rs == 9 && P.seg[1].b_cs == 1 &&
                    P.seg[2].mode != 0 && P.seg[2].b_cs == 2 && P.seg[3].mode != 0 && P.seg[3].b_cs == 2 &&
                    P.seg[4].mode != 0 && P.seg[4].b_cs == 1 && !getenv("B200CTL_NO_GYM_LAYOUT");
-  // one-wave launches: a thread PAIR per env (osc_pair_kernel) unless B200CTL_NO_PAIR is set (A/B switch for profiles/)
-  static const bool use_pair = getenv("B200CTL_NO_PAIR") == nullptr;
+  const bool use_pair = pair_form_allowed();      // one-wave launches: a thread PAIR per env (osc_pair_kernel)
 #define LAUNCH_OSC(T, G)                                                                                     \
   do {                                                                                                       \
     B200_TRY(set_smem(osc_kernel<T, G, B200_OSC_RSQRT, false>, smem));                                       \
@@ -2613,7 +2621,7 @@ extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm
     launch_pdl(pick_osc_kernel<T, V>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, \
                (float)kd, (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);                             \
   } while (0)
-  static const bool use_pair = getenv("B200CTL_NO_PAIR") == nullptr;      // A/B switch for profiles/
+  const bool use_pair = pair_form_allowed();
   if (precision != 0) LAUNCH_PICK(float, B200_OSC_RSQRT);
   else if (short_chain_launch(n, tile, dev) && use_pair && tile == kTileEnvs) {
     B200_TRY(set_smem(pick_osc_pair_kernel<double, kRsqrtShortChain>, smem));

@@ -361,10 +361,11 @@ def test_out_of_range_gather_index_gives_nan_not_a_fault():
     ctl._hand_index = None
 
 
-@pytest.mark.parametrize("n", [1, 7, 64, 593, 4096, 20_003])
+@pytest.mark.parametrize("n", [1, 7, 64, 593, 4096, 9_999, 20_003])
 def test_osc_lanes_form_gives_the_same_bits(n):
     """b200ctl_osc runs small fp64-chain launches with 8 or 4 lanes per env (osc_lanes_kernel: direct global loads, three
-    shared-memory meetings, redundant factorisations) and larger ones with one thread per env (TMA-staged tiles).  Every
+    shared-memory meetings, redundant factorisations), one-wave launches above that with a thread PAIR per env
+    (osc_pair_kernel) and larger ones with one thread per env (persistent TMA-staged tiles).  Every
     value is produced by the same operations in the same order, so the forms must agree BIT FOR BIT -- full and ragged
     sizes, index-gathered hand velocity incl. out-of-range rows, strided output, statistics."""
     fi = syn.franka_inputs(n, seed=40 + n % 7)
@@ -375,7 +376,7 @@ def test_osc_lanes_form_gives_the_same_bits(n):
     ctl.bind_hand(d.rb_states, idx)
     outs, stats = {}, {}
     try:
-        for lanes in (0, 4, 8, -1):
+        for lanes in (1, 0, 4, 8, -1):      # 1: one thread per env throughout; 0: thread pairs where they apply, no lane form
             _lib.osc_set_lanes(lanes)
             eff = torch.full((n, 9), 3.0, device=DEV)
             st = _lib.stats_buffer(torch.device(DEV))
@@ -385,14 +386,14 @@ def test_osc_lanes_form_gives_the_same_bits(n):
     finally:
         _lib.osc_set_lanes(-1)
         ctl._hand_index = None
-    for lanes in (4, 8, -1):
-        a, b = outs[0], outs[lanes]
+    for lanes in (0, 4, 8, -1):
+        a, b = outs[1], outs[lanes]
         assert torch.equal(torch.isnan(a), torch.isnan(b))
         assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), f"lanes={lanes} differs from the tile kernel"
         assert stats[lanes][_lib_stat("N_ENV")] == n
-        assert stats[lanes][_lib_stat("N_NONFINITE")] == stats[0][_lib_stat("N_NONFINITE")] == (2 if n > 64 else 0)
+        assert stats[lanes][_lib_stat("N_NONFINITE")] == stats[1][_lib_stat("N_NONFINITE")] == (2 if n > 64 else 0)
         for k in ("SUM_ABS", "SUM_SQ"):
-            assert abs(float(stats[lanes][_lib_stat(k)]) - float(stats[0][_lib_stat(k)])) <= 1e-12 * abs(float(stats[0][_lib_stat(k)]))
+            assert abs(float(stats[lanes][_lib_stat(k)]) - float(stats[1][_lib_stat(k)])) <= 1e-12 * abs(float(stats[1][_lib_stat(k)]))
     # and against the fp64 oracle (the tile kernel's gate)
     f = lambda t: t.double()
     hv = fi.rb_states[fi.hand_idxs, 7:]

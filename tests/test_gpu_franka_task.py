@@ -210,7 +210,7 @@ def test_lane_forms_of_ik_and_pick_steps_give_the_same_bits(n):
         box_idx[3], hand_idx[n - 5] = -7, ti.rb_states.shape[0] + 1
     res = {}
     try:
-        for lanes in (0, 4, 8, -1):
+        for lanes in (1, 0, 4, 8, -1):      # 1: one thread per env throughout; 0: thread pairs where they apply
             _lib.osc_set_lanes(lanes)
             out = {}
             ctl.bind(damping=0.05, kp=150., kd=2.0 * np.sqrt(150.), kp_null=10., kd_null=2.0 * np.sqrt(10.), j_eef=fd.j_eef,
@@ -238,12 +238,12 @@ def test_lane_forms_of_ik_and_pick_steps_give_the_same_bits(n):
     finally:
         _lib.osc_set_lanes(-1)
         ctl._hand_index = None
-    for lanes in (4, 8, -1):
-        a, b = res[0], res[lanes]
+    for lanes in (0, 4, 8, -1):
+        a, b = res[1], res[lanes]
         assert _same(a["ik7"], b["ik7"]) and _same(a["ik9"], b["ik9"]), f"control_ik, lanes={lanes}"
         assert torch.equal(a["osc_counts"], b["osc_counts"]) and a["osc_counts"][0] == n
         for tag in ("osc", "ik"):
             for x, y in zip(a[tag], b[tag]):
                 assert _same(x.float(), y.float()), f"pick_{tag}, lanes={lanes}"
     if n > 64:
-        assert int(res[0]["osc_counts"][1]) >= 2      # the two envs with a bad index are counted, not dereferenced
+        assert int(res[1]["osc_counts"][1]) >= 2      # the two envs with a bad index are counted, not dereferenced
