@@ -505,7 +505,7 @@ def family_numbers(device, peak_gbs):
     # Small launches -- the reference scripts' own default is 256 envs.  north_star's "one warp (or a warp group) per env" form:
     # launches of at most 32 envs per SM run with EIGHT LANES per env (osc_lanes_kernel and its ik / pick twins: direct coalesced
     # global loads, three shared-memory meetings, redundant factorisations; bit-identical to the tile kernels), timed here next
-    # to the one-thread-per-env tile kernel forced with b200ctl_osc_set_lanes(0)
+    # to the one-thread-per-env tile kernel forced with b200ctl_osc_set_lanes(1)
     small = {"_note": "us per launch, fp64 chain, CUDA-graph replays over 40 rotating sets (L2-resident at these sizes whatever "
                       "the rotation); lanes8 = the form b200ctl picks by itself at this size, tile = one thread per env forced"}
     for n in (256, 4096):
@@ -517,7 +517,7 @@ def family_numbers(device, peak_gbs):
             d = d0_ if k_ == 0 else dev_clone(d0_)
             keep.append((t, d, torch.zeros(n, 9, device=device), torch.zeros(n, 9, device=device),
                          ctl.TaskStep(t.rb_states, t.box_idxs, t.hand_idxs, t.dof_pos, t.init_pos, t.init_rot, t.hand_restart, "osc")))
-        for form, mode in (("lanes8", -1), ("tile", 0)):
+        for form, mode in (("lanes8", -1), ("tile", 1)):
             _lib.osc_set_lanes(mode)
             calls = {"osc": [], "ik": [], "pick_osc": [], "pick_ik": []}
             for (t, d, pos_action, effort, task) in keep:
