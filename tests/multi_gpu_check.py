@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Multi-GPU check, run under torchrun on >= 2 GPUs (not collected by pytest: the driver's GPU tier has one GPU):
+"""Multi-GPU check, run under torchrun on >= 2 GPUs (tests/test_gpu_multi.py launches it on two GPUs when the box has them):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
 
