@@ -245,6 +245,15 @@ struct StagePlan {
                           //    readable once its mbarrier phase completes, and the only cp.async copies in flight are the
                           //    ones a thread issued for ITS OWN env (the index-gathered extras), which it may wait for later
   int smem_floats;        // dynamic shared memory, in floats (max of both plans)
+  // what thread 0 needs to issue a tile's bulk copies, packed: the fields above are spread over ~100 bytes per operand and the
+  // issue used to walk them with a mode test per operand -- ~250 instructions of constant-bank loads and uniform-datapath
+  // arithmetic between the dependency wait and the last TMA instruction (0.7 us at 16,384 envs, profiles/r02_osc_trace.txt)
+  struct Issue {
+    const char* src0;           // aligned address of the operand's block of tile 0
+    long long tile_pitch;       // bytes from one tile's block to the next
+    unsigned dst_off, bytes;    // destination (floats into the tile buffer); bytes == 0: not a one-copy-per-tile operand
+  } issue[kMaxSeg];
+  unsigned bulk_bytes;          // sum of issue[].bytes + tmap_bytes: the transaction count of a tile
 };
 struct SAddr { int off, es, rs, cs; };   // resolved smem addressing of one operand for this CTA
 // The same with the row / column strides known at compile time: an operand staged in its Isaac Gym layout (jacobian rows
@@ -442,20 +451,14 @@ __device__ __forceinline__ void stage_issue(const StagePlan& P, const CUtensorMa
   const bool bulk = tile_is_bulk(P, t, ntiles);
   if (B200_OSC_DEBUG == 2) return;
   if (bulk) {
-    unsigned my_bytes = threadIdx.x == 0 ? P.tmap_bytes : 0u;
+    const bool t0 = threadIdx.x == 0;
+    mbar_arrive_expect_tx(bar, t0 ? P.bulk_bytes : 0u);     // every thread arrives; the phase completes when all bytes landed
+    if (t0) {
+      if (P.tmap_bytes) tensor2d_g2s(tile + P.tmap_region, tmap, 0, (int)env0, bar);
 #pragma unroll
-    for (int i = 0; i < NSEG; ++i) {
-      const StageSeg& s = P.seg[i];
-      if (s.mode == 1 && threadIdx.x == 0) my_bytes += s.bytes;
-    }
-    mbar_arrive_expect_tx(bar, my_bytes);     // every thread arrives; the phase completes when all bytes landed
-    if (threadIdx.x == 0 && P.tmap_bytes) tensor2d_g2s(tile + P.tmap_region, tmap, 0, (int)env0, bar);
-#pragma unroll
-    for (int i = 0; i < NSEG; ++i) {
-      const StageSeg& s = P.seg[i];
-      if (s.mode == 1 && threadIdx.x == 0) {
-        const char* src = reinterpret_cast<const char*>(s.base + env0 * s.s0) - s.delta;
-        bulk_g2s(tile + s.region, src, s.bytes, bar);
+      for (int i = 0; i < NSEG; ++i) {
+        const StagePlan::Issue& q = P.issue[i];
+        if (q.bytes) bulk_g2s(tile + q.dst_off, q.src0 + (long long)t * q.tile_pitch, q.bytes, bar);
       }
     }
   }
@@ -1552,6 +1555,18 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
       for (int i = 0; i < nseg; ++i) P.seg[i].mode = 0;
     } else if (bulk_floats > P.smem_floats) {
       P.smem_floats = bulk_floats;
+    }
+  }
+  P.bulk_bytes = P.tmap_bytes;
+  for (int i = 0; i < nseg; ++i) {
+    const StageSeg& s = P.seg[i];
+    StagePlan::Issue& q = P.issue[i];
+    if (P.bulk_ok && s.mode == 1) {
+      q.src0 = reinterpret_cast<const char*>(s.base) - s.delta;
+      q.tile_pitch = (long long)tile * s.s0 * 4;
+      q.dst_off = (unsigned)s.region;
+      q.bytes = s.bytes;
+      P.bulk_bytes += s.bytes;
     }
   }
   return P;
