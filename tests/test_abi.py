@@ -58,6 +58,8 @@ def test_argument_checks_that_need_no_gpu():
     assert L.b200ctl_measure_fma_peak(2, 0, 3, C.byref(best), C.byref(med)) == -6          # E_VALUE: dtype
     assert L.b200ctl_reserve_cta_slots(99, 1) == -2 and L.b200ctl_reserve_cta_slots(0, -1) == -6
     assert L.b200ctl_reserve_cta_slots(0, 0) == 0
+    assert L.b200ctl_osc_set_lanes(3) == -6 and L.b200ctl_osc_set_lanes(16) == -6          # -1 (auto), 0, 1, 4, 8 only
+    assert all(L.b200ctl_osc_set_lanes(m) == 0 for m in (0, 1, 4, 8, -1))
     boxes = (C.c_void_p * 2)()
     assert L.b200ctl_stats_allreduce_peer(boxes, 2, 2, 0, 0, None, 8, None, None, 2.0, 0, None) == -1   # NULL stats
     assert L.b200ctl_peer_mailbox_create(0, None, None) == -1
