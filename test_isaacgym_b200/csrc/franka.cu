@@ -44,10 +44,10 @@ namespace b200ctl {
 
 constexpr float kPiF = 3.14159265358979323846f;
 constexpr float kTwoPiF = 6.28318530717958647692f;
-constexpr int kTileEnvs = 64;        // envs per tile = threads per CTA ...
+constexpr int kTileEnvs = 64;        // threads per CTA (per role); envs per tile <= that: the plan's tile_envs ...
 constexpr int kMaxTileEnvs = 128;    // ... or 128 when the whole batch is then ONE tile per SM (pick_tile): device code
                                      // takes the tile size from blockDim.x
-#define TILE_ENVS ((int)blockDim.x)
+#define TILE_ENVS (P.tile_envs)      // envs per tile: a field of the launch's staging plan (`P` in every function that tiles)
 constexpr int kMaxSeg = 6;
 #ifndef B200_OSC_L2PF
 #define B200_OSC_L2PF 0       // A/B knob: 1 = the persistent OSC kernel L2-prefetches its next-but-one tile
@@ -235,6 +235,7 @@ struct StageSeg {
 struct StagePlan {
   StageSeg seg[kMaxSeg];
   int nseg;
+  int tile_envs;          // envs per tile (<= threads per CTA role; threads past it idle like those of a ragged last tile)
   int canon_ts;           // canonical plan: dense row of every operand (+ extras), odd stride
   int bulk_ts;            // bulk plan: dense row of the LDGSTS operands (+ extras) only, odd stride
   int x_off_c, x_off_b;   // offset of the extras (gathered hand velocity) in either plan's row
@@ -367,7 +368,7 @@ __device__ __forceinline__ void gather_copy(const TView& v, int64_t row, int nen
 
 // The last tile always takes the LDGSTS plan: bulk copies fetch whole aligned blocks past the operand.
 __device__ __forceinline__ bool tile_is_bulk(const StagePlan& P, int t, int ntiles) { return P.bulk_ok && (t + 1 < ntiles); }
-__device__ __forceinline__ int tile_count(int64_t n) { return (int)((n + TILE_ENVS - 1) / TILE_ENVS); }
+#define tile_count(n) ((int)(((n) + TILE_ENVS - 1) / TILE_ENVS))
 
 // Staging is split in three so a persistent CTA can refill its tile buffer while it computes:
 //   stage_begin  once per CTA (mbarrier init),
@@ -430,7 +431,7 @@ __device__ __forceinline__ void stage_prefetch_first(const StagePlan& P, const C
   if ((int)blockIdx.x >= ntiles) return;
   stage_prefetch<NSEG>(P, tmap, blockIdx.x, ntiles);
 }
-__device__ __forceinline__ void gather_prefetch(const TView& index, int has_index, const TView& rows, int64_t n) {
+__device__ __forceinline__ void gather_prefetch(const StagePlan& P, const TView& index, int has_index, const TView& rows, int64_t n) {
 #ifdef B200_NO_PREWAIT_PF
   return;
 #endif
@@ -702,7 +703,7 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
 #endif
   stage_begin(P, &tmap, &bar, hand_vel, hand_index, q_default, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   stage_prefetch_first<5>(P, &tmap, n);
-  gather_prefetch(hand_index, has_index, hand_vel, n);
+  gather_prefetch(P, hand_index, has_index, hand_vel, n);
   // everything that depends on the launch parameters only is resolved while the previous kernel is still running
   SAddr a[5];
   stage_addr<5>(P, a);
@@ -854,7 +855,7 @@ osc_pair_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView han
   stage_begin(P, &tmap, &bar, hand_vel, hand_index, q_default, out);
   if (solver) {
     stage_prefetch_first<5>(P, &tmap, n);
-    gather_prefetch(hand_index, has_index, hand_vel, n);
+    gather_prefetch(P, hand_index, has_index, hand_vel, n);
   }
   SAddr a[5];
   stage_addr<5>(P, a);
@@ -957,8 +958,8 @@ pick_osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb,
   __shared__ __align__(8) uint64_t bar;
   stage_begin(P, &tmap, &bar, rb, box_index, hand_index, q_default, dpose_out, grip, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   stage_prefetch_first<6>(P, &tmap, n);
-  gather_prefetch(box_index, 1, rb, n);
-  gather_prefetch(hand_index, 1, rb, n);
+  gather_prefetch(P, box_index, 1, rb, n);
+  gather_prefetch(P, hand_index, 1, rb, n);
   pdl_prologue();
   const int ntiles = tile_count(n);
   const int64_t env0 = (int64_t)blockIdx.x * TILE_ENVS;
@@ -1046,8 +1047,8 @@ pick_osc_pair_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TVie
   stage_begin(P, &tmap, &bar, rb, box_index, hand_index, q_default, dpose_out, grip, out);
   if (solver) {
     stage_prefetch_first<6>(P, &tmap, n);
-    gather_prefetch(box_index, 1, rb, n);
-    gather_prefetch(hand_index, 1, rb, n);
+    gather_prefetch(P, box_index, 1, rb, n);
+    gather_prefetch(P, hand_index, 1, rb, n);
   }
   pdl_prologue();
   const int ntiles = tile_count(n);
@@ -1161,8 +1162,8 @@ pick_ik_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView rb, 
   __shared__ __align__(8) uint64_t bar;
   stage_begin(P, &tmap, &bar, rb, box_index, hand_index, dpose_out, grip, out);      // mbarrier set-up touches no global memory: ahead of the dependency wait
   stage_prefetch_first<4>(P, &tmap, n);
-  gather_prefetch(box_index, 1, rb, n);
-  gather_prefetch(hand_index, 1, rb, n);
+  gather_prefetch(P, box_index, 1, rb, n);
+  gather_prefetch(P, hand_index, 1, rb, n);
   pdl_prologue();
   const int64_t env0 = (int64_t)blockIdx.x * TILE_ENVS;
   const int nenv = (int)((n - env0) < TILE_ENVS ? (n - env0) : TILE_ENVS);
@@ -1275,7 +1276,7 @@ franka_osc_step_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TV
   __shared__ __align__(8) uint64_t bar;
   stage_begin(P, &tmap, &bar, rb, hand_index, dpose_out, out);
   stage_prefetch_first<5>(P, &tmap, n);
-  gather_prefetch(hand_index, 1, rb, n);
+  gather_prefetch(P, hand_index, 1, rb, n);
   pdl_prologue();
   const int ntiles = tile_count(n);
   const int64_t env0 = (int64_t)blockIdx.x * TILE_ENVS;
@@ -1362,15 +1363,25 @@ static int vec_rows(const DLTensor* t, const char* name, int64_t n, int64_t min_
 
 static inline int tiles(int64_t n, int tile) { return (int)((n + tile - 1) / tile); }
 
-// Tile size of a launch: 64 envs (two warps; four tiles resident per SM at the throughput sizes).  The device code takes
-// the tile size from blockDim.x, so B200CTL_TILE_ENVS=128 can select 128-env tiles for experiments.  Measured and
-// rejected as a dispatch for 16,384 envs (one 128-env tile per SM instead of 108 SMs with two 64-env tiles and 40 with
-// one): osc 7.81 -> 8.96 us, pick_osc 8.57 -> 10.18 us, ik 4.02 -> 4.61 us (profiles/r02_osc_trace.txt).
+// Tile size of a launch.  Throughput launches: 64 envs (two warps; four tiles resident per SM).  A launch that fits the device
+// with ONE tile per SM (n <= 64 x SMs) is balanced instead: tile = ceil(n / SMs) rounded up to a multiple of four (bulk copies
+// move whole 16-byte blocks), at least 32 -- every SM then holds one tile of the same size instead of some SMs holding a
+// 64-env tile and others none (8,192 envs: 128 tiles of 64 -> 147 tiles of 56; osc 5.32 -> 4.94 us).  With two tiles per SM the
+// same balancing LOSES (16,384 envs, 293 tiles of 56: osc 6.61 -> 7.46 us, pick_osc 7.65 -> 8.25) and is not applied.
+// The CTA keeps 64 threads per role (block_threads): threads past the tile idle like those of a ragged last tile.
+// B200CTL_TILE_ENVS=<multiple of 4 in [32, 128]> forces a size (A/B knob; 128-env tiles measured and rejected for 16,384 envs:
+// osc 7.81 -> 8.96 us, pick_osc 8.57 -> 10.18 us, ik 4.02 -> 4.61 us, profiles/r02_osc_trace.txt).
 static int pick_tile(int64_t n, int dev) {
-  (void)n; (void)dev;
   static const int forced = [] { const char* e = getenv("B200CTL_TILE_ENVS"); return e ? atoi(e) : 0; }();
-  return (forced == kMaxTileEnvs || forced == 32) ? forced : kTileEnvs;
+  if (forced >= 32 && forced <= kMaxTileEnvs && forced % 4 == 0) return forced;
+  const int64_t sms = sm_count(dev);
+  if (forced != -1 && n > kTileEnvs / 2 * sms && n <= kTileEnvs * sms) {
+    const int t = (int)(((n + sms - 1) / sms + 3) / 4 * 4);
+    return t < 32 ? 32 : (t > kTileEnvs ? kTileEnvs : t);
+  }
+  return kTileEnvs;
 }
+static inline int block_threads(int tile) { return tile <= kTileEnvs ? kTileEnvs : kMaxTileEnvs; }
 
 // Launches of at most two 64-env tiles per SM (every warp has a scheduler to itself: the launch is ONE latency chain) take the
 // short-chain refinement of the Cholesky pivots (rsqrt_t form 2).  Measured crossover for osc_kernel: 16,384 envs 7.58 -> 6.95 us,
@@ -1464,6 +1475,7 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
   memset(tmap, 0, sizeof(*tmap));
   bool tmap_used = false;
   P.nseg = nseg;
+  P.tile_envs = tile;
   int canon = 0;
   for (int i = 0; i < nseg; ++i) {
     StageSeg& s = P.seg[i];
@@ -1657,7 +1669,7 @@ extern "C" int b200ctl_ik_dls(const DLTensor* j_eef, const DLTensor* dpose, doub
 #define LAUNCH_IK(T, DD)                                                          \
   do {                                                                            \
     B200_TRY(set_smem(ik_dls_kernel<T, DD>, smem));                               \
-    launch_pdl(ik_dls_kernel<T, DD>, tiles(n, tile), tile, smem, s, P, tmap, l2, has_pos, o, n); \
+    launch_pdl(ik_dls_kernel<T, DD>, tiles(n, tile), block_threads(tile), smem, s, P, tmap, l2, has_pos, o, n); \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_IK(double, 7); else LAUNCH_IK(float, 7); }
   else        { if (precision == 0) LAUNCH_IK(double, 9); else LAUNCH_IK(float, 9); }
@@ -1735,17 +1747,17 @@ extern "C" int b200ctl_osc(const DLTensor* j_eef, const DLTensor* mm, const DLTe
 #define LAUNCH_OSC(T, G)                                                                                     \
   do {                                                                                                       \
     B200_TRY(set_smem(osc_kernel<T, G, B200_OSC_RSQRT, false>, smem));                                       \
-    B200_TRY(persistent_grid(osc_kernel<T, G, B200_OSC_RSQRT, false>, smem, tiles(n, tile), tile, &grid));   \
-    if (sizeof(T) == 8 && short_chain_launch(n, tile, dev) && use_pair && tile == kTileEnvs) {               \
+    B200_TRY(persistent_grid(osc_kernel<T, G, B200_OSC_RSQRT, false>, smem, tiles(n, tile), block_threads(tile), &grid));   \
+    if (sizeof(T) == 8 && short_chain_launch(n, tile, dev) && use_pair && tile <= kTileEnvs) {               \
       B200_TRY(set_smem(osc_pair_kernel<T, G, kRsqrtShortChain>, smem));                                     \
       launch_pdl(osc_pair_kernel<T, G, kRsqrtShortChain>, tiles(n, tile), dim3(kTileEnvs, 2), smem, s, P, tmap, hv, hi, has_index, qdef, \
                  (float)kp, (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                         \
     } else if (sizeof(T) == 8 && short_chain_launch(n, tile, dev)) {                                         \
       B200_TRY(set_smem(osc_kernel<T, G, kRsqrtShortChain, B200_OSC_ONE>, smem));                            \
-      launch_pdl(osc_kernel<T, G, kRsqrtShortChain, B200_OSC_ONE>, tiles(n, tile), tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
+      launch_pdl(osc_kernel<T, G, kRsqrtShortChain, B200_OSC_ONE>, tiles(n, tile), block_threads(tile), smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
                  (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                                    \
     } else {                                                                                                 \
-      launch_pdl(osc_kernel<T, G, B200_OSC_RSQRT, false>, grid, tile, smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
+      launch_pdl(osc_kernel<T, G, B200_OSC_RSQRT, false>, grid, block_threads(tile), smem, s, P, tmap, hv, hi, has_index, qdef, (float)kp, \
                  (float)kd, (float)kp_null, (float)kd_null, o, n, stats);                                    \
     }                                                                                                        \
   } while (0)
@@ -1787,7 +1799,7 @@ extern "C" int b200ctl_osc_full(const DLTensor* j_eef, const DLTensor* mm, const
 #define LAUNCH_FULL(T, DD)                                                       \
   do {                                                                           \
     B200_TRY(set_smem(osc_full_kernel<T, DD>, smem));                            \
-    launch_pdl(osc_full_kernel<T, DD>, tiles(n, tile), tile, smem, s, P, tmap, fkp, fkv, o, n); \
+    launch_pdl(osc_full_kernel<T, DD>, tiles(n, tile), block_threads(tile), smem, s, P, tmap, fkp, fkv, o, n); \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_FULL(double, 7); else LAUNCH_FULL(float, 7); }
   else        { if (precision == 0) LAUNCH_FULL(double, 9); else LAUNCH_FULL(float, 9); }
@@ -1841,7 +1853,7 @@ extern "C" int b200ctl_franka_osc_step(const DLTensor* j_eef, const DLTensor* mm
 #define LAUNCH_STEP(T, DD)                                                              \
   do {                                                                                  \
     B200_TRY(set_smem(franka_osc_step_kernel<T, DD>, smem));                            \
-    launch_pdl(franka_osc_step_kernel<T, DD>, tiles(n, tile), tile, smem, s, P, tmap, rb, hi, fkp, fkv, pos_control ? 1 : 0, \
+    launch_pdl(franka_osc_step_kernel<T, DD>, tiles(n, tile), block_threads(tile), smem, s, P, tmap, rb, hi, fkp, fkv, pos_control ? 1 : 0, \
                dp, has_dpose, o, n);                                                    \
   } while (0)
   if (D == 7) { if (precision == 0) LAUNCH_STEP(double, 7); else LAUNCH_STEP(float, 7); }
@@ -1914,12 +1926,12 @@ extern "C" int b200ctl_franka_pick_osc(const DLTensor* j_eef, const DLTensor* mm
 #define LAUNCH_PICK(T, V)                                                                                              \
   do {                                                                                                                 \
     B200_TRY(set_smem(pick_osc_kernel<T, V>, smem));                                                                   \
-    launch_pdl(pick_osc_kernel<T, V>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, \
+    launch_pdl(pick_osc_kernel<T, V>, tiles(n, tile), block_threads(tile), smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, qdef, (float)kp, \
                (float)kd, (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);                             \
   } while (0)
   const bool use_pair = pair_form_allowed();
   if (precision != 0) LAUNCH_PICK(float, B200_OSC_RSQRT);
-  else if (short_chain_launch(n, tile, dev) && use_pair && tile == kTileEnvs) {
+  else if (short_chain_launch(n, tile, dev) && use_pair && tile <= kTileEnvs) {
     B200_TRY(set_smem(pick_osc_pair_kernel<double, kRsqrtShortChain>, smem));
     launch_pdl(pick_osc_pair_kernel<double, kRsqrtShortChain>, tiles(n, tile), dim3(kTileEnvs, 2), smem, s, P, tmap, rb, bi, hi, hrp,
                hr.s[0], tk, qdef, (float)kp, (float)kd, (float)kp_null, (float)kd_null, dp, has_dpose, gr, o, n, stats);
@@ -1980,10 +1992,10 @@ extern "C" int b200ctl_franka_pick_ik(const DLTensor* j_eef, const DLTensor* dof
   const int smem = P.smem_floats * 4;
   if (precision == 0) {
     B200_TRY(set_smem(pick_ik_kernel<double>, smem));
-    launch_pdl(pick_ik_kernel<double>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+    launch_pdl(pick_ik_kernel<double>, tiles(n, tile), block_threads(tile), smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
   } else {
     B200_TRY(set_smem(pick_ik_kernel<float>, smem));
-    launch_pdl(pick_ik_kernel<float>, tiles(n, tile), tile, smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
+    launch_pdl(pick_ik_kernel<float>, tiles(n, tile), block_threads(tile), smem, s, P, tmap, rb, bi, hi, hrp, hr.s[0], tk, l2, dp, has_dpose, gr, o, n);
   }
   return post_launch("pick_ik_kernel");
 }
