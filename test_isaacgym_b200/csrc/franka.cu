@@ -1366,8 +1366,10 @@ static inline int tiles(int64_t n, int tile) { return (int)((n + tile - 1) / til
 // Tile size of a launch.  Throughput launches: 64 envs (two warps; four tiles resident per SM).  A launch that fits the device
 // with ONE tile per SM (n <= 64 x SMs) is balanced instead: tile = ceil(n / SMs) rounded up to a multiple of four (bulk copies
 // move whole 16-byte blocks), at least 32 -- every SM then holds one tile of the same size instead of some SMs holding a
-// 64-env tile and others none (8,192 envs: 128 tiles of 64 -> 147 tiles of 56; osc 5.32 -> 4.94 us).  With two tiles per SM the
-// same balancing LOSES (16,384 envs, 293 tiles of 56: osc 6.61 -> 7.46 us, pick_osc 7.65 -> 8.25) and is not applied.
+// 64-env tile and others none (8,192 envs, 128 tiles of 64 -> 147 tiles of 56: osc 5.57 -> 4.43 us, ik 3.41 -> 2.94, pick_osc
+// 6.99 -> 6.50, pick_ik 4.83 -> 4.20, franka_osc_step 7.64 -> 6.52).  With TWO tiles per SM the balanced size is not the best
+// one (same-box sweeps over 36 / 44 / 48 / 56 / 64-env tiles: 10,240 envs best at 48, 12,288 at 56, 14,336 at 64, 16,384 at
+// 56 ~ 64; the balanced sizes 36 / 44 / 52 / 56 lose by up to 15 %): those launches keep 64 (profiles/r02_osc_trace.txt).
 // The CTA keeps 64 threads per role (block_threads): threads past the tile idle like those of a ragged last tile.
 // B200CTL_TILE_ENVS=<multiple of 4 in [32, 128]> forces a size (A/B knob; 128-env tiles measured and rejected for 16,384 envs:
 // osc 7.81 -> 8.96 us, pick_osc 8.57 -> 10.18 us, ik 4.02 -> 4.61 us, profiles/r02_osc_trace.txt).
