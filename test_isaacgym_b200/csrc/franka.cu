@@ -236,6 +236,7 @@ struct StagePlan {
   StageSeg seg[kMaxSeg];
   int nseg;
   int tile_envs;          // envs per tile (<= threads per CTA role; threads past it idle like those of a ragged last tile)
+  int ntiles;             // ceil(n / tile_envs)
   int canon_ts;           // canonical plan: dense row of every operand (+ extras), odd stride
   int bulk_ts;            // bulk plan: dense row of the LDGSTS operands (+ extras) only, odd stride
   int x_off_c, x_off_b;   // offset of the extras (gathered hand velocity) in either plan's row
@@ -368,7 +369,7 @@ __device__ __forceinline__ void gather_copy(const TView& v, int64_t row, int nen
 
 // The last tile always takes the LDGSTS plan: bulk copies fetch whole aligned blocks past the operand.
 __device__ __forceinline__ bool tile_is_bulk(const StagePlan& P, int t, int ntiles) { return P.bulk_ok && (t + 1 < ntiles); }
-#define tile_count(n) ((int)(((n) + TILE_ENVS - 1) / TILE_ENVS))
+#define tile_count(n) (P.ntiles)      // host-computed: a 64-bit division on the device's critical path otherwise
 
 // Staging is split in three so a persistent CTA can refill its tile buffer while it computes:
 //   stage_begin  once per CTA (mbarrier init),
@@ -714,7 +715,7 @@ osc_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView hand_vel
   typename Lay::DP aDp(a[4]);
   const int x_ts = stage_extras_ts(P);
   int hv_off = stage_extras_off(P) + (int)threadIdx.x * x_ts;
-  int ntiles = (int)((n + TILE_ENVS - 1) / TILE_ENVS);
+  int ntiles = P.ntiles;
   pin(aJ.off); pin(aJ.es); pin(aM.off); pin(aM.es); pin(aQ.off); pin(aQD.off); pin(aDp.off); pin(hv_off); pin(ntiles);
   pdl_prologue();
   OSC_TRACE(1);
@@ -866,7 +867,7 @@ osc_pair_kernel(StagePlan P, const __grid_constant__ CUtensorMap tmap, TView han
   typename Lay::DP aDp(a[4]);
   const int x_ts = stage_extras_ts(P);
   int hv_off = stage_extras_off(P) + (int)threadIdx.x * x_ts;
-  int ntiles = (int)((n + TILE_ENVS - 1) / TILE_ENVS);
+  int ntiles = P.ntiles;
   pin(aJ.off); pin(aJ.es); pin(aM.off); pin(aM.es); pin(aQ.off); pin(aQD.off); pin(aDp.off); pin(hv_off); pin(ntiles);
   pdl_prologue();
   const int t = blockIdx.x;      // one CTA per tile
@@ -1478,6 +1479,7 @@ static StagePlan make_plan(const SegSpec* spec, int nseg, int extras, int64_t n,
   bool tmap_used = false;
   P.nseg = nseg;
   P.tile_envs = tile;
+  P.ntiles = (int)((n + tile - 1) / tile);
   int canon = 0;
   for (int i = 0; i < nseg; ++i) {
     StageSeg& s = P.seg[i];
