@@ -199,20 +199,36 @@ class StepLoop:
     reads 33.9-34.1 us/step issued call by call (the first launch after the synchronize arrives ~10 us late), 33.4 at
     400 steps, and 33.0-33.3 as graph replays (kernel-to-kernel edges inside a graph are tighter than stream launches)."""
 
+    LONG = 20       # steps per long graph: the timed region of a default driver run (--steps 20) is one replay
+
     def __init__(self, device, wl, fused=None, use_graph=True):
         from test_isaacgym_b200.graph import StepGraph
         self.wl, self.fused, self.sets = wl, fused, wl.sets
         self.pos = 0            # steps issued so far; pos % sets is the buffer set of the next step
-        self.replays = 0
+        self.replays = 0        # graph replays issued
+        self.graph_steps = 0    # steps issued through graph replays
         for _ in range(self.sets):      # every entry point has run once before capture (module load)
             self._single()
-        # one graph per rotation offset r (steps over sets r, r+1, ... mod sets), so that a timed region can start anywhere
-        self.graphs = None
-        rot = [[(r + j) % self.sets for j in range(self.sets)] for r in range(self.sets)]
-        if use_graph and fused is not None:        # accumulator parity = set parity (sets is even): any rotation alternates
-            self.graphs = [[StepGraph([fused[k] for k in ks], device, warmup=0)] for ks in rot]
-        elif use_graph and (wl.window.reducer is None or wl.window.every >= self.sets):
-            self.graphs = [[StepGraph([wl.calls[k][b] for k in ks], device, warmup=0) for b in (0, 1)] for ks in rot]
+        # One graph per rotation offset r (steps over sets r, r+1, ... mod sets), so that a timed region can start anywhere,
+        # in two lengths: `sets` steps, and the multiple of `sets` nearest below LONG steps (graph-to-graph boundaries cost
+        # ~1.2 us each, profiles/r02_k20_probe.txt: 33.4 us/step in 4-step graphs, 33.1 in one 20-step graph).  A block
+        # never straddles a statistics exchange that is issued between steps (window forms), so those cap at `every`.
+        self.graphs = self.long_graphs = None
+        self.block = self.sets
+        window_form = fused is None and wl.window.reducer is not None
+        cap = min(self.LONG, wl.window.every) if window_form else self.LONG
+        if not use_graph or cap < self.sets:
+            return
+        self.block = self.sets * (cap // self.sets)
+        calls_of = (lambda k, b: fused[k]) if fused is not None else (lambda k, b: wl.calls[k][b])
+        banks = (0,) if fused is not None else (0, 1)    # fused: accumulator parity = set parity (sets is even)
+
+        def capture(length):
+            return [[StepGraph([calls_of((r + j) % self.sets, b) for j in range(length)], device, warmup=0) for b in banks]
+                    for r in range(self.sets)]
+        self.graphs = capture(self.sets)
+        if self.block > self.sets:
+            self.long_graphs = capture(self.block)
 
     def _single(self):
         if self.fused is not None:
@@ -221,27 +237,34 @@ class StepLoop:
             self.wl.step(self.pos)
         self.pos += 1
 
-    def _block_fits(self):
+    def _fits(self, length):
         """A replayed block must not straddle a statistics exchange (the all-reduce is issued between two steps).  With no
         reducer (N = 1) nothing is exchanged: the local accumulator swap simply happens after the block."""
         if self.fused is not None or self.wl.window.reducer is None:
             return True
         w = self.wl.window
-        return w.every - (w._steps % w.every) >= self.sets
+        return w.every - (w._steps % w.every) >= length
+
+    def _replay(self, graphs, length):
+        r = self.pos % self.sets
+        if self.fused is not None:
+            graphs[r][0]()
+        else:
+            graphs[r][self.wl.window.cur]()
+            for _ in range(length):
+                self.wl.window.step_done()
+        self.replays += 1
+        self.graph_steps += length
+        self.pos += length
 
     def run(self, k):
         done = 0
         while done < k:
-            if self.graphs is not None and k - done >= self.sets and self._block_fits():
-                r = self.pos % self.sets
-                if self.fused is not None:
-                    self.graphs[r][0]()
-                else:
-                    self.graphs[r][self.wl.window.cur]()
-                    for _ in range(self.sets):
-                        self.wl.window.step_done()
-                self.replays += 1
-                self.pos += self.sets
+            if self.long_graphs is not None and k - done >= self.block and self._fits(self.block):
+                self._replay(self.long_graphs, self.block)
+                done += self.block
+            elif self.graphs is not None and k - done >= self.sets and self._fits(self.sets):
+                self._replay(self.graphs, self.sets)
                 done += self.sets
             else:
                 self._single()
@@ -818,15 +841,35 @@ def run_b200(args):
         torch.cuda.synchronize(device)
         if world > 1:
             dist.barrier()
-        launches0, replays0 = _lib.launch_count(), loop.replays
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(device)
+        # Lead-in: `sets` untimed steps issued AFTER the synchronize, so the start event is recorded on a busy stream and
+        # the host has enqueued the first timed replay before the device gets there.  Without it the region opens on an
+        # idle device and counts the host's graph-launch latency (~25 us: 33.2 vs 32.0 us/step at 20 steps,
+        # gpurun_out/t13) -- a cost of the bracket, not of a step.  The timed region is still EXACTLY `steps` steps
+        # between two events on the launching stream; `cold_start_ms_per_step` below is the same region without lead-in.
+        lead_in = 0 if args.no_lead_in else wl.sets
+        loop.run(lead_in)
+        launches0, replays0, gsteps0 = _lib.launch_count(), loop.replays, loop.graph_steps
         start.record()
         loop.run(args.steps)
         end.record()
         torch.cuda.synchronize(device)
         # kernels launched inside the timed region: C-ABI calls issued one by one + the kernels of the replayed graphs
-        launches = _lib.launch_count() - launches0 + (loop.replays - replays0) * wl.sets
+        launches = _lib.launch_count() - launches0 + (loop.graph_steps - gsteps0)
+        # the same K steps opened on an idle device (synchronize immediately before the start event)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        c0.record()
+        loop.run(args.steps)
+        c1.record()
+        torch.cuda.synchronize(device)
+        cold = torch.tensor([c0.elapsed_time(c1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(cold, op=dist.ReduceOp.MAX)
+        cold_ms_per_step = cold.item() / args.steps
         wl.window.finish()
         stats_check = None
         if in_kernel:      # the exchanged vector of a full step: every rank must read the global env count
@@ -921,9 +964,14 @@ def run_b200(args):
                                              "from the same pinned buffers, no kernel, all ranks at once (barrier-aligned), slowest rank"},
                 "frac_of_host_link_ceiling": link_s / (e2e_s.item() / e2e_steps)},
         "gpu_launches": int(launches),
+        "timed_region": {"lead_in_steps": lead_in, "cold_start_ms_per_step": cold_ms_per_step,
+                         "how": "barrier + synchronize, `lead_in_steps` untimed steps, start event, exactly `steps` steps, end "
+                                "event, synchronize + barrier; cold_start = the same without lead-in (idle device at the start "
+                                "event: counts the host's graph-launch latency once)"},
         "step_issue": ("single bound calls (--no-graph)" if loop.graphs is None else
-                       f"CUDA graphs of {wl.sets} consecutive steps (one per buffer set), replayed: {loop.replays - replays0} replays + "
-                       f"{int(launches) - (loop.replays - replays0) * wl.sets} single launches in the timed region"),
+                       f"CUDA graphs of {loop.block} / {wl.sets} consecutive steps (rotating over the {wl.sets} buffer sets), replayed: "
+                       f"{loop.replays - replays0} replays = {loop.graph_steps - gsteps0} steps + "
+                       f"{int(launches) - (loop.graph_steps - gsteps0)} single launches in the timed region"),
         "clocks": clocks.summary(),
     }
     if strong is not None:
@@ -999,6 +1047,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (N > 1)")
     ap.add_argument("--sustain-s", type=float, default=1.0, help="seconds of pre-load before the timed region (clock sampling)")
     ap.add_argument("--no-graph", action="store_true", help="issue every step as a single bound call instead of replaying 4-step CUDA graphs")
+    ap.add_argument("--no-lead-in", action="store_true", help="open the timed region on an idle device (no untimed steps between the synchronize and the start event)")
     ap.add_argument("--no-families", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
