@@ -856,7 +856,8 @@ def run_b200(args):
         end.record()
         torch.cuda.synchronize(device)
         # kernels launched inside the timed region: C-ABI calls issued one by one + the kernels of the replayed graphs
-        launches = _lib.launch_count() - launches0 + (loop.graph_steps - gsteps0)
+        timed_replays, timed_gsteps = loop.replays - replays0, loop.graph_steps - gsteps0
+        launches = _lib.launch_count() - launches0 + timed_gsteps
         # the same K steps opened on an idle device (synchronize immediately before the start event)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(device)
@@ -970,8 +971,8 @@ def run_b200(args):
                                 "event: counts the host's graph-launch latency once)"},
         "step_issue": ("single bound calls (--no-graph)" if loop.graphs is None else
                        f"CUDA graphs of {loop.block} / {wl.sets} consecutive steps (rotating over the {wl.sets} buffer sets), replayed: "
-                       f"{loop.replays - replays0} replays = {loop.graph_steps - gsteps0} steps + "
-                       f"{int(launches) - (loop.graph_steps - gsteps0)} single launches in the timed region"),
+                       f"{timed_replays} replays = {timed_gsteps} steps + "
+                       f"{int(launches) - timed_gsteps} single launches in the timed region"),
         "clocks": clocks.summary(),
     }
     if strong is not None:
