@@ -270,6 +270,49 @@ __device__ __forceinline__ void block_stats_commit(double (&d)[ND], unsigned (&u
   if (lane < ND + NI && v != 0.0) atomicAdd(stats + slot, v);
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// The same commit for kernels whose per-thread partial sums are fp32 already (the servo step): a persistent servo grid of
+// four waves runs it once per 1.7 tiles, so its instruction count is paid per tile -- the fp64 form above was ~95 warp
+// instructions per CTA-warp, a third of what a statistics-carrying 1M-env step executes on top of the plain one
+// (ncu smsp__inst_executed 29.7 M vs 25.7 M).  Here: one fp32 butterfly per warp (one SHFL + one FADD per level and
+// sum), REDUX for the counts, lane j keeps entry j and stores it with ONE predicated STS; after the barrier lane j of
+// warp 0 adds the per-warp partials of ITS entry in fp64 (no second butterfly) and issues the CTA's one RED instruction.
+// Counts stay exact (a warp's count is far below 2^24).  Every thread of the CTA must call it; at most 32 warps.
+template <int NF, int NI>
+__device__ __forceinline__ void block_stats_commit_f32(float (&f)[NF], unsigned (&u)[NI], double* stats,
+                                                       const int (&slots)[NF + NI]) {
+  static_assert(NF + NI <= 8, "statistics vector has 8 entries");
+  __shared__ float s_p[NF + NI][32];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NF; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], o);
+  }
+#pragma unroll
+  for (int k = 0; k < NI; ++k) u[k] = __reduce_add_sync(0xffffffffu, u[k]);
+  float v = 0.f;
+  int slot = 0;
+#pragma unroll
+  for (int j = 0; j < NF; ++j) { v = (lane == j) ? f[j] : v; slot = (lane == j) ? slots[j] : slot; }
+#pragma unroll
+  for (int j = 0; j < NI; ++j) { v = (lane == NF + j) ? (float)u[j] : v; slot = (lane == NF + j) ? slots[NF + j] : slot; }
+  if (lane < NF + NI) s_p[lane][warp] = v;
+  __syncthreads();
+  if (warp != 0 || lane >= NF + NI) return;
+  const int nwarp = (blockDim.x * blockDim.y + 31) >> 5;
+  double tot = 0.0;
+#pragma unroll 1      // two to eight trips at the cold tail of the kernel: size counts, not trip overhead
+  for (int w = 0; w < nwarp; ++w) tot += (double)s_p[lane][w];
+  if (tot != 0.0) atomicAdd(stats + slot, tot);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace b200ctl

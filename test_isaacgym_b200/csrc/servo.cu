@@ -236,7 +236,11 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
       // a unit quaternion's components cannot overflow their sum: the sum is finite iff all four are
       const bool finite = isfinite((oq[0] + oq[1]) + (oq[2] + oq[3]));
       if (!isfinite(err2)) err2 = 0.f;
+#ifdef B200_SERVO_COMMIT_F64
       acc_f[0] += sqrtf(err2);
+#else
+      acc_f[0] += sqrt_approx(err2);      // statistics only: MUFU-grade (2^-22) instead of the IEEE-rounded sequence
+#endif
       acc_f[1] += err2;
       acc_u[0] += 1u;
       acc_u[1] += behind ? 1u : 0u;
@@ -269,8 +273,12 @@ __device__ __forceinline__ void servo_step_body(float* __restrict__ state, int64
   if (STATS) {
     const int slots[5] = {B200CTL_STAT_SUM_ABS, B200CTL_STAT_SUM_SQ, B200CTL_STAT_N_ENV, B200CTL_STAT_N_SAT,
                           B200CTL_STAT_N_NONFINITE};
+#ifdef B200_SERVO_COMMIT_F64      // A/B knob (profiles/): the generic fp64 commit
     double acc_d[2] = {(double)acc_f[0], (double)acc_f[1]};
     block_stats_commit<2, 3>(acc_d, acc_u, stats, slots);      // (uses its own shared arrays, not the tile buffers)
+#else
+    block_stats_commit_f32<2, 3>(acc_f, acc_u, stats, slots);
+#endif
   }
   if (NBUF == 2 && threadIdx.x == 0) bulk_wait_read();   // shared memory outlives the last write-back's read
   SERVO_TRACE(3);
@@ -656,7 +664,9 @@ extern "C" int b200ctl_servo_step(DLTensor* root_state, const b200ctl_servo_para
   // stride at the tail, many waves pay one commit per CTA.  Per 1M envs, reference precision (64-env tiles, fp64 stages)
   // 2 / 4 / 8 / 16 waves: 39.8 / 39.0 / 42.5 / 42.5 us -> FOUR; fp32 mode (128-env tiles) 37.2 / 35.4 / 35.0 / 34.9 us
   // -> SIXTEEN, i.e. one CTA per tile, where its statistics are free (34.9 us without them)
-  // (profiles/r02_ab_servo_stats.txt; A/B knob B200_SERVO_STATS_WAVES).
+  // (profiles/r02_ab_servo_stats.txt; A/B knob B200_SERVO_STATS_WAVES).  With the fp32 commit (block_stats_commit_f32:
+  // 41 -> 37.6 us) 3 / 4 / 5 / 6 / 8 waves read 38.6 / 37.7 / 39.2 / 39.0 / 40.3 us: four waves of 14 x 148 CTAs are 8,288 CTAs for
+  // 16,384 tiles -- two tiles per CTA almost exactly, so the static tile stride leaves no tail.
 #ifdef B200_SERVO_STATS_WAVES
   const int waves = B200_SERVO_STATS_WAVES;
 #else
