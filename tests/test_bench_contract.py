@@ -67,3 +67,67 @@ def test_stdout_carries_the_json_line_only():
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("\n") == 1 and json.loads(r.stdout) == {"metric": "m", "value": 1.0}
     assert "NCCL version" in r.stderr and "python-level noise" in r.stderr
+
+
+@pytest.mark.parametrize("window_form,every", [(False, 16), (True, 16), (True, 4), (True, 3)])
+def test_step_loop_blocks_issue_the_same_steps_as_single_calls(monkeypatch, window_form, every):
+    """The headline loop replays 20-step and 4-step graphs and falls back to single bound calls: whatever mix it picks,
+    the (buffer set, accumulator bank) sequence must be the one single calls would issue, the step counts must add up,
+    and with a statistics exchange between steps (window forms) no replayed block may straddle a window boundary."""
+    import bench
+    import test_isaacgym_b200.graph as graph_mod
+
+    log = []
+
+    class FakeGraph:
+        def __init__(self, calls, device, warmup=0, restore=()):
+            self.calls = calls
+
+        def __call__(self):
+            FakeWindow.block_open = len(self.calls)
+            for c in self.calls:
+                c()
+
+    class FakeWindow:
+        block_open = 0      # steps of the replay in flight whose step_done() has not been called yet
+
+        def __init__(self):
+            self.reducer, self.every, self.cur, self._steps, self.boundaries_inside_blocks = (object() if window_form else None), every, 0, 0, 0
+
+        def step_done(self):
+            self._steps += 1
+            if FakeWindow.block_open:
+                FakeWindow.block_open -= 1
+            if self._steps % self.every == 0:
+                if FakeWindow.block_open:       # an exchange would be due while later steps of the block are already enqueued
+                    self.boundaries_inside_blocks += 1
+                self.cur ^= 1
+
+    class FakeWorkload:
+        sets = 4
+
+        def __init__(self):
+            self.window = FakeWindow()
+            self.calls = [[(lambda k=k, b=b: log.append((k, b))) for b in (0, 1)] for k in range(self.sets)]
+
+        def step(self, i):
+            self.calls[i % self.sets][self.window.cur]()
+            self.window.step_done()
+
+    monkeypatch.setattr(graph_mod, "StepGraph", FakeGraph)
+    for ks in ([20], [3, 20, 23, 1, 7, 44], [400], [5, 5, 5, 64]):
+        log.clear()
+        wl = FakeWorkload()
+        loop = bench.StepLoop(None, wl)
+        assert loop.block == (20 if not window_form or every >= 20 else max(4, 4 * (min(20, every) // 4)) if every >= 4 else 4)
+        issued = wl.sets
+        for k in ks:
+            before = len(log)
+            loop.run(k)
+            issued += k
+            assert len(log) - before == k and loop.pos == issued
+        assert [s for s, _ in log] == [i % wl.sets for i in range(issued)]
+        if window_form:
+            assert wl.window.boundaries_inside_blocks == 0
+            assert [b for _, b in log] == [(i // every) & 1 for i in range(issued)]
+        assert loop.graph_steps <= issued and (every < 4 and window_form) == (loop.graphs is None)
