@@ -77,7 +77,10 @@ B200CTL_API uint64_t b200ctl_launch_count(void);
 /* ---- per-step statistics vector -------------------------------------------
  * double[B200CTL_STATS_LEN] in device memory, ACCUMULATED (atomicAdd) by the
  * kernels that take a `stats` argument; the caller zeroes it.  All entries are
- * sums, so one ncclAllReduce(sum) merges env slices across GPUs.
+ * sums, so one ncclAllReduce(sum) merges env slices across GPUs.  Counts are
+ * exact.  Sums: P and O add fp64 per-thread sums (P: independent of how envs
+ * are sliced over GPUs up to fp64 summation order); S adds fp32 per-thread /
+ * per-warp partial sums of fp32-grade norms in fp64 (~1e-7 relative).
  * The reference has no episode statistics: this is new surface. */
 #define B200CTL_STATS_LEN 8
 enum {
