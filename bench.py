@@ -71,6 +71,52 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def copy_bandwidth_here(device, index, seconds=1.0):
+    """The measurement behind MEASURED_PEAKS.json's hbm_gbs, repeated on THIS box in THIS process: `b.copy_(a)` over 1 Gi
+    bf16 elements (read + write bytes), best of 10 single launches (burst) and back to back for `seconds` (sustained: the
+    state the headline loop runs in), once over ZEROS and once over RANDOM BITS, with SM clock / board power / throttle
+    reasons sampled during each sustained run.  The board's power depends on the data: the same copy draws ~660-790 W
+    over zeros and sits at the 1,000 W cap over random bits (profiles/r02_pd_power.txt) -- the PD loop streams real floats.
+    Informational: `roofline.frac` stays against the driver-written peak."""
+    n = 1 << 30
+    b = torch.empty(n, dtype=torch.bfloat16, device=device)
+    nbytes = 2.0 * n * 2
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    out = {"how": "torch b.copy_(a) over 1 Gi bf16 elements, read + write bytes: best of 10 launches (burst) / back to back for "
+                  f"{seconds} s (sustained), this box, this process, right after the headline loop; source = zeros / random bits"}
+    for tag in ("zeros", "random"):
+        a = (torch.zeros(n, dtype=torch.bfloat16, device=device) if tag == "zeros" else
+             torch.randint(-32768, 32767, (n,), dtype=torch.int16, device=device).view(torch.bfloat16))
+        for _ in range(3):
+            b.copy_(a)
+        torch.cuda.synchronize(device)
+        best = 1e9
+        for _ in range(10):
+            s, e = ev(), ev()
+            s.record(); b.copy_(a); e.record()
+            torch.cuda.synchronize(device)
+            best = min(best, s.elapsed_time(e))
+        with ClockSampler(index) as smp:
+            reps, t0 = 0, time.perf_counter()
+            s, e = ev(), ev()
+            s.record()
+            while time.perf_counter() - t0 < seconds:
+                for _ in range(32):
+                    b.copy_(a)
+                reps += 32
+                if reps % 256 == 0:
+                    torch.cuda.synchronize(device)      # bound the launch queue
+            e.record()
+            torch.cuda.synchronize(device)
+        c = smp.summary()
+        out[tag] = {"burst_gbs": nbytes / best / 1e6, "sustained_gbs": nbytes / (s.elapsed_time(e) / reps) / 1e6,
+                    "sm_mhz": c.get("sm_mhz"), "board_w": c.get("board_w"), "reasons": c.get("reasons")}
+        del a
+    del b
+    torch.cuda.empty_cache()
+    return out
+
+
 def workload_name():
     return f"pd_torque: {ENVS_PER_GPU} envs x {NUM_DOFS} DOF per GPU (BASELINE configs[3], one env slice per GPU)"
 
@@ -90,7 +136,7 @@ class ClockSampler:
 
     def __init__(self, index: int, period_s: float = 0.02):
         self.index, self.period = index, period_s
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.watts = [], set(), []
         self.max_mhz = None
         self._stop = threading.Event()
         self._thread = None
@@ -116,6 +162,10 @@ class ClockSampler:
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
                     nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
                 self.samples.append((mhz, util))
+                try:
+                    self.watts.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1e3)
+                except Exception:
+                    pass
                 for bit, name in self._NAMES.items():
                     if mask & bit and name != "gpu_idle":
                         self.reasons.add(name)
@@ -138,8 +188,11 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
         busy = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(self.samples)}
+        if self.watts:
+            out["board_w"] = statistics.median(self.watts[len(self.watts) // 2:])      # settled half of the run
+        return out
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -989,6 +1042,11 @@ def run_b200(args):
             line["roofline"]["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
         except Exception:
             pass
+    if rank == 0 and world == 1 and not args.no_copy_probe:
+        here = copy_bandwidth_here(device, local_rank)
+        line["roofline"]["copy_here"] = here
+        line["roofline"]["frac_of_sustained_copy_here"] = {"zeros": achieved / here["zeros"]["sustained_gbs"],
+                                                            "random": achieved / here["random"]["sustained_gbs"]}
     if rank == 0 and world == 1 and not args.no_families:
         # give the headline's 1.6 GB of buffers back first: the family entries are then laid out in device memory as
         # in a process of their own (with the buffers alive the 262,144-env OSC entry read 53.9 us instead of 50.9)
@@ -1049,6 +1107,7 @@ def main():
     ap.add_argument("--sustain-s", type=float, default=1.0, help="seconds of pre-load before the timed region (clock sampling)")
     ap.add_argument("--no-graph", action="store_true", help="issue every step as a single bound call instead of replaying 4-step CUDA graphs")
     ap.add_argument("--no-lead-in", action="store_true", help="open the timed region on an idle device (no untimed steps between the synchronize and the start event)")
+    ap.add_argument("--no-copy-probe", action="store_true", help="skip the in-process copy-bandwidth probe (roofline.copy_here)")
     ap.add_argument("--no-families", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -145,6 +145,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, dim3 block, si
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#ifdef B200_NO_PDL      // A/B knob: plain stream-ordered launches
+  cfg.numAttrs = 0;
+#endif
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 template <typename... KArgs, typename... Args>

@@ -232,12 +232,14 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
   // 65,536-env launch.
   idx_t v = v0;
   float4 s0, s1, tg, qd = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef B200_PD_NO_ROTATE       // A/B knob: loads at the top of each iteration instead of one iteration ahead
   if (v < nvec) {
     s0 = ldg_stream4(state + 2 * v);       // q0 qd0 q1 qd1
     s1 = ldg_stream4(state + 2 * v + 1);   // q2 qd2 q3 qd3
     tg = ldg_stream4(q_tgt + v);
     if (HAS_QD) qd = ldg_stream4(qd_tgt + v);
   }
+#endif
   float* s_kp = s_par;
   float* s_kd = s_par + num_dofs;
   float* s_tm = s_par + 2 * num_dofs;
@@ -258,6 +260,12 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
   int dfirst = (int)((4 * (uint64_t)v0) % (unsigned)num_dofs);
   const int dstep = (int)((4 * (uint64_t)stride) % (unsigned)num_dofs);
   while (v < nvec) {
+#ifdef B200_PD_NO_ROTATE
+    s0 = ldg_stream4(state + 2 * v);
+    s1 = ldg_stream4(state + 2 * v + 1);
+    tg = ldg_stream4(q_tgt + v);
+    if (HAS_QD) qd = ldg_stream4(qd_tgt + v);
+#endif
     const int d0 = dfirst;
     dfirst += dstep;
     if (dfirst >= num_dofs) dfirst -= num_dofs;
@@ -290,12 +298,14 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
     o.w = pd_element<WRAP, CLAMP_TGT, HAS_QD, HAS_TMAX>(s1.z, s1.w, tg.w, qd.w, kp.w, kd.w, tm.w, lo.w, hi.w);
     stg_stream4(tau_out + v, o);
     v += stride;
+#ifndef B200_PD_NO_ROTATE
     if (v < nvec) {                        // next iteration's loads, all issued before their first use
       s0 = ldg_stream4(state + 2 * v);
       s1 = ldg_stream4(state + 2 * v + 1);
       tg = ldg_stream4(q_tgt + v);
       if (HAS_QD) qd = ldg_stream4(qd_tgt + v);
     }
+#endif
     if (STATS) acc.add4<HAS_TMAX>(o, tm);  // under the loads just issued
   }
 #ifdef B200_PD_STATS_NOCOMMIT      // diagnostic: the accumulation without the reduction / atomics (results unusable)
@@ -365,6 +375,10 @@ static int pd_grid(K kernel, size_t smem, int dev, int64_t work_items, int block
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t full = waves == 1 ? (int64_t)usable_slots(dev, per_sm) : (int64_t)sm_count(dev) * per_sm * waves;
   const int64_t need = (work_items + block - 1) / block;
+#ifdef B200_PD_GRID_PER_SM      // A/B knob (profiles/experiments/pd_power_probe.py): resident CTAs per SM of the grid-stride grids
+  const int64_t cap = (int64_t)sm_count(dev) * B200_PD_GRID_PER_SM;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+#endif
   return (int)(need < full ? (need > 0 ? need : 1) : full);
 }
 
