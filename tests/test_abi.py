@@ -81,3 +81,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_plain_c_consumer(tmp_path):
+    """include/b200ctl.h is a C header (C99, -pedantic -Werror) and a gcc-built program can link the library and use
+    the error channel: the boundary a non-Python host binding (cgo / JNI / N-API) would sit on.  No GPU needed: every
+    call is refused by argument validation before any CUDA call."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cc = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "tests", "c_abi", "consumer.c"), "-o", str(exe), "-L", libdir,
+                         "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0 and "consumer OK" in run.stdout, run.stdout + run.stderr
