@@ -19,7 +19,6 @@
 // statistics epilogue (one RED instruction per CTA), four without.
 // Arithmetic is fp32 with explicit round-to-nearest intrinsics (no FMA
 // contraction): bit-identical to the torch expression of the reference.
-#include <type_traits>
 #include "peer.cuh"
 
 #include <string.h>
@@ -260,21 +259,6 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
   // instructions than the law itself
   int dfirst = (int)((4 * (uint64_t)v0) % (unsigned)num_dofs);
   const int dstep = (int)((4 * (uint64_t)stride) % (unsigned)num_dofs);
-  // FIXED: the grid's stride is a multiple of D elements (the host rounds the grid for it), so a thread meets the SAME
-  // four DOFs in every iteration and reads their parameters once, ahead of the loop, instead of three to five LDS.128
-  // and the DOF bookkeeping per iteration.
-  auto run = [&](auto fixed_tag) {
-  constexpr bool FIXED = decltype(fixed_tag)::value;
-  float4 kp = make_float4(0.f, 0.f, 0.f, 0.f), kd = kp, tm = kp, lo = kp, hi = kp;
-  if (FIXED) {
-    kp = *reinterpret_cast<const float4*>(s_kp + dfirst);
-    kd = *reinterpret_cast<const float4*>(s_kd + dfirst);
-    if (HAS_TMAX) tm = *reinterpret_cast<const float4*>(s_tm + dfirst);
-    if (CLAMP_TGT) {
-      lo = *reinterpret_cast<const float4*>(s_lo + dfirst);
-      hi = *reinterpret_cast<const float4*>(s_hi + dfirst);
-    }
-  }
   while (v < nvec) {
 #ifdef B200_PD_NO_ROTATE
     s0 = ldg_stream4(state + 2 * v);
@@ -283,13 +267,10 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
     if (HAS_QD) qd = ldg_stream4(qd_tgt + v);
 #endif
     const int d0 = dfirst;
-    if (!FIXED) {
-      dfirst += dstep;
-      if (dfirst >= num_dofs) dfirst -= num_dofs;
-    }
-    if (FIXED) {
-      // parameters were read once, ahead of the loop
-    } else if (!DANY) {
+    dfirst += dstep;
+    if (dfirst >= num_dofs) dfirst -= num_dofs;
+    float4 kp, kd, tm = make_float4(0.f, 0.f, 0.f, 0.f), lo = tm, hi = tm;
+    if (!DANY) {
       kp = *reinterpret_cast<const float4*>(s_kp + d0);
       kd = *reinterpret_cast<const float4*>(s_kd + d0);
       if (HAS_TMAX) tm = *reinterpret_cast<const float4*>(s_tm + d0);
@@ -327,13 +308,6 @@ pd_torque_vec4_kernel(const float4* __restrict__ state, const float4* __restrict
 #endif
     if (STATS) acc.add4<HAS_TMAX>(o, tm);  // under the loads just issued
   }
-  };
-#ifdef B200_PD_FIXED_DOF
-  if constexpr (!DANY) {
-    if (dstep == 0) { run(std::true_type{}); } else { run(std::false_type{}); }
-  } else
-#endif
-  { run(std::false_type{}); }
 #ifdef B200_PD_STATS_NOCOMMIT      // diagnostic: the accumulation without the reduction / atomics (results unusable)
   if (STATS && acc.sum_abs == -1.0) stats[0] = acc.sum_sq + acc.n_sat + acc.n_bad;
 #else
@@ -419,14 +393,6 @@ static void pd_launch_one(const PdLaunch& L) {
     // without -- same speed, and a co-resident kernel of another stream then costs its share of the SM slots instead
     // of pushing a straggler wave behind a one-wave grid.
     int grid = pd_grid(kern, smem, L.dev, L.num_envs * L.num_dofs / 4, block, STATS ? 1 : 4);
-#ifdef B200_PD_FIXED_DOF
-    if (L.num_dofs % 4 == 0) {           // a stride of whole envs' worth of vectors: every thread keeps its four DOFs
-      int a = L.num_dofs, b = block * 4;
-      while (b) { const int t = a % b; a = b; b = t; }
-      const int m = L.num_dofs / a;      // grid must be a multiple of D / gcd(D, 4 * block)
-      if (m > 1 && m <= 16 && grid >= 8 * m && (int64_t)grid * block < L.num_envs * L.num_dofs / 4) grid -= grid % m;
-    }
-#endif
     if (STATS && L.pub.world > 0) {      // one slot of the persistent grid goes to the publisher CTA
       const int slots = usable_slots(L.dev, pd_ctas(true));
       grid = (grid >= slots && grid > 1 ? slots - 1 : grid) + 1;
