@@ -16,13 +16,19 @@ NVLink peer memory and sums the rows of the step before).  Other forms: the libr
 all-reduce kernel (peer / peer-lagged, every --stats-every steps) or NCCL (nccl).  N > 1 lines
 also carry `strong` (1,048,576 envs IN TOTAL split over the N GPUs) and `per_step_stats` (the same
 loop under the other exchange forms, measured side by side in this process).  The loop is issued the
-way the rollout harness issues control steps: 4 consecutive steps (one per rotating buffer set)
-captured once as a CUDA graph and replayed (`step_issue`; --no-graph issues single bound calls).
+way the rollout harness issues control steps: consecutive steps over the rotating buffer sets captured
+once as CUDA graphs (20 steps, and 4 for what does not fill 20) and replayed (`step_issue`; --no-graph
+issues single bound calls).  The timed region is exactly K steps between two CUDA events on the launching
+stream, bracketed by barrier + synchronize; one untimed buffer rotation is enqueued between the
+synchronize and the start event so that the region opens on a busy stream (`timed_region`, which also
+reports the same K steps opened on an idle device; --no-lead-in makes that the headline).
 If the peer mailboxes cannot be mapped (no peer access) every rank falls back to NCCL in order and
 the line says so (`stats_collective_note`).
 
 Printed keys beyond the base contract:
-  roofline      dominant kernel vs measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes
+  roofline      dominant kernel vs measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes; `copy_here` = the peak's
+                own measurement (torch copy, burst / sustained) repeated in this process over zeros and over random bits
+                with SM clock / board power: the sustained loop runs at the board's power cap, and power follows the data
   cpu_baseline  the oracle port (torch-CPU restatement of the reference expression) on the host cores
   e2e           same metric through the public host-tensor API (pinned host buffers, H2D + D2H timed)
   families      per-GPU numbers for the other laws / sizes of BASELINE.json configs (rank 0, N=1)
